@@ -1,0 +1,298 @@
+// Fused SetCriterion: forward (2 launches) and backward (1 launch) for ALL decoder layers at once.
+//
+// Replaces detr/loss.py:198-231: per layer { loss_labels (57-95), loss_cardinality (97-121), loss_boxes (123-164) },
+// i.e. ~60 ATen kernels + CPU-index -> CUDA-index copies per layer, by
+//   criterion_fwd_kernel       one CTA per (image, layer): one pass over the logits gives log-sum-exp, weighted NLL
+//                              numerator/denominator, arg-max (cardinality, class_error); one pass over the matched
+//                              pairs gives the L1 and GIoU sums.  Per-problem partial sums, no float atomics.
+//   criterion_finalize_kernel  fixed-order reduction over images -> the L x 5 loss table (deterministic).
+//   criterion_bwd_kernel       dense grad_logits (softmax - onehot, scaled) and grad_boxes (analytic L1 + GIoU).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace detr {
+
+constexpr int kCritThreads = 128;
+constexpr int kPartials = 8;  // {sum w*nll, sum w, n_pred_nonempty, n_correct, l1_sum, giou_sum, n_pairs, unused}
+
+struct CritParams {
+    const float* logits; int64_t lg_sb, lg_sl, lg_sq;
+    const float* boxes;  int64_t bx_sb, bx_sl, bx_sq;
+    const int64_t* gt_labels; const float* gt_boxes; const int32_t* gt_off; const int32_t* match_off;
+    const int64_t* idx_q; const int64_t* idx_gt;
+    const float* class_weight; const float* num_boxes;
+    int B, L, Q, K;
+    float w_ce, w_l1, w_giou;
+    float* partials; float* lse; int32_t* tgt; float* wsum; float* losses;
+    int32_t* status;
+    // backward only
+    const float* grad_losses; float* grad_logits; float* grad_boxes;
+};
+
+struct Box4 { float x1, y1, x2, y2; };
+
+__device__ __forceinline__ Box4 cxcywh_to_xyxy(float4 c) {
+    Box4 r;
+    r.x1 = __fsub_rn(c.x, __fdiv_rn(c.z, 2.f));
+    r.y1 = __fsub_rn(c.y, __fdiv_rn(c.w, 2.f));
+    r.x2 = __fadd_rn(c.z, r.x1);
+    r.y2 = __fadd_rn(c.w, r.y1);
+    return r;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red /*[4]*/, int tid) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    return (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+__global__ void __launch_bounds__(kCritThreads) criterion_fwd_kernel(const CritParams p) {
+    extern __shared__ int s_tgt[];  // [Q] target class per query, then [Q] matched flag
+    __shared__ float red[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
+    const int Q = p.Q, K = p.K;
+    int* s_matched = s_tgt + Q;
+    const int g0 = p.gt_off[b], M = p.gt_off[b + 1] - g0;
+    const int n = min(Q, M);
+    const int64_t moff = (int64_t)p.L * p.match_off[b] + (int64_t)l * n;
+    const float* lg = p.logits + b * p.lg_sb + l * p.lg_sl;
+    const float* bx = p.boxes + b * p.bx_sb + l * p.bx_sl;
+
+    for (int q = tid; q < Q; q += kCritThreads) { s_tgt[q] = K - 1; s_matched[q] = 0; }
+    __syncthreads();
+    // scatter the matched labels (detr/loss.py:79-85) and accumulate the box losses of the matched pairs
+    float l1 = 0.f, gi = 0.f, npairs = 0.f;
+    for (int k = tid; k < n; k += kCritThreads) {
+        const int64_t q = p.idx_q[moff + k], g = p.idx_gt[moff + k];
+        if (q < 0 || q >= Q || g < 0 || g >= M) continue;  // poisoned by a failed assignment: status already set
+        int64_t lab = p.gt_labels[g0 + g];
+        if (lab < 0 || lab >= K) { atomicOr(p.status, DETR_ST_BAD_LABEL); lab = K - 1; }
+        s_tgt[q] = (int)lab;
+        s_matched[q] = 1;
+        npairs += 1.f;
+        const float4 s = *reinterpret_cast<const float4*>(bx + q * p.bx_sq);
+        const float4 t = *reinterpret_cast<const float4*>(p.gt_boxes + (int64_t)(g0 + g) * 4);
+        // L1 against cxcywh(target) (detr/loss.py:149-156)
+        const float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
+        const float tcx = __fdiv_rn(__fadd_rn(__fmul_rn(t.x, 2.f), tw), 2.f);
+        const float tcy = __fdiv_rn(__fadd_rn(__fmul_rn(t.y, 2.f), th), 2.f);
+        l1 += fabsf(s.x - tcx) + fabsf(s.y - tcy) + fabsf(s.z - tw) + fabsf(s.w - th);
+        // GIoU loss with eps (torchvision giou_loss.py:47-62, _utils.py:87-106)
+        const Box4 a = cxcywh_to_xyxy(s);
+        const float eps = 1e-7f;
+        const float ix1 = fmaxf(a.x1, t.x), iy1 = fmaxf(a.y1, t.y), ix2 = fminf(a.x2, t.z), iy2 = fminf(a.y2, t.w);
+        const float inter = (iy2 > iy1 && ix2 > ix1) ? __fmul_rn(ix2 - ix1, iy2 - iy1) : 0.f;
+        const float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.x2 - a.x1, a.y2 - a.y1), __fmul_rn(t.z - t.x, t.w - t.y)), inter);
+        const float iou = __fdiv_rn(inter, uni + eps);
+        const float hull = __fmul_rn(fmaxf(a.x2, t.z) - fminf(a.x1, t.x), fmaxf(a.y2, t.w) - fminf(a.y1, t.y));
+        gi += 1.f - (iou - __fdiv_rn(hull - uni, hull + eps));
+    }
+    __syncthreads();
+
+    // one query row per warp: log-sum-exp, weighted NLL, arg-max
+    float wnll = 0.f, wsum = 0.f, nonempty = 0.f, correct = 0.f;
+    float* lse_out = p.lse + (int64_t)blockIdx.x * Q;
+    int32_t* tgt_out = p.tgt + (int64_t)blockIdx.x * Q;
+    for (int q = warp; q < Q; q += kCritThreads / 32) {
+        const float* row = lg + (int64_t)q * p.lg_sq;
+        float mx = -CUDART_INF_F;
+        int am = 0x7fffffff;
+        for (int k = lane; k < K; k += 32) {
+            const float v = row[k];
+            if (v > mx) { mx = v; am = k; }
+        }
+        // warp arg-max, lowest index wins ties (torch.argmax / topk behaviour on distinct values is unaffected)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float omx = __shfl_xor_sync(FULL_MASK, mx, o);
+            const int oam = __shfl_xor_sync(FULL_MASK, am, o);
+            if (omx > mx || (omx == mx && oam < am)) { mx = omx; am = oam; }
+        }
+        float sum = 0.f;
+        for (int k = lane; k < K; k += 32) sum += expf(row[k] - mx);
+        sum = warp_sum(sum);
+        if (lane == 0) {
+            const int t = s_tgt[q];
+            const float lse = mx + logf(sum);
+            const float w = p.class_weight[t];
+            wnll += w * (lse - row[t]);
+            wsum += w;
+            nonempty += (am != K - 1) ? 1.f : 0.f;
+            if (s_matched[q]) correct += (am == t) ? 1.f : 0.f;
+            lse_out[q] = lse;
+            tgt_out[q] = t;
+        }
+    }
+    float* out = p.partials + (int64_t)blockIdx.x * kPartials;
+    const float r0 = block_sum(wnll, red, tid), r1 = block_sum(wsum, red, tid), r2 = block_sum(nonempty, red, tid),
+                r3 = block_sum(correct, red, tid), r4 = block_sum(l1, red, tid), r5 = block_sum(gi, red, tid),
+                r6 = block_sum(npairs, red, tid);
+    if (tid == 0) {
+        out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3; out[4] = r4; out[5] = r5; out[6] = r6; out[7] = 0.f;
+    }
+}
+
+// one warp per layer; images are folded in a fixed order -> bitwise reproducible losses
+__global__ void criterion_finalize_kernel(const CritParams p) {
+    const int l = blockIdx.x, lane = threadIdx.x;
+    float acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int b = lane; b < p.B; b += 32) {
+        const float* s = p.partials + ((int64_t)b * p.L + l) * kPartials;
+        const float m = (float)(p.gt_off[b + 1] - p.gt_off[b]);
+        acc[0] += s[0]; acc[1] += s[1]; acc[2] += fabsf(s[2] - m); acc[3] += s[3]; acc[4] += s[4]; acc[5] += s[5]; acc[6] += s[6];
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc[k] = warp_sum(acc[k]);
+    if (lane == 0) {
+        const float nb = p.num_boxes ? *p.num_boxes : fmaxf((float)p.gt_off[p.B], 1.f);  // detr/loss.py:142
+        float* o = p.losses + l * 5;
+        o[0] = p.w_ce * (acc[0] / acc[1]);                 // weighted mean CE (detr/loss.py:90-91)
+        o[1] = acc[2] / (float)p.B;                        // cardinality error (detr/loss.py:121)
+        o[2] = p.w_l1 * acc[4] / nb;                       // detr/loss.py:152-156
+        o[3] = p.w_giou * acc[5] / nb;                     // detr/loss.py:158-162
+        o[4] = acc[6] > 0.f ? 100.f - acc[3] * (100.f / acc[6]) : 100.f;  // detr/loss.py:93, detr/utils.py:100-116
+        p.wsum[l] = acc[1];
+        // A data fault (degenerate box, NaN cost, infeasible assignment) raises in the reference; here it
+        // poisons the losses so that the step cannot silently train on a wrong assignment.
+        if (*p.status != 0) { o[0] = o[1] = o[2] = o[3] = o[4] = CUDART_NAN_F; }
+    }
+}
+
+__device__ __forceinline__ float step_gt(float a, float b) { return a > b ? 1.f : (a == b ? 0.5f : 0.f); }
+
+__global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritParams p) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
+    const int Q = p.Q, K = p.K;
+    const int g0 = p.gt_off[b], M = p.gt_off[b + 1] - g0;
+    const int n = min(Q, M);
+    const int64_t moff = (int64_t)p.L * p.match_off[b] + (int64_t)l * n;
+    const float* lg = p.logits + b * p.lg_sb + l * p.lg_sl;
+    const float* bx = p.boxes + b * p.bx_sb + l * p.bx_sl;
+    const float g_ce = p.grad_losses[l * 5 + 0], g_l1 = p.grad_losses[l * 5 + 2], g_gi = p.grad_losses[l * 5 + 3];
+    const float nb = p.num_boxes ? *p.num_boxes : fmaxf((float)p.gt_off[p.B], 1.f);
+
+    // ---- d CE / d logits = g * w_ce * w[t]/W * (softmax - onehot) ----
+    const float ce_scale = g_ce * p.w_ce / p.wsum[l];
+    const float* lse = p.lse + (int64_t)blockIdx.x * Q;
+    const int32_t* tgt = p.tgt + (int64_t)blockIdx.x * Q;
+    float* dlg = p.grad_logits + (int64_t)blockIdx.x * Q * K;
+    for (int q = warp; q < Q; q += kCritThreads / 32) {
+        const float* row = lg + (int64_t)q * p.lg_sq;
+        const int t = tgt[q];
+        const float c = ce_scale * p.class_weight[t];
+        const float ls = lse[q];
+        for (int k = lane; k < K; k += 32) dlg[(int64_t)q * K + k] = c * (expf(row[k] - ls) - (k == t ? 1.f : 0.f));
+    }
+    // ---- d boxes: zero everywhere, analytic L1 + GIoU on matched queries ----
+    float4* dbx = reinterpret_cast<float4*>(p.grad_boxes + (int64_t)blockIdx.x * Q * 4);
+    for (int q = tid; q < Q; q += kCritThreads) dbx[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const float s_l1 = g_l1 * p.w_l1 / nb, s_gi = g_gi * p.w_giou / nb;
+    for (int k = tid; k < n; k += kCritThreads) {
+        const int64_t q = p.idx_q[moff + k], g = p.idx_gt[moff + k];
+        if (q < 0 || q >= Q || g < 0 || g >= M) continue;
+        const float4 s = *reinterpret_cast<const float4*>(bx + q * p.bx_sq);
+        const float4 t = *reinterpret_cast<const float4*>(p.gt_boxes + (int64_t)(g0 + g) * 4);
+        const float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
+        const float tcx = __fdiv_rn(__fadd_rn(__fmul_rn(t.x, 2.f), tw), 2.f);
+        const float tcy = __fdiv_rn(__fadd_rn(__fmul_rn(t.y, 2.f), th), 2.f);
+        auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+        float dcx = s_l1 * sgn(s.x - tcx), dcy = s_l1 * sgn(s.y - tcy), dw = s_l1 * sgn(s.z - tw), dh = s_l1 * sgn(s.w - th);
+
+        const Box4 a = cxcywh_to_xyxy(s);
+        const float eps = 1e-7f;
+        const float ix1 = fmaxf(a.x1, t.x), iy1 = fmaxf(a.y1, t.y), ix2 = fminf(a.x2, t.z), iy2 = fminf(a.y2, t.w);
+        const bool ok = (iy2 > iy1) && (ix2 > ix1);
+        const float iw = ix2 - ix1, ih = iy2 - iy1;
+        const float inter = ok ? iw * ih : 0.f;
+        const float aw = a.x2 - a.x1, ah = a.y2 - a.y1;
+        const float uni = aw * ah + (t.z - t.x) * (t.w - t.y) - inter;
+        const float hx1 = fminf(a.x1, t.x), hy1 = fminf(a.y1, t.y), hx2 = fmaxf(a.x2, t.z), hy2 = fmaxf(a.y2, t.w);
+        const float hw = hx2 - hx1, hh = hy2 - hy1;
+        const float hull = hw * hh;
+        // partial derivatives w.r.t. (x1, y1, x2, y2) of the predicted box; max/min split ties 0.5/0.5 like autograd
+        float dI[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ok) {
+            dI[0] = -ih * step_gt(a.x1, t.x); dI[1] = -iw * step_gt(a.y1, t.y);
+            dI[2] = ih * step_gt(t.z, a.x2);  dI[3] = iw * step_gt(t.w, a.y2);
+        }
+        const float dA[4] = {-ah, -aw, ah, aw};
+        const float dH[4] = {-hh * step_gt(t.x, a.x1), -hw * step_gt(t.y, a.y1), hh * step_gt(a.x2, t.z), hw * step_gt(a.y2, t.w)};
+        const float ue = uni + eps, he = hull + eps;
+        float dxy[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float dU = dA[c] - dI[c];
+            const float d_iou = dI[c] / ue - inter * dU / (ue * ue);
+            const float d_pen = (dH[c] - dU) / he - (hull - uni) * dH[c] / (he * he);
+            dxy[c] = s_gi * (-d_iou + d_pen);
+        }
+        // chain through x1 = cx - w/2, x2 = w + x1  =>  d/dcx = dx1 + dx2 ; d/dw = -dx1/2 + dx2/2
+        dcx += dxy[0] + dxy[2]; dcy += dxy[1] + dxy[3];
+        dw += 0.5f * (dxy[2] - dxy[0]); dh += 0.5f * (dxy[3] - dxy[1]);
+        dbx[q] = make_float4(dcx, dcy, dw, dh);
+    }
+}
+
+static int check_common(const CritParams& p, const char* who) {
+    DETR_CHECK_ARG(p.B >= 1 && p.L >= 1 && p.Q >= 1 && p.K >= 1, "%s: bad sizes B=%d L=%d Q=%d K=%d", who, p.B, p.L, p.Q, p.K);
+    DETR_CHECK_ARG(((uintptr_t)p.boxes % 16) == 0 && (p.bx_sb % 4) == 0 && (p.bx_sl % 4) == 0 && (p.bx_sq % 4) == 0, "%s: pred boxes must be 16-byte aligned rows", who);
+    DETR_CHECK_ARG(((uintptr_t)p.gt_boxes % 16) == 0, "%s: gt boxes must be 16-byte aligned", who);
+    return 0;
+}
+
+}  // namespace detr
+
+using namespace detr;
+
+extern "C" int detr_criterion_fwd_f32(const float* logits, int64_t lg_sb, int64_t lg_sl, int64_t lg_sq,
+                                      const float* boxes, int64_t bx_sb, int64_t bx_sl, int64_t bx_sq,
+                                      const int64_t* gt_labels, const float* gt_boxes, const int32_t* gt_off,
+                                      const int32_t* match_off, const int64_t* idx_q, const int64_t* idx_gt,
+                                      const float* class_weight, const float* num_boxes, int B, int L, int Q, int K,
+                                      float w_ce, float w_l1, float w_giou, float* partials, float* lse, int32_t* tgt,
+                                      float* wsum, float* losses, int32_t* status, void* stream) {
+    CritParams p{};
+    p.logits = logits; p.lg_sb = lg_sb; p.lg_sl = lg_sl; p.lg_sq = lg_sq;
+    p.boxes = boxes; p.bx_sb = bx_sb; p.bx_sl = bx_sl; p.bx_sq = bx_sq;
+    p.gt_labels = gt_labels; p.gt_boxes = gt_boxes; p.gt_off = gt_off; p.match_off = match_off;
+    p.idx_q = idx_q; p.idx_gt = idx_gt; p.class_weight = class_weight; p.num_boxes = num_boxes;
+    p.B = B; p.L = L; p.Q = Q; p.K = K; p.w_ce = w_ce; p.w_l1 = w_l1; p.w_giou = w_giou;
+    p.partials = partials; p.lse = lse; p.tgt = tgt; p.wsum = wsum; p.losses = losses; p.status = status;
+    if (check_common(p, "criterion_fwd")) return 1;
+    DETR_CHECK_ARG(partials && lse && tgt && wsum && losses && status, "criterion_fwd: null output/workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    criterion_fwd_kernel<<<B * L, kCritThreads, 2 * Q * sizeof(int), st>>>(p);
+    DETR_CHECK_LAUNCH("criterion_fwd");
+    criterion_finalize_kernel<<<L, 32, 0, st>>>(p);
+    DETR_CHECK_LAUNCH("criterion_finalize");
+    return 0;
+}
+
+extern "C" int detr_criterion_bwd_f32(const float* grad_losses, const float* logits, int64_t lg_sb, int64_t lg_sl,
+                                      int64_t lg_sq, const float* boxes, int64_t bx_sb, int64_t bx_sl, int64_t bx_sq,
+                                      const float* gt_boxes, const int32_t* gt_off, const int32_t* match_off,
+                                      const int64_t* idx_q, const int64_t* idx_gt, const float* class_weight,
+                                      const float* num_boxes, const float* lse, const int32_t* tgt, const float* wsum,
+                                      int B, int L, int Q, int K, float w_ce, float w_l1, float w_giou,
+                                      float* grad_logits, float* grad_boxes, void* stream) {
+    CritParams p{};
+    p.logits = logits; p.lg_sb = lg_sb; p.lg_sl = lg_sl; p.lg_sq = lg_sq;
+    p.boxes = boxes; p.bx_sb = bx_sb; p.bx_sl = bx_sl; p.bx_sq = bx_sq;
+    p.gt_boxes = gt_boxes; p.gt_off = gt_off; p.match_off = match_off;
+    p.idx_q = idx_q; p.idx_gt = idx_gt; p.class_weight = class_weight; p.num_boxes = num_boxes;
+    p.B = B; p.L = L; p.Q = Q; p.K = K; p.w_ce = w_ce; p.w_l1 = w_l1; p.w_giou = w_giou;
+    p.lse = const_cast<float*>(lse); p.tgt = const_cast<int32_t*>(tgt); p.wsum = const_cast<float*>(wsum);
+    p.grad_losses = grad_losses; p.grad_logits = grad_logits; p.grad_boxes = grad_boxes;
+    if (check_common(p, "criterion_bwd")) return 1;
+    DETR_CHECK_ARG(grad_losses && grad_logits && grad_boxes && lse && tgt && wsum, "criterion_bwd: null pointer");
+    DETR_CHECK_ARG(((uintptr_t)grad_boxes % 16) == 0, "criterion_bwd: grad_boxes must be 16-byte aligned");
+    criterion_bwd_kernel<<<B * L, kCritThreads, 0, (cudaStream_t)stream>>>(p);
+    DETR_CHECK_LAUNCH("criterion_bwd");
+    return 0;
+}

@@ -1,0 +1,87 @@
+"""ctypes binding of libdetr_b200.so (C ABI declared in include/detr_b200.h).
+
+The library is the product: there is NO fallback.  If the shared object is missing or the device is not an
+sm_100 part, importing a kernel entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdetr_b200.so")
+_lib = None
+_checked_devices: set[int] = set()
+
+P = c_void_p
+_STRIDES3 = [c_int64, c_int64, c_int64]
+
+# name -> argtypes ; mirrors include/detr_b200.h one to one
+SIGNATURES = {
+    "detr_b200_abi_version": [],
+    "detr_b200_last_error": [ctypes.c_char_p, c_int],
+    "detr_b200_check_device": [c_int],
+    "detr_matcher_smem_bytes": [c_int, c_int, c_int],
+    "detr_cost_matrix_f32": [P, *_STRIDES3, P, *_STRIDES3, P, P, P, c_int, c_int, c_int, c_int, c_int,
+                             c_float, c_float, c_float, P, P, P],
+    "detr_hungarian_match_f32": [P, *_STRIDES3, P, *_STRIDES3, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
+                                 c_float, c_float, c_float, P, P, P, P, P],
+    "detr_lsap_f32": [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P],
+    "detr_lsap_f64": [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P],
+    "detr_criterion_fwd_f32": [P, *_STRIDES3, P, *_STRIDES3, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int,
+                               c_float, c_float, c_float, P, P, P, P, P, P, P],
+    "detr_criterion_bwd_f32": [P, P, *_STRIDES3, P, *_STRIDES3, P, P, P, P, P, P, P, P, P, P,
+                               c_int, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P],
+}
+_RESTYPE = {"detr_matcher_smem_bytes": c_int64}
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (built by detr-object-detection_b200/build.py). Raises if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python detr-object-detection_b200/build.py` "
+                "(there is no CPU or PyTorch fallback for the hot path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI drifted
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPE.get(name, c_int)
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    buf = ctypes.create_string_buffer(512)
+    load().detr_b200_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = last_error()
+        if "all costs can't be 0" in msg:
+            raise AssertionError(msg)  # detr/matcher.py:38
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: expected a CUDA tensor, got {t.device}; detr_b200 has no CPU path")
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if dev not in _checked_devices:
+        check(load().detr_b200_check_device(dev), "device check")
+        _checked_devices.add(dev)
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,160 @@
+"""SetCriterion -- same constructor, forward signature, `empty_weight` buffer and 25 output keys as the reference
+(detr/loss.py:18-231), executed as: 1 matcher launch + 2 criterion launches for ALL decoder layers (forward) and
+1 launch (backward), with no host synchronisation and no CPU-index -> CUDA-index copies.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from .matcher import HungarianMatcher, _rows
+from .targets import PackedTargets, pack_targets
+
+
+class _CriterionFn(torch.autograd.Function):
+    """(logits (B,L,Q,K), boxes (B,L,Q,4)) -> losses (L,5) = [ce, cardinality, l1, giou, class_error] per layer."""
+
+    @staticmethod
+    def forward(ctx, logits, boxes, pt: PackedTargets, idx_q, idx_gt, class_weight, num_boxes, status, w):
+        B, L, Q, K = logits.shape
+        dev = logits.device
+        lg, bx = _rows(logits, K), _rows(boxes, 4)
+        ws = torch.empty(B * L * 8 + B * L * Q + L, dtype=torch.float32, device=dev)
+        partials, lse, wsum = ws[:B * L * 8], ws[B * L * 8:B * L * 8 + B * L * Q], ws[B * L * 8 + B * L * Q:]
+        tgt = torch.empty(B * L * Q, dtype=torch.int32, device=dev)
+        losses = torch.empty(L, 5, dtype=torch.float32, device=dev)
+        rc = _lib.load().detr_criterion_fwd_f32(
+            lg.data_ptr(), lg.stride(0), lg.stride(1), lg.stride(2), bx.data_ptr(), bx.stride(0), bx.stride(1), bx.stride(2),
+            pt.labels.data_ptr(), pt.boxes.data_ptr(), pt.gt_off.data_ptr(), pt.match_off.data_ptr(),
+            idx_q.data_ptr(), idx_gt.data_ptr(), class_weight.data_ptr(), _lib.ptr(num_boxes),
+            B, L, Q, K, w[0], w[1], w[2], partials.data_ptr(), lse.data_ptr(), tgt.data_ptr(), wsum.data_ptr(),
+            losses.data_ptr(), status.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "detr_criterion_fwd_f32")
+        ctx.save_for_backward(lg, bx, idx_q, idx_gt, class_weight, lse, tgt, wsum, pt.boxes, pt.gt_off, pt.match_off)
+        ctx.num_boxes = num_boxes
+        ctx.w = w
+        ctx.shape = (B, L, Q, K)
+        return losses
+
+    @staticmethod
+    def backward(ctx, grad_losses):
+        lg, bx, idx_q, idx_gt, class_weight, lse, tgt, wsum, gt_boxes, gt_off, match_off = ctx.saved_tensors
+        B, L, Q, K = ctx.shape
+        g = grad_losses.contiguous().float()
+        d_logits = torch.empty(B, L, Q, K, dtype=torch.float32, device=lg.device)
+        d_boxes = torch.empty(B, L, Q, 4, dtype=torch.float32, device=lg.device)
+        w = ctx.w
+        rc = _lib.load().detr_criterion_bwd_f32(
+            g.data_ptr(), lg.data_ptr(), lg.stride(0), lg.stride(1), lg.stride(2),
+            bx.data_ptr(), bx.stride(0), bx.stride(1), bx.stride(2), gt_boxes.data_ptr(), gt_off.data_ptr(),
+            match_off.data_ptr(), idx_q.data_ptr(), idx_gt.data_ptr(), class_weight.data_ptr(), _lib.ptr(ctx.num_boxes),
+            lse.data_ptr(), tgt.data_ptr(), wsum.data_ptr(), B, L, Q, K, w[0], w[1], w[2],
+            d_logits.data_ptr(), d_boxes.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "detr_criterion_bwd_f32")
+        return d_logits, d_boxes, None, None, None, None, None, None, None
+
+
+class SetCriterion(nn.Module):
+    def __init__(self, num_classes: int, matcher: nn.Module, weight_label_ce: float = 1.0, weight_bbox_l1: float = 5.0,
+                 weight_bbox_giou: float = 2.0, eos_coef=0.1, sync_num_boxes: bool = True):
+        """Arguments as detr/loss.py:26-55.  `sync_num_boxes`: when torch.distributed is initialised with more than one
+        rank, normalise the box losses by the all-reduced mean box count (BASELINE north_star "num_boxes all-reduce");
+        the reference normalises by the local count (detr/loss.py:142), which is what happens at world size 1."""
+        super().__init__()
+        self.num_classes = num_classes
+        self.matcher = matcher
+        self.weight_label_ce = weight_label_ce
+        self.weight_bbox_l1 = weight_bbox_l1
+        self.weight_bbox_giou = weight_bbox_giou
+        self.eos_coef = eos_coef
+        self.sync_num_boxes = sync_num_boxes
+        empty_weight = torch.ones(self.num_classes + 1)
+        empty_weight[-1] = self.eos_coef
+        self.register_buffer("empty_weight", empty_weight)
+        self._own_status = None
+        self.last_indices = None  # (idx_q, idx_gt, PackedTargets) of the most recent forward, for inspection
+
+    # -- helpers ------------------------------------------------------------------------------------------
+    def _status(self, device):
+        if isinstance(self.matcher, HungarianMatcher):
+            return self.matcher.status_tensor(device)
+        if self._own_status is None or self._own_status.device != device:
+            self._own_status = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._own_status
+
+    def check_status(self) -> None:
+        """Synchronising check of the device fault word; raises the reference's exception types."""
+        if isinstance(self.matcher, HungarianMatcher):
+            self.matcher.check_status()
+
+    def _num_boxes(self, pt: PackedTargets, device):
+        if not (self.sync_num_boxes and torch.distributed.is_available() and torch.distributed.is_initialized()
+                and torch.distributed.get_world_size() > 1):
+            return None  # kernel uses max(local sum, 1) exactly as detr/loss.py:142
+        nb = torch.tensor([float(pt.total)], dtype=torch.float32).to(device, non_blocking=True)
+        torch.distributed.all_reduce(nb)
+        return (nb / torch.distributed.get_world_size()).clamp_(min=1.0)
+
+    def _match(self, logits, boxes, targets, pt: PackedTargets):
+        if isinstance(self.matcher, HungarianMatcher):
+            return self.matcher.match_layers(logits.detach(), boxes.detach(), pt)
+        # foreign matcher (e.g. the reference's SciPy one): call it per layer and pack its answer
+        B, L, Q, _ = logits.shape
+        per_layer = [self.matcher(logits[:, l].detach(), boxes[:, l].detach(), targets["class_idx"],
+                                  targets["boxes_normalized"]) for l in range(L)]
+        iq = [per_layer[l][b][0] for b in range(B) for l in range(L)]
+        ig = [per_layer[l][b][1] for b in range(B) for l in range(L)]
+        dev = logits.device
+        cat = lambda xs: (torch.cat([x.reshape(-1).to(torch.int64) for x in xs]).to(dev) if xs else
+                          torch.zeros(0, dtype=torch.int64, device=dev))
+        iq, ig = cat(iq), cat(ig)
+        if iq.numel() == 0:
+            iq = torch.zeros(1, dtype=torch.int64, device=dev)[:0]
+            ig = iq.clone()
+        return iq, ig
+
+    # -- reference API ------------------------------------------------------------------------------------
+    def forward(self, outputs: Dict[str, torch.Tensor], targets: Dict[str, list]) -> Dict[str, torch.Tensor]:
+        logits = outputs["pred_logits"]  # (B, L, Q, K)
+        boxes = outputs["pred_boxes"]    # (B, L, Q, 4)
+        _lib.require_cuda(logits, "SetCriterion")
+        if logits.dim() != 4 or boxes.dim() != 4:
+            raise ValueError("pred_logits / pred_boxes must be (batch, layers, queries, .)")
+        B, L, Q, K = logits.shape
+        if K != self.num_classes + 1:
+            raise ValueError(f"pred_logits has {K} classes, criterion was built for {self.num_classes}+1")
+        logits, boxes = logits.float(), boxes.float()
+        pt = pack_targets(targets["class_idx"], targets["boxes_normalized"], Q, logits.device)
+        num_boxes = self._num_boxes(pt, logits.device)  # async all-reduce: hidden behind the matcher launch
+        idx_q, idx_gt = self._match(logits, boxes, targets, pt)
+        self.last_indices = (idx_q, idx_gt, pt, L)
+        w = (float(self.weight_label_ce), float(self.weight_bbox_l1), float(self.weight_bbox_giou))
+        table = _CriterionFn.apply(logits, boxes, pt, idx_q, idx_gt, self.empty_weight.float(), num_boxes,
+                                   self._status(logits.device), w)
+        losses: Dict[str, torch.Tensor] = {}
+        cols = table.unbind(1)  # 5 x (L,)
+        for l in range(L):
+            sfx = f"_{l}" if l < L - 1 else ""
+            if l == L - 1:
+                losses["class_error"] = cols[4][l].detach()
+            losses[f"loss_label_ce{sfx}"] = cols[0][l]
+            losses[f"cardinality_error{sfx}"] = cols[1][l].detach()
+            losses[f"loss_l1_bbox{sfx}"] = cols[2][l]
+            losses[f"loss_giou{sfx}"] = cols[3][l]
+        return losses
+
+    def indices_as_lists(self) -> List[List[Tuple[torch.Tensor, torch.Tensor]]]:
+        """[layer][image] -> (idx_q, idx_gt) views of the last forward's assignment (debug / tests)."""
+        idx_q, idx_gt, pt, n_layers = self.last_indices
+        out = []
+        for l in range(n_layers):
+            per_img, base = [], 0
+            for n in pt.n_match:
+                o = n_layers * base + l * n
+                per_img.append((idx_q[o:o + n], idx_gt[o:o + n]))
+                base += n
+            out.append(per_img)
+        return out

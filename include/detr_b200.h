@@ -1,0 +1,112 @@
+/*
+ * detr_b200.h -- C ABI of the B200-native DETR training hot path (libdetr_b200.so).
+ *
+ * The reference (anenbergb/DETR-object-detection) has no FFI layer: its hot path is reached through
+ * Python class identity.  Every entry point below names the reference interface it
+ * replaces (file:line under /root/reference).  Conventions:
+ *   - plain pointers and sizes only, no torch types; all pointers are DEVICE pointers unless marked host;
+ *   - every launcher enqueues on `stream` (a cudaStream_t passed as void*), never synchronises, never
+ *     allocates, is re-entrant and graph-capturable;
+ *   - return 0 on success, non-zero on a configuration/launch error (text via detr_b200_last_error);
+ *   - data-dependent faults (degenerate boxes, NaN costs, infeasible assignment) are reported by OR-ing
+ *     bits into a caller-owned device int32 `status` word, checked by the host at its next sync point.
+ *
+ * Packed ground truth ("CSR targets"): the reference passes List[Tensor] per image
+ * (detr/matcher.py:44-46, detr/loss.py:217); here the lists are concatenated:
+ *   gt_labels int64[sumM], gt_boxes float[sumM*4] (XYXY, normalised), gt_off int32[B+1] (prefix of M_b),
+ *   match_off int32[B+1] (prefix of n_b = min(Q, M_b)).
+ * A "problem" is one (image b, decoder layer l) pair, p = b*L + l.
+ *   cost matrix of p : float[Q*M_b] row-major (query, gt) at  cost + Q*(L*gt_off[b] + l*M_b)
+ *   matches of p     : n_b pairs at  idx_q/idx_gt + L*match_off[b] + l*n_b   (idx_q ascending)
+ */
+#ifndef DETR_B200_H
+#define DETR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DETR_B200_ABI_VERSION 1
+
+/* status bits (device-side, sticky) -- mirror the reference's failure modes */
+#define DETR_ST_DEGENERATE_BOX 1 /* AssertionError at detr/utils.py:87-88 */
+#define DETR_ST_INVALID_COST 2   /* SciPy ValueError "matrix contains invalid numeric entries" */
+#define DETR_ST_INFEASIBLE 4     /* SciPy ValueError "cost matrix is infeasible" */
+#define DETR_ST_BAD_LABEL 8      /* label outside [0,K) (PyTorch would raise an index error) */
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int detr_b200_abi_version(void);
+/* copies the calling thread's last error text into buf (NUL terminated); returns its length */
+int detr_b200_last_error(char* buf, int n);
+/* 0 if `device` is an sm_100 part this library was built for, non-zero otherwise */
+int detr_b200_check_device(int device);
+/* bytes of dynamic shared memory the matcher needs for (Q, max_M); <0 if it must use the global path */
+int64_t detr_matcher_smem_bytes(int Q, int max_m, int elem_size);
+
+/* ---- HungarianMatcher (detr/matcher.py:40-99) ------------------------------------------------- */
+/* Cost matrices only: C = w_bbox*L1(cxcywh) + w_class*(-softmax(logits)[:,label]) + w_giou*(-GIoU)
+ * (detr/matcher.py:66-93, detr/utils.py:57-97).  logits: element strides for (image, layer, query),
+ * class stride 1; boxes likewise with 4 contiguous floats (cx,cy,w,h). */
+int detr_cost_matrix_f32(const float* logits, int64_t lg_sb, int64_t lg_sl, int64_t lg_sq,
+                         const float* boxes, int64_t bx_sb, int64_t bx_sl, int64_t bx_sq,
+                         const int64_t* gt_labels, const float* gt_boxes, const int32_t* gt_off,
+                         int B, int L, int Q, int K, int max_m,
+                         float w_class, float w_bbox, float w_giou,
+                         float* cost_out, int32_t* status, void* stream);
+
+/* Fused matcher: cost matrix kept in shared memory + assignment, one CTA per problem.
+ * Replaces the per-image loop + `.cpu()` + scipy call of detr/matcher.py:69-97 for all images and all
+ * decoder layers (detr/loss.py:213-217) in ONE launch.  cost_out may be NULL (not exported). */
+int detr_hungarian_match_f32(const float* logits, int64_t lg_sb, int64_t lg_sl, int64_t lg_sq,
+                             const float* boxes, int64_t bx_sb, int64_t bx_sl, int64_t bx_sq,
+                             const int64_t* gt_labels, const float* gt_boxes, const int32_t* gt_off,
+                             const int32_t* match_off, int B, int L, int Q, int K, int max_m,
+                             float w_class, float w_bbox, float w_giou,
+                             float* cost_out, int64_t* idx_q, int64_t* idx_gt, int32_t* status,
+                             void* stream);
+
+/* Batched rectangular linear-sum assignment on caller-provided cost matrices: the drop-in for
+ * scipy.optimize.linear_sum_assignment at detr/matcher.py:94 (bit-exact indices).
+ * Problem p: nr[p] x nc[p] row-major at cost + cost_off[p]; writes min(nr,nc) pairs at out_off[p]
+ * (rows ascending).  max_nr/max_nc: host-known maxima (size the launch). */
+int detr_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* nr, const int32_t* nc,
+                  int n_problems, int max_nr, int max_nc, const int64_t* out_off, int64_t* rows_out,
+                  int64_t* cols_out, int32_t* status, void* stream);
+int detr_lsap_f64(const double* cost, const int64_t* cost_off, const int32_t* nr, const int32_t* nc,
+                  int n_problems, int max_nr, int max_nc, const int64_t* out_off, int64_t* rows_out,
+                  int64_t* cols_out, int32_t* status, void* stream);
+
+/* ---- SetCriterion (detr/loss.py:57-164, 198-231) ---------------------------------------------- */
+/* Forward, all layers at once.  Outputs:
+ *   losses float[L*5] = {loss_label_ce, cardinality_error, loss_l1_bbox, loss_giou, class_error} per layer
+ *   (already multiplied by w_ce/w_l1/w_giou as detr/loss.py:91,152-162 does);
+ * saved for backward: lse float[B*L*Q], tgt int32[B*L*Q], wsum float[L];
+ * partials float[B*L*8] is scratch.  class_weight float[K] is SetCriterion.empty_weight (detr/loss.py:53-55).
+ * num_boxes: optional device scalar (the all-reduced normaliser); NULL -> max(sumM,1) local
+ * as detr/loss.py:142 does. */
+int detr_criterion_fwd_f32(const float* logits, int64_t lg_sb, int64_t lg_sl, int64_t lg_sq,
+                           const float* boxes, int64_t bx_sb, int64_t bx_sl, int64_t bx_sq,
+                           const int64_t* gt_labels, const float* gt_boxes, const int32_t* gt_off,
+                           const int32_t* match_off, const int64_t* idx_q, const int64_t* idx_gt,
+                           const float* class_weight, const float* num_boxes,
+                           int B, int L, int Q, int K, float w_ce, float w_l1, float w_giou,
+                           float* partials, float* lse, int32_t* tgt, float* wsum, float* losses,
+                           int32_t* status, void* stream);
+
+/* Backward of the 3 differentiable losses per layer.  grad_losses float[L*5] (same layout as `losses`;
+ * columns 1 and 4 ignored).  Writes dense grad_logits float[B*L*Q*K] and grad_boxes float[B*L*Q*4]
+ * (both contiguous, (B,L,Q,.) order). */
+int detr_criterion_bwd_f32(const float* grad_losses,
+                           const float* logits, int64_t lg_sb, int64_t lg_sl, int64_t lg_sq,
+                           const float* boxes, int64_t bx_sb, int64_t bx_sl, int64_t bx_sq,
+                           const float* gt_boxes, const int32_t* gt_off, const int32_t* match_off,
+                           const int64_t* idx_q, const int64_t* idx_gt, const float* class_weight,
+                           const float* num_boxes, const float* lse, const int32_t* tgt, const float* wsum,
+                           int B, int L, int Q, int K, float w_ce, float w_l1, float w_giou,
+                           float* grad_logits, float* grad_boxes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DETR_B200_H */
