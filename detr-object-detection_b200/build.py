@@ -26,7 +26,7 @@ def _stamp() -> str:
     h = hashlib.sha256(" ".join(FLAGS).encode())
     for f in sorted(glob.glob(os.path.join(CSRC, "*")) + [os.path.join(HERE, "..", "include", "detr_b200.h")]):
         with open(f, "rb") as fh:
-            h.update(f.encode() + fh.read())
+            h.update(os.path.basename(f).encode() + fh.read())
     return h.hexdigest()
 
 
@@ -40,10 +40,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in srcs]
     headers = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "detr_b200.h")]
     newest_h = max(os.path.getmtime(h) for h in headers)
+    flags_file = os.path.join(OBJ, "flags")
+    same_flags = os.path.exists(flags_file) and open(flags_file).read() == " ".join(FLAGS)
 
     def cc(pair):
         s, o = pair
-        if not force and os.path.exists(o) and os.path.getmtime(o) > max(os.path.getmtime(s), newest_h):
+        if not force and os.path.exists(o) and os.path.getmtime(o) > max(os.path.getmtime(s), newest_h) and same_flags:
             return
         cmd = [NVCC, *FLAGS, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else [])
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -57,6 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     subprocess.check_call([NVCC, "-shared", "-o", OUT, *objs, "-lcudart", "-lcuda"])
     with open(stamp_file, "w") as f:
         f.write(stamp)
+    with open(flags_file, "w") as f:
+        f.write(" ".join(FLAGS))
     return OUT
 
 

@@ -11,6 +11,12 @@ for p in (ROOT, os.path.join(ROOT, "detr-object-detection_b200")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # never test a stale shared object: rebuild (no-op when sources are unchanged) before collection
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("detr_b200_build", os.path.join(ROOT, "detr-object-detection_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
 
 
 @pytest.fixture(scope="session")
