@@ -1,0 +1,53 @@
+"""Attention core of ScaledDotProductAttention (detr/model.py:317-352) on tcgen05/TMA kernels.
+
+q (B,L,C), k/v (B,S,C) are the *projected* bf16 tensors in nn.Linear's layout; heads are 32-channel slices, so
+no view/transpose/contiguous round trip is needed.  Returns (B,L,C) bf16.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+HEAD_DIM = 32
+
+
+def _tma_ok(t: torch.Tensor) -> torch.Tensor:
+    """TMA needs channel stride 1, 16-byte aligned base and row/batch strides that are multiples of 8 elements."""
+    if t.dtype != torch.bfloat16:
+        t = t.to(torch.bfloat16)
+    if t.stride(2) != 1 or t.data_ptr() % 16 or t.stride(0) % 8 or t.stride(1) % 8:
+        t = t.contiguous()
+    return t
+
+
+def _mask_bytes(m: Optional[torch.Tensor], shape, name: str) -> Optional[torch.Tensor]:
+    if m is None:
+        return None
+    if tuple(m.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(m.shape)}")
+    m = m.to(torch.bool) if m.dtype != torch.bool else m
+    return m.contiguous().view(torch.uint8)
+
+
+def attention_forward(q, k, v, key_padding_mask=None, attention_mask=None, dropout_p: float = 0.0, seed: int = 0):
+    """Raw forward launch -> (out bf16 (B,L,C), lse fp32 (B,nh,L))."""
+    _lib.require_cuda(q, "attention")
+    B, L, C = q.shape
+    S = k.shape[1]
+    if C % HEAD_DIM:
+        raise ValueError(f"hidden size {C} is not a multiple of the head size {HEAD_DIM} this kernel is built for")
+    nh = C // HEAD_DIM
+    q, k, v = _tma_ok(q), _tma_ok(k), _tma_ok(v)
+    kpm = _mask_bytes(key_padding_mask, (B, S), "key_padding_mask")
+    am = _mask_bytes(attention_mask, (L, S), "attention_mask")
+    out = torch.empty(B, L, C, dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty(B, nh, L, dtype=torch.float32, device=q.device)
+    rc = _lib.load().detr_attention_fwd_bf16(
+        q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0), v.stride(1),
+        out.data_ptr(), out.stride(0), out.stride(1), lse.data_ptr(), _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0,
+        _lib.ptr(am), B, nh, L, S, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.stream_ptr())
+    _lib.check(rc, "detr_attention_fwd_bf16")
+    return out, lse

@@ -106,6 +106,20 @@ int detr_criterion_bwd_f32(const float* grad_losses,
                            int B, int L, int Q, int K, float w_ce, float w_l1, float w_giou,
                            float* grad_logits, float* grad_boxes, void* stream);
 
+/* ---- ScaledDotProductAttention core (detr/model.py:317-352) ------------------------------------ */
+/* O = dropout(softmax(Q K^T / sqrt(32) + masks)) V for head_dim 32, bf16 in / bf16 out, fp32 softmax.
+ * q (B,L,nh*32), k/v (B,S,nh*32), o (B,L,nh*32): bf16, channel stride 1, element strides (batch, row) given;
+ * head h is channels [32h, 32h+32) -- i.e. the layout nn.Linear produces, so the view/transpose/contiguous of
+ * detr/model.py:317-319,352 disappear.  lse float[B*nh*L] (natural log, saved for backward).
+ * key_padding_mask: (B,S) bytes, non-zero = ignore (detr/model.py:326-330), row stride kpm_sb, may be NULL;
+ * attention_mask: (L,S) bytes contiguous, non-zero = ignore (detr/model.py:332-334), may be NULL.
+ * dropout_p is quantised to k/256 (in-kernel counter-based mask from `seed`; 0 disables, as in eval()). */
+int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
+                            const void* v, int64_t v_sb, int64_t v_sl, void* o, int64_t o_sb, int64_t o_sl,
+                            float* lse, const uint8_t* key_padding_mask, int64_t kpm_sb,
+                            const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
+                            uint64_t seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

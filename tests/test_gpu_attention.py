@@ -1,0 +1,87 @@
+"""GPU parity of the tcgen05 flash-attention kernels against a plain fp32 PyTorch restatement of
+detr/model.py:317-352 (oracle.detr_oracle.sdpa's core).  Inputs are bf16 (what nn.Linear emits under autocast);
+tolerance: bf16 output rounding + bf16 P rounding -> 2e-2 abs on O(1) outputs, and never worse than 2x the
+error of the reference's own bf16 path + 1e-3."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_core(q, k, v, nh, kpm=None, am=None, dtype=torch.float32):
+    B, L, C = q.shape
+    S = k.shape[1]
+    d = C // nh
+    qh = q.to(dtype).view(B, L, nh, d).transpose(1, 2)
+    kh = k.to(dtype).view(B, S, nh, d).transpose(1, 2)
+    vh = v.to(dtype).view(B, S, nh, d).transpose(1, 2)
+    s = (qh @ kh.transpose(2, 3)) / math.sqrt(d)
+    if kpm is not None:
+        s = s.masked_fill(kpm[:, None, None, :], torch.finfo(s.dtype).min)
+    if am is not None:
+        s = s.masked_fill(am, torch.finfo(s.dtype).min)
+    p = torch.softmax(s.float(), dim=-1)
+    lse = torch.logsumexp(s.float(), dim=-1)
+    o = (p.to(dtype) @ vh).transpose(1, 2).reshape(B, L, C)
+    return o.float(), lse
+
+
+def _check(q, k, v, nh, kpm=None, am=None):
+    from detr_b200.attention import attention_forward
+    out, lse = attention_forward(q, k, v, kpm, am)
+    torch.cuda.synchronize()
+    ref, ref_lse = ref_core(q, k, v, nh, kpm, am)
+    ref_bf16, _ = ref_core(q, k, v, nh, kpm, am, dtype=torch.bfloat16)
+    err = (out.float() - ref).abs().max().item()
+    err_ref = (ref_bf16 - ref).abs().max().item()
+    assert err <= 2e-2 and err <= 2 * err_ref + 1e-3, (err, err_ref)
+    full = None if kpm is None else kpm.all(dim=1)
+    l_err = (lse - ref_lse).abs()
+    if full is not None:
+        l_err = l_err[~full]  # a fully masked row has an arbitrary (huge negative) LSE in both implementations
+    assert l_err.max().item() <= 2e-3 if l_err.numel() else True
+    return err
+
+
+@pytest.mark.parametrize("B,L,S,nh", [(2, 128, 128, 2), (1, 256, 384, 8), (2, 100, 100, 8), (2, 100, 850, 8), (2, 850, 850, 8), (1, 37, 5, 1)])
+def test_attention_forward_shapes(cuda, B, L, S, nh):
+    g = torch.Generator(device="cpu").manual_seed(L * 1000 + S)
+    C = nh * 32
+    q = torch.randn(B, L, C, generator=g).mul(1.5).to(cuda, torch.bfloat16)
+    k = torch.randn(B, S, C, generator=g).mul(1.5).to(cuda, torch.bfloat16)
+    v = torch.randn(B, S, C, generator=g).to(cuda, torch.bfloat16)
+    _check(q, k, v, nh)
+
+
+def test_attention_forward_masks_and_strides(cuda):
+    g = torch.Generator(device="cpu").manual_seed(7)
+    B, L, S, nh = 3, 150, 300, 4
+    C = nh * 32
+    qkv = torch.randn(B, S, 3 * C, generator=g).to(cuda, torch.bfloat16)  # fused-projection style strided views
+    q, k, v = qkv[:, :L, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    kpm = torch.zeros(B, S, dtype=torch.bool, device=cuda)
+    kpm[0, 200:] = True          # tail padding
+    kpm[1, ::3] = True           # scattered
+    kpm[2, :] = True             # fully masked image: the reference yields a uniform distribution, not NaN
+    _check(q, k, v, nh, kpm=kpm)
+    am = torch.rand(L, S, generator=g).to(cuda) < 0.3
+    _check(q, k, v, nh, kpm=kpm, am=am)
+    _check(q, k, v, nh, am=am)
+
+
+def test_attention_dropout_statistics(cuda):
+    """Dropout mask: keep-rate ~ 1 - round(p*256)/256, rescaled by 1/keep; same seed -> same output."""
+    from detr_b200.attention import attention_forward
+    B, L, S, nh = 1, 256, 256, 2
+    q = torch.zeros(B, L, nh * 32, device=cuda, dtype=torch.bfloat16)   # uniform attention
+    k = torch.zeros(B, S, nh * 32, device=cuda, dtype=torch.bfloat16)
+    v = torch.ones(B, S, nh * 32, device=cuda, dtype=torch.bfloat16)
+    o1, _ = attention_forward(q, k, v, dropout_p=0.1, seed=1234)
+    o2, _ = attention_forward(q, k, v, dropout_p=0.1, seed=1234)
+    o3, _ = attention_forward(q, k, v, dropout_p=0.1, seed=99)
+    assert torch.equal(o1, o2) and not torch.equal(o1, o3)
+    # each output = (#kept / S) / keep_prob: mean 1, std sqrt(p/(1-p)/S) ~ 0.021
+    assert abs(o1.float().mean().item() - 1.0) < 5e-3
+    assert 0.01 < o1.float()[..., 0].std().item() < 0.04
