@@ -268,7 +268,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 reinterpret_cast<uint4*>(dst)[g] = w;
             }
             // natural-log LSE of the scaled scores: m/sqrt(d) + ln(l)
-            p.lse[((int64_t)b * p.nh + h) * p.L + q] = (m_run * sc + log2f(l_run)) * 0.6931471805599453f;
+            // a row whose keys are all masked is flagged with +inf: the backward kernels then skip it
+            p.lse[((int64_t)b * p.nh + h) * p.L + q] =
+                m_run == kMaskedScore ? CUDART_INF_F : (m_run * sc + log2f(l_run)) * 0.6931471805599453f;
         }
     }
     __syncthreads();

@@ -51,3 +51,50 @@ def attention_forward(q, k, v, key_padding_mask=None, attention_mask=None, dropo
         _lib.ptr(am), B, nh, L, S, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.stream_ptr())
     _lib.check(rc, "detr_attention_fwd_bf16")
     return out, lse
+
+
+def attention_backward(d_out, q, k, v, out, lse, key_padding_mask=None, attention_mask=None, dropout_p: float = 0.0,
+                       seed: int = 0):
+    """Raw backward launches -> (dq, dk, dv) bf16 with the shapes of q, k, v."""
+    B, L, C = q.shape
+    S = k.shape[1]
+    nh = C // HEAD_DIM
+    q, k, v, out, d_out = _tma_ok(q), _tma_ok(k), _tma_ok(v), _tma_ok(out), _tma_ok(d_out)
+    kpm = _mask_bytes(key_padding_mask, (B, S), "key_padding_mask")
+    am = _mask_bytes(attention_mask, (L, S), "attention_mask")
+    dq = torch.empty(B, L, C, dtype=torch.bfloat16, device=q.device)
+    dkv = torch.empty(2, B, S, C, dtype=torch.bfloat16, device=q.device)
+    delta = torch.empty(B, nh, L, dtype=torch.float32, device=q.device)
+    st = lambda t: (t.data_ptr(), t.stride(0), t.stride(1))
+    rc = _lib.load().detr_attention_bwd_bf16(
+        *st(q), *st(k), *st(v), *st(out), *st(d_out), lse.data_ptr(), delta.data_ptr(), *st(dq), *st(dkv[0]), *st(dkv[1]),
+        _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0, _lib.ptr(am), B, nh, L, S, float(dropout_p),
+        int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.stream_ptr())
+    _lib.check(rc, "detr_attention_bwd_bf16")
+    return dq, dkv[0], dkv[1]
+
+
+class _FlashAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, key_padding_mask, attention_mask, dropout_p, seed):
+        out, lse = attention_forward(q, k, v, key_padding_mask, attention_mask, dropout_p, seed)
+        ctx.save_for_backward(q, k, v, out, lse, key_padding_mask, attention_mask)
+        ctx.dropout_p, ctx.seed = dropout_p, seed
+        ctx.in_dtypes = (q.dtype, k.dtype, v.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k, v, out, lse, kpm, am = ctx.saved_tensors
+        dq, dk, dv = attention_backward(d_out, q, k, v, out, lse, kpm, am, ctx.dropout_p, ctx.seed)
+        tq, tk, tv = ctx.in_dtypes
+        return dq.to(tq), dk.to(tk), dv.to(tv), None, None, None, None
+
+
+def flash_attention(q, k, v, key_padding_mask: Optional[torch.Tensor] = None,
+                    attention_mask: Optional[torch.Tensor] = None, dropout_p: float = 0.0,
+                    seed: Optional[int] = None) -> torch.Tensor:
+    """Differentiable attention core: softmax(q k^T / sqrt(32) + masks) -> dropout -> @ v, heads = 32-channel slices."""
+    if dropout_p > 0.0 and seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # host RNG: follows torch.manual_seed, no device sync
+    return _FlashAttention.apply(q, k, v, key_padding_mask, attention_mask, float(dropout_p), int(seed or 0))

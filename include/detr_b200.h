@@ -120,6 +120,17 @@ int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const voi
                             const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
                             uint64_t seed, void* stream);
 
+/* Backward of the call above: dq (B,L,C), dk/dv (B,S,C) bf16 from d_o (B,L,C) bf16, the forward's inputs, output
+ * `o` and `lse`.  delta float[B*nh*L] is scratch (rowsum(dO o O)).  Same masks / dropout_p / seed as forward.
+ * Three launches: delta, dK+dV (CTA per key tile), dQ (CTA per query tile); deterministic, no atomics. */
+int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
+                            const void* v, int64_t v_sb, int64_t v_sl, const void* o, int64_t o_sb, int64_t o_sl,
+                            const void* d_o, int64_t do_sb, int64_t do_sl, const float* lse, float* delta,
+                            void* dq, int64_t dq_sb, int64_t dq_sl, void* dk, int64_t dk_sb, int64_t dk_sl,
+                            void* dv, int64_t dv_sb, int64_t dv_sl, const uint8_t* key_padding_mask, int64_t kpm_sb,
+                            const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
+                            uint64_t seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,3 +85,70 @@ def test_attention_dropout_statistics(cuda):
     # each output = (#kept / S) / keep_prob: mean 1, std sqrt(p/(1-p)/S) ~ 0.021
     assert abs(o1.float().mean().item() - 1.0) < 5e-3
     assert 0.01 < o1.float()[..., 0].std().item() < 0.04
+
+
+def _check_backward(q, k, v, nh, kpm=None, am=None):
+    """dQ/dK/dV against autograd through the fp32 restatement (same bf16 inputs).  Tolerance: bf16 rounding of
+    P / dS / outputs -> relative to the gradient scale; never worse than 2x the bf16 reference path + 1e-3*scale."""
+    from detr_b200.attention import flash_attention
+    g = torch.Generator(device="cpu").manual_seed(11)
+    w = torch.randn(q.shape, generator=g).to(q.device, torch.bfloat16)
+    qa, ka, va = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+    out = flash_attention(qa, ka, va, kpm, am)
+    (out.float() * w.float()).sum().backward()
+    res = {}
+    for dt in (torch.float32, torch.bfloat16):
+        qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+        o, _ = ref_core(qr, kr, vr, nh, kpm, am, dtype=dt)
+        (o * w.float()).sum().backward()
+        res[dt] = (qr.grad, kr.grad, vr.grad)
+    for name, mine, r32, r16 in zip("qkv", (qa.grad, ka.grad, va.grad), res[torch.float32], res[torch.bfloat16]):
+        scale = r32.abs().max().item() + 1e-6
+        err = (mine.float() - r32).abs().max().item() / scale
+        err_ref = (r16 - r32).abs().max().item() / scale
+        assert err <= 3e-2 and err <= 2 * err_ref + 4e-3, (name, err, err_ref)
+
+
+@pytest.mark.parametrize("B,L,S,nh", [(1, 128, 128, 1), (2, 256, 384, 2), (2, 100, 100, 8), (2, 100, 850, 8), (1, 850, 850, 8), (1, 37, 5, 1)])
+def test_attention_backward_shapes(cuda, B, L, S, nh):
+    g = torch.Generator(device="cpu").manual_seed(L * 1000 + S + 1)
+    C = nh * 32
+    q = torch.randn(B, L, C, generator=g).to(cuda, torch.bfloat16)
+    k = torch.randn(B, S, C, generator=g).to(cuda, torch.bfloat16)
+    v = torch.randn(B, S, C, generator=g).to(cuda, torch.bfloat16)
+    _check_backward(q, k, v, nh)
+
+
+def test_attention_backward_masks(cuda):
+    g = torch.Generator(device="cpu").manual_seed(8)
+    B, L, S, nh = 2, 150, 300, 4
+    C = nh * 32
+    q = torch.randn(B, L, C, generator=g).to(cuda, torch.bfloat16)
+    k = torch.randn(B, S, C, generator=g).to(cuda, torch.bfloat16)
+    v = torch.randn(B, S, C, generator=g).to(cuda, torch.bfloat16)
+    kpm = torch.zeros(B, S, dtype=torch.bool, device=cuda)
+    kpm[0, 200:] = True
+    kpm[1, ::3] = True
+    _check_backward(q, k, v, nh, kpm=kpm)
+    am = torch.rand(L, S, generator=g).to(cuda) < 0.3
+    _check_backward(q, k, v, nh, kpm=kpm, am=am)
+
+
+def test_attention_backward_dropout_consistency(cuda):
+    """With dropout the backward must regenerate the forward's mask: check d/dV of sum(out) analytically.
+    out = P~ V  =>  d sum(out) / dV[k, :] = sum_q P~[q, k]; with q = k = 0 (uniform P = 1/S) this is
+    (#queries that kept key k) / (S * keep_prob), and it must equal what forward produced through V = one-hot."""
+    from detr_b200.attention import flash_attention
+    B, L, S, nh = 1, 256, 128, 1
+    q = torch.zeros(B, L, 32, device=cuda, dtype=torch.bfloat16)
+    k = torch.zeros(B, S, 32, device=cuda, dtype=torch.bfloat16)
+    v = torch.zeros(B, S, 32, device=cuda, dtype=torch.bfloat16)
+    v[0, :32, :] = torch.eye(32, device=cuda, dtype=torch.bfloat16)      # out[q, d] = P~[q, key d] for d < 32
+    va = v.clone().requires_grad_(True)
+    out = flash_attention(q, k, va, dropout_p=0.25, seed=42)
+    out.float().sum().backward()
+    colsum_fwd = out.float()[0].sum(0)            # sum_q P~[q, key d]
+    colsum_bwd = va.grad.float()[0, :32, 0]       # d/dV[key, 0] = sum_q P~[q, key]
+    assert torch.allclose(colsum_fwd, colsum_bwd, rtol=2e-2, atol=1e-3), (colsum_fwd, colsum_bwd)
+    kept = (out.float()[0] > 0).float().mean().item()
+    assert abs(kept - 0.75) < 0.03
