@@ -1,0 +1,189 @@
+"""Caller of the hot path for benchmarks and end-to-end tests: a DETR-R50/R101 wrapper with the reference's
+parameter names (detr/model.py:31-94) and the reference's training-step body (detr/train.py:258-267).
+
+The backbone (torchvision ResNet + FrozenBatchNorm, cuDNN), the 1x1 input projection and the prediction heads are
+OUT OF SCOPE of the B200 rewrite: they stay plain PyTorch here exactly as in the reference.
+What this module adds is the glue the reference's DETR.forward does around Encoder/Decoder, with the per-image
+host loops of detr/position_encoding.py:57-67 and detr/model.py:96-114 replaced by vectorised device code.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .model import DETRConfig, Decoder, Encoder
+
+
+def positional_encoding_device(embed_h: int, embed_w: int, heights: torch.Tensor, widths: torch.Tensor, scale: int = 32,
+                               num_pos_feats: int = 128, temperature: float = 10000.0) -> torch.Tensor:
+    """(B, 2*num_pos_feats, H', W') fp32, same values as detr/position_encoding.py:5-97 without its per-image loop:
+    coordinates are linspace(0,1,n) inside the valid ceil(h/scale) x ceil(w/scale) window and 0 in the padding."""
+    dev = heights.device
+    hs = torch.ceil(heights.float() / scale)
+    ws = torch.ceil(widths.float() / scale)
+    iy = torch.arange(embed_h, device=dev, dtype=torch.float32)[None, :, None]
+    ix = torch.arange(embed_w, device=dev, dtype=torch.float32)[None, None, :]
+    inside = (iy < hs[:, None, None]) & (ix < ws[:, None, None])
+    gy = torch.where(inside, iy / (hs[:, None, None] - 1).clamp(min=1), torch.zeros((), device=dev))
+    gx = torch.where(inside, ix / (ws[:, None, None] - 1).clamp(min=1), torch.zeros((), device=dev))
+    freq = temperature ** (torch.arange(0, num_pos_feats, 2, device=dev, dtype=torch.float32) / num_pos_feats)
+    ay = (gy * (2 * math.pi))[..., None] / freq
+    ax = (gx * (2 * math.pi))[..., None] / freq
+    py = torch.stack((ay.sin(), ay.cos()), dim=-1).flatten(-2)
+    px = torch.stack((ax.sin(), ax.cos()), dim=-1).flatten(-2)
+    return torch.cat((py, px), dim=-1).permute(0, 3, 1, 2)
+
+
+def padding_mask_device(embed_h: int, embed_w: int, heights: torch.Tensor, widths: torch.Tensor, scale: int = 32) -> torch.Tensor:
+    """(B, H', W') bool, True only on the bottom-right corner [ceil(h/s):, ceil(w/s):] -- the reference's own rule
+    (detr/model.py:96-114)."""
+    dev = heights.device
+    hs = torch.ceil(heights.float() / scale)[:, None, None]
+    ws = torch.ceil(widths.float() / scale)[:, None, None]
+    iy = torch.arange(embed_h, device=dev, dtype=torch.float32)[None, :, None]
+    ix = torch.arange(embed_w, device=dev, dtype=torch.float32)[None, None, :]
+    return (iy >= hs) & (ix >= ws)
+
+
+class _MLP(nn.Module):
+    """Box head (detr/model.py:359-392): Linear/GELU(tanh) stack, keys `net.N.*`."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers, initializer_range=0.02):
+        super().__init__()
+        layers = []
+        for i in range(num_layers):
+            layers.append(nn.Linear(input_dim if i == 0 else hidden_dim, output_dim if i == num_layers - 1 else hidden_dim))
+            if i < num_layers - 1:
+                layers.append(nn.GELU(approximate="tanh"))
+        self.net = nn.Sequential(*layers)
+        for m in self.net:
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, mean=0, std=initializer_range)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class _Backbone(nn.Module):
+    """torchvision ResNet C5 with FrozenBatchNorm2d, random init (no network here) -- detr/model.py:427-438."""
+
+    def __init__(self, name: str):
+        super().__init__()
+        from torchvision.models import get_model
+        from torchvision.models._utils import IntermediateLayerGetter
+        from torchvision.ops import FrozenBatchNorm2d
+        model = get_model(name, weights=None, norm_layer=FrozenBatchNorm2d)
+        self.backbone = IntermediateLayerGetter(model, return_layers={"layer4": "final_feature_map"})
+        self.num_channels = 2048
+        self.scale = 32
+
+    def forward(self, x):
+        return self.backbone(x)["final_feature_map"]
+
+
+class DetrHarness(nn.Module):
+    """DETR.forward (detr/model.py:68-94) around pluggable encoder/decoder implementations."""
+
+    def __init__(self, config: DETRConfig, encoder_fn: Optional[Callable] = None, decoder_fn: Optional[Callable] = None):
+        super().__init__()
+        self.config = config
+        self.backbone = _Backbone(config.backbone)
+        self.input_proj = nn.Conv2d(self.backbone.num_channels, config.hidden_size, kernel_size=1)
+        self.object_query_embedding = nn.Embedding(config.num_object_queries, config.hidden_size)
+        self.encoder = Encoder(config)
+        self.decoder = Decoder(config)
+        self.class_embedding = nn.Linear(config.hidden_size, config.num_classes + 1)
+        self.bbox_embedding = _MLP(config.hidden_size, config.hidden_size, 4, config.box_embedding_mlp_num_layers,
+                                   config.initializer_range)
+        nn.init.xavier_uniform_(self.input_proj.weight)
+        nn.init.zeros_(self.input_proj.bias)
+        nn.init.normal_(self.object_query_embedding.weight, mean=0.0, std=config.initializer_range)
+        nn.init.xavier_uniform_(self.class_embedding.weight)
+        nn.init.zeros_(self.class_embedding.bias)
+        # optional functional replacements (the CPU oracle plugs in here for the reference arm of bench.py)
+        self._encoder_fn = encoder_fn
+        self._decoder_fn = decoder_fn
+
+    def forward(self, images: torch.Tensor, heights: torch.Tensor, widths: torch.Tensor) -> Dict[str, torch.Tensor]:
+        x = self.input_proj(self.backbone(images))
+        B, C, H, W = x.shape
+        pos = positional_encoding_device(H, W, heights, widths, self.backbone.scale, C // 2, self.config.temperature)
+        mask = padding_mask_device(H, W, heights, widths, self.backbone.scale).flatten(1)
+        x = x.flatten(2).permute(0, 2, 1)
+        pos = pos.flatten(2).permute(0, 2, 1)
+        query_embed = self.object_query_embedding.weight.unsqueeze(0).expand(B, -1, -1)
+        if self._encoder_fn is None:
+            memory = self.encoder(x, position_embedding=pos, key_padding_mask=mask)
+            decoded = self.decoder(memory, position_embedding=pos, object_query_embedding=query_embed, key_padding_mask=mask)
+        else:
+            memory = self._encoder_fn(self.encoder, x, pos, mask)
+            decoded = self._decoder_fn(self.decoder, memory, pos, query_embed, mask)
+        return {"pred_logits": self.class_embedding(decoded), "pred_boxes": self.bbox_embedding(decoded).sigmoid()}
+
+
+def make_optimizer(model: nn.Module, lr: float = 3e-4, lr_backbone_scale: float = 0.1, weight_decay: float = 1e-4, fused: bool = True):
+    """AdamW with two parameter groups, backbone at 0.1x (detr/train.py:172-182)."""
+    inner = model.module if hasattr(model, "module") else model
+    bb = [p for n, p in inner.named_parameters() if n.startswith("backbone.") and p.requires_grad]
+    rest = [p for n, p in inner.named_parameters() if not n.startswith("backbone.") and p.requires_grad]
+    groups = [{"params": rest, "lr": lr}, {"params": bb, "lr": lr * lr_backbone_scale}]
+    return torch.optim.AdamW(groups, lr=lr, weight_decay=weight_decay, fused=fused)
+
+
+def train_step(model: nn.Module, criterion: nn.Module, optimizer, batch: Dict, autocast_dtype=torch.bfloat16,
+               max_grad_norm: float = 1.0) -> torch.Tensor:
+    """Body of the reference's step (detr/train.py:258-267): forward + criterion under autocast, sum of the
+    `loss*` entries, backward (DDP all-reduce fires here), clip, AdamW, zero_grad.  Returns the detached loss."""
+    dev_type = batch["image"].device.type
+    with torch.autocast(device_type=dev_type, dtype=autocast_dtype, enabled=autocast_dtype is not None):
+        outputs = model(batch["image"], batch["height"], batch["width"])
+    # Accelerate hands the criterion fp32 outputs (convert_outputs_to_fp32); matcher + criterion are fp32
+    outputs = {k: v.float() for k, v in outputs.items()}
+    losses = criterion(outputs, batch)
+    loss = sum(v for k, v in losses.items() if k.startswith("loss"))
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
+    optimizer.step()
+    optimizer.zero_grad(set_to_none=True)
+    return loss.detach()
+
+
+def synthetic_batch(batch: int, height: int = 800, width: int = 1066, num_classes: int = 91, max_gt: int = 20, seed: int = 0,
+                    device: str | torch.device = "cpu", pin: bool = False) -> Dict:
+    """SURVEY.md 8(d) config 1/2 input: randn image zero-padded to a multiple of 32 (detr/data.py:196-203), int32
+    sizes, per-image GT lists (centres U(.2,.8), sizes U(.02,.32), XYXY) with M ~ U{1..max_gt}."""
+    g = torch.Generator().manual_seed(seed)
+    wp = (width + 31) // 32 * 32
+    hp = (height + 31) // 32 * 32
+    img = torch.zeros(batch, 3, hp, wp)
+    img[:, :, :height, :width] = torch.randn(batch, 3, height, width, generator=g)
+    counts = torch.randint(1, max_gt + 1, (batch,), generator=g).tolist()
+    labels, boxes = [], []
+    for m in counts:
+        c = torch.rand(m, 2, generator=g) * 0.6 + 0.2
+        s = torch.rand(m, 2, generator=g) * 0.30 + 0.02
+        boxes.append(torch.cat([c - s / 2, c + s / 2], dim=1))
+        labels.append(torch.randint(0, num_classes, (m,), generator=g, dtype=torch.int64))
+    out = {"image": img, "height": torch.full((batch,), height, dtype=torch.int32),
+           "width": torch.full((batch,), width, dtype=torch.int32), "class_idx": labels, "boxes_normalized": boxes}
+    if pin:
+        out = {k: (v.pin_memory() if torch.is_tensor(v) else [t.pin_memory() for t in v]) for k, v in out.items()}
+    return batch_to(out, device) if str(device) != "cpu" else out
+
+
+def batch_to(batch: Dict, device, non_blocking: bool = True) -> Dict:
+    return {k: (v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else [t.to(device, non_blocking=non_blocking) for t in v])
+            for k, v in batch.items()}
+
+
+def batch_bytes(batch: Dict) -> int:
+    n = 0
+    for v in batch.values():
+        for t in (v if isinstance(v, list) else [v]):
+            n += t.numel() * t.element_size()
+    return n

@@ -1,0 +1,218 @@
+"""Pre-LN transformer encoder / decoder of DETR with the reference's class names, constructor and forward
+signatures and state_dict keys (detr/model.py:117-356, 395-424), running the attention core on the tcgen05
+flash-attention kernels of libdetr_b200.so.
+
+state_dict keys:  layers.N.self_attention.{query,key,value,output}_proj.{weight,bias},
+layers.N.cross_attention.* (decoder), layers.N.ffn.layers.{0,3}.{weight,bias}, layers.N.norm{1,2,3}.*, norm.*
+
+What changes relative to the reference's execution (not its maths):
+  * scores / probabilities are never materialised (flash attention; fp32 softmax, bf16 tensor-core operands);
+  * q and k projections of self-attention run as ONE GEMM (query is key there);
+  * head split/merge needs no transpose/contiguous copies (heads are 32-channel slices of the projection output);
+  * `memory + pos` of the cross-attention keys is hoisted out of the 6-layer decoder loop (detr/model.py:179);
+  * attention-probability dropout is generated in-kernel (counter-based, regenerated in backward).
+There is no CPU path: inputs must be CUDA tensors.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .attention import HEAD_DIM, flash_attention
+
+
+@dataclass
+class DETRConfig:
+    """Field-for-field mirror of detr/model.py:13-28 (any object with these attributes works)."""
+    backbone: str = field(default="resnet50")
+    temperature: int = field(default=10000)
+    num_object_queries: int = field(default=100)
+    num_encoder_layers: int = field(default=6)
+    num_decoder_layers: int = field(default=6)
+    num_attention_heads: int = field(default=8)
+    hidden_size: int = field(default=256)
+    ffn_scale_factor: int = field(default=8)
+    hidden_dropout_prob: float = field(default=0.1)
+    attention_probs_dropout_prob: float = field(default=0.1)
+    box_embedding_mlp_num_layers: int = field(default=3)
+    initializer_range: float = field(default=0.02)
+    layer_norm_eps: float = field(default=1e-5)
+    num_classes: int = field(default=80)
+
+
+def _init_weights(module: nn.Module, std: float) -> None:
+    """Linear ~ N(0, std), bias 0; LayerNorm 1/0 (detr/model.py:126-135, 195-204)."""
+    if isinstance(module, nn.Linear):
+        module.weight.data.normal_(mean=0.0, std=std)
+        if module.bias is not None:
+            module.bias.data.zero_()
+    elif isinstance(module, nn.LayerNorm):
+        module.weight.data.fill_(1.0)
+        module.bias.data.zero_()
+
+
+class ScaledDotProductAttention(nn.Module):
+    """detr/model.py:228-356."""
+
+    def __init__(self, config):
+        super().__init__()
+        assert config.hidden_size % config.num_attention_heads == 0
+        self.query_proj = nn.Linear(config.hidden_size, config.hidden_size)
+        self.key_proj = nn.Linear(config.hidden_size, config.hidden_size)
+        self.value_proj = nn.Linear(config.hidden_size, config.hidden_size)
+        self.output_proj = nn.Linear(config.hidden_size, config.hidden_size)
+        self.dropout_attn = nn.Dropout(config.attention_probs_dropout_prob)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self.hidden_size = config.hidden_size
+        self.n_head = config.num_attention_heads
+        self.head_size = config.hidden_size // config.num_attention_heads
+        if self.head_size != HEAD_DIM:
+            raise ValueError(f"detr_b200 attention kernels are built for head size {HEAD_DIM}, got {self.head_size}")
+
+    def project_kv(self, key: torch.Tensor, value: torch.Tensor):
+        return (F.linear(key, self.key_proj.weight, self.key_proj.bias),
+                F.linear(value, self.value_proj.weight, self.value_proj.bias))
+
+    def forward(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
+                key_padding_mask: Optional[torch.BoolTensor] = None,
+                attention_mask: Optional[torch.BoolTensor] = None) -> torch.Tensor:
+        C = self.hidden_size
+        if key is query:
+            # self-attention: one GEMM for both projections; q/k are strided views the TMA descriptors take as they are
+            w = torch.cat((self.query_proj.weight, self.key_proj.weight), dim=0)
+            b = torch.cat((self.query_proj.bias, self.key_proj.bias), dim=0)
+            qk = F.linear(query, w, b)
+            q, k = qk[..., :C], qk[..., C:]
+            v = F.linear(value, self.value_proj.weight, self.value_proj.bias)
+        else:
+            q = F.linear(query, self.query_proj.weight, self.query_proj.bias)
+            k, v = self.project_kv(key, value)
+        p_drop = self.dropout_attn.p if self.training else 0.0
+        y = flash_attention(q, k, v, key_padding_mask, attention_mask, p_drop)
+        if not torch.is_autocast_enabled():
+            y = y.to(query.dtype)
+        y = F.linear(y, self.output_proj.weight, self.output_proj.bias)
+        return self.dropout(y)
+
+
+class FFN(nn.Module):
+    """detr/model.py:395-424 (Linear -> GELU(tanh) -> Dropout -> Linear -> Dropout); cuBLASLt GEMMs."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.layers = nn.Sequential(
+            nn.Linear(config.hidden_size, config.hidden_size * config.ffn_scale_factor),
+            nn.GELU(approximate="tanh"),
+            nn.Dropout(config.hidden_dropout_prob),
+            nn.Linear(config.hidden_size * config.ffn_scale_factor, config.hidden_size),
+            nn.Dropout(config.hidden_dropout_prob),
+        )
+
+    def forward(self, x):
+        return self.layers(x)
+
+
+class EncoderLayer(nn.Module):
+    """detr/model.py:212-225."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.self_attention = ScaledDotProductAttention(config)
+        self.ffn = FFN(config)
+        self.norm1 = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.norm2 = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+
+    def forward(self, x: torch.Tensor, position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
+        x_attn = self.norm1(x)
+        query = x_attn + position_embedding
+        x = x + self.self_attention(query, query, value=x_attn, key_padding_mask=key_padding_mask)
+        x = x + self.ffn(self.norm2(x))
+        return x
+
+
+class Encoder(nn.Module):
+    """pre-LN Transformer Encoder (detr/model.py:186-209)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.layers = nn.ModuleList([EncoderLayer(config) for _ in range(config.num_encoder_layers)])
+        self.norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.apply(lambda m: _init_weights(m, config.initializer_range))
+
+    def forward(self, x: torch.Tensor, position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
+        for layer in self.layers:
+            x = layer(x, position_embedding, key_padding_mask)
+        return self.norm(x)
+
+
+class DecoderLayer(nn.Module):
+    """detr/model.py:154-183.  `cross_key` (= encoded_image_tokens + position_embedding) may be passed pre-computed."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.self_attention = ScaledDotProductAttention(config)
+        self.cross_attention = ScaledDotProductAttention(config)
+        self.norm1 = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.norm2 = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.norm3 = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.ffn = FFN(config)
+
+    def forward(self, x: torch.Tensor, encoded_image_tokens: torch.Tensor, object_query_embedding: torch.Tensor,
+                position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor,
+                cross_key: Optional[torch.Tensor] = None):
+        x_attn = self.norm1(x)
+        query = x_attn + object_query_embedding
+        x = x + self.self_attention(query, query, value=x_attn)
+        x_attn = self.norm2(x)
+        query = x_attn + object_query_embedding
+        key = cross_key if cross_key is not None else encoded_image_tokens + position_embedding
+        x = x + self.cross_attention(query, key, value=encoded_image_tokens, key_padding_mask=key_padding_mask)
+        x = x + self.ffn(self.norm3(x))
+        return x
+
+
+class Decoder(nn.Module):
+    """pre-LN Transformer Decoder (detr/model.py:117-151): returns (B, num_layers, Q, C); the shared final
+    LayerNorm is applied to every layer's output."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.layers = nn.ModuleList([DecoderLayer(config) for _ in range(config.num_decoder_layers)])
+        self.norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.apply(lambda m: _init_weights(m, config.initializer_range))
+
+    def forward(self, encoded_image_tokens: torch.Tensor, position_embedding: torch.Tensor,
+                object_query_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
+        x = torch.zeros_like(object_query_embedding)
+        cross_key = encoded_image_tokens + position_embedding   # layer-invariant: computed once, not 6 times
+        outputs = []
+        for layer in self.layers:
+            x = layer(x, encoded_image_tokens, object_query_embedding, position_embedding, key_padding_mask,
+                      cross_key=cross_key)
+            outputs.append(x)
+        # one LayerNorm launch over all layers' outputs instead of one per layer
+        stacked = torch.stack(outputs, dim=1)
+        return self.norm(stacked)
+
+
+def patch(detr_model_module, detr_train_module=None) -> None:
+    """Rebind the reference's names to the B200 classes: call before `DETR(config)` /
+    `train_DETR(...)`.  `detr_model_module` is the imported `detr.model`; `detr_train_module` the imported
+    `detr.train` (optional, it needs `accelerate`)."""
+    from .loss import SetCriterion
+    from .matcher import HungarianMatcher
+    detr_model_module.ScaledDotProductAttention = ScaledDotProductAttention
+    detr_model_module.FFN = FFN
+    detr_model_module.EncoderLayer = EncoderLayer
+    detr_model_module.DecoderLayer = DecoderLayer
+    detr_model_module.Encoder = Encoder
+    detr_model_module.Decoder = Decoder
+    if detr_train_module is not None:
+        detr_train_module.HungarianMatcher = HungarianMatcher
+        detr_train_module.SetCriterion = SetCriterion

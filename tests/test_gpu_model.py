@@ -1,0 +1,122 @@
+"""GPU parity of Encoder / Decoder (reference signatures + state_dict keys) against the golden fixture produced
+by the real reference and against the fp32 oracle at full size.  Dropout off (eval), as parity is defined.
+
+Tolerance: the attention core runs bf16 tensor-core operands with fp32 softmax/accumulation inside an otherwise
+fp32 (or bf16-autocast) model; outputs are LayerNorm-ed, O(1).  Bar: max abs err <= 3e-2 and mean abs err <= 3e-3
+for activations in fp32 mode; under bf16 autocast the error must not exceed 2x the reference-style bf16 autocast
+oracle's own error + 1e-2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import detr_oracle as O
+from util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(C, nh, ffn, ne, nd, Q):
+    from detr_b200.model import DETRConfig
+    return DETRConfig(num_object_queries=Q, num_encoder_layers=ne, num_decoder_layers=nd, num_attention_heads=nh,
+                      hidden_size=C, ffn_scale_factor=ffn)
+
+
+def test_state_dict_keys_match_reference_layout():
+    from detr_b200.model import Decoder, Encoder
+    fx = load_golden("transformer_tiny")
+    cfg = _cfg(*fx["cfg"].tolist())
+    enc, dec = Encoder(cfg), Decoder(cfg)
+    ref_e = {k[4:]: v.shape for k, v in fx.items() if k.startswith("enc/")}
+    ref_d = {k[4:]: v.shape for k, v in fx.items() if k.startswith("dec/")}
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == ref_e
+    assert {k: tuple(v.shape) for k, v in dec.state_dict().items()} == ref_d
+
+
+def test_encoder_decoder_vs_golden(cuda):
+    from detr_b200.model import Decoder, Encoder
+    fx = load_golden("transformer_tiny")
+    cfg = _cfg(*fx["cfg"].tolist())
+    enc, dec = Encoder(cfg).to(cuda).eval(), Decoder(cfg).to(cuda).eval()
+    enc.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in fx.items() if k.startswith("enc/")})
+    dec.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in fx.items() if k.startswith("dec/")})
+    x = torch.from_numpy(fx["x"]).to(cuda).requires_grad_(True)
+    pos, mask = torch.from_numpy(fx["pos"]).to(cuda), torch.from_numpy(fx["mask"]).to(cuda)
+    qe = torch.from_numpy(fx["query_embed"]).to(cuda)[None].expand(x.shape[0], -1, -1)
+    mem = enc(x, position_embedding=pos, key_padding_mask=mask)
+    out = dec(mem, position_embedding=pos, object_query_embedding=qe, key_padding_mask=mask)
+    assert out.shape == fx["decoded"].shape
+    e_mem = np.abs(mem.detach().cpu().numpy() - fx["memory"])
+    e_out = np.abs(out.detach().cpu().numpy() - fx["decoded"])
+    assert e_mem.max() <= 3e-2 and e_mem.mean() <= 3e-3, (e_mem.max(), e_mem.mean())
+    assert e_out.max() <= 3e-2 and e_out.mean() <= 3e-3, (e_out.max(), e_out.mean())
+    (out * torch.from_numpy(fx["w_out"]).to(cuda)).sum().backward()
+    g, gr = x.grad.cpu().numpy(), fx["grad_x"]
+    assert np.abs(g - gr).max() <= 5e-2 * np.abs(gr).max(), (np.abs(g - gr).max(), np.abs(gr).max())
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_full_size_encoder_decoder_vs_oracle(cuda, autocast):
+    """Default DETRConfig (C=256, 8 heads, 6+6 layers, Q=100) on a 10x13 feature map with the corner mask."""
+    from detr_b200.harness import padding_mask_device, positional_encoding_device
+    from detr_b200.model import DETRConfig, Decoder, Encoder
+    torch.manual_seed(3)
+    cfg = DETRConfig(num_classes=91)
+    enc, dec = Encoder(cfg).eval(), Decoder(cfg).eval()
+    with torch.no_grad():
+        for p in list(enc.parameters()) + list(dec.parameters()):
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+    B, eh, ew = 2, 10, 13
+    heights, widths = torch.tensor([320, 200], dtype=torch.int32), torch.tensor([416, 300], dtype=torch.int32)
+    x = torch.randn(B, eh * ew, 256)
+    qe = 0.5 * torch.randn(100, 256)
+    pos = O.positional_encoding(eh, ew, heights, widths).flatten(2).permute(0, 2, 1)
+    mask = O.padding_mask(eh, ew, heights, widths).flatten(1)
+    # vectorised device versions of the two host loops
+    pos_d = positional_encoding_device(eh, ew, heights.to(cuda), widths.to(cuda)).flatten(2).permute(0, 2, 1)
+    assert (pos_d.cpu() - pos).abs().max() <= 1e-5
+    assert torch.equal(padding_mask_device(eh, ew, heights.to(cuda), widths.to(cuda)).flatten(1).cpu(), mask)
+
+    xr = x.clone().requires_grad_(True)
+    esd, dsd = dict(enc.named_parameters()), dict(dec.named_parameters())
+    mem_r = O.encoder(esd, xr, pos, mask, 6, 8)
+    out_r = O.decoder(dsd, mem_r, pos, qe[None].expand(B, -1, -1), mask, 6, 8)
+    w = torch.randn_like(out_r)
+    (out_r * w).sum().backward()
+    # the reference's own bf16-autocast error, for scale (CPU autocast of the oracle)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        out_b = O.decoder(dsd, O.encoder(esd, x, pos, mask, 6, 8), pos, qe[None].expand(B, -1, -1), mask, 6, 8)
+    err_ref = (out_b.float() - out_r).abs().max().item()
+
+    enc, dec = enc.to(cuda), dec.to(cuda)
+    xg = x.to(cuda).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        mem = enc(xg, position_embedding=pos_d, key_padding_mask=mask.to(cuda))
+        out = dec(mem, position_embedding=pos_d, object_query_embedding=qe.to(cuda)[None].expand(B, -1, -1),
+                  key_padding_mask=mask.to(cuda))
+    assert out.shape == (B, 6, 100, 256)
+    err = (out.float().cpu() - out_r).abs().max().item()
+    if autocast:
+        assert err <= 2 * err_ref + 1e-2, (err, err_ref)
+    else:
+        assert err <= 3e-2 and err <= 2 * err_ref + 1e-3, (err, err_ref)
+    (out.float() * w.to(cuda)).sum().backward()
+    gscale = xr.grad.abs().max().item()
+    gerr = (xg.grad.cpu() - xr.grad).abs().max().item()
+    assert gerr <= (0.15 if autocast else 0.06) * gscale, (gerr, gscale)
+    # parameter gradients reach every tensor
+    for n, p in list(enc.named_parameters()) + list(dec.named_parameters()):
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_train_mode_dropout_runs_and_is_seeded(cuda):
+    from detr_b200.model import DETRConfig, Encoder
+    cfg = DETRConfig()
+    enc = Encoder(cfg).to(cuda).train()
+    x = torch.randn(2, 130, 256, device=cuda)
+    pos = torch.randn(2, 130, 256, device=cuda)
+    mask = torch.zeros(2, 130, dtype=torch.bool, device=cuda)
+    torch.manual_seed(5); a = enc(x, pos, mask)
+    torch.manual_seed(5); b = enc(x, pos, mask)
+    torch.manual_seed(6); c = enc(x, pos, mask)
+    assert torch.equal(a, b) and not torch.equal(a, c) and torch.isfinite(a).all()
