@@ -60,6 +60,56 @@ def load() -> ctypes.CDLL:
     return _lib
 
 
+# kernels launched per C-ABI call (bench.py's gpu_launches is counted from this table)
+KERNELS_PER_CALL = {"detr_cost_matrix_f32": 1, "detr_hungarian_match_f32": 1, "detr_lsap_f32": 1, "detr_lsap_f64": 1,
+                    "detr_criterion_fwd_f32": 2, "detr_criterion_bwd_f32": 1, "detr_attention_fwd_bf16": 1,
+                    "detr_attention_bwd_bf16": 3}
+launch_count = 0          # kernels of libdetr_b200.so launched by this process
+_profile = None           # when a list: (name, tag, start_event, end_event) per call
+
+
+class profile:
+    """Context manager: CUDA-event timing of every C-ABI launch on its own stream.
+
+        with _lib.profile() as prof: step()
+        torch.cuda.synchronize(); rows = prof.summary()   # {(name, tag): (calls, total_ms)}
+    """
+
+    def __enter__(self):
+        global _profile
+        self.records = []
+        _profile = self.records
+        return self
+
+    def __exit__(self, *exc):
+        global _profile
+        _profile = None
+        return False
+
+    def summary(self):
+        out = {}
+        for name, tag, a, b in self.records:
+            n, t = out.get((name, tag), (0, 0.0))
+            out[(name, tag)] = (n + 1, t + a.elapsed_time(b))
+        return out
+
+
+def call(name: str, *args, tag=None) -> None:
+    """Invoke a launcher of the C ABI, count its kernels, raise on a non-zero return code."""
+    global launch_count
+    fn = getattr(load(), name)
+    launch_count += KERNELS_PER_CALL[name]
+    if _profile is None:
+        rc = fn(*args)
+    else:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        _profile.append((name, tag, a, b))
+    check(rc, name)
+
+
 def last_error() -> str:
     buf = ctypes.create_string_buffer(512)
     load().detr_b200_last_error(buf, 512)

@@ -45,11 +45,11 @@ def attention_forward(q, k, v, key_padding_mask=None, attention_mask=None, dropo
     am = _mask_bytes(attention_mask, (L, S), "attention_mask")
     out = torch.empty(B, L, C, dtype=torch.bfloat16, device=q.device)
     lse = torch.empty(B, nh, L, dtype=torch.float32, device=q.device)
-    rc = _lib.load().detr_attention_fwd_bf16(
+    _lib.call(
+        "detr_attention_fwd_bf16",
         q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0), v.stride(1),
         out.data_ptr(), out.stride(0), out.stride(1), lse.data_ptr(), _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0,
-        _lib.ptr(am), B, nh, L, S, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.stream_ptr())
-    _lib.check(rc, "detr_attention_fwd_bf16")
+        _lib.ptr(am), B, nh, L, S, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.stream_ptr(), tag=(B, nh, L, S))
     return out, lse
 
 
@@ -66,11 +66,11 @@ def attention_backward(d_out, q, k, v, out, lse, key_padding_mask=None, attentio
     dkv = torch.empty(2, B, S, C, dtype=torch.bfloat16, device=q.device)
     delta = torch.empty(B, nh, L, dtype=torch.float32, device=q.device)
     st = lambda t: (t.data_ptr(), t.stride(0), t.stride(1))
-    rc = _lib.load().detr_attention_bwd_bf16(
+    _lib.call(
+        "detr_attention_bwd_bf16",
         *st(q), *st(k), *st(v), *st(out), *st(d_out), lse.data_ptr(), delta.data_ptr(), *st(dq), *st(dkv[0]), *st(dkv[1]),
         _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0, _lib.ptr(am), B, nh, L, S, float(dropout_p),
-        int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.stream_ptr())
-    _lib.check(rc, "detr_attention_bwd_bf16")
+        int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.stream_ptr(), tag=(B, nh, L, S))
     return dq, dkv[0], dkv[1]
 
 

@@ -26,13 +26,13 @@ class _CriterionFn(torch.autograd.Function):
         partials, lse, wsum = ws[:B * L * 8], ws[B * L * 8:B * L * 8 + B * L * Q], ws[B * L * 8 + B * L * Q:]
         tgt = torch.empty(B * L * Q, dtype=torch.int32, device=dev)
         losses = torch.empty(L, 5, dtype=torch.float32, device=dev)
-        rc = _lib.load().detr_criterion_fwd_f32(
+        _lib.call(
+            "detr_criterion_fwd_f32",
             lg.data_ptr(), lg.stride(0), lg.stride(1), lg.stride(2), bx.data_ptr(), bx.stride(0), bx.stride(1), bx.stride(2),
             pt.labels.data_ptr(), pt.boxes.data_ptr(), pt.gt_off.data_ptr(), pt.match_off.data_ptr(),
             idx_q.data_ptr(), idx_gt.data_ptr(), class_weight.data_ptr(), _lib.ptr(num_boxes),
             B, L, Q, K, w[0], w[1], w[2], partials.data_ptr(), lse.data_ptr(), tgt.data_ptr(), wsum.data_ptr(),
             losses.data_ptr(), status.data_ptr(), _lib.stream_ptr())
-        _lib.check(rc, "detr_criterion_fwd_f32")
         ctx.save_for_backward(lg, bx, idx_q, idx_gt, class_weight, lse, tgt, wsum, pt.boxes, pt.gt_off, pt.match_off)
         ctx.num_boxes = num_boxes
         ctx.w = w
@@ -47,13 +47,13 @@ class _CriterionFn(torch.autograd.Function):
         d_logits = torch.empty(B, L, Q, K, dtype=torch.float32, device=lg.device)
         d_boxes = torch.empty(B, L, Q, 4, dtype=torch.float32, device=lg.device)
         w = ctx.w
-        rc = _lib.load().detr_criterion_bwd_f32(
+        _lib.call(
+            "detr_criterion_bwd_f32",
             g.data_ptr(), lg.data_ptr(), lg.stride(0), lg.stride(1), lg.stride(2),
             bx.data_ptr(), bx.stride(0), bx.stride(1), bx.stride(2), gt_boxes.data_ptr(), gt_off.data_ptr(),
             match_off.data_ptr(), idx_q.data_ptr(), idx_gt.data_ptr(), class_weight.data_ptr(), _lib.ptr(ctx.num_boxes),
             lse.data_ptr(), tgt.data_ptr(), wsum.data_ptr(), B, L, Q, K, w[0], w[1], w[2],
             d_logits.data_ptr(), d_boxes.data_ptr(), _lib.stream_ptr())
-        _lib.check(rc, "detr_criterion_bwd_f32")
         return d_logits, d_boxes, None, None, None, None, None, None, None
 
 

@@ -82,13 +82,13 @@ class HungarianMatcher(nn.Module):
         need_ws = _lib.load().detr_matcher_smem_bytes(Q, pt.max_count, 4) < 0
         cost = torch.empty(max(Q * L * pt.total, 1), dtype=torch.float32, device=dev) if (export_cost or need_ws) else None
         st = self.status_tensor(dev)
-        rc = _lib.load().detr_hungarian_match_f32(
+        _lib.call(
+            "detr_hungarian_match_f32",
             logits.data_ptr(), logits.stride(0), logits.stride(1), logits.stride(2),
             boxes.data_ptr(), boxes.stride(0), boxes.stride(1), boxes.stride(2),
             pt.labels.data_ptr(), pt.boxes.data_ptr(), pt.gt_off.data_ptr(), pt.match_off.data_ptr(),
             B, L, Q, K, pt.max_count, float(self.cost_class), float(self.cost_bbox), float(self.cost_giou),
             _lib.ptr(cost), idx[0].data_ptr(), idx[1].data_ptr(), st.data_ptr(), _lib.stream_ptr())
-        _lib.check(rc, "detr_hungarian_match_f32")
         return (idx[0][:n_out], idx[1][:n_out], cost) if export_cost else (idx[0][:n_out], idx[1][:n_out])
 
     @torch.no_grad()
@@ -101,12 +101,12 @@ class HungarianMatcher(nn.Module):
         lg, bx = _rows(logits, K), _rows(boxes, 4)
         cost = torch.empty(max(Q * pt.total, 1), dtype=torch.float32, device=logits.device)
         st = self.status_tensor(logits.device)
-        rc = _lib.load().detr_cost_matrix_f32(
+        _lib.call(
+            "detr_cost_matrix_f32",
             lg.data_ptr(), lg.stride(0), 0, lg.stride(1), bx.data_ptr(), bx.stride(0), 0, bx.stride(1),
             pt.labels.data_ptr(), pt.boxes.data_ptr(), pt.gt_off.data_ptr(), B, 1, Q, K, pt.max_count,
             float(self.cost_class), float(self.cost_bbox), float(self.cost_giou), cost.data_ptr(), st.data_ptr(),
             _lib.stream_ptr())
-        _lib.check(rc, "detr_cost_matrix_f32")
         out, o = [], 0
         for m in pt.counts:
             out.append(cost[o:o + Q * m].view(Q, m))
@@ -156,11 +156,9 @@ def linear_sum_assignment_cuda(costs: Sequence[torch.Tensor], status: torch.Tens
     own_status = status is None
     if own_status:
         status = torch.zeros(1, dtype=torch.int32, device=dev)
-    fn = _lib.load().detr_lsap_f32 if dt == torch.float32 else _lib.load().detr_lsap_f64
-    rc = fn(flat.data_ptr(), meta64[0].data_ptr(), meta32[0].data_ptr(), meta32[1].data_ptr(), len(costs),
+    _lib.call("detr_lsap_f32" if dt == torch.float32 else "detr_lsap_f64", flat.data_ptr(), meta64[0].data_ptr(), meta32[0].data_ptr(), meta32[1].data_ptr(), len(costs),
             max(nr), max(nc), meta64[1].data_ptr(), rows.data_ptr(), cols.data_ptr(), status.data_ptr(),
             _lib.stream_ptr())
-    _lib.check(rc, "detr_lsap")
     if own_status:
         raise_for_status(int(status.item()))
     out, o = [], 0
