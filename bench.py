@@ -151,6 +151,14 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    if args.ncu_step:
+        # profiling aid (never a bench number): `ncu --profile-from-start off ... bench.py --ncu-step` captures one step
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -293,6 +301,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--ncu-step", action="store_true", help="warm up, then run exactly one step between cudaProfilerStart/Stop")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

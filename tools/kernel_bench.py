@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Stand-alone timing of every kernel of libdetr_b200.so at the BASELINE shapes (CUDA events on the launching
+stream, >=3 warm-ups, L2 flushed between timed iterations by writing a 256 MB buffer).  Prints one JSON line per
+kernel with its algorithmic work and roofline fraction (peaks: MEASURED_PEAKS.json, burst figure -- kernels timed
+alone).  Also the command `ncu` is pointed at (tools/kernel_bench.py --only attention --iters 1)."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "detr-object-detection_b200"))
+import torch  # noqa: E402
+
+from detr_b200 import HungarianMatcher, SetCriterion, _lib, pack_targets  # noqa: E402
+from detr_b200.attention import attention_backward, attention_forward  # noqa: E402
+from oracle import detr_oracle as O  # noqa: E402
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p["bf16_tflops"], p["hbm_gbs"], "measured burst"
+    except Exception:
+        return 1590.0, 6650.0, "fallback"
+
+
+def timeit(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.fill_(1.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--dropout", type=float, default=0.1)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    tf, hbm, src = peaks()
+    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    out = []
+
+    def attn(name, B, nh, L, S):
+        C = nh * 32
+        q = torch.randn(B, L, C, device=dev).bfloat16(); k = torch.randn(B, S, C, device=dev).bfloat16()
+        v = torch.randn(B, S, C, device=dev).bfloat16(); do = torch.randn(B, L, C, device=dev).bfloat16()
+        o, lse = attention_forward(q, k, v, dropout_p=args.dropout, seed=1)
+        f_ms = timeit(lambda: attention_forward(q, k, v, dropout_p=args.dropout, seed=1), args.iters, flush)
+        b_ms = timeit(lambda: attention_backward(do, q, k, v, o, lse, dropout_p=args.dropout, seed=1), args.iters, flush)
+        fl = 4.0 * L * S * C * B
+        byt = (2 * C * (2 * L + 2 * S) + 4 * nh * L) * B
+        for tag, ms, f in (("fwd", f_ms, fl), ("bwd", b_ms, 2.5 * fl)):
+            out.append({"kernel": f"attention_{tag} {name}", "shape": [B, nh, L, S], "ms": round(ms, 4), "flops": f, "bytes_fwd_algorithmic": byt,
+                        "achieved_tflops": round(f / ms / 1e9, 2), "frac_of_tensor_peak": round(f / ms / 1e9 / tf, 4), "bound": "tensor (MUFU-limited at d=32)",
+                        "dropout_p": args.dropout})
+
+    if not args.only or "attention" in args.only:
+        attn("encoder self (config 2)", 8, 8, 850, 850)
+        attn("decoder cross (config 2)", 8, 8, 100, 850)
+        attn("decoder self (config 2)", 8, 8, 100, 100)
+        attn("encoder self DC5 (config 4)", 2, 8, 3350, 3350)
+
+    if not args.only or "matcher" in args.only:
+        for (B, L, maxm, tag) in ((256, 6, 100, "config 3"), (8, 6, 20, "config 2")):
+            Q, NC = 100, 91
+            logits, boxes = O.synth_predictions(B, L, Q, NC, seed=0)
+            labels, gts = O.synth_targets(B, maxm, NC, seed=1)
+            logits, boxes = logits.to(dev), boxes.to(dev)
+            pt = pack_targets([l.to(dev) for l in labels], [g.to(dev) for g in gts], Q, dev)
+            m = HungarianMatcher(1.0, 5.0, 2.0)
+            ms = timeit(lambda: m.match_layers(logits, boxes, pt), args.iters, flush)
+            byt = sum(38400 + 40 * c for c in pt.counts) * L
+            out.append({"kernel": f"hungarian_match (cost + assignment fused) {tag}", "shape": [B, L, Q, NC + 1], "sum_gt": pt.total, "ms": round(ms, 4),
+                        "bytes_algorithmic": byt, "achieved_gbs": round(byt / ms / 1e6, 2), "frac_of_hbm_peak": round(byt / ms / 1e6 / hbm, 5),
+                        "images_per_s": round(B / ms * 1e3, 1), "bound": "latency (serial augmenting paths), reported against HBM for transparency"})
+            crit = SetCriterion(NC, m).to(dev)
+            lg = logits.clone().requires_grad_(True); bx = boxes.clone().requires_grad_(True)
+            tg = {"class_idx": [l.to(dev) for l in labels], "boxes_normalized": [g.to(dev) for g in gts]}
+            with _lib.profile() as prof:
+                for _ in range(5):
+                    flush.fill_(1.0)
+                    loss = sum(v for k, v in crit({"pred_logits": lg, "pred_boxes": bx}, tg).items() if k.startswith("loss"))
+                    flush.fill_(1.0)
+                    loss.backward()
+            torch.cuda.synchronize()
+            for (n, _), (c, t) in prof.summary().items():
+                if "criterion" in n:
+                    ms_c = t / c
+                    byt_c = sum((36800 + 40 * cc) if "fwd" in n else (36800 * 2 + 1600 + 40 * cc) for cc in pt.counts) * L
+                    out.append({"kernel": f"{n} {tag}", "ms": round(ms_c, 4), "bytes_algorithmic": byt_c, "achieved_gbs": round(byt_c / ms_c / 1e6, 2),
+                                "frac_of_hbm_peak": round(byt_c / ms_c / 1e6 / hbm, 5), "bound": "hbm"})
+    for r in out:
+        r["peak_source"] = src
+        print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()
