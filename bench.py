@@ -240,6 +240,7 @@ def build_cpu_reference():
 
     torch.manual_seed(0)
     model = DetrHarness(cfg, encoder_fn=enc_fn, decoder_fn=dec_fn).train()
+    model.backbone.fold_bn = False   # the reference's stock path: FrozenBatchNorm2d modules, unfused
 
     class OracleCriterion(torch.nn.Module):
         def forward(self, outputs, targets):

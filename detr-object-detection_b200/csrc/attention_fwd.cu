@@ -2,15 +2,19 @@
 //
 //   O[b,q,h,:] = dropout(softmax(Q K^T / sqrt(32) + mask)) V        LSE[b,h,q] saved for the backward kernels
 //
-// One CTA = one (batch, head, 128-query tile); 6 warps:
-//   warps 0-3  softmax: thread r owns query row r (TMEM lane r): two passes over the 128x128 fp32 score tile
-//              in TMEM (row max, then exp2 / row sum / dropout / bf16 P into swizzled shared memory) and the
-//              running O row (32 fp32 registers), rescaled on-line.
-//   warp 4     TMA producer: Q once, then K/V tiles of 128 keys through a 2-stage ring (SWIZZLE_64B boxes).
-//   warp 5     TMEM allocation + single-thread tcgen05.mma issue: S = Q K^T (M128 N128 K32) and
-//              O_tile = P V (M128 N32 K128, V consumed MN-major straight from its natural [key][d] layout).
-// Two CTAs are resident per SM (256 TMEM columns and ~80 KB of shared memory each) so that one CTA's
-// exponentials overlap the other's tensor work: with d = 32 the kernel is MUFU-bound, not tensor-bound.
+// One CTA = one (batch, head, 128-query tile); 12 warps in 3 warpgroups:
+//   warps 0-7   softmax.  Warp w owns TMEM lanes (query rows) 32*(w%4).. and the key columns 64*(w/4)..+63 of each
+//               128x128 fp32 score tile: ONE TMEM read into 64 registers, local row max, a 64-thread named barrier
+//               to exchange the max with the warp holding the other half of the row, exp2 / row sum / dropout /
+//               bf16 P into SWIZZLE_128B shared memory (the K-major A operand of P V), and 16 of the 32 running
+//               O columns in registers (rescaled on-line).
+//   warp 8      TMA producer: Q once, then K/V tiles of 128 keys through a 3-stage ring (SWIZZLE_64B boxes).
+//   warp 9      TMEM allocation + single-thread tcgen05.mma issue: S = Q K^T (M128 N128 K32) and
+//               O_tile = P V (M128 N32 K128, V consumed MN-major straight from its natural [key][d] layout).
+//   warps 10-11 idle (complete the third warpgroup so that setmaxnreg can move its registers to the softmax warps).
+// The score columns are released right after they are copied to registers, so S_{j+1} = Q K_{j+1}^T runs under the
+// exponentials of tile j.  Two CTAs are resident per SM (256 TMEM columns, ~92 KB shared memory each): with d = 32
+// the kernel is bound by MUFU/issue slots, not by the tensor pipe, and needs the warps.
 //
 // Masking follows the reference: key_padding_mask / attention_mask entries get a huge FINITE negative score
 // (detr/model.py:326-334 uses finfo.min, so a fully masked row is uniform, not NaN); keys beyond S (tile
@@ -26,8 +30,8 @@ using namespace tc;
 constexpr int kBM = 128;          // queries per CTA
 constexpr int kBN = 128;          // keys per tile
 constexpr int kD = 32;            // head dim
-constexpr int kStages = 2;
-constexpr int kFwdThreads = 192;
+constexpr int kStages = 3;
+constexpr int kFwdThreads = 384;
 constexpr uint32_t kTileBytes = kBN * kD * 2;  // 8 KB: one Q, K or V tile
 constexpr uint32_t kTmemCols = 256;            // S: [0,128)  O: [128,160)
 // Masked score: huge, finite, and a POWER OF TWO (-2^126) so that score*scale is exact and the fused
@@ -43,6 +47,7 @@ struct AttnFwdParams {
     float scale_log2;                      // log2(e) / sqrt(32)
     uint32_t drop_thresh;                  // 0 = no dropout; drop key if byte < thresh
     float drop_scale;                      // 256 / (256 - thresh)
+    float drop_log2_scale;                 // log2(drop_scale): folded into the exponent
     uint64_t seed;
 };
 
@@ -50,11 +55,67 @@ struct FwdSmem {
     static constexpr uint32_t q = 0;
     static constexpr uint32_t k = q + kTileBytes;
     static constexpr uint32_t v = k + kStages * kTileBytes;
-    static constexpr uint32_t p = v + kStages * kTileBytes;      // 128 x 128 bf16, two 64-wide K blocks, SWIZZLE_128B
-    static constexpr uint32_t bars = p + kBM * kBN * 2;
+    static constexpr uint32_t p = 57344;                          // 128 x 128 bf16, two 64-key blocks, SWIZZLE_128B
+    static constexpr uint32_t xch = p + kBM * kBN * 2;            // float[2 parity][2 halves][128 rows] row-max exchange
+    static constexpr uint32_t bars = xch + 2 * 2 * kBM * 4;
     static constexpr uint32_t flags = bars + 128;
 };
-static_assert(FwdSmem::p % 1024 == 0, "P tile must be 1024-byte aligned for SWIZZLE_128B");
+static_assert(FwdSmem::v + kStages * kTileBytes <= FwdSmem::p && FwdSmem::p % 1024 == 0, "smem layout");
+
+// One 64-column half of a score tile for one query row: max, exponentials, P store.  MASKED / DROP are warp-uniform.
+template <bool MASKED, bool DROP>
+__device__ __forceinline__ void softmax_half_tile(uint32_t (&s)[64], const AttnFwdParams& p, const uint8_t* kf /*64 flags*/,
+                                                  const uint8_t* arow /*attention-mask row at this tile's first key of the half, or null*/,
+                                                  int keys_left /*S - first key of the half*/, float& m_run, float& l_run, float& alpha_out,
+                                                  float* xch_mine, const float* xch_other, uint32_t bar_id, uint32_t row_key, uint32_t k4_base,
+                                                  uint8_t* p_row /*this row inside the half's 64-key block*/, int row7) {
+    const float sc = p.scale_log2;
+    if (MASKED) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            const uint32_t f = kf[i];
+            const bool am = arow != nullptr && i < keys_left && arow[i] != 0;
+            float v = __uint_as_float(s[i]);
+            v = (f == 1u || am) ? kMaskedScore : v;
+            v = (f == 2u) ? -CUDART_INF_F : v;
+            s[i] = __float_as_uint(v);
+        }
+    }
+    float mx = fmaxf(__uint_as_float(s[0]), __uint_as_float(s[1]));
+#pragma unroll
+    for (int i = 2; i < 64; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+    // exchange with the warp that holds the other 64 columns of this row
+    *xch_mine = mx;
+    named_bar_sync(bar_id, 64);
+    mx = fmaxf(mx, *xch_other);
+    const float m_new = fmaxf(m_run, mx);                 // finite: every tile has at least one in-range key
+    alpha_out = ex2((m_run - m_new) * sc);                // first tile: exp2(-inf) = 0
+    const float bias = DROP ? fmaf(-m_new, sc, p.drop_log2_scale) : -m_new * sc;   // kept entries come out pre-scaled by 1/(1-p)
+    const uint32_t th = p.drop_thresh << 24;
+    float rsum = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {                         // 8 values = one 16-byte chunk of the P row
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            e[i] = ex2(fmaf(__uint_as_float(s[g * 8 + i]), sc, bias));
+            rsum += e[i];
+        }
+        if (DROP) {
+            const uint32_t b0 = dropout_bits4(row_key, k4_base + 2 * g), b1 = dropout_bits4(row_key, k4_base + 2 * g + 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                e[i] = dropout_keep(b0, i, th) ? e[i] : 0.f;
+                e[4 + i] = dropout_keep(b1, i, th) ? e[4 + i] : 0.f;
+            }
+        }
+        uint4 w;
+        w.x = pack_bf16x2(e[0], e[1]); w.y = pack_bf16x2(e[2], e[3]); w.z = pack_bf16x2(e[4], e[5]); w.w = pack_bf16x2(e[6], e[7]);
+        *reinterpret_cast<uint4*>(p_row + ((g ^ row7) << 4)) = w;
+    }
+    l_run = l_run * alpha_out + rsum;                     // (pre-scaled by 1/(1-p) when DROP; undone in the epilogue)
+    m_run = m_new;
+}
 
 __global__ void __launch_bounds__(kFwdThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -80,10 +141,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     if (tid == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < kStages; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
-        mbar_init(s_full, 1); mbar_init(s_empty, 128); mbar_init(p_full, 128); mbar_init(o_full, 1); mbar_init(o_empty, 128);
+        mbar_init(s_full, 1); mbar_init(s_empty, 256); mbar_init(p_full, 256); mbar_init(o_full, 1); mbar_init(o_empty, 256);
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 9) tmem_alloc(tmem_slot, kTmemCols);
     for (int k = tid; k < T * kBN; k += kFwdThreads)
         kflag[k] = k >= p.S ? 2 : ((p.kpm && p.kpm[b * p.kpm_sb + k]) ? 1 : 0);
     tc_fence_before();
@@ -92,23 +153,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
 
-    if (warp == 4) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+    if (warp >= 8) {
+        reg_dealloc<24>();
+        if (warp == 8 && lane == 0) {
+            // ================= TMA producer =================
             tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
             mbar_expect_tx(q_full, kTileBytes);
             tma_load_3d(smem + FwdSmem::q, &tm_q, q_full, h * kD, q0, b);
             for (int j = 0; j < T; ++j) {
                 const int s = j % kStages;
-                if (j >= kStages) mbar_wait(kv_empty + s, ((j / kStages) - 1) & 1);
+                if (j >= kStages) mbar_wait_sleep(kv_empty + s, ((j / kStages) - 1) & 1);
                 mbar_expect_tx(kv_full + s, 2 * kTileBytes);
                 tma_load_3d(smem + FwdSmem::k + s * kTileBytes, &tm_k, kv_full + s, h * kD, j * kBN, b);
                 tma_load_3d(smem + FwdSmem::v + s * kTileBytes, &tm_v, kv_full + s, h * kD, j * kBN, b);
             }
-        }
-    } else if (warp == 5) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        } else if (warp == 9 && lane == 0) {
+            // ================= MMA issuer =================
             constexpr uint32_t idesc_s = make_idesc_bf16(kBM, kBN, false, false);
             constexpr uint32_t idesc_o = make_idesc_bf16(kBM, kD, false, true);
             const uint32_t sq = smem_u32(smem + FwdSmem::q), sp = smem_u32(smem + FwdSmem::p);
@@ -120,19 +180,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                               idesc_s, ks > 0);
                 umma_commit(s_full);
             };
-            mbar_wait(q_full, 0);
-            mbar_wait(kv_full + 0, 0);
+            mbar_wait_sleep(q_full, 0);
+            mbar_wait_sleep(kv_full + 0, 0);
             tc_fence_after();
             issue_s(0);
             for (int j = 0; j < T; ++j) {
                 if (j + 1 < T) {
-                    mbar_wait(kv_full + ((j + 1) % kStages), ((j + 1) / kStages) & 1);
-                    mbar_wait(s_empty, j & 1);        // softmax has read S_j out of TMEM
+                    mbar_wait_sleep(kv_full + ((j + 1) % kStages), ((j + 1) / kStages) & 1);
+                    mbar_wait_sleep(s_empty, j & 1);        // the softmax warps hold S_j in registers
                     tc_fence_after();
                     issue_s(j + 1);
                 }
-                mbar_wait(p_full, j & 1);             // P_j is in shared memory
-                if (j > 0) mbar_wait(o_empty, (j - 1) & 1);  // O_{j-1} has been read out of TMEM
+                mbar_wait_sleep(p_full, j & 1);             // P_j is in shared memory
+                if (j > 0) mbar_wait_sleep(o_empty, (j - 1) & 1);  // O_{j-1} has been read out of TMEM
                 tc_fence_after();
                 const uint32_t sv = smem_u32(smem + FwdSmem::v + (j % kStages) * kTileBytes);
 #pragma unroll
@@ -149,132 +209,104 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
     } else {
         // ================= softmax warps =================
-        const int row = warp * 32 + lane;
+        reg_alloc<104>();   // 384 x 80 launch registers: 128 x 24 stay with warps 8-11, 256 x 104 <= the rest
+        const int wq = warp & 3, half = warp >> 2;
+        const int row = wq * 32 + lane;
         const int q = q0 + row;
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        const float sc = p.scale_log2;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
         const uint32_t bh = (uint32_t)(b * p.nh + h);
-        const uint32_t row_key = p.drop_thresh ? dropout_row_key(p.seed, bh, (uint32_t)q) : 0u;
+        const bool drop = p.drop_thresh != 0;
+        const uint32_t row_key = drop ? dropout_row_key(p.seed, bh, (uint32_t)q) : 0u;
         const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S : nullptr;
-        uint8_t* prow = smem + FwdSmem::p + (row >> 3) * 1024 + (row & 7) * 128;
+        uint8_t* p_row = smem + FwdSmem::p + half * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
+        float* xch = reinterpret_cast<float*>(smem + FwdSmem::xch);
         float m_run = -CUDART_INF_F, l_run = 0.f;
-        float acc[kD];
+        float acc[16];
 #pragma unroll
-        for (int i = 0; i < kD; ++i) acc[i] = 0.f;
-        uint32_t r[32];
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+        uint32_t s[64];
 
         for (int j = 0; j < T; ++j) {
-            const uint8_t* kf = kflag + j * kBN;
-            // does this tile need masking at all?  (common case: only the tail tile)
-            uint32_t any = arow ? 1u : 0u;
-            if (!any) {
+            const int key0 = j * kBN + half * 64;
+            const uint8_t* kf = kflag + key0;
+            uint32_t any = p.amask ? 1u : 0u;                 // warp-uniform: does this half tile need masking at all?
+            {
                 const uint4* kf4 = reinterpret_cast<const uint4*>(kf);
 #pragma unroll
-                for (int i = 0; i < kBN / 16; ++i) { const uint4 w = kf4[i]; any |= w.x | w.y | w.z | w.w; }
+                for (int i = 0; i < 4; ++i) { const uint4 w = kf4[i]; any |= w.x | w.y | w.z | w.w; }
             }
-            auto masked = [&](float s, int col) -> float {
-                const uint8_t f = kf[col];
-                if (f == 2) return -CUDART_INF_F;
-                if (f == 1 || (arow && (j * kBN + col) < p.S && arow[j * kBN + col])) return kMaskedScore;
-                return s;
-            };
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            // ---- pass 1: row max ----
-            float mx = -CUDART_INF_F;
-#pragma unroll 1
-            for (int c = 0; c < kBN / 32; ++c) {
-                tmem_ld32(tmem_s + lane_addr + c * 32, r);
-                tmem_ld_wait();
-                if (any) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, masked(__uint_as_float(r[i]), c * 32 + i));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                }
-            }
-            const float m_new = fmaxf(m_run, mx);
-            const float alpha = ex2((m_run - m_new) * sc);  // first tile: exp2(-inf) = 0
-            const float neg_m = -m_new * sc;
-            // ---- fold in the previous tile's P V (also frees the P buffer and the O columns) ----
-            if (j > 0) {
+            tmem_ld32(tmem_s + lane_addr + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+            tmem_ld32(tmem_s + lane_addr + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_empty);                             // S_{j+1} may now overwrite the score columns
+
+            if (j > 0) {   // the P buffer is free once P V of the previous tile has completed (o_full)
                 mbar_wait(o_full, (j - 1) & 1);
                 tc_fence_after();
-                tmem_ld32(tmem_o + lane_addr, r);
+            }
+            float alpha;
+            float* xm = xch + (j & 1) * 256 + half * 128 + row;
+            const float* xo = xch + (j & 1) * 256 + (half ^ 1) * 128 + row;
+            const uint32_t k4 = (uint32_t)(key0 >> 2);
+            const uint8_t* ar = arow ? arow + key0 : nullptr;
+            // previous tile's O columns (16 per thread) are loaded first so the TMEM read overlaps the row-max exchange
+            uint32_t o_prev[16];
+            if (j > 0) tmem_ld16(tmem_o + lane_addr + half * 16, o_prev);
+            if (any) {
+                if (drop) softmax_half_tile<true, true>(s, p, kf, ar, p.S - key0, m_run, l_run, alpha, xm, xo, 1 + wq, row_key, k4, p_row, row & 7);
+                else softmax_half_tile<true, false>(s, p, kf, ar, p.S - key0, m_run, l_run, alpha, xm, xo, 1 + wq, row_key, k4, p_row, row & 7);
+            } else {
+                if (drop) softmax_half_tile<false, true>(s, p, kf, ar, p.S - key0, m_run, l_run, alpha, xm, xo, 1 + wq, row_key, k4, p_row, row & 7);
+                else softmax_half_tile<false, false>(s, p, kf, ar, p.S - key0, m_run, l_run, alpha, xm, xo, 1 + wq, row_key, k4, p_row, row & 7);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(p_full);
+            if (j > 0) {
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(o_empty);
 #pragma unroll
-                for (int i = 0; i < kD; ++i) acc[i] = (acc[i] + __uint_as_float(r[i])) * alpha;
+                for (int i = 0; i < 16; ++i) acc[i] = (acc[i] + __uint_as_float(o_prev[i])) * alpha;
             }
-            // ---- pass 2: probabilities ----
-            float rsum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < kBN / 32; ++c) {
-                tmem_ld32(tmem_s + lane_addr + c * 32, r);
-                tmem_ld_wait();
-                float pv[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float s = __uint_as_float(r[i]);
-                    if (any) s = masked(s, c * 32 + i);
-                    pv[i] = ex2(fmaf(s, sc, neg_m));
-                    rsum += pv[i];
-                }
-                if (p.drop_thresh) {
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const uint32_t bits = dropout_bits4(row_key, (uint32_t)((j * kBN + c * 32) >> 2) + g);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            pv[g * 4 + e] = ((bits >> (8 * e)) & 0xffu) < p.drop_thresh ? 0.f : pv[g * 4 + e] * p.drop_scale;
-                    }
-                }
-                // 32 bf16 = four 16-byte chunks of this row, XOR-swizzled by (row % 8) inside the 128-byte line
-                uint8_t* blk = prow + (c >> 1) * 16384;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int chunk = (c & 1) * 4 + g;
-                    uint4 w;
-                    w.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]); w.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
-                    w.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]); w.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
-                    *reinterpret_cast<uint4*>(blk + ((chunk ^ (row & 7)) << 4)) = w;
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(s_empty);
-            fence_proxy_async_smem();
-            mbar_arrive(p_full);
-            l_run = l_run * alpha + rsum;
-            m_run = m_new;
         }
         // ---- epilogue: last P V, normalise, store ----
         mbar_wait(o_full, (T - 1) & 1);
         tc_fence_after();
-        tmem_ld32(tmem_o + lane_addr, r);
+        uint32_t o_last[16];
+        tmem_ld16(tmem_o + lane_addr + half * 16, o_last);
+        // total row sum = sum of the two halves (same running max, same alpha history)
+        float* xm = xch + (T & 1) * 256 + half * 128 + row;
+        const float* xo = xch + (T & 1) * 256 + (half ^ 1) * 128 + row;
+        *xm = l_run;
+        named_bar_sync(1 + wq, 64);
+        float l_tot = l_run + *xo;
+        if (drop) l_tot *= 1.f / p.drop_scale;              // the exponentials were pre-scaled by 1/(1-p)
         tmem_ld_wait();
         tc_fence_before();
         if (q < p.L) {
-            const float inv = 1.f / l_run;
-            __nv_bfloat16* dst = p.O + b * p.o_sb + (int64_t)q * p.o_sl + h * kD;
+            const float inv = 1.f / l_tot;
+            __nv_bfloat16* dst = p.O + b * p.o_sb + (int64_t)q * p.o_sl + h * kD + half * 16;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 2; ++g) {
                 uint4 w;
                 float o[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = (acc[g * 8 + e] + __uint_as_float(r[g * 8 + e])) * inv;
+                for (int e = 0; e < 8; ++e) o[e] = (acc[g * 8 + e] + __uint_as_float(o_last[g * 8 + e])) * inv;
                 w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
                 reinterpret_cast<uint4*>(dst)[g] = w;
             }
-            // natural-log LSE of the scaled scores: m/sqrt(d) + ln(l)
-            // a row whose keys are all masked is flagged with +inf: the backward kernels then skip it
-            p.lse[((int64_t)b * p.nh + h) * p.L + q] =
-                m_run == kMaskedScore ? CUDART_INF_F : (m_run * sc + log2f(l_run)) * 0.6931471805599453f;
+            // natural-log LSE of the scaled scores: m/sqrt(d) + ln(l).  A row whose keys are all masked is flagged
+            // with +inf: the backward kernels then skip it.
+            if (half == 0)
+                p.lse[((int64_t)b * p.nh + h) * p.L + q] =
+                    m_run == kMaskedScore ? CUDART_INF_F : (m_run * p.scale_log2 + log2f(l_tot)) * 0.6931471805599453f;
         }
     }
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 9) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -339,6 +371,7 @@ extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)kD);
     p.drop_thresh = (uint32_t)lrintf(dropout_p * 256.f);
     p.drop_scale = 256.f / (256.f - (float)p.drop_thresh);
+    p.drop_log2_scale = log2f(p.drop_scale);
     p.seed = seed;
     const int T = (S + kBN - 1) / kBN;
     const size_t smem = FwdSmem::flags + (size_t)T * kBN + 1024;  // +1024: manual alignment slack

@@ -69,10 +69,31 @@ class _MLP(nn.Module):
         return self.net(x)
 
 
-class _Backbone(nn.Module):
-    """torchvision ResNet C5 with FrozenBatchNorm2d, random init (no network here) -- detr/model.py:427-438."""
+def _conv_bn(x, conv: nn.Conv2d, bn) -> torch.Tensor:
+    """conv followed by FrozenBatchNorm2d with the frozen affine folded into the convolution:
+    conv(x, W) * s + t == conv(x, W * s) + t, s = gamma / sqrt(var + eps), t = beta - mean * s.
+    Same parameters / buffers / state_dict keys as torchvision's modules and the same gradient w.r.t. W; it only
+    removes the fp32-promoting elementwise passes FrozenBatchNorm2d makes over every activation under autocast."""
+    scale = bn.weight * (bn.running_var + bn.eps).rsqrt()
+    shift = bn.bias - bn.running_mean * scale
+    return F.conv2d(x, conv.weight * scale.view(-1, 1, 1, 1), shift, conv.stride, conv.padding, conv.dilation, conv.groups)
 
-    def __init__(self, name: str):
+
+def _bottleneck_forward(blk, x):
+    identity = x
+    out = F.relu(_conv_bn(x, blk.conv1, blk.bn1), inplace=True)
+    out = F.relu(_conv_bn(out, blk.conv2, blk.bn2), inplace=True)
+    out = _conv_bn(out, blk.conv3, blk.bn3)
+    if blk.downsample is not None:
+        identity = _conv_bn(x, blk.downsample[0], blk.downsample[1])
+    return F.relu(out + identity, inplace=True)
+
+
+class _Backbone(nn.Module):
+    """torchvision ResNet C5 with FrozenBatchNorm2d, random init (no network here) -- detr/model.py:427-438.
+    OUT OF SCOPE code (library convolutions); executed with the frozen BN folded into the conv weights."""
+
+    def __init__(self, name: str, fold_bn: bool = True):
         super().__init__()
         from torchvision.models import get_model
         from torchvision.models._utils import IntermediateLayerGetter
@@ -81,9 +102,18 @@ class _Backbone(nn.Module):
         self.backbone = IntermediateLayerGetter(model, return_layers={"layer4": "final_feature_map"})
         self.num_channels = 2048
         self.scale = 32
+        self.fold_bn = fold_bn
 
     def forward(self, x):
-        return self.backbone(x)["final_feature_map"]
+        if not self.fold_bn:
+            return self.backbone(x)["final_feature_map"]
+        m = self.backbone
+        x = F.relu(_conv_bn(x, m.conv1, m.bn1), inplace=True)
+        x = m.maxpool(x)
+        for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
+            for blk in layer:
+                x = _bottleneck_forward(blk, x)
+        return x
 
 
 class DetrHarness(nn.Module):
