@@ -15,6 +15,8 @@
 // a query row whose keys are ALL masked is stored with LSE = +inf by the forward kernel and contributes nothing.
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -53,7 +55,7 @@ struct Smem {
     static constexpr uint32_t pt = ds + kT * kT * 2;                       // P~ (kDKV only)
     static constexpr uint32_t bars = pt + kT * kT * 2;
     static constexpr uint32_t flags = bars + 128;
-    static constexpr uint32_t total = flags + kT + 1024;
+    // + ceil(S/128)*128 key flags + 1024 bytes of alignment slack (computed on the host)
 };
 static_assert(Smem::ds % 1024 == 0 && Smem::pt % 1024 == 0, "swizzled tiles must be 1024-byte aligned");
 
@@ -77,7 +79,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     uint64_t* ds_empty = sdp_full + 3;
     uint64_t* acc_full = sdp_full + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 5);
-    uint8_t* kflag = smem + Smem::flags;   // flags of the CURRENT key tile (kDKV: fixed; kDQ: rewritten per step by warp 8)
+    uint8_t* kflag = smem + Smem::flags;
 
     if (tid == 0) {
         mbar_init(fixed_full, 1);
@@ -86,6 +88,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         fence_barrier_init();
     }
     if (warp == 9) tmem_alloc(tmem_slot, kTmemCols);
+    {   // key flags: 0 normal, 1 masked, 2 beyond S.  kDQ: all keys; kDKV: the CTA's own 128 keys
+        const int nk = kDQ ? T * kT : kT, base = kDQ ? 0 : t0;
+        for (int k = tid; k < nk; k += kThreads)
+            kflag[k] = (base + k) >= p.S ? 2 : ((p.kpm && p.kpm[b * p.kpm_sb + base + k]) ? 1 : 0);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -101,7 +108,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             tma_load_3d(smem + Smem::fixed + kTileBytes, kDQ ? &tm_do : &tm_v, fixed_full, h * kD, t0, b);
             for (int t = 0; t < T; ++t) {
                 const int s = t % kStages;
-                if (t >= kStages) mbar_wait(ring_empty + s, ((t / kStages) - 1) & 1);
+                if (t >= kStages) mbar_wait_sleep(ring_empty + s, ((t / kStages) - 1) & 1);
                 mbar_expect_tx(ring_full + s, 2 * kTileBytes);
                 uint8_t* dst = smem + Smem::ring + s * 2 * kTileBytes;
                 tma_load_3d(dst, kDQ ? &tm_k : &tm_q, ring_full + s, h * kD, t * kT, b);
@@ -126,18 +133,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 for (int ks = 0; ks < kD / 16; ++ks) umma_bf16(tmem_dp, kmaj64(ado, ks), kmaj64(bv, ks), idesc_sc, ks > 0);
                 umma_commit(sdp_full);
             };
-            mbar_wait(fixed_full, 0);
-            mbar_wait(ring_full + 0, 0);
+            mbar_wait_sleep(fixed_full, 0);
+            mbar_wait_sleep(ring_full + 0, 0);
             tc_fence_after();
             issue_scores(0);
             for (int t = 0; t < T; ++t) {
                 if (t + 1 < T) {
-                    mbar_wait(ring_full + ((t + 1) % kStages), ((t + 1) / kStages) & 1);
-                    mbar_wait(sdp_empty, t & 1);
+                    mbar_wait_sleep(ring_full + ((t + 1) % kStages), ((t + 1) / kStages) & 1);
+                    mbar_wait_sleep(sdp_empty, t & 1);
                     tc_fence_after();
                     issue_scores(t + 1);
                 }
-                mbar_wait(ds_full, t & 1);
+                mbar_wait_sleep(ds_full, t & 1);
                 tc_fence_after();
                 const uint32_t r0 = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes), r1 = r0 + kTileBytes;
 #pragma unroll
@@ -165,21 +172,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int row = (warp & 3) * 32 + lane;       // TMEM lane = query within the tile
         const int ch = warp >> 2;                     // which 64-key half of the tile
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        const float sc = p.scale_log2;
         const uint32_t bh = (uint32_t)(b * p.nh + h);
         const float* lse_bh = p.lse + (int64_t)bh * p.L;
         const float* dl_bh = p.delta + (int64_t)bh * p.L;
         uint8_t* ds_row = smem + Smem::ds + ch * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
         uint8_t* pt_row = smem + Smem::pt + ch * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
-
-        auto load_flags = [&](int key0) {   // cooperative: 256 threads, 128 keys
-            if (tid < kT) {
-                const int k = key0 + tid;
-                kflag[tid] = k >= p.S ? 2 : ((p.kpm && p.kpm[b * p.kpm_sb + k]) ? 1 : 0);
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-        };
-        if (!kDQ) load_flags(t0);
+        const bool drop = p.drop_thresh != 0;
 
         float lse2 = 0.f, dlt = 0.f;
         uint32_t row_key = 0;
@@ -190,20 +188,22 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             const float l = ok ? lse_bh[q] : CUDART_INF_F;
             lse2 = l * 1.4426950408889634f;            // +inf (padding row / fully masked row) -> p = 0
             dlt = ok ? dl_bh[q] : 0.f;
-            row_key = p.drop_thresh ? dropout_row_key(p.seed, bh, (uint32_t)q) : 0u;
+            row_key = drop ? dropout_row_key(p.seed, bh, (uint32_t)q) : 0u;
         };
         if (kDQ) load_row(t0 + row);
 
         uint32_t s0[32], s1[32], d0[32], d1[32];
         for (int t = 0; t < T; ++t) {
-            const int key0 = kDQ ? t * kT : t0;
-            if (kDQ) {
-                if (t > 0) asm volatile("bar.sync 2, 256;" ::: "memory");   // everyone is done with the previous tile's flags
-                load_flags(key0);
-            } else {
-                load_row(t * kT + row);
+            const int key0 = (kDQ ? t * kT : t0) + ch * 64;      // first key of this thread's 64-column half
+            if (!kDQ) load_row(t * kT + row);
+            const uint8_t* kf = kflag + (kDQ ? t * kT : 0) + ch * 64;
+            const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S + key0 : nullptr;
+            uint32_t any = p.amask ? 1u : 0u;
+            {
+                const uint4* kf4 = reinterpret_cast<const uint4*>(kf);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const uint4 w = kf4[i]; any |= w.x | w.y | w.z | w.w; }
             }
-            const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S : nullptr;
             mbar_wait(sdp_full, t & 1);
             tc_fence_after();
             tmem_ld32(tmem_s + lane_addr + ch * 64, s0);
@@ -215,44 +215,51 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             mbar_arrive(sdp_empty);                         // score columns may be overwritten by the next tile
             if (t > 0) mbar_wait(ds_empty, (t - 1) & 1);    // previous accumulation MMAs have consumed dS / P~
 
+            auto half_tile = [&](auto masked_c, auto drop_c, const uint32_t* sv, const uint32_t* dv, int hf) {
+                constexpr bool MASKED = decltype(masked_c)::value, DROP = decltype(drop_c)::value;
+                const uint32_t th = p.drop_thresh << 24;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const uint32_t* sv = half ? s1 : s0;
-                const uint32_t* dv = half ? d1 : d0;
-                float pt[32], dsv[32];
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const int col = ch * 64 + half * 32 + g * 4;    // key within the tile
-                    uint32_t bits = 0xffffffffu;
-                    if (p.drop_thresh) bits = dropout_bits4(row_key, (uint32_t)((key0 + col) >> 2));
-                    const uint32_t kf4 = *reinterpret_cast<const uint32_t*>(kflag + col);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = g * 4 + e;
-                        float pr = ex2(fmaf(__uint_as_float(sv[i]), sc, -lse2));
-                        const bool masked = ((kf4 >> (8 * e)) & 0xffu) != 0 ||
-                                            (arow && (key0 + col + e) < p.S && arow[key0 + col + e]);
-                        if (masked) pr = 0.f;
-                        float keep = 1.f;
-                        if (p.drop_thresh) keep = ((bits >> (8 * e)) & 0xffu) < p.drop_thresh ? 0.f : p.drop_scale;
-                        pt[i] = pr * keep;
-                        dsv[i] = pr * (__uint_as_float(dv[i]) * keep - dlt) * p.scale;
+                for (int g = 0; g < 4; ++g) {               // 8 keys = one 16-byte chunk of the dS / P~ rows
+                    float pt[8], dsv[8];
+                    uint32_t b0 = 0, b1 = 0;
+                    if (DROP) {
+                        const uint32_t k4 = (uint32_t)((key0 + hf * 32 + g * 8) >> 2);
+                        b0 = dropout_bits4(row_key, k4); b1 = dropout_bits4(row_key, k4 + 1);
                     }
-                }
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int chunk = half * 4 + g;
-                    const uint32_t off = (uint32_t)((chunk ^ (row & 7)) << 4);
+                    for (int e = 0; e < 8; ++e) {
+                        const int i = g * 8 + e;
+                        float pr = ex2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -lse2));
+                        if (MASKED) {
+                            const int c = hf * 32 + i;
+                            const bool m = kf[c] != 0 || (arow != nullptr && (key0 + c) < p.S && arow[c] != 0);
+                            pr = m ? 0.f : pr;
+                        }
+                        float keep = 1.f;
+                        if (DROP) keep = dropout_keep(e < 4 ? b0 : b1, e & 3, th) ? p.drop_scale : 0.f;
+                        pt[e] = DROP ? pr * keep : pr;
+                        // dS without the 1/sqrt(d) factor: it is applied once to the dQ / dK accumulators in the epilogue
+                        dsv[e] = pr * (DROP ? fmaf(__uint_as_float(dv[i]), keep, -dlt) : (__uint_as_float(dv[i]) - dlt));
+                    }
+                    const uint32_t off = (uint32_t)(((hf * 4 + g) ^ (row & 7)) << 4);
                     uint4 w;
-                    w.x = pack_bf16x2(dsv[g * 8 + 0], dsv[g * 8 + 1]); w.y = pack_bf16x2(dsv[g * 8 + 2], dsv[g * 8 + 3]);
-                    w.z = pack_bf16x2(dsv[g * 8 + 4], dsv[g * 8 + 5]); w.w = pack_bf16x2(dsv[g * 8 + 6], dsv[g * 8 + 7]);
+                    w.x = pack_bf16x2(dsv[0], dsv[1]); w.y = pack_bf16x2(dsv[2], dsv[3]);
+                    w.z = pack_bf16x2(dsv[4], dsv[5]); w.w = pack_bf16x2(dsv[6], dsv[7]);
                     *reinterpret_cast<uint4*>(ds_row + off) = w;
                     if (!kDQ) {
-                        w.x = pack_bf16x2(pt[g * 8 + 0], pt[g * 8 + 1]); w.y = pack_bf16x2(pt[g * 8 + 2], pt[g * 8 + 3]);
-                        w.z = pack_bf16x2(pt[g * 8 + 4], pt[g * 8 + 5]); w.w = pack_bf16x2(pt[g * 8 + 6], pt[g * 8 + 7]);
+                        w.x = pack_bf16x2(pt[0], pt[1]); w.y = pack_bf16x2(pt[2], pt[3]);
+                        w.z = pack_bf16x2(pt[4], pt[5]); w.w = pack_bf16x2(pt[6], pt[7]);
                         *reinterpret_cast<uint4*>(pt_row + off) = w;
                     }
                 }
+            };
+            using TT = std::true_type; using FF = std::false_type;
+            if (any) {
+                if (drop) { half_tile(TT{}, TT{}, s0, d0, 0); half_tile(TT{}, TT{}, s1, d1, 1); }
+                else      { half_tile(TT{}, FF{}, s0, d0, 0); half_tile(TT{}, FF{}, s1, d1, 1); }
+            } else {
+                if (drop) { half_tile(FF{}, TT{}, s0, d0, 0); half_tile(FF{}, TT{}, s1, d1, 1); }
+                else      { half_tile(FF{}, FF{}, s0, d0, 0); half_tile(FF{}, FF{}, s1, d1, 1); }
             }
             fence_proxy_async_smem();
             mbar_arrive(ds_full);
@@ -268,13 +275,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             if (gr < n_rows) {
                 __nv_bfloat16* dst = (kDQ || ch == 0) ? p.out0 + b * p.o0_sb + (int64_t)gr * p.o0_sl + h * kD
                                                       : p.out1 + b * p.o1_sb + (int64_t)gr * p.o1_sl + h * kD;
+                const float f = (kDQ || ch == 0) ? p.scale : 1.f;   // dQ and dK carry the 1/sqrt(d) of the scores; dV does not
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint4 w;
-                    w.x = pack_bf16x2(__uint_as_float(s0[g * 8 + 0]), __uint_as_float(s0[g * 8 + 1]));
-                    w.y = pack_bf16x2(__uint_as_float(s0[g * 8 + 2]), __uint_as_float(s0[g * 8 + 3]));
-                    w.z = pack_bf16x2(__uint_as_float(s0[g * 8 + 4]), __uint_as_float(s0[g * 8 + 5]));
-                    w.w = pack_bf16x2(__uint_as_float(s0[g * 8 + 6]), __uint_as_float(s0[g * 8 + 7]));
+                    w.x = pack_bf16x2(f * __uint_as_float(s0[g * 8 + 0]), f * __uint_as_float(s0[g * 8 + 1]));
+                    w.y = pack_bf16x2(f * __uint_as_float(s0[g * 8 + 2]), f * __uint_as_float(s0[g * 8 + 3]));
+                    w.z = pack_bf16x2(f * __uint_as_float(s0[g * 8 + 4]), f * __uint_as_float(s0[g * 8 + 5]));
+                    w.w = pack_bf16x2(f * __uint_as_float(s0[g * 8 + 6]), f * __uint_as_float(s0[g * 8 + 7]));
                     reinterpret_cast<uint4*>(dst)[g] = w;
                 }
             }
@@ -353,22 +361,24 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.drop_thresh = (uint32_t)lrintf(dropout_p * 256.f);
     p.drop_scale = 256.f / (256.f - (float)p.drop_thresh);
     p.seed = seed;
+    const size_t smem_dq = Smem::flags + (size_t)((S + kT - 1) / kT) * kT + 1024, smem_dkv = Smem::flags + kT + 1024;
+    DETR_CHECK_ARG(smem_dq <= 200 * 1024, "attention_bwd: S=%d needs %zu B of shared memory", S, smem_dq);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e1 = cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem::total);
-        cudaError_t e2 = cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem::total);
+        cudaError_t e1 = cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e2 = cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attention_bwd: cudaFuncSetAttribute failed"); return 2; }
         attr_set = true;
     }
     // dK, dV
     p.out0 = reinterpret_cast<__nv_bfloat16*>(dk); p.o0_sb = dk_sb; p.o0_sl = dk_sl;
     p.out1 = reinterpret_cast<__nv_bfloat16*>(dv); p.o1_sb = dv_sb; p.o1_sl = dv_sl;
-    attention_bwd_kernel<false><<<dim3((S + kT - 1) / kT, nh, B), kThreads, Smem::total, st>>>(tq, tk, tv, tdo, p);
+    attention_bwd_kernel<false><<<dim3((S + kT - 1) / kT, nh, B), kThreads, smem_dkv, st>>>(tq, tk, tv, tdo, p);
     DETR_CHECK_LAUNCH("attention_bwd_dkv");
     // dQ
     p.out0 = reinterpret_cast<__nv_bfloat16*>(dq); p.o0_sb = dq_sb; p.o0_sl = dq_sl;
     p.out1 = nullptr; p.o1_sb = p.o1_sl = 0;
-    attention_bwd_kernel<true><<<dim3((L + kT - 1) / kT, nh, B), kThreads, Smem::total, st>>>(tq, tk, tv, tdo, p);
+    attention_bwd_kernel<true><<<dim3((L + kT - 1) / kT, nh, B), kThreads, smem_dq, st>>>(tq, tk, tv, tdo, p);
     DETR_CHECK_LAUNCH("attention_bwd_dq");
     return 0;
 }
