@@ -93,7 +93,7 @@ class ClockSampler:
 def run_b200(args):
     import torch.distributed as dist
     from detr_b200 import HungarianMatcher, SetCriterion, _lib
-    from detr_b200.harness import DetrHarness, batch_bytes, batch_to, make_optimizer, synthetic_batch, train_step
+    from detr_b200.harness import DetrHarness, GraphedTrainStep, batch_bytes, batch_to, make_optimizer, synthetic_batch, train_step
     from detr_b200.model import DETRConfig
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -112,24 +112,45 @@ def run_b200(args):
     torch.manual_seed(1234 + rank)
 
     cfg = DETRConfig(num_classes=NUM_CLASSES)
+    torch.manual_seed(1234)   # identical replicas on every rank (data differs per rank)
     model = DetrHarness(cfg).to(dev).to(memory_format=torch.channels_last).train()
     crit = SetCriterion(NUM_CLASSES, HungarianMatcher(cost_class=1.0, cost_bbox=5.0, cost_giou=2.0), 1.0, 5.0, 2.0, 0.1).to(dev).train()
-    step_model = model
-    if world > 1:
-        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
-    opt = make_optimizer(step_model)
+    torch.manual_seed(1234 + rank)
 
     host = synthetic_batch(PER_GPU_BATCH, H, W, NUM_CLASSES, 20, seed=100 + rank, pin=True)
     host["image"] = host["image"].contiguous(memory_format=torch.channels_last).pin_memory()
-    resident = batch_to(host, dev)
-    torch.cuda.synchronize()
 
-    def step_resident():
-        return train_step(step_model, crit, opt, resident)
+    if args.eager:
+        # eager path: DDP bucketed all-reduce overlapped with backward, one Python-launched kernel at a time
+        step_model = model
+        if world > 1:
+            step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+        opt = make_optimizer(step_model)
+        resident = batch_to(host, dev)
+        torch.cuda.synchronize()
 
-    def step_e2e():
-        b = batch_to(host, dev, non_blocking=True)     # H2D of this step's inputs from pinned memory
-        return float(train_step(step_model, crit, opt, b).item())   # D2H read of the step's loss
+        def step_resident():
+            return train_step(step_model, crit, opt, resident)
+
+        def step_e2e():
+            b = batch_to(host, dev, non_blocking=True)     # H2D of this step's inputs from pinned memory
+            return float(train_step(step_model, crit, opt, b).item())   # D2H read of the step's loss
+        h2d = batch_bytes(host)
+        own_launches = None
+    else:
+        # default: the same step captured in CUDA graphs (harness.GraphedTrainStep) -- replay is GPU-bound
+        opt = make_optimizer(model, capturable=True)
+        graphed = GraphedTrainStep(model, crit, opt, host)
+        h2d = graphed.load(host)
+        torch.cuda.synchronize()
+
+        def step_resident():
+            return graphed.step()
+
+        def step_e2e():
+            graphed.load(host)                              # H2D of images + repacked ground truth from pinned memory
+            return float(graphed.step().item())             # D2H read of the step's loss
+        own_launches = graphed.own_launches_per_step
 
     def barrier():
         if world > 1:
@@ -164,7 +185,7 @@ def run_b200(args):
         sampler.start()
     l0 = _lib.launch_count
     ms = timed(step_resident, args.steps)
-    launches = _lib.launch_count - l0
+    launches = (_lib.launch_count - l0) if own_launches is None else own_launches * args.steps
     clocks = sampler.stop() if rank == 0 else None
     crit.check_status()
     for _ in range(2):
@@ -172,9 +193,18 @@ def run_b200(args):
     ms_e2e = timed(step_e2e, args.steps)
 
     # ---- live per-kernel timing of the library's launches (CUDA events on the launching stream), 3 extra steps ----
+    # (graph replays cannot be instrumented from the host, so these 3 steps run the SAME kernels eagerly)
+    if args.eager:
+        prof_step = step_resident
+    else:
+        eager_opt = make_optimizer(model)
+        resident = batch_to(host, dev)
+        prof_step = lambda: train_step(model, crit, eager_opt, resident)
+        if world > 1:
+            prof_step = lambda: None   # ranks would diverge without the gradient all-reduce: profile at N=1 only
     with _lib.profile() as prof:
         for _ in range(3):
-            step_resident()
+            prof_step()
     torch.cuda.synchronize()
     rows = prof.summary()
     step_ms = ms / args.steps
@@ -209,8 +239,9 @@ def run_b200(args):
             "dtype": "bf16", "data": "synthetic", "impl": "b200",
             "config": {"workload": WORKLOAD, "global_batch": imgs, "per_gpu_batch": PER_GPU_BATCH, "parallelism": f"dp{world}",
                        "mode": "train (dropout on)", "optimizer": "AdamW fused, clip 1.0",
+                       "execution": "eager + DDP" if args.eager else "CUDA graphs (fwd+bwd | NCCL all-reduce of flat grads | clip+AdamW)",
                        "l2": "no explicit flush: every step streams >1 GB of ResNet activations through the 126 MB L2"},
-            "e2e": {"value": round(imgs * args.steps / (ms_e2e * 1e-3), 3), "unit": UNIT, "h2d_bytes_per_step": batch_bytes(host),
+            "e2e": {"value": round(imgs * args.steps / (ms_e2e * 1e-3), 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "own_kernels": {"ms_per_step": round(own_ms, 3), "share_of_step": round(own_ms / step_ms, 4), "by_call": own},
@@ -302,6 +333,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--eager", action="store_true", help="do not capture the step in CUDA graphs (DDP eager path)")
     ap.add_argument("--ncu-step", action="store_true", help="warm up, then run exactly one step between cudaProfilerStart/Stop")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -45,7 +45,7 @@ struct Params {
     const uint8_t* amask;
     int B, nh, L, S;
     float scale_log2, scale;   // log2(e)/sqrt(d), 1/sqrt(d)
-    uint32_t drop_thresh; float drop_scale; uint64_t seed;
+    uint32_t drop_thresh; float drop_scale; uint64_t seed; const uint64_t* seed_ptr;
 };
 
 struct Smem {
@@ -188,7 +188,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             const float l = ok ? lse_bh[q] : CUDART_INF_F;
             lse2 = l * 1.4426950408889634f;            // +inf (padding row / fully masked row) -> p = 0
             dlt = ok ? dl_bh[q] : 0.f;
-            row_key = drop ? dropout_row_key(p.seed, bh, (uint32_t)q) : 0u;
+            row_key = drop ? dropout_row_key(p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull), bh, (uint32_t)q) : 0u;
         };
         if (kDQ) load_row(t0 + row);
 
@@ -331,7 +331,7 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
                                        void* dq, int64_t dq_sb, int64_t dq_sl, void* dk, int64_t dk_sb, int64_t dk_sl,
                                        void* dv, int64_t dv_sb, int64_t dv_sl, const uint8_t* key_padding_mask, int64_t kpm_sb,
                                        const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
-                                       uint64_t seed, void* stream) {
+                                       uint64_t seed, const uint64_t* seed_ptr, void* stream) {
     using namespace detr::bwd;
     DETR_CHECK_ARG(B >= 1 && nh >= 1 && L >= 1 && S >= 1, "attention_bwd: bad sizes B=%d nh=%d L=%d S=%d", B, nh, L, S);
     DETR_CHECK_ARG(B <= 65535 && nh <= 65535, "attention_bwd: B and nh must fit the grid");
@@ -360,7 +360,7 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.scale_log2 = 1.4426950408889634f * p.scale;
     p.drop_thresh = (uint32_t)lrintf(dropout_p * 256.f);
     p.drop_scale = 256.f / (256.f - (float)p.drop_thresh);
-    p.seed = seed;
+    p.seed = seed; p.seed_ptr = seed_ptr;
     const size_t smem_dq = Smem::flags + (size_t)((S + kT - 1) / kT) * kT + 1024, smem_dkv = Smem::flags + kT + 1024;
     DETR_CHECK_ARG(smem_dq <= 200 * 1024, "attention_bwd: S=%d needs %zu B of shared memory", S, smem_dq);
     static bool attr_set = false;

@@ -48,7 +48,7 @@ struct AttnFwdParams {
     uint32_t drop_thresh;                  // 0 = no dropout; drop key if byte < thresh
     float drop_scale;                      // 256 / (256 - thresh)
     float drop_log2_scale;                 // log2(drop_scale): folded into the exponent
-    uint64_t seed;
+    uint64_t seed; const uint64_t* seed_ptr; // effective seed = seed + *seed_ptr (device side: CUDA-graph replays get fresh masks)
 };
 
 struct FwdSmem {
@@ -216,7 +216,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
         const uint32_t bh = (uint32_t)(b * p.nh + h);
         const bool drop = p.drop_thresh != 0;
-        const uint32_t row_key = drop ? dropout_row_key(p.seed, bh, (uint32_t)q) : 0u;
+        const uint32_t row_key = drop ? dropout_row_key(p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull), bh, (uint32_t)q) : 0u;
         const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S : nullptr;
         uint8_t* p_row = smem + FwdSmem::p + half * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
         float* xch = reinterpret_cast<float*>(smem + FwdSmem::xch);
@@ -354,7 +354,7 @@ extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
                                        const void* v, int64_t v_sb, int64_t v_sl, void* o, int64_t o_sb, int64_t o_sl,
                                        float* lse, const uint8_t* key_padding_mask, int64_t kpm_sb,
                                        const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
-                                       uint64_t seed, void* stream) {
+                                       uint64_t seed, const uint64_t* seed_ptr, void* stream) {
     DETR_CHECK_ARG(B >= 1 && nh >= 1 && L >= 1 && S >= 1, "attention_fwd: bad sizes B=%d nh=%d L=%d S=%d", B, nh, L, S);
     DETR_CHECK_ARG(B <= 65535 && nh <= 65535, "attention_fwd: B and nh must fit the grid");
     DETR_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attention_fwd: dropout_p must be in [0,1)");
@@ -372,7 +372,7 @@ extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.drop_thresh = (uint32_t)lrintf(dropout_p * 256.f);
     p.drop_scale = 256.f / (256.f - (float)p.drop_thresh);
     p.drop_log2_scale = log2f(p.drop_scale);
-    p.seed = seed;
+    p.seed = seed; p.seed_ptr = seed_ptr;
     const int T = (S + kBN - 1) / kBN;
     const size_t smem = FwdSmem::flags + (size_t)T * kBN + 1024;  // +1024: manual alignment slack
     DETR_CHECK_ARG(smem <= 110 * 1024, "attention_fwd: S=%d needs %zu B of shared memory", S, smem);

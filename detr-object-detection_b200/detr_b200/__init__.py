@@ -6,6 +6,6 @@ Host code is Python/PyTorch; every kernel lives in libdetr_b200.so (C ABI: inclu
 from . import _lib
 from .loss import SetCriterion
 from .matcher import HungarianMatcher, linear_sum_assignment_cuda
-from .targets import PackedTargets, pack_targets
+from .targets import PackedTargets, StaticTargets, pack_targets
 
-__all__ = ["HungarianMatcher", "SetCriterion", "linear_sum_assignment_cuda", "PackedTargets", "pack_targets", "_lib"]
+__all__ = ["HungarianMatcher", "SetCriterion", "linear_sum_assignment_cuda", "PackedTargets", "StaticTargets", "pack_targets", "_lib"]

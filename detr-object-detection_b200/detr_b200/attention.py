@@ -32,7 +32,8 @@ def _mask_bytes(m: Optional[torch.Tensor], shape, name: str) -> Optional[torch.T
     return m.contiguous().view(torch.uint8)
 
 
-def attention_forward(q, k, v, key_padding_mask=None, attention_mask=None, dropout_p: float = 0.0, seed: int = 0):
+def attention_forward(q, k, v, key_padding_mask=None, attention_mask=None, dropout_p: float = 0.0, seed: int = 0,
+                      seed_tensor: Optional[torch.Tensor] = None):
     """Raw forward launch -> (out bf16 (B,L,C), lse fp32 (B,nh,L))."""
     _lib.require_cuda(q, "attention")
     B, L, C = q.shape
@@ -49,12 +50,13 @@ def attention_forward(q, k, v, key_padding_mask=None, attention_mask=None, dropo
         "detr_attention_fwd_bf16",
         q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0), v.stride(1),
         out.data_ptr(), out.stride(0), out.stride(1), lse.data_ptr(), _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0,
-        _lib.ptr(am), B, nh, L, S, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.stream_ptr(), tag=(B, nh, L, S))
+        _lib.ptr(am), B, nh, L, S, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_tensor), _lib.stream_ptr(),
+        tag=(B, nh, L, S))
     return out, lse
 
 
 def attention_backward(d_out, q, k, v, out, lse, key_padding_mask=None, attention_mask=None, dropout_p: float = 0.0,
-                       seed: int = 0):
+                       seed: int = 0, seed_tensor: Optional[torch.Tensor] = None):
     """Raw backward launches -> (dq, dk, dv) bf16 with the shapes of q, k, v."""
     B, L, C = q.shape
     S = k.shape[1]
@@ -70,31 +72,47 @@ def attention_backward(d_out, q, k, v, out, lse, key_padding_mask=None, attentio
         "detr_attention_bwd_bf16",
         *st(q), *st(k), *st(v), *st(out), *st(d_out), lse.data_ptr(), delta.data_ptr(), *st(dq), *st(dkv[0]), *st(dkv[1]),
         _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0, _lib.ptr(am), B, nh, L, S, float(dropout_p),
-        int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.stream_ptr(), tag=(B, nh, L, S))
+        int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_tensor), _lib.stream_ptr(), tag=(B, nh, L, S))
     return dq, dkv[0], dkv[1]
 
 
 class _FlashAttention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, key_padding_mask, attention_mask, dropout_p, seed):
-        out, lse = attention_forward(q, k, v, key_padding_mask, attention_mask, dropout_p, seed)
-        ctx.save_for_backward(q, k, v, out, lse, key_padding_mask, attention_mask)
+    def forward(ctx, q, k, v, key_padding_mask, attention_mask, dropout_p, seed, seed_tensor):
+        out, lse = attention_forward(q, k, v, key_padding_mask, attention_mask, dropout_p, seed, seed_tensor)
+        ctx.save_for_backward(q, k, v, out, lse, key_padding_mask, attention_mask, seed_tensor)
         ctx.dropout_p, ctx.seed = dropout_p, seed
         ctx.in_dtypes = (q.dtype, k.dtype, v.dtype)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        q, k, v, out, lse, kpm, am = ctx.saved_tensors
-        dq, dk, dv = attention_backward(d_out, q, k, v, out, lse, kpm, am, ctx.dropout_p, ctx.seed)
+        q, k, v, out, lse, kpm, am, seed_tensor = ctx.saved_tensors
+        dq, dk, dv = attention_backward(d_out, q, k, v, out, lse, kpm, am, ctx.dropout_p, ctx.seed, seed_tensor)
         tq, tk, tv = ctx.in_dtypes
-        return dq.to(tq), dk.to(tk), dv.to(tv), None, None, None, None
+        return dq.to(tq), dk.to(tk), dv.to(tv), None, None, None, None, None
 
 
 def flash_attention(q, k, v, key_padding_mask: Optional[torch.Tensor] = None,
                     attention_mask: Optional[torch.Tensor] = None, dropout_p: float = 0.0,
                     seed: Optional[int] = None) -> torch.Tensor:
-    """Differentiable attention core: softmax(q k^T / sqrt(32) + masks) -> dropout -> @ v, heads = 32-channel slices."""
+    """Differentiable attention core: softmax(q k^T / sqrt(32) + masks) -> dropout -> @ v, heads = 32-channel slices.
+
+    Dropout seed = host draw (follows torch.manual_seed, no device sync) + the device-side step counter registered with
+    `set_dropout_step_tensor` (so a captured CUDA graph draws a fresh mask at every replay)."""
     if dropout_p > 0.0 and seed is None:
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # host RNG: follows torch.manual_seed, no device sync
-    return _FlashAttention.apply(q, k, v, key_padding_mask, attention_mask, float(dropout_p), int(seed or 0))
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    st = _STEP_TENSOR if (dropout_p > 0.0 and _STEP_TENSOR is not None and _STEP_TENSOR.device == q.device) else None
+    return _FlashAttention.apply(q, k, v, key_padding_mask, attention_mask, float(dropout_p), int(seed or 0), st)
+
+
+_STEP_TENSOR: Optional[torch.Tensor] = None
+
+
+def set_dropout_step_tensor(t: Optional[torch.Tensor]) -> None:
+    """Register a device uint64/int64 scalar that is ADDED to every dropout seed inside the kernels.  A training step
+    captured in a CUDA graph increments it once per replay; eager code can leave it unset."""
+    global _STEP_TENSOR
+    if t is not None and (t.numel() != 1 or t.dtype not in (torch.int64, torch.uint64) or not t.is_cuda):
+        raise ValueError("dropout step tensor must be a CUDA int64/uint64 scalar")
+    _STEP_TENSOR = t

@@ -156,13 +156,14 @@ class DetrHarness(nn.Module):
         return {"pred_logits": self.class_embedding(decoded), "pred_boxes": self.bbox_embedding(decoded).sigmoid()}
 
 
-def make_optimizer(model: nn.Module, lr: float = 3e-4, lr_backbone_scale: float = 0.1, weight_decay: float = 1e-4, fused: bool = True):
+def make_optimizer(model: nn.Module, lr: float = 3e-4, lr_backbone_scale: float = 0.1, weight_decay: float = 1e-4, fused: bool = True,
+                   capturable: bool = False):
     """AdamW with two parameter groups, backbone at 0.1x (detr/train.py:172-182)."""
     inner = model.module if hasattr(model, "module") else model
     bb = [p for n, p in inner.named_parameters() if n.startswith("backbone.") and p.requires_grad]
     rest = [p for n, p in inner.named_parameters() if not n.startswith("backbone.") and p.requires_grad]
     groups = [{"params": rest, "lr": lr}, {"params": bb, "lr": lr * lr_backbone_scale}]
-    return torch.optim.AdamW(groups, lr=lr, weight_decay=weight_decay, fused=fused)
+    return torch.optim.AdamW(groups, lr=lr, weight_decay=weight_decay, fused=fused, capturable=capturable)
 
 
 def train_step(model: nn.Module, criterion: nn.Module, optimizer, batch: Dict, autocast_dtype=torch.bfloat16,
@@ -217,3 +218,106 @@ def batch_bytes(batch: Dict) -> int:
         for t in (v if isinstance(v, list) else [v]):
             n += t.numel() * t.element_size()
     return n
+
+
+class GraphedTrainStep:
+    """The reference's step body (detr/train.py:258-267) captured ONCE in CUDA graphs and replayed: the eager step is
+    host-launch-bound (~2 500 launches), the replay is GPU-bound.
+
+    graph A: autocast forward, matcher + criterion, backward (+ gradient flattening when world > 1)
+    [world > 1: one NCCL all-reduce of the flat gradient over NVLink -- the only collective besides num_boxes]
+    graph B: (un-flatten, average) clip_grad_norm 1.0, fused AdamW step
+
+    Inputs live in static buffers: `load(batch)` copies a host batch in (pinned, async) and repacks the ground truth
+    into `StaticTargets`; attention dropout draws fresh masks at every replay through a device-side step counter.
+    Requirements: fixed image size and batch size (one graph per shape), at most `gt_cap` boxes per image.
+    """
+
+    def __init__(self, model: nn.Module, criterion: nn.Module, optimizer, example: Dict, gt_cap: int = 100,
+                 autocast_dtype=torch.bfloat16, max_grad_norm: float = 1.0, warmup: int = 3):
+        from . import attention
+        from .targets import StaticTargets
+        import torch.distributed as dist
+        self.model, self.criterion, self.opt = model, criterion, optimizer
+        self.dev = next(model.parameters()).device
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.autocast_dtype, self.max_grad_norm = autocast_dtype, max_grad_norm
+        B = example["image"].shape[0]
+        self.images = torch.empty_like(example["image"], device=self.dev, memory_format=torch.channels_last)
+        self.heights = torch.empty(B, dtype=torch.int32, device=self.dev)
+        self.widths = torch.empty(B, dtype=torch.int32, device=self.dev)
+        self.targets = StaticTargets(B, model.config.num_object_queries, gt_cap, self.dev)
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        attention.set_dropout_step_tensor(self.step_counter)
+        self.loss = torch.zeros((), device=self.dev)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.load(example)
+        # warm-up on a side stream (allocator, cuDNN autotune, lazy attribute setup), then capture
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._forward_backward()
+                self._allreduce()
+                self._update()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.opt.zero_grad(set_to_none=True)
+        from . import _lib
+        l0 = _lib.launch_count
+        self.graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_a):
+            self._forward_backward()
+        self.own_launches_per_step = _lib.launch_count - l0   # kernels of libdetr_b200.so inside one replay
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+            self._update()
+
+    # -- pieces -------------------------------------------------------------------------------------------
+    def _forward_backward(self):
+        self.step_counter.add_(1)
+        with torch.autocast(device_type="cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
+            out = self.model(self.images, self.heights, self.widths)
+        out = {k: v.float() for k, v in out.items()}
+        losses = self.criterion(out, {"packed": self.targets.packed, "num_boxes": self.targets.num_boxes})
+        loss = sum(v for k, v in losses.items() if k.startswith("loss"))
+        loss.backward()
+        self.loss.copy_(loss.detach())
+        if self.world > 1:
+            self.flat = torch.cat([p.grad.reshape(-1) for p in self.params])
+
+    def _allreduce(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat)
+
+    def _update(self):
+        if self.world > 1:
+            grads = [p.grad for p in self.params]
+            views = torch.split(self.flat, [g.numel() for g in grads])
+            torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(views, grads)])
+            torch._foreach_div_(grads, float(self.world))
+        torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm)
+        self.opt.step()
+
+    # -- public -------------------------------------------------------------------------------------------
+    def load(self, batch: Dict) -> int:
+        """Copy a (host, ideally pinned) batch into the static buffers. Returns the bytes moved host->device."""
+        import torch.distributed as dist
+        self.images.copy_(batch["image"], non_blocking=True)
+        self.heights.copy_(batch["height"], non_blocking=True)
+        self.widths.copy_(batch["width"], non_blocking=True)
+        n = self.targets.update(batch["class_idx"], batch["boxes_normalized"])
+        self.targets.set_num_boxes(float(n))
+        if self.world > 1 and getattr(self.criterion, "sync_num_boxes", True):
+            t = self.targets.num_boxes.clone()
+            dist.all_reduce(t)                         # the num_boxes all-reduce (SURVEY.md N2): 1 scalar, no host sync
+            self.targets.num_boxes.copy_((t / self.world).clamp_(min=1.0))
+        return (batch["image"].numel() * batch["image"].element_size() + 8 * self.heights.numel() + self.targets.bytes_per_update())
+
+    def step(self) -> torch.Tensor:
+        """One optimizer step on whatever `load()` put in the static buffers. Returns the (device) loss scalar."""
+        self.graph_a.replay()
+        self._allreduce()
+        self.graph_b.replay()
+        return self.loss

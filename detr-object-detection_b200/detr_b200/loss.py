@@ -127,8 +127,14 @@ class SetCriterion(nn.Module):
         if K != self.num_classes + 1:
             raise ValueError(f"pred_logits has {K} classes, criterion was built for {self.num_classes}+1")
         logits, boxes = logits.float(), boxes.float()
-        pt = pack_targets(targets["class_idx"], targets["boxes_normalized"], Q, logits.device)
-        num_boxes = self._num_boxes(pt, logits.device)  # async all-reduce: hidden behind the matcher launch
+        if "packed" in targets:
+            # pre-packed targets in static device buffers (detr_b200.targets.StaticTargets: CUDA-graph replay); the
+            # normaliser -- already all-reduced by the caller when world size > 1 -- comes as a device scalar
+            pt = targets["packed"]
+            num_boxes = targets.get("num_boxes")
+        else:
+            pt = pack_targets(targets["class_idx"], targets["boxes_normalized"], Q, logits.device)
+            num_boxes = self._num_boxes(pt, logits.device)  # async all-reduce: hidden behind the matcher launch
         idx_q, idx_gt = self._match(logits, boxes, targets, pt)
         self.last_indices = (idx_q, idx_gt, pt, L)
         w = (float(self.weight_label_ce), float(self.weight_bbox_l1), float(self.weight_bbox_giou))

@@ -53,3 +53,56 @@ def pack_targets(gt_labels: Sequence[torch.Tensor], gt_boxes: Sequence[torch.Ten
     if device.type == "cuda":
         offs = offs.pin_memory().to(device, non_blocking=True)
     return PackedTargets(labels, boxes, offs[0], offs[1], counts, n_match, num_queries)
+
+
+class StaticTargets:
+    """Packed targets in FIXED device buffers (capacity `cap` boxes per image) so that a CUDA graph captured once can
+    be replayed on new ground truth: `update()` repacks on the host into pinned staging and issues async H2D copies;
+    the kernels read the actual per-image counts from the device offsets."""
+
+    def __init__(self, batch: int, num_queries: int, cap: int, device: torch.device):
+        self.batch, self.num_queries, self.cap, self.device = batch, num_queries, cap, device
+        n = batch * cap
+        self._h_labels = torch.zeros(n, dtype=torch.int64).pin_memory() if device.type == "cuda" else torch.zeros(n, dtype=torch.int64)
+        self._h_boxes = torch.zeros(n, 4).pin_memory() if device.type == "cuda" else torch.zeros(n, 4)
+        self._h_offs = torch.zeros(2, batch + 1, dtype=torch.int32)
+        self._h_offs = self._h_offs.pin_memory() if device.type == "cuda" else self._h_offs
+        self._h_nb = torch.ones(1).pin_memory() if device.type == "cuda" else torch.ones(1)
+        self.labels = torch.zeros(n, dtype=torch.int64, device=device)
+        self.boxes = torch.zeros(n, 4, device=device)
+        self.offs = torch.zeros(2, batch + 1, dtype=torch.int32, device=device)
+        self.num_boxes = torch.ones(1, device=device)      # normaliser read by the criterion kernels
+        self.actual_counts = [0] * batch
+
+    def update(self, gt_labels: Sequence[torch.Tensor], gt_boxes: Sequence[torch.Tensor]) -> int:
+        """Repack (host tensors expected; device tensors are copied back first). Returns the local box count."""
+        counts = [int(l.shape[0]) for l in gt_labels]
+        if len(counts) != self.batch or max(counts, default=0) > self.cap:
+            raise ValueError(f"StaticTargets(batch={self.batch}, cap={self.cap}) cannot hold counts {counts}")
+        o = 0
+        for l, b in zip(gt_labels, gt_boxes):
+            m = l.shape[0]
+            self._h_labels[o:o + m] = l.reshape(-1)
+            self._h_boxes[o:o + m] = b.reshape(-1, 4)
+            o += m
+        c = torch.tensor(counts, dtype=torch.int32)
+        self._h_offs[0, 1:] = c.cumsum(0)
+        self._h_offs[1, 1:] = c.clamp(max=self.num_queries).cumsum(0)
+        self.labels.copy_(self._h_labels, non_blocking=True)
+        self.boxes.copy_(self._h_boxes, non_blocking=True)
+        self.offs.copy_(self._h_offs, non_blocking=True)
+        self.actual_counts = counts
+        return o
+
+    def set_num_boxes(self, value: float) -> None:
+        self._h_nb[0] = max(float(value), 1.0)
+        self.num_boxes.copy_(self._h_nb, non_blocking=True)
+
+    def bytes_per_update(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self._h_labels, self._h_boxes, self._h_offs, self._h_nb))
+
+    @property
+    def packed(self) -> PackedTargets:
+        """Capacity-sized view for the launchers: host-side sizes are upper bounds, device offsets are exact."""
+        return PackedTargets(self.labels, self.boxes, self.offs[0], self.offs[1], [self.cap] * self.batch,
+                             [min(self.num_queries, self.cap)] * self.batch, self.num_queries)

@@ -1,0 +1,60 @@
+"""The CUDA-graph-captured training step (harness.GraphedTrainStep) against the eager step (harness.train_step, the
+replay of detr/train.py:258-267) from identical initial weights: same losses step after step (dropout off so the two
+are comparable), fresh ground truth between replays, fresh dropout masks per replay in train mode."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(cuda, train):
+    from detr_b200 import HungarianMatcher, SetCriterion
+    from detr_b200.harness import DetrHarness
+    from detr_b200.model import DETRConfig
+    torch.manual_seed(0)
+    cfg = DETRConfig(num_classes=11, num_object_queries=20, num_encoder_layers=2, num_decoder_layers=2)
+    model = DetrHarness(cfg).to(cuda).to(memory_format=torch.channels_last)
+    model.train(train)
+    crit = SetCriterion(11, HungarianMatcher(1.0, 5.0, 2.0)).to(cuda)
+    return model, crit
+
+
+def test_graphed_step_matches_eager(cuda):
+    from detr_b200.harness import GraphedTrainStep, batch_to, make_optimizer, synthetic_batch, train_step
+    m1, c1 = _make(cuda, train=False)
+    m2, c2 = copy.deepcopy(m1), copy.deepcopy(c1)
+    batches = [synthetic_batch(2, 160, 200, 11, 6, seed=s) for s in (1, 2, 3)]
+    o1 = make_optimizer(m1, lr=1e-4)
+    eager = [float(train_step(m1, c1, o1, batch_to(b, cuda))) for b in batches]
+    o2 = make_optimizer(m2, lr=1e-4, capturable=True)
+    snapshot = copy.deepcopy(m2.state_dict())
+    g = GraphedTrainStep(m2, c2, o2, batches[0], gt_cap=8, warmup=2)
+    # warm-up inside the constructor already stepped the weights: rewind model and optimizer state, then replay
+    m2.load_state_dict(snapshot)
+    for st in o2.state.values():
+        for k, v in st.items():
+            if torch.is_tensor(v):
+                v.zero_()
+    graphed = []
+    for b in batches:
+        g.load(b)
+        graphed.append(float(g.step()))
+    for a, b in zip(eager, graphed):
+        assert a == pytest.approx(b, rel=2e-2), (eager, graphed)
+    assert g.own_launches_per_step > 0
+    c2.check_status()
+
+
+def test_graph_replays_draw_fresh_dropout_masks(cuda):
+    from detr_b200.harness import GraphedTrainStep, make_optimizer, synthetic_batch
+    m, c = _make(cuda, train=True)
+    for p in m.parameters():
+        p.requires_grad_(True)
+    opt = make_optimizer(m, lr=0.0, weight_decay=0.0, capturable=True)   # lr 0: weights frozen, only the masks change
+    b = synthetic_batch(2, 160, 200, 11, 6, seed=4)
+    g = GraphedTrainStep(m, c, opt, b, gt_cap=8, warmup=2)
+    losses = [float(g.step()) for _ in range(4)]
+    assert len(set(round(l, 6) for l in losses)) > 1, losses
+    assert int(g.step_counter.item()) >= 6
