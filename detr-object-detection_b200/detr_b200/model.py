@@ -23,6 +23,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .attention import HEAD_DIM, flash_attention
+from .rowops import linear
 
 
 @dataclass
@@ -74,8 +75,8 @@ class ScaledDotProductAttention(nn.Module):
             raise ValueError(f"detr_b200 attention kernels are built for head size {HEAD_DIM}, got {self.head_size}")
 
     def project_kv(self, key: torch.Tensor, value: torch.Tensor):
-        return (F.linear(key, self.key_proj.weight, self.key_proj.bias),
-                F.linear(value, self.value_proj.weight, self.value_proj.bias))
+        return (linear(key, self.key_proj.weight, self.key_proj.bias),
+                linear(value, self.value_proj.weight, self.value_proj.bias))
 
     def forward(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
                 key_padding_mask: Optional[torch.BoolTensor] = None,
@@ -85,17 +86,17 @@ class ScaledDotProductAttention(nn.Module):
             # self-attention: one GEMM for both projections; q/k are strided views the TMA descriptors take as they are
             w = torch.cat((self.query_proj.weight, self.key_proj.weight), dim=0)
             b = torch.cat((self.query_proj.bias, self.key_proj.bias), dim=0)
-            qk = F.linear(query, w, b)
+            qk = linear(query, w, b)
             q, k = qk[..., :C], qk[..., C:]
-            v = F.linear(value, self.value_proj.weight, self.value_proj.bias)
+            v = linear(value, self.value_proj.weight, self.value_proj.bias)
         else:
-            q = F.linear(query, self.query_proj.weight, self.query_proj.bias)
+            q = linear(query, self.query_proj.weight, self.query_proj.bias)
             k, v = self.project_kv(key, value)
         p_drop = self.dropout_attn.p if self.training else 0.0
         y = flash_attention(q, k, v, key_padding_mask, attention_mask, p_drop)
         if not torch.is_autocast_enabled():
             y = y.to(query.dtype)
-        y = F.linear(y, self.output_proj.weight, self.output_proj.bias)
+        y = linear(y, self.output_proj.weight, self.output_proj.bias)
         return self.dropout(y)
 
 
@@ -113,7 +114,8 @@ class FFN(nn.Module):
         )
 
     def forward(self, x):
-        return self.layers(x)
+        fc1, act, drop1, fc2, drop2 = self.layers
+        return drop2(linear(drop1(act(linear(x, fc1.weight, fc1.bias))), fc2.weight, fc2.bias))
 
 
 class EncoderLayer(nn.Module):

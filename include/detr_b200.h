@@ -132,6 +132,12 @@ int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const voi
                             const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
                             uint64_t seed, const uint64_t* seed_ptr, void* stream);
 
+/* ---- transformer block row operations ------------------------------------------------------------ */
+/* Bias gradient of nn.Linear (backward of detr/model.py:312-314,354,405-411): out[n] = sum_m g[m][n], g bf16 (M,N)
+ * row stride ld.  partial float[detr_colsum_chunks(M,N) * N] is scratch.  Deterministic two-stage reduction. */
+int detr_colsum_chunks(int M, int N);
+int detr_colsum_bf16(const void* g, int64_t ld, int M, int N, float* partial, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,3 +120,36 @@ def test_train_mode_dropout_runs_and_is_seeded(cuda):
     torch.manual_seed(5); b = enc(x, pos, mask)
     torch.manual_seed(6); c = enc(x, pos, mask)
     assert torch.equal(a, b) and not torch.equal(a, c) and torch.isfinite(a).all()
+
+
+@pytest.mark.parametrize("M,N", [(6800, 2048), (6800, 256), (800, 512), (37, 8), (1, 256), (5000, 264)])
+def test_colsum_kernel(cuda, M, N):
+    from detr_b200.rowops import colsum
+    g = torch.randn(M, N, device=cuda).bfloat16()
+    ref = g.double().sum(0)
+    got = colsum(g)
+    assert got.dtype == torch.float32
+    assert (got.double() - ref).abs().max().item() <= 1e-3 * max(1.0, M ** 0.5)
+    v = g[:, : N // 2] if (N // 2) % 8 == 0 else g
+    assert (colsum(v).double() - v.double().sum(0)).abs().max().item() <= 1e-3 * max(1.0, M ** 0.5)
+
+
+def test_linear_fn_matches_autocast_linear(cuda):
+    from detr_b200.rowops import linear
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(256, 512).to(cuda)
+    x = torch.randn(4, 333, 256, device=cuda, requires_grad=True)
+    w = torch.randn(4, 333, 512, device=cuda)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y1 = linear(x, lin.weight, lin.bias)
+    (y1.float() * w).sum().backward()
+    g1 = (x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    x.grad = None; lin.zero_grad()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y2 = torch.nn.functional.linear(x, lin.weight, lin.bias)
+    (y2.float() * w).sum().backward()
+    assert torch.equal(y1, y2)
+    assert torch.allclose(g1[0], x.grad, rtol=1e-2, atol=1e-2) and g1[1].dtype == torch.float32
+    assert torch.allclose(g1[1], lin.weight.grad, rtol=2e-2, atol=2e-1)
+    ref_b = w.sum((0, 1))
+    assert (g1[2] - ref_b).abs().max() <= (lin.bias.grad - ref_b).abs().max() + 0.5   # at least as accurate as ATen's bf16 reduction
