@@ -79,8 +79,48 @@ def _conv_bn(x, conv: nn.Conv2d, bn) -> torch.Tensor:
     return F.conv2d(x, conv.weight * scale.view(-1, 1, 1, 1), shift, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
-def _bottleneck_forward(blk, x):
+class _ConvBiasAct(torch.autograd.Function):
+    """cuDNN fused conv + bias (+ residual) + ReLU forward (`cudnn_convolution_relu` / `_add_relu`, one kernel instead of
+    conv, bias add, residual add and ReLU) with the standard convolution backward.  Library calls only (out of scope)."""
+
+    @staticmethod
+    def forward(ctx, x, w, shift, z, stride, padding, dilation, groups):
+        if z is None:
+            y = torch.cudnn_convolution_relu(x, w, shift, stride, padding, dilation, groups)
+        else:
+            y = torch.cudnn_convolution_add_relu(x, w, z, 1.0, shift, stride, padding, dilation, groups)
+        ctx.save_for_backward(x, w, y)
+        ctx.conf = (stride, padding, dilation, groups, z is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, y = ctx.saved_tensors
+        stride, padding, dilation, groups, has_z = ctx.conf
+        g = torch.ops.aten.threshold_backward(g, y, 0)
+        dx, dw, _ = torch.ops.aten.convolution_backward(g, x, w, None, stride, padding, dilation, False, [0, 0], groups,
+                                                        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        return dx, dw, None, (g if has_z else None), None, None, None, None
+
+
+def _conv_bn_relu(x, conv: nn.Conv2d, bn, z=None) -> torch.Tensor:
+    """relu(conv_bn(x) [+ z]) through the fused cuDNN kernel (bf16, channels_last)."""
+    scale = bn.weight * (bn.running_var + bn.eps).rsqrt()
+    shift = (bn.bias - bn.running_mean * scale).to(torch.bfloat16)
+    w = (conv.weight * scale.view(-1, 1, 1, 1)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x = x.to(torch.bfloat16)
+    with torch.autocast("cuda", enabled=False):
+        return _ConvBiasAct.apply(x, w, shift, z, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
+def _bottleneck_forward(blk, x, fused: bool):
     identity = x
+    if fused:
+        out = _conv_bn_relu(x, blk.conv1, blk.bn1)
+        out = _conv_bn_relu(out, blk.conv2, blk.bn2)
+        if blk.downsample is not None:
+            identity = _conv_bn(x, blk.downsample[0], blk.downsample[1])
+        return _conv_bn_relu(out, blk.conv3, blk.bn3, z=identity)
     out = F.relu(_conv_bn(x, blk.conv1, blk.bn1), inplace=True)
     out = F.relu(_conv_bn(out, blk.conv2, blk.bn2), inplace=True)
     out = _conv_bn(out, blk.conv3, blk.bn3)
@@ -103,16 +143,21 @@ class _Backbone(nn.Module):
         self.num_channels = 2048
         self.scale = 32
         self.fold_bn = fold_bn
+        self.fuse_relu = True   # cuDNN conv+bias(+add)+ReLU epilogues; needs CUDA bf16 autocast, else plain path
 
     def forward(self, x):
         if not self.fold_bn:
             return self.backbone(x)["final_feature_map"]
         m = self.backbone
-        x = F.relu(_conv_bn(x, m.conv1, m.bn1), inplace=True)
+        fused = (self.fuse_relu and x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16)
+        if fused:
+            x = _conv_bn_relu(x.contiguous(memory_format=torch.channels_last), m.conv1, m.bn1)
+        else:
+            x = F.relu(_conv_bn(x, m.conv1, m.bn1), inplace=True)
         x = m.maxpool(x)
         for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
             for blk in layer:
-                x = _bottleneck_forward(blk, x)
+                x = _bottleneck_forward(blk, x, fused)
         return x
 
 
