@@ -1,7 +1,8 @@
 // Row-wise helper kernels of the transformer blocks (HBM-bound, coalesced 16-byte accesses):
 //   colsum_bf16   bias gradient of nn.Linear: db[n] = sum_m g[m][n]  (detr/model.py:312-314,354,405-411 backward).
 //                 ATen's generic reduce_kernel needs ~27 us for a 6800 x 2048 bf16 matrix; this is one pass at
-//                 HBM speed: grid = column tiles x row chunks, fp32 partials, fixed-order second stage (deterministic).
+//                 HBM speed: grid = column tiles x row chunks, fp32 partials; the last CTA of each column tile folds them
+//                 in a fixed order (deterministic, single launch).
 #include "common.cuh"
 #include <cuda_bf16.h>
 
@@ -10,9 +11,11 @@ namespace detr {
 constexpr int kColsPerCta = 256;   // 32 lanes x 8 bf16 (16 bytes)
 constexpr int kCsThreads = 256;    // 8 warps: each warp takes every 8th row of the chunk
 
-__global__ void __launch_bounds__(kCsThreads) colsum_partial_kernel(const __nv_bfloat16* __restrict__ g, int64_t ld, int M, int N,
-                                                                      int rows_per_cta, float* __restrict__ partial) {
+__global__ void __launch_bounds__(kCsThreads) colsum_kernel(const __nv_bfloat16* __restrict__ g, int64_t ld, int M, int N, int rows_per_cta,
+                                                              float* __restrict__ partial, float* __restrict__ out,
+                                                              unsigned* __restrict__ counters /* one per column tile, zero on entry and on exit */) {
     __shared__ float red[kCsThreads / 32][kColsPerCta];
+    __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * kColsPerCta + lane * 8;
     const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
@@ -31,21 +34,26 @@ __global__ void __launch_bounds__(kCsThreads) colsum_partial_kernel(const __nv_b
 #pragma unroll
     for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = acc[e];
     __syncthreads();
-    const int c = threadIdx.x;
-    if (blockIdx.x * kColsPerCta + c < N) {
+    const int c = threadIdx.x, col = blockIdx.x * kColsPerCta + c;
+    if (col < N) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kCsThreads / 32; ++w) s += red[w][c];
-        partial[(int64_t)blockIdx.y * N + blockIdx.x * kColsPerCta + c] = s;
+        partial[(int64_t)blockIdx.y * N + col] = s;
     }
-}
-
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float s = 0.f;
-    for (int k = 0; k < chunks; ++k) s += partial[(int64_t)k * N + n];
-    out[n] = s;
+    // the last CTA of this column tile folds the row chunks in a fixed order (deterministic) -- no second launch
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&counters[blockIdx.x], 1u) == gridDim.y - 1;
+    __syncthreads();
+    if (is_last) {
+        if (col < N) {
+            float s = 0.f;
+            for (int k = 0; k < (int)gridDim.y; ++k) s += __ldcg(&partial[(int64_t)k * N + col]);
+            out[col] = s;
+        }
+        if (threadIdx.x == 0) counters[blockIdx.x] = 0;
+    }
 }
 
 }  // namespace detr
@@ -54,21 +62,244 @@ using namespace detr;
 
 extern "C" int detr_colsum_chunks(int M, int N) {
     const int col_tiles = (N + kColsPerCta - 1) / kColsPerCta;
-    int chunks = (4 * 148 + col_tiles - 1) / col_tiles;          // ~4 CTAs per SM in flight
-    const int max_chunks = (M + 63) / 64;                        // at least 64 rows per CTA
+    int chunks = (2 * 148 + col_tiles - 1) / col_tiles;          // ~2 CTAs per SM in flight
+    const int max_chunks = (M + 31) / 32;                        // at least 32 rows per CTA
     if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks > 64) chunks = 64;                                // bounds the serial fold of the last CTA
     return chunks < 1 ? 1 : chunks;
 }
 
-extern "C" int detr_colsum_bf16(const void* g, int64_t ld, int M, int N, float* partial, float* out, void* stream) {
+extern "C" int detr_colsum_bf16(const void* g, int64_t ld, int M, int N, float* partial, float* out, uint32_t* counters, void* stream) {
     DETR_CHECK_ARG(M >= 1 && N >= 8 && (N % 8) == 0 && (ld % 8) == 0 && ((uintptr_t)g % 16) == 0,
                    "colsum: need N %% 8 == 0, ld %% 8 == 0 and a 16-byte aligned matrix (M=%d N=%d ld=%lld)", M, N, (long long)ld);
     const int chunks = detr_colsum_chunks(M, N);
     const int rows_per_cta = (M + chunks - 1) / chunks;
     dim3 grid((N + kColsPerCta - 1) / kColsPerCta, chunks);
-    colsum_partial_kernel<<<grid, kCsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(g), ld, M, N, rows_per_cta, partial);
-    DETR_CHECK_LAUNCH("colsum_partial");
-    colsum_final_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partial, chunks, N, out);
-    DETR_CHECK_LAUNCH("colsum_final");
+    DETR_CHECK_ARG(counters != nullptr && N <= 64 * kColsPerCta, "colsum: counters required (64 zeroed uint32), N <= %d", 64 * kColsPerCta);
+    colsum_kernel<<<grid, kCsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(g), ld, M, N, rows_per_cta, partial, out, counters);
+    DETR_CHECK_LAUNCH("colsum");
+    return 0;
+}
+
+// =========================================================================================================
+// Fused pre-LN prologue (detr/model.py:221-222, 173-174, 177-178, 224, 182, 209, 148):
+//   y  = LayerNorm(x) * gamma + beta                      (value input of the attention / input of the FFN)
+//   y2 = y + addend                                       (query/key input: + positional or query embedding)
+// one pass over x, both outputs written in the GEMM's input dtype (no fp32 round trip, no separate add / cast
+// kernels).  One warp per row, the row lives in registers, two-pass variance.  Backward: dx and per-CTA partial
+// dgamma / dbeta folded by the last CTA (single launch, deterministic).
+// =========================================================================================================
+namespace detr {
+
+constexpr int kLnThreads = 128;
+constexpr int kLnMaxPerLane = 32;   // C <= 1024
+
+template <typename T> __device__ __forceinline__ float ld1(const T* p);
+template <> __device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld1<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void st1(T* p, float v);
+template <> __device__ __forceinline__ void st1<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st1<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// lane owns the contiguous columns [lane*K, lane*K + K), K = C/32; 8-element (16/32-byte) vector accesses when K % 8 == 0
+template <typename T> __device__ __forceinline__ void load_row(const T* row, int lane, int K, float* v) {
+    const T* p = row + lane * K;
+    if ((K & 7) == 0) {
+        _Pragma("unroll") for (int i = 0; i < K; i += 8) {
+            if (sizeof(T) == 2) {
+                const uint4 u = *reinterpret_cast<const uint4*>(p + i);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[i + 2 * e] = f.x; v[i + 2 * e + 1] = f.y; }
+            } else {
+                const float4 a = *reinterpret_cast<const float4*>(p + i), b = *reinterpret_cast<const float4*>(p + i + 4);
+                v[i] = a.x; v[i + 1] = a.y; v[i + 2] = a.z; v[i + 3] = a.w; v[i + 4] = b.x; v[i + 5] = b.y; v[i + 6] = b.z; v[i + 7] = b.w;
+            }
+        }
+    } else {
+        _Pragma("unroll") for (int i = 0; i < K; ++i) v[i] = ld1<T>(p + i);
+    }
+}
+template <typename T> __device__ __forceinline__ void store_row(T* row, int lane, int K, const float* v) {
+    T* p = row + lane * K;
+    if ((K & 7) == 0) {
+        _Pragma("unroll") for (int i = 0; i < K; i += 8) {
+            if (sizeof(T) == 2) {
+                uint4 u;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[i + 2 * e], v[i + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(p + i) = u;
+            } else {
+                *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                *reinterpret_cast<float4*>(p + i + 4) = make_float4(v[i + 4], v[i + 5], v[i + 6], v[i + 7]);
+            }
+        }
+    } else {
+        _Pragma("unroll") for (int i = 0; i < K; ++i) st1<T>(p + i, v[i]);
+    }
+}
+
+struct LnParams {
+    const void* x; int64_t x_ld;
+    const float* gamma; const float* beta;
+    const void* addend; int64_t add_sb, add_sr; int rows_per_batch;   // addend row of (b, r) = addend + b*add_sb + r*add_sr (elements)
+    void* y; void* y2;                                                 // either may be null
+    float* mean; float* rstd;
+    int rows, C; float eps;
+    // backward
+    const void* dy; const void* dy2; void* dx;
+    float* partial; float* dgamma; float* dbeta; unsigned* counters;
+};
+
+// KT > 0: compile-time columns per lane (rows stay in registers); KT == 0: run-time (local-memory arrays)
+template <typename TX, typename TO, int KT>
+__global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const LnParams p) {
+    using TA = float;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = KT ? KT : p.C / 32;
+    constexpr int KA = KT ? KT : kLnMaxPerLane;
+    float v[KA], g[KA], b[KA];
+    load_row<float>(p.gamma, lane, K, g);
+    load_row<float>(p.beta, lane, K, b);
+    for (int r = blockIdx.x * (kLnThreads / 32) + warp; r < p.rows; r += gridDim.x * (kLnThreads / 32)) {
+        load_row<TX>(reinterpret_cast<const TX*>(p.x) + (int64_t)r * p.x_ld, lane, K, v);
+        float s = 0.f;
+        _Pragma("unroll") for (int i = 0; i < K; ++i) s += v[i];
+        const float mu = warp_sum(s) / (float)p.C;
+        float q = 0.f;
+        _Pragma("unroll") for (int i = 0; i < K; ++i) { const float d = v[i] - mu; q += d * d; }
+        const float rs = rsqrtf(warp_sum(q) / (float)p.C + p.eps);
+        if (lane == 0) { p.mean[r] = mu; p.rstd[r] = rs; }
+        _Pragma("unroll") for (int i = 0; i < K; ++i) v[i] = (v[i] - mu) * rs * g[i] + b[i];
+        if (p.y) store_row<TO>(reinterpret_cast<TO*>(p.y) + (int64_t)r * p.C, lane, K, v);
+        if (p.y2) {
+            float a[KA];
+            const int bb = r / p.rows_per_batch, rr = r - bb * p.rows_per_batch;
+            load_row<TA>(reinterpret_cast<const TA*>(p.addend) + bb * p.add_sb + rr * p.add_sr, lane, K, a);
+            _Pragma("unroll") for (int i = 0; i < K; ++i) v[i] += a[i];
+            store_row<TO>(reinterpret_cast<TO*>(p.y2) + (int64_t)r * p.C, lane, K, v);
+        }
+    }
+}
+
+// dy / dy2: gradients w.r.t. y / y2 (type TG, row stride C, either may be null); dx in TX
+template <typename TX, typename TG, int KT>
+__global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnParams p) {
+    extern __shared__ float sm[];   // [4 warps][2][C]
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = KT ? KT : p.C / 32, C = p.C;
+    constexpr int KA = KT ? KT : kLnMaxPerLane;
+    float g[KA], dg[KA], db[KA];
+    load_row<float>(p.gamma, lane, K, g);
+    _Pragma("unroll") for (int i = 0; i < K; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+    for (int r = blockIdx.x * (kLnThreads / 32) + warp; r < p.rows; r += gridDim.x * (kLnThreads / 32)) {
+        float x[KA], d[KA];
+        load_row<TX>(reinterpret_cast<const TX*>(p.x) + (int64_t)r * p.x_ld, lane, K, x);
+        if (p.dy) load_row<TG>(reinterpret_cast<const TG*>(p.dy) + (int64_t)r * C, lane, K, d);
+        else _Pragma("unroll") for (int i = 0; i < K; ++i) d[i] = 0.f;
+        if (p.dy2) {
+            float d2[KA];
+            load_row<TG>(reinterpret_cast<const TG*>(p.dy2) + (int64_t)r * C, lane, K, d2);
+            _Pragma("unroll") for (int i = 0; i < K; ++i) d[i] += d2[i];
+        }
+        const float mu = p.mean[r], rs = p.rstd[r];
+        float c1 = 0.f, c2 = 0.f;
+        _Pragma("unroll") for (int i = 0; i < K; ++i) {
+            x[i] = (x[i] - mu) * rs;            // xhat
+            dg[i] += d[i] * x[i];
+            db[i] += d[i];
+            d[i] *= g[i];                       // wdy
+            c1 += d[i] * x[i];
+            c2 += d[i];
+        }
+        c1 = warp_sum(c1) / (float)C;
+        c2 = warp_sum(c2) / (float)C;
+        _Pragma("unroll") for (int i = 0; i < K; ++i) d[i] = rs * (d[i] - c2 - x[i] * c1);
+        store_row<TX>(reinterpret_cast<TX*>(p.dx) + (int64_t)r * C, lane, K, d);
+    }
+    // ---- dgamma / dbeta: warps -> CTA partial -> last CTA folds all partials ----
+    _Pragma("unroll") for (int i = 0; i < K; ++i) { sm[(warp * 2 + 0) * C + lane * K + i] = dg[i]; sm[(warp * 2 + 1) * C + lane * K + i] = db[i]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) {
+        const int which = c / C, col = c - which * C;
+        float s = 0.f;
+        for (int w = 0; w < kLnThreads / 32; ++w) s += sm[(w * 2 + which) * C + col];
+        p.partial[(int64_t)blockIdx.x * 2 * C + c] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&p.counters[0], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last) {
+        for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) {
+            float s = 0.f;
+            for (int k = 0; k < (int)gridDim.x; ++k) s += __ldcg(&p.partial[(int64_t)k * 2 * C + c]);
+            if (c < C) p.dgamma[c] = s; else p.dbeta[c - C] = s;
+        }
+        if (threadIdx.x == 0) p.counters[0] = 0;
+    }
+}
+
+static int ln_grid(int rows) {
+    int g = (rows + kLnThreads / 32 - 1) / (kLnThreads / 32);
+    return g > 2 * 148 ? 2 * 148 : (g < 1 ? 1 : g);
+}
+
+}  // namespace detr
+
+extern "C" int detr_layernorm_grid(int rows) { return detr::ln_grid(rows); }
+
+// dtype codes: 0 = float32, 1 = bfloat16
+extern "C" int detr_layernorm_fwd(const void* x, int x_dtype, int64_t x_ld, const float* gamma, const float* beta,
+                                  const void* addend, int add_dtype, int64_t add_sb, int64_t add_sr, int rows_per_batch,
+                                  void* y, void* y2, int out_dtype, float* mean, float* rstd, int rows, int C, float eps, void* stream) {
+    DETR_CHECK_ARG(rows >= 1 && C >= 32 && C % 32 == 0 && C <= 32 * kLnMaxPerLane, "layernorm: C=%d must be a multiple of 32, <= %d", C, 32 * kLnMaxPerLane);
+    DETR_CHECK_ARG((y2 == nullptr) == (addend == nullptr) || y2 == nullptr, "layernorm: y2 needs an addend");
+    DETR_CHECK_ARG(x_ld % 8 == 0 && ((uintptr_t)x % 16) == 0 && (!addend || (((uintptr_t)addend % 16) == 0 && add_sb % 8 == 0 && add_sr % 8 == 0)),
+                   "layernorm: rows must be 16-byte aligned");
+    LnParams p{};
+    p.x = x; p.x_ld = x_ld; p.gamma = gamma; p.beta = beta; p.addend = addend; p.add_sb = add_sb; p.add_sr = add_sr;
+    p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : rows; p.y = y; p.y2 = y2; p.mean = mean; p.rstd = rstd; p.rows = rows; p.C = C; p.eps = eps;
+    const int grid = ln_grid(rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    DETR_CHECK_ARG(!addend || add_dtype == 0, "layernorm: the addend must be float32");
+#define LN_FWD(TX, TO)                                                            \
+    do {                                                                          \
+        if (C == 256) ln_fwd_kernel<TX, TO, 8><<<grid, kLnThreads, 0, st>>>(p);   \
+        else ln_fwd_kernel<TX, TO, 0><<<grid, kLnThreads, 0, st>>>(p);            \
+    } while (0)
+    if (x_dtype == 0 && out_dtype == 0) LN_FWD(float, float);
+    else if (x_dtype == 0) LN_FWD(float, __nv_bfloat16);
+    else if (out_dtype == 0) LN_FWD(__nv_bfloat16, float);
+    else LN_FWD(__nv_bfloat16, __nv_bfloat16);
+#undef LN_FWD
+    DETR_CHECK_LAUNCH("layernorm_fwd");
+    return 0;
+}
+
+extern "C" int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, const void* x, int x_dtype, int64_t x_ld,
+                                  const float* gamma, const float* mean, const float* rstd, void* dx, float* partial,
+                                  float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* stream) {
+    DETR_CHECK_ARG(rows >= 1 && C >= 32 && C % 32 == 0 && C <= 32 * kLnMaxPerLane, "layernorm_bwd: bad C=%d", C);
+    DETR_CHECK_ARG(dy != nullptr || dy2 != nullptr, "layernorm_bwd: no incoming gradient");
+    LnParams p{};
+    p.x = x; p.x_ld = x_ld; p.gamma = gamma; p.mean = const_cast<float*>(mean); p.rstd = const_cast<float*>(rstd); p.rows = rows; p.C = C;
+    p.dy = dy; p.dy2 = dy2; p.dx = dx; p.partial = partial; p.dgamma = dgamma; p.dbeta = dbeta; p.counters = counters;
+    const int grid = ln_grid(rows);
+    const size_t smem = (size_t)(kLnThreads / 32) * 2 * C * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LN_BWD(TX, TG)                                                               \
+    do {                                                                             \
+        if (C == 256) ln_bwd_kernel<TX, TG, 8><<<grid, kLnThreads, smem, st>>>(p);   \
+        else ln_bwd_kernel<TX, TG, 0><<<grid, kLnThreads, smem, st>>>(p);            \
+    } while (0)
+    if (x_dtype == 0 && g_dtype == 0) LN_BWD(float, float);
+    else if (x_dtype == 0) LN_BWD(float, __nv_bfloat16);
+    else if (g_dtype == 0) LN_BWD(__nv_bfloat16, float);
+    else LN_BWD(__nv_bfloat16, __nv_bfloat16);
+#undef LN_BWD
+    DETR_CHECK_LAUNCH("layernorm_bwd");
     return 0;
 }

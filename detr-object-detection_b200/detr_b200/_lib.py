@@ -40,7 +40,10 @@ SIGNATURES = {
     "detr_attention_bwd_bf16": [P, c_int64, c_int64] * 5 + [P, P] + [P, c_int64, c_int64] * 3 +
                                [P, c_int64, P, c_int, c_int, c_int, c_int, c_float, ctypes.c_uint64, P, P],
     "detr_colsum_chunks": [c_int, c_int],
-    "detr_colsum_bf16": [P, c_int64, c_int, c_int, P, P, P],
+    "detr_colsum_bf16": [P, c_int64, c_int, c_int, P, P, P, P],
+    "detr_layernorm_grid": [c_int],
+    "detr_layernorm_fwd": [P, c_int, c_int64, P, P, P, c_int, c_int64, c_int64, c_int, P, P, c_int, P, P, c_int, c_int, c_float, P],
+    "detr_layernorm_bwd": [P, P, c_int, P, c_int, c_int64, P, P, P, P, P, P, P, P, c_int, c_int, P],
 }
 _RESTYPE = {"detr_matcher_smem_bytes": c_int64}
 
@@ -65,7 +68,7 @@ def load() -> ctypes.CDLL:
 # kernels launched per C-ABI call (bench.py's gpu_launches is counted from this table)
 KERNELS_PER_CALL = {"detr_cost_matrix_f32": 1, "detr_hungarian_match_f32": 1, "detr_lsap_f32": 1, "detr_lsap_f64": 1,
                     "detr_criterion_fwd_f32": 2, "detr_criterion_bwd_f32": 1, "detr_attention_fwd_bf16": 1,
-                    "detr_attention_bwd_bf16": 3, "detr_colsum_bf16": 2}
+                    "detr_attention_bwd_bf16": 3, "detr_colsum_bf16": 1, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 1}
 launch_count = 0          # kernels of libdetr_b200.so launched by this process
 _profile = None           # when a list: (name, tag, start_event, end_event) per call
 
@@ -133,6 +136,19 @@ def require_cuda(t: torch.Tensor, what: str) -> None:
     if dev not in _checked_devices:
         check(load().detr_b200_check_device(dev), "device check")
         _checked_devices.add(dev)
+
+
+_zero_counters: dict = {}
+
+
+def zero_counters(device: torch.device) -> torch.Tensor:
+    """Per-device block of 64 zeroed uint32 used by single-launch reductions (each kernel leaves it zeroed)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    t = _zero_counters.get(key)
+    if t is None:
+        t = torch.zeros(64, dtype=torch.int32, device=device)
+        _zero_counters[key] = t
+    return t
 
 
 def stream_ptr() -> int:

@@ -74,9 +74,8 @@ def _conv_bn(x, conv: nn.Conv2d, bn) -> torch.Tensor:
     conv(x, W) * s + t == conv(x, W * s) + t, s = gamma / sqrt(var + eps), t = beta - mean * s.
     Same parameters / buffers / state_dict keys as torchvision's modules and the same gradient w.r.t. W; it only
     removes the fp32-promoting elementwise passes FrozenBatchNorm2d makes over every activation under autocast."""
-    scale = bn.weight * (bn.running_var + bn.eps).rsqrt()
-    shift = bn.bias - bn.running_mean * scale
-    return F.conv2d(x, conv.weight * scale.view(-1, 1, 1, 1), shift, conv.stride, conv.padding, conv.dilation, conv.groups)
+    scale, shift, _ = _bn_constants(bn)
+    return F.conv2d(x, conv.weight * scale, shift, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
 class _ConvBiasAct(torch.autograd.Function):
@@ -103,11 +102,23 @@ class _ConvBiasAct(torch.autograd.Function):
         return dx, dw, None, (g if has_z else None), None, None, None, None
 
 
+def _bn_constants(bn):
+    """(scale (C,1,1,1) fp32, shift fp32, shift bf16) of a FrozenBatchNorm2d: its buffers never change, so the affine is
+    computed once per module and device instead of with five tiny kernels per convolution per step."""
+    c = bn.__dict__.get("_detr_affine")
+    if c is None or c[0].device != bn.weight.device:
+        with torch.no_grad():
+            scale = bn.weight * (bn.running_var + bn.eps).rsqrt()
+            shift = bn.bias - bn.running_mean * scale
+        c = (scale.view(-1, 1, 1, 1).contiguous(), shift.contiguous(), shift.to(torch.bfloat16))
+        bn.__dict__["_detr_affine"] = c   # plain attribute: not a buffer, not in the state_dict
+    return c
+
+
 def _conv_bn_relu(x, conv: nn.Conv2d, bn, z=None) -> torch.Tensor:
     """relu(conv_bn(x) [+ z]) through the fused cuDNN kernel (bf16, channels_last)."""
-    scale = bn.weight * (bn.running_var + bn.eps).rsqrt()
-    shift = (bn.bias - bn.running_mean * scale).to(torch.bfloat16)
-    w = (conv.weight * scale.view(-1, 1, 1, 1)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    scale, _, shift = _bn_constants(bn)
+    w = (conv.weight * scale).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     x = x.to(torch.bfloat16)
     with torch.autocast("cuda", enabled=False):
         return _ConvBiasAct.apply(x, w, shift, z, conv.stride, conv.padding, conv.dilation, conv.groups)

@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .attention import HEAD_DIM, flash_attention
-from .rowops import linear
+from .rowops import layer_norm_add, linear
 
 
 @dataclass
@@ -129,10 +129,9 @@ class EncoderLayer(nn.Module):
         self.norm2 = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
 
     def forward(self, x: torch.Tensor, position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
-        x_attn = self.norm1(x)
-        query = x_attn + position_embedding
+        x_attn, query = layer_norm_add(x, self.norm1, position_embedding)      # LN and "+ pos" in one kernel
         x = x + self.self_attention(query, query, value=x_attn, key_padding_mask=key_padding_mask)
-        x = x + self.ffn(self.norm2(x))
+        x = x + self.ffn(layer_norm_add(x, self.norm2)[0])
         return x
 
 
@@ -149,7 +148,7 @@ class Encoder(nn.Module):
     def forward(self, x: torch.Tensor, position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
         for layer in self.layers:
             x = layer(x, position_embedding, key_padding_mask)
-        return self.norm(x)
+        return layer_norm_add(x, self.norm)[0]
 
 
 class DecoderLayer(nn.Module):
@@ -167,14 +166,12 @@ class DecoderLayer(nn.Module):
     def forward(self, x: torch.Tensor, encoded_image_tokens: torch.Tensor, object_query_embedding: torch.Tensor,
                 position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor,
                 cross_key: Optional[torch.Tensor] = None):
-        x_attn = self.norm1(x)
-        query = x_attn + object_query_embedding
+        x_attn, query = layer_norm_add(x, self.norm1, object_query_embedding)
         x = x + self.self_attention(query, query, value=x_attn)
-        x_attn = self.norm2(x)
-        query = x_attn + object_query_embedding
+        _, query = layer_norm_add(x, self.norm2, object_query_embedding, want_y=False)
         key = cross_key if cross_key is not None else encoded_image_tokens + position_embedding
         x = x + self.cross_attention(query, key, value=encoded_image_tokens, key_padding_mask=key_padding_mask)
-        x = x + self.ffn(self.norm3(x))
+        x = x + self.ffn(layer_norm_add(x, self.norm3)[0])
         return x
 
 
@@ -200,7 +197,9 @@ class Decoder(nn.Module):
             outputs.append(x)
         # one LayerNorm launch over all layers' outputs instead of one per layer
         stacked = torch.stack(outputs, dim=1)
-        return self.norm(stacked)
+        B, L, Q, C = stacked.shape
+        with torch.autocast("cuda", enabled=False):   # the prediction heads get the reference's fp32 LayerNorm output
+            return layer_norm_add(stacked.view(B, L * Q, C), self.norm)[0].view(B, L, Q, C)
 
 
 def patch(detr_model_module, detr_train_module=None) -> None:

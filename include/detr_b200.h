@@ -134,9 +134,25 @@ int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const voi
 
 /* ---- transformer block row operations ------------------------------------------------------------ */
 /* Bias gradient of nn.Linear (backward of detr/model.py:312-314,354,405-411): out[n] = sum_m g[m][n], g bf16 (M,N)
- * row stride ld.  partial float[detr_colsum_chunks(M,N) * N] is scratch.  Deterministic two-stage reduction. */
+ * row stride ld.  partial float[detr_colsum_chunks(M,N) * N] is scratch; counters: 64 uint32 that are zero on entry
+ * (the kernel leaves them zero).  One launch, deterministic. */
 int detr_colsum_chunks(int M, int N);
-int detr_colsum_bf16(const void* g, int64_t ld, int M, int N, float* partial, float* out, void* stream);
+int detr_colsum_bf16(const void* g, int64_t ld, int M, int N, float* partial, float* out, uint32_t* counters, void* stream);
+
+/* Fused pre-LN prologue (detr/model.py:221-222,173-174,177-178,224,182,209,148): y = LayerNorm(x)*gamma+beta and
+ * y2 = y + addend (the positional / query embedding added to the attention's query and key inputs only) in one pass,
+ * written in the consumer GEMM's dtype.  dtype codes: 0 float32, 1 bfloat16.  x (rows,C) row stride x_ld; addend row
+ * of (batch b, row r) at addend + b*add_sb + r*add_sr (so a (Q,C) embedding broadcasts with add_sb = 0); y / y2
+ * (rows,C) contiguous, either may be NULL; mean/rstd float[rows] saved for backward.  C % 32 == 0, C <= 1024. */
+int detr_layernorm_grid(int rows);
+int detr_layernorm_fwd(const void* x, int x_dtype, int64_t x_ld, const float* gamma, const float* beta,
+                       const void* addend, int add_dtype, int64_t add_sb, int64_t add_sr, int rows_per_batch,
+                       void* y, void* y2, int out_dtype, float* mean, float* rstd, int rows, int C, float eps, void* stream);
+/* Backward: dy / dy2 are the gradients of y / y2 (dtype g_dtype, contiguous rows, either may be NULL); dx has x's
+ * dtype, contiguous; dgamma/dbeta float[C]; partial float[detr_layernorm_grid(rows)*2*C] scratch; counters as colsum. */
+int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, const void* x, int x_dtype, int64_t x_ld,
+                       const float* gamma, const float* mean, const float* rstd, void* dx, float* partial,
+                       float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -153,3 +153,36 @@ def test_linear_fn_matches_autocast_linear(cuda):
     assert torch.allclose(g1[1], lin.weight.grad, rtol=2e-2, atol=2e-1)
     ref_b = w.sum((0, 1))
     assert (g1[2] - ref_b).abs().max() <= (lin.bias.grad - ref_b).abs().max() + 0.5   # at least as accurate as ATen's bf16 reduction
+
+
+@pytest.mark.parametrize("xdt,odt,C", [(torch.float32, torch.float32, 256), (torch.bfloat16, torch.bfloat16, 256),
+                                       (torch.float32, torch.bfloat16, 256), (torch.float32, torch.float32, 64), (torch.bfloat16, torch.bfloat16, 512)])
+def test_fused_layernorm_add(cuda, xdt, odt, C):
+    """Fused LN(+addend) forward/backward against F.layer_norm autograd in fp32."""
+    from detr_b200.rowops import _LayerNormAdd
+    torch.manual_seed(1)
+    B, R = 3, 157
+    x = torch.randn(B, R, C, device=cuda).mul(2).add(0.5).to(xdt)
+    ln = torch.nn.LayerNorm(C).to(cuda)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5); ln.bias.normal_(0, 0.2)
+    emb = torch.randn(R, C, device=cuda, requires_grad=True)
+    w1, w2 = torch.randn(B, R, C, device=cuda), torch.randn(B, R, C, device=cuda)
+    xa = x.clone().requires_grad_(True)
+    y, y2 = _LayerNormAdd.apply(xa, ln.weight, ln.bias, emb[None].expand(B, -1, -1), ln.eps, odt, True)
+    assert y.dtype == odt and y2.dtype == odt
+    (y.float() * w1 + y2.float() * w2).sum().backward()
+    got = (y.float(), y2.float(), xa.grad.float(), ln.weight.grad.clone(), ln.bias.grad.clone(), emb.grad.clone())
+    ln.zero_grad(); emb.grad = None
+    xr = x.float().clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (C,), ln.weight, ln.bias, ln.eps)
+    y2r = yr + emb[None]
+    (yr * w1 + y2r * w2).sum().backward()
+    ref = (yr, y2r, xr.grad, ln.weight.grad, ln.bias.grad, emb.grad)
+    lo = xdt == torch.bfloat16 or odt == torch.bfloat16
+    for name, a, b in zip(("y", "y2", "dx", "dgamma", "dbeta", "dadd"), got, ref):
+        tol = (3e-2 if lo else 2e-5) * max(1.0, b.abs().max().item())
+        assert (a - b).abs().max().item() <= tol, (name, (a - b).abs().max().item(), tol)
+    # y2-only variant (decoder cross-attention query)
+    _, q = _LayerNormAdd.apply(x, ln.weight, ln.bias, emb[None].expand(B, -1, -1), ln.eps, odt, False)
+    assert _ is None and (q.float() - y2r).abs().max().item() <= (3e-2 if lo else 2e-5) * y2r.abs().max().item()
