@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .attention import HEAD_DIM, flash_attention
-from .rowops import layer_norm_add, linear
+from .rowops import ShadowedLinears, layer_norm_add, linear
 
 
 @dataclass
@@ -74,9 +74,24 @@ class ScaledDotProductAttention(nn.Module):
         if self.head_size != HEAD_DIM:
             raise ValueError(f"detr_b200 attention kernels are built for head size {HEAD_DIM}, got {self.head_size}")
 
-    def project_kv(self, key: torch.Tensor, value: torch.Tensor):
-        return (linear(key, self.key_proj.weight, self.key_proj.bias),
-                linear(value, self.value_proj.weight, self.value_proj.bias))
+    _shadows: Optional[ShadowedLinears] = None   # set by the owning Encoder / Decoder (plain attribute, not a submodule)
+
+    _skey: str = ""
+
+    def register_shadows(self, sh: ShadowedLinears, prefix: str) -> None:
+        object.__setattr__(self, "_shadows", sh)
+        object.__setattr__(self, "_skey", prefix)
+        sh.register((prefix, "qk"), (self.query_proj.weight, self.key_proj.weight), (self.query_proj.bias, self.key_proj.bias))
+        for name in ("query", "key", "value", "output"):
+            lin = getattr(self, name + "_proj")
+            sh.register((prefix, name), (lin.weight,), (lin.bias,))
+
+    def _lin(self, x, name):
+        w16, b16 = self._shadows.get((self._skey, name)) if (self._shadows is not None and torch.is_autocast_enabled()) else (None, None)
+        if name == "qk":
+            return linear(x, (self.query_proj.weight, self.key_proj.weight), (self.query_proj.bias, self.key_proj.bias), w16, b16)
+        lin = getattr(self, name + "_proj")
+        return linear(x, lin.weight, lin.bias, w16, b16)
 
     def forward(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
                 key_padding_mask: Optional[torch.BoolTensor] = None,
@@ -84,19 +99,16 @@ class ScaledDotProductAttention(nn.Module):
         C = self.hidden_size
         if key is query:
             # self-attention: one GEMM for both projections; q/k are strided views the TMA descriptors take as they are
-            w = torch.cat((self.query_proj.weight, self.key_proj.weight), dim=0)
-            b = torch.cat((self.query_proj.bias, self.key_proj.bias), dim=0)
-            qk = linear(query, w, b)
+            qk = self._lin(query, "qk")
             q, k = qk[..., :C], qk[..., C:]
-            v = linear(value, self.value_proj.weight, self.value_proj.bias)
         else:
-            q = linear(query, self.query_proj.weight, self.query_proj.bias)
-            k, v = self.project_kv(key, value)
+            q, k = self._lin(query, "query"), self._lin(key, "key")
+        v = self._lin(value, "value")
         p_drop = self.dropout_attn.p if self.training else 0.0
         y = flash_attention(q, k, v, key_padding_mask, attention_mask, p_drop)
         if not torch.is_autocast_enabled():
             y = y.to(query.dtype)
-        y = linear(y, self.output_proj.weight, self.output_proj.bias)
+        y = self._lin(y, "output")
         return self.dropout(y)
 
 
@@ -113,9 +125,22 @@ class FFN(nn.Module):
             nn.Dropout(config.hidden_dropout_prob),
         )
 
+    _shadows: Optional[ShadowedLinears] = None
+
+    _skey: str = ""
+
+    def register_shadows(self, sh: ShadowedLinears, prefix: str) -> None:
+        object.__setattr__(self, "_shadows", sh)
+        object.__setattr__(self, "_skey", prefix)
+        sh.register((prefix, 0), (self.layers[0].weight,), (self.layers[0].bias,))
+        sh.register((prefix, 3), (self.layers[3].weight,), (self.layers[3].bias,))
+
     def forward(self, x):
         fc1, act, drop1, fc2, drop2 = self.layers
-        return drop2(linear(drop1(act(linear(x, fc1.weight, fc1.bias))), fc2.weight, fc2.bias))
+        use = self._shadows is not None and torch.is_autocast_enabled()
+        s1 = self._shadows.get((self._skey, 0)) if use else (None, None)
+        s2 = self._shadows.get((self._skey, 3)) if use else (None, None)
+        return drop2(linear(drop1(act(linear(x, fc1.weight, fc1.bias, *s1))), fc2.weight, fc2.bias, *s2))
 
 
 class EncoderLayer(nn.Module):
@@ -144,8 +169,10 @@ class Encoder(nn.Module):
         self.layers = nn.ModuleList([EncoderLayer(config) for _ in range(config.num_encoder_layers)])
         self.norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self.apply(lambda m: _init_weights(m, config.initializer_range))
+        _attach_shadows(self)
 
     def forward(self, x: torch.Tensor, position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
+        _refresh_shadows(self, x)
         for layer in self.layers:
             x = layer(x, position_embedding, key_padding_mask)
         return layer_norm_add(x, self.norm)[0]
@@ -185,9 +212,11 @@ class Decoder(nn.Module):
         self.layers = nn.ModuleList([DecoderLayer(config) for _ in range(config.num_decoder_layers)])
         self.norm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
         self.apply(lambda m: _init_weights(m, config.initializer_range))
+        _attach_shadows(self)
 
     def forward(self, encoded_image_tokens: torch.Tensor, position_embedding: torch.Tensor,
                 object_query_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
+        _refresh_shadows(self, encoded_image_tokens)
         x = torch.zeros_like(object_query_embedding)
         cross_key = encoded_image_tokens + position_embedding   # layer-invariant: computed once, not 6 times
         outputs = []
@@ -200,6 +229,20 @@ class Decoder(nn.Module):
         B, L, Q, C = stacked.shape
         with torch.autocast("cuda", enabled=False):   # the prediction heads get the reference's fp32 LayerNorm output
             return layer_norm_add(stacked.view(B, L * Q, C), self.norm)[0].view(B, L, Q, C)
+
+
+def _attach_shadows(root: nn.Module) -> None:
+    """One ShadowedLinears per Encoder / Decoder covering every attention / FFN Linear below it."""
+    sh = ShadowedLinears()
+    for name, m in root.named_modules():
+        if isinstance(m, (ScaledDotProductAttention, FFN)):
+            m.register_shadows(sh, name)
+    object.__setattr__(root, "_shadows", sh)
+
+
+def _refresh_shadows(root: nn.Module, like: torch.Tensor) -> None:
+    if torch.is_autocast_enabled() and like.is_cuda and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        root._shadows.refresh(like.device)
 
 
 def patch(detr_model_module, detr_train_module=None) -> None:

@@ -22,43 +22,90 @@ def colsum(g: torch.Tensor) -> torch.Tensor:
 
 
 class _LinearFn(torch.autograd.Function):
-    """y = x W^T + b with cuBLASLt (bias in the GEMM epilogue) and a backward whose bias gradient is ONE pass of the
-    colsum kernel instead of ATen's generic reduction."""
+    """y = x W^T + b with cuBLASLt (bias in the GEMM epilogue) and a backward that (a) produces dW directly in fp32
+    from the bf16 GEMM (no cast launch), (b) computes db with ONE pass of the colsum kernel instead of ATen's generic
+    reduction.  `w16` / `b16` are bf16 shadows of the fp32 parameters (refreshed once per forward for the whole
+    encoder / decoder by `ShadowedLinears.refresh`); when absent they are cast here.  `weights` / `biases` may hold
+    several parameters that are stacked along the output dimension (the fused q|k projection)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        # x bf16; weight / bias are the fp32 parameters: cast here so that their gradients come back in fp32
-        w16 = weight.to(x.dtype)
+    def forward(ctx, x, w16, b16, n_w, *params):
+        weights, biases = params[:n_w], params[n_w:]
+        if w16 is None:
+            w16 = (weights[0] if n_w == 1 else torch.cat(weights, 0)).to(x.dtype)
+        if b16 is None and biases:
+            b16 = (biases[0] if len(biases) == 1 else torch.cat(biases, 0)).to(x.dtype)
         ctx.save_for_backward(x, w16)
-        ctx.has_bias = bias is not None
-        ctx.w_dtype = weight.dtype
-        return F.linear(x, w16, None if bias is None else bias.to(x.dtype))
+        ctx.n_w, ctx.n_b = n_w, len(biases)
+        ctx.splits = [w.shape[0] for w in weights]
+        ctx.w_dtype = weights[0].dtype
+        return F.linear(x, w16, b16)
 
     @staticmethod
     def backward(ctx, g):
-        x, weight = ctx.saved_tensors
+        x, w16 = ctx.saved_tensors
         g2 = g.reshape(-1, g.shape[-1])
         x2 = x.reshape(-1, x.shape[-1])
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = (g2 @ weight).view(x.shape)
-        if ctx.needs_input_grad[1]:
-            dw = torch.mm(g2.t(), x2, out_dtype=ctx.w_dtype) if ctx.w_dtype == torch.float32 else (g2.t() @ x2).to(ctx.w_dtype)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(g2 if g2.is_contiguous() or g2.stride(1) == 1 else g2.contiguous())
-        return dx, dw, db
+        dx = (g2 @ w16).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = torch.mm(g2.t(), x2, out_dtype=torch.float32) if ctx.w_dtype == torch.float32 else (g2.t() @ x2).to(ctx.w_dtype)
+        dws = (dw,) if ctx.n_w == 1 else torch.split(dw, ctx.splits, 0)
+        dbs = ()
+        if ctx.n_b:
+            db = colsum(g2 if g2.stride(1) == 1 else g2.contiguous())
+            dbs = (db,) if ctx.n_b == 1 else torch.split(db, ctx.splits, 0)
+        return (dx, None, None, None, *dws, *dbs)
 
 
-def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None) -> torch.Tensor:
-    """nn.functional.linear under bf16 autocast with the fast bias-gradient; plain F.linear otherwise."""
-    if torch.is_autocast_enabled() and x.is_cuda:
-        dt = torch.get_autocast_dtype("cuda")
-        if dt == torch.bfloat16:
-            with torch.autocast("cuda", enabled=False):
-                return _LinearFn.apply(x.to(dt), weight, bias)
-    return F.linear(x, weight, bias)
+def linear(x: torch.Tensor, weight, bias, w16=None, b16=None) -> torch.Tensor:
+    """nn.functional.linear under bf16 autocast through `_LinearFn`; plain F.linear otherwise (fp32 mode).
+    `weight` / `bias` may be tuples of parameters stacked along the output dimension."""
+    ws = weight if isinstance(weight, (tuple, list)) else (weight,)
+    bs = () if bias is None else (bias if isinstance(bias, (tuple, list)) else (bias,))
+    if torch.is_autocast_enabled() and x.is_cuda and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        with torch.autocast("cuda", enabled=False):
+            return _LinearFn.apply(x.to(torch.bfloat16), w16, b16, len(ws), *ws, *bs)
+    w = ws[0] if len(ws) == 1 else torch.cat(tuple(ws), 0)
+    b = None if not bs else (bs[0] if len(bs) == 1 else torch.cat(tuple(bs), 0))
+    return F.linear(x, w, b)
 
 
+class ShadowedLinears:
+    """bf16 shadows of a module tree's Linear weights and biases, refreshed with ONE multi-tensor copy per forward
+    (instead of one cast kernel per weight per use under autocast).  Groups of parameters that are used stacked
+    (q|k of self-attention) share one shadow buffer, so no torch.cat is launched either."""
+
+    def __init__(self):
+        self.groups = []      # (key, [weights], [biases])
+        self.shadow = {}      # key -> (w16, b16)
+        self._src, self._dst = [], []
+        self._device = None
+
+    def register(self, key, weights, biases):
+        self.groups.append((key, list(weights), list(biases)))
+
+    def _build(self, device):
+        self.shadow.clear(); self._src, self._dst = [], []
+        for key, ws, bs in self.groups:
+            out = sum(w.shape[0] for w in ws)
+            w16 = torch.empty(out, ws[0].shape[1], dtype=torch.bfloat16, device=device)
+            b16 = torch.empty(out, dtype=torch.bfloat16, device=device) if bs else None
+            o = 0
+            for i, w in enumerate(ws):
+                self._src.append(w); self._dst.append(w16[o:o + w.shape[0]])
+                if bs:
+                    self._src.append(bs[i]); self._dst.append(b16[o:o + w.shape[0]])
+                o += w.shape[0]
+            self.shadow[key] = (w16, b16)
+        self._device = device
+
+    @torch.no_grad()
+    def refresh(self, device):
+        if self._device != device:
+            self._build(device)
+        torch._foreach_copy_(self._dst, [p.detach() for p in self._src])
+
+    def get(self, key):
+        return self.shadow.get(key, (None, None))
 # ------------------------------------------------------------------------------------------------ fused LayerNorm
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
