@@ -1,15 +1,19 @@
 // Flash attention backward for head_dim = 32 (gradient of detr/model.py:317-352), tcgen05 + TMA + TMEM.
 //
-// Two deterministic kernels (no atomics) built from one template; both recompute, per 128x128 tile,
+// ONE pass over the (query tile, key tile) pairs.  CTA = (batch, head, 128-key tile); it streams the query tiles and,
+// per 128x128 pair, recomputes
 //     S = Q K^T,  dP~ = dO V^T,  P = exp(S/sqrt(d) - LSE),  P~ = dropout(P),
 //     dS = P o (dropout(dP~) - D) / sqrt(d),     D = rowsum(dO o O)
-// with queries on the TMEM lanes (so LSE, D and the dropout key are per-thread scalars, exactly as in forward):
-//   kDQ   CTA = (batch, head, 128-query tile), streams key tiles :  dQ += dS K            (dS as K-major A operand)
-//   kDKV  CTA = (batch, head, 128-key tile),  streams query tiles:  dV += P~^T dO, dK += dS^T Q
-//                                                                   (P~, dS consumed as MN-major A operands)
-// Warps 0-7 compute (warp w: TMEM lanes 32*(w%4).., key columns 64*(w/4)..), warp 8 = TMA, warp 9 = MMA issue.
-// TMEM (512 columns): S [0,128) | dP [128,256) | acc0 [256,288) (dQ or dK) | acc1 [288,320) (dV).
-// S/dP are copied to registers and released immediately, so the next tile's score MMAs overlap this tile's math.
+// exactly once, with queries on the TMEM lanes (so LSE, D and the dropout key are per-thread scalars, as in forward):
+//     dV += P~^T dO,  dK += dS^T Q      accumulate in TMEM over the whole stream (P~, dS consumed as MN-major A operands)
+//     dQ_part = dS K                     per pair (the SAME dS tile consumed as a K-major A operand), written as an fp32
+//                                        partial per key tile; attention_dq_reduce_kernel sums the partials in a fixed
+//                                        order -> deterministic, no atomics.
+// 20 warps: 0-15 compute (warp w: TMEM lanes 32*(w%4).., key columns 32*(w/4)..+31 of the pair), 16 = TMA producer,
+// 17 = tcgen05.mma issuer, 18-19 complete the fifth warpgroup so that setmaxnreg can move its registers to the math.
+// TMEM (512 columns): S [0,128) | dP [128,256) | dK [256,288) | dV [288,320) | dQ_part x2 [320,384).
+// S / dP are copied to registers and released at once, so the next pair's score MMAs run under this pair's math;
+// the dS / P~ shared-memory tiles and the dQ_part columns are double buffered, so the math never waits for the MMAs.
 //
 // Masked keys (key_padding_mask / attention_mask) receive zero gradient as in the reference (masked_fill);
 // a query row whose keys are ALL masked is stored with LSE = +inf by the forward kernel and contributes nothing.
@@ -30,107 +34,111 @@ namespace bwd {
 
 constexpr int kT = 128;            // tile edge (queries and keys)
 constexpr int kD = 32;
-constexpr int kStages = 2;
-constexpr int kThreads = 320;
+constexpr int kStages = 3;
+constexpr int kComputeWarps = 16;
+constexpr int kComputeThreads = kComputeWarps * 32;
+constexpr int kThreads = 640;      // 5 warpgroups
 constexpr uint32_t kTileBytes = kT * kD * 2;  // 8 KB
 constexpr uint32_t kTmemCols = 512;
 
 struct Params {
-    // outputs (bf16, channel stride 1)
-    __nv_bfloat16* out0; int64_t o0_sb, o0_sl;   // dQ (kDQ)  or dK (kDKV)
-    __nv_bfloat16* out1; int64_t o1_sb, o1_sl;   // unused     or dV
+    __nv_bfloat16* dk; int64_t dk_sb, dk_sl;
+    __nv_bfloat16* dv; int64_t dv_sb, dv_sl;
+    float* dq_part;       // [key tiles][B][L][nh*32] fp32 partial dQ (without the 1/sqrt(d) factor)
     const float* lse;     // (B, nh, L) natural log
     const float* delta;   // (B, nh, L) rowsum(dO o O)
     const uint8_t* kpm; int64_t kpm_sb;
     const uint8_t* amask;
     int B, nh, L, S;
     float scale_log2, scale;   // log2(e)/sqrt(d), 1/sqrt(d)
-    uint32_t drop_thresh; float drop_scale; uint64_t seed; const uint64_t* seed_ptr;
+    uint32_t drop_thresh;      // 0 = no dropout; a key is dropped if its 7 random bits < thresh
+    float drop_log2_scale;     // log2(128 / (128 - thresh)): folded into the exponent, P comes out pre-scaled by 1/(1-p)
+    float drop_keep;           // (128 - thresh) / 128
+    uint64_t seed; const uint64_t* seed_ptr;
 };
 
 struct Smem {
-    static constexpr uint32_t fixed = 0;                                   // 2 tiles
-    static constexpr uint32_t ring = fixed + 2 * kTileBytes;               // kStages x 2 tiles
-    static constexpr uint32_t ds = ring + kStages * 2 * kTileBytes;        // 128x128 bf16, SWIZZLE_128B, two 64-key blocks
-    static constexpr uint32_t pt = ds + kT * kT * 2;                       // P~ (kDKV only)
-    static constexpr uint32_t bars = pt + kT * kT * 2;
-    static constexpr uint32_t flags = bars + 128;
-    // + ceil(S/128)*128 key flags + 1024 bytes of alignment slack (computed on the host)
+    static constexpr uint32_t fixed = 0;                                   // K tile, V tile
+    static constexpr uint32_t ring = fixed + 2 * kTileBytes;               // kStages x (Q tile, dO tile)
+    static constexpr uint32_t ds = 65536;                                  // 2 x (128x128 bf16, SWIZZLE_128B, two 64-key blocks)
+    static constexpr uint32_t pt = ds + 2 * kT * kT * 2;                   // 2 x P~
+    static constexpr uint32_t bars = pt + 2 * kT * kT * 2;
+    static constexpr uint32_t flags = bars + 256;                          // 128 key flags
+    static constexpr uint32_t total = flags + kT + 1024;                   // + alignment slack
 };
-static_assert(Smem::ds % 1024 == 0 && Smem::pt % 1024 == 0, "swizzled tiles must be 1024-byte aligned");
+static_assert(Smem::ring + kStages * 2 * kTileBytes <= Smem::ds && Smem::ds % 1024 == 0 && Smem::pt % 1024 == 0, "smem layout");
 
-template <bool kDQ>
 __global__ void __launch_bounds__(kThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t0 = blockIdx.x * kT, h = blockIdx.y, b = blockIdx.z;   // fixed tile origin (queries for kDQ, keys for kDKV)
-    const int T = kDQ ? (p.S + kT - 1) / kT : (p.L + kT - 1) / kT;    // number of streamed tiles
+    const int kt = blockIdx.x, k0 = kt * kT, h = blockIdx.y, b = blockIdx.z;
+    const int T = (p.L + kT - 1) / kT;    // number of streamed query tiles
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
     uint64_t* fixed_full = bars + 0;
-    uint64_t* ring_full = bars + 1;
-    uint64_t* ring_empty = bars + 1 + kStages;
-    uint64_t* sdp_full = bars + 1 + 2 * kStages;
+    uint64_t* ring_full = bars + 1;                    // [kStages]
+    uint64_t* ring_empty = ring_full + kStages;        // [kStages]
+    uint64_t* sdp_full = ring_empty + kStages;
     uint64_t* sdp_empty = sdp_full + 1;
-    uint64_t* ds_full = sdp_full + 2;
-    uint64_t* ds_empty = sdp_full + 3;
-    uint64_t* acc_full = sdp_full + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 5);
+    uint64_t* ds_full = sdp_full + 2;                  // [2]
+    uint64_t* ds_empty = sdp_full + 4;                 // [2]
+    uint64_t* dq_full = sdp_full + 6;                  // [2]
+    uint64_t* dq_empty = sdp_full + 8;                 // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 10);
     uint8_t* kflag = smem + Smem::flags;
 
     if (tid == 0) {
         mbar_init(fixed_full, 1);
         for (int s = 0; s < kStages; ++s) { mbar_init(ring_full + s, 1); mbar_init(ring_empty + s, 1); }
-        mbar_init(sdp_full, 1); mbar_init(sdp_empty, 256); mbar_init(ds_full, 256); mbar_init(ds_empty, 1); mbar_init(acc_full, 1);
+        mbar_init(sdp_full, 1); mbar_init(sdp_empty, kComputeThreads);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(ds_full + s, kComputeThreads); mbar_init(ds_empty + s, 1);
+            mbar_init(dq_full + s, 1); mbar_init(dq_empty + s, kComputeThreads);
+        }
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, kTmemCols);
-    {   // key flags: 0 normal, 1 masked, 2 beyond S.  kDQ: all keys; kDKV: the CTA's own 128 keys
-        const int nk = kDQ ? T * kT : kT, base = kDQ ? 0 : t0;
-        for (int k = tid; k < nk; k += kThreads)
-            kflag[k] = (base + k) >= p.S ? 2 : ((p.kpm && p.kpm[b * p.kpm_sb + base + k]) ? 1 : 0);
-    }
+    if (warp == 17) tmem_alloc(tmem_slot, kTmemCols);
+    if (tid < kT)   // key flags of the CTA's own 128 keys: 0 normal, 1 masked, 2 beyond S
+        kflag[tid] = (k0 + tid) >= p.S ? 2 : ((p.kpm && p.kpm[b * p.kpm_sb + k0 + tid]) ? 1 : 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_a0 = tmem_base + 256, tmem_a1 = tmem_base + 288;
+    const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dk = tmem_base + 256, tmem_dv = tmem_base + 288,
+                   tmem_dq = tmem_base + 320;
 
-    if (warp == 8) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+    if (warp >= kComputeWarps) {
+        reg_dealloc<24>();   // the CTA's register pool is what its own warps release: 128 x (96-24) >= 512 x (112-96)
+        if (warp == 16 && lane == 0) {
+            // ================= TMA producer =================
             tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
             mbar_expect_tx(fixed_full, 2 * kTileBytes);
-            tma_load_3d(smem + Smem::fixed, kDQ ? &tm_q : &tm_k, fixed_full, h * kD, t0, b);
-            tma_load_3d(smem + Smem::fixed + kTileBytes, kDQ ? &tm_do : &tm_v, fixed_full, h * kD, t0, b);
+            tma_load_3d(smem + Smem::fixed, &tm_k, fixed_full, h * kD, k0, b);
+            tma_load_3d(smem + Smem::fixed + kTileBytes, &tm_v, fixed_full, h * kD, k0, b);
             for (int t = 0; t < T; ++t) {
                 const int s = t % kStages;
                 if (t >= kStages) mbar_wait_sleep(ring_empty + s, ((t / kStages) - 1) & 1);
                 mbar_expect_tx(ring_full + s, 2 * kTileBytes);
                 uint8_t* dst = smem + Smem::ring + s * 2 * kTileBytes;
-                tma_load_3d(dst, kDQ ? &tm_k : &tm_q, ring_full + s, h * kD, t * kT, b);
-                tma_load_3d(dst + kTileBytes, kDQ ? &tm_v : &tm_do, ring_full + s, h * kD, t * kT, b);
+                tma_load_3d(dst, &tm_q, ring_full + s, h * kD, t * kT, b);
+                tma_load_3d(dst + kTileBytes, &tm_do, ring_full + s, h * kD, t * kT, b);
             }
-        }
-    } else if (warp == 9) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        } else if (warp == 17 && lane == 0) {
+            // ================= MMA issuer =================
             constexpr uint32_t idesc_sc = make_idesc_bf16(kT, kT, false, false);   // scores: both operands K-major (contract over d)
             constexpr uint32_t idesc_dq = make_idesc_bf16(kT, kD, false, true);    // dS (K-major) x K (MN-major)
             constexpr uint32_t idesc_kv = make_idesc_bf16(kT, kD, true, true);     // P~^T / dS^T (MN-major) x dO / Q (MN-major)
-            const uint32_t fx0 = smem_u32(smem + Smem::fixed), fx1 = fx0 + kTileBytes;
-            const uint32_t sds = smem_u32(smem + Smem::ds), spt = smem_u32(smem + Smem::pt);
+            const uint32_t sk = smem_u32(smem + Smem::fixed), sv = sk + kTileBytes;
             auto kmaj64 = [](uint32_t a, int ks) { return make_smem_desc(a + ks * 32, 16, 512, SWZ_64B); };
             auto issue_scores = [&](int t) {
-                const uint32_t r0 = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes), r1 = r0 + kTileBytes;
-                const uint32_t aq = kDQ ? fx0 : r0, bk = kDQ ? r0 : fx0, ado = kDQ ? fx1 : r1, bv = kDQ ? r1 : fx1;
+                const uint32_t sq = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes), sdo = sq + kTileBytes;
 #pragma unroll
-                for (int ks = 0; ks < kD / 16; ++ks) umma_bf16(tmem_s, kmaj64(aq, ks), kmaj64(bk, ks), idesc_sc, ks > 0);
+                for (int ks = 0; ks < kD / 16; ++ks) umma_bf16(tmem_s, kmaj64(sq, ks), kmaj64(sk, ks), idesc_sc, ks > 0);
 #pragma unroll
-                for (int ks = 0; ks < kD / 16; ++ks) umma_bf16(tmem_dp, kmaj64(ado, ks), kmaj64(bv, ks), idesc_sc, ks > 0);
+                for (int ks = 0; ks < kD / 16; ++ks) umma_bf16(tmem_dp, kmaj64(sdo, ks), kmaj64(sv, ks), idesc_sc, ks > 0);
                 umma_commit(sdp_full);
             };
             mbar_wait_sleep(fixed_full, 0);
@@ -138,151 +146,184 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             tc_fence_after();
             issue_scores(0);
             for (int t = 0; t < T; ++t) {
+                const int buf = t & 1;
                 if (t + 1 < T) {
                     mbar_wait_sleep(ring_full + ((t + 1) % kStages), ((t + 1) / kStages) & 1);
-                    mbar_wait_sleep(sdp_empty, t & 1);
+                    mbar_wait_sleep(sdp_empty, t & 1);          // the compute warps hold S_t / dP_t in registers
                     tc_fence_after();
                     issue_scores(t + 1);
                 }
-                mbar_wait_sleep(ds_full, t & 1);
+                mbar_wait_sleep(ds_full + buf, (t >> 1) & 1);   // dS_t and P~_t are in shared memory
+                if (t >= 2) mbar_wait_sleep(dq_empty + buf, ((t >> 1) - 1) & 1);   // dQ_part of pair t-2 has been read out
                 tc_fence_after();
-                const uint32_t r0 = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes), r1 = r0 + kTileBytes;
+                const uint32_t sq = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes), sdo = sq + kTileBytes;
+                const uint32_t sds = smem_u32(smem + Smem::ds + buf * (kT * kT * 2)), spt = smem_u32(smem + Smem::pt + buf * (kT * kT * 2));
 #pragma unroll
                 for (int ks = 0; ks < kT / 16; ++ks) {
-                    if (kDQ) {
-                        // dQ += dS K_t : A K-major SWIZZLE_128B (64-key blocks of 16 KB), B = K tile MN-major SWIZZLE_64B
-                        umma_bf16(tmem_a0, make_smem_desc(sds + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, SWZ_128B),
-                                  make_smem_desc(r0 + ks * 1024, 512, 512, SWZ_64B), idesc_dq, t > 0 || ks > 0);
-                    } else {
-                        // contraction over queries: A = [query][key] tiles read MN-major (keys = M): 16 queries = 2048 B per step,
-                        // the second 64-key block 16 KB further (LBO), 8-query groups 1024 B apart (SBO)
-                        const uint64_t b_do = make_smem_desc(r1 + ks * 1024, 512, 512, SWZ_64B);
-                        const uint64_t b_q = make_smem_desc(r0 + ks * 1024, 512, 512, SWZ_64B);
-                        umma_bf16(tmem_a1, make_smem_desc(spt + ks * 2048, 16384, 1024, SWZ_128B), b_do, idesc_kv, t > 0 || ks > 0);
-                        umma_bf16(tmem_a0, make_smem_desc(sds + ks * 2048, 16384, 1024, SWZ_128B), b_q, idesc_kv, t > 0 || ks > 0);
-                    }
+                    // contraction over queries: A = [query][key] tiles read MN-major (keys = M): 16 queries = 2048 B per step,
+                    // the second 64-key block 16 KB further (LBO), 8-query groups 1024 B apart (SBO)
+                    const uint64_t b_do = make_smem_desc(sdo + ks * 1024, 512, 512, SWZ_64B);
+                    const uint64_t b_q = make_smem_desc(sq + ks * 1024, 512, 512, SWZ_64B);
+                    umma_bf16(tmem_dv, make_smem_desc(spt + ks * 2048, 16384, 1024, SWZ_128B), b_do, idesc_kv, t > 0 || ks > 0);
+                    umma_bf16(tmem_dk, make_smem_desc(sds + ks * 2048, 16384, 1024, SWZ_128B), b_q, idesc_kv, t > 0 || ks > 0);
                 }
-                umma_commit(ds_empty);
+#pragma unroll
+                for (int ks = 0; ks < kT / 16; ++ks) {
+                    // dQ_part = dS K: A K-major SWIZZLE_128B (64-key blocks of 16 KB), B = K tile MN-major SWIZZLE_64B
+                    umma_bf16(tmem_dq + buf * kD, make_smem_desc(sds + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, SWZ_128B),
+                              make_smem_desc(sk + ks * 1024, 512, 512, SWZ_64B), idesc_dq, ks > 0);
+                }
+                umma_commit(ds_empty + buf);
                 umma_commit(ring_empty + (t % kStages));
+                umma_commit(dq_full + buf);                     // (also covers dK / dV of the last pair for the epilogue)
             }
-            umma_commit(acc_full);
         }
     } else {
         // ================= compute warps =================
-        const int row = (warp & 3) * 32 + lane;       // TMEM lane = query within the tile
-        const int ch = warp >> 2;                     // which 64-key half of the tile
-        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        reg_alloc<112>();
+        const int lq = warp & 3, kq = warp >> 2;      // TMEM lane quarter, 32-key quarter of the tile
+        const int row = lq * 32 + lane;               // TMEM lane = query within the tile
+        const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
         const uint32_t bh = (uint32_t)(b * p.nh + h);
         const float* lse_bh = p.lse + (int64_t)bh * p.L;
         const float* dl_bh = p.delta + (int64_t)bh * p.L;
-        uint8_t* ds_row = smem + Smem::ds + ch * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
-        uint8_t* pt_row = smem + Smem::pt + ch * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
+        const int C = p.nh * kD;
         const bool drop = p.drop_thresh != 0;
+        const uint64_t seed = drop ? p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull) : 0ull;
+        const uint32_t thr4 = p.drop_thresh * 0x01010101u;
+        const int key0 = k0 + kq * 32;                // first key of this thread's 32 columns
+        const uint8_t* kf = kflag + kq * 32;
+        // byte offset of this thread's row inside a [query][64-key block] SWIZZLE_128B tile; its 4 chunks are (kq&1)*4 + g
+        const uint32_t row_off = (uint32_t)((kq >> 1) * 16384 + (row >> 3) * 1024 + (row & 7) * 128);
+        const uint32_t chunk0 = (uint32_t)((kq & 1) * 4);
+        float* dq_dst_base = p.dq_part + (((int64_t)kt * p.B + b) * p.L) * C + h * kD + kq * 8;
 
-        float lse2 = 0.f, dlt = 0.f;
-        uint32_t row_key = 0;
-        int q = 0;
-        auto load_row = [&](int qq) {
-            q = qq;
-            const bool ok = q < p.L;
-            const float l = ok ? lse_bh[q] : CUDART_INF_F;
-            lse2 = l * 1.4426950408889634f;            // +inf (padding row / fully masked row) -> p = 0
-            dlt = ok ? dl_bh[q] : 0.f;
-            row_key = drop ? dropout_row_key(p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull), bh, (uint32_t)q) : 0u;
-        };
-        if (kDQ) load_row(t0 + row);
-
-        uint32_t s0[32], s1[32], d0[32], d1[32];
-        for (int t = 0; t < T; ++t) {
-            const int key0 = (kDQ ? t * kT : t0) + ch * 64;      // first key of this thread's 64-column half
-            if (!kDQ) load_row(t * kT + row);
-            const uint8_t* kf = kflag + (kDQ ? t * kT : 0) + ch * 64;
-            const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S + key0 : nullptr;
-            uint32_t any = p.amask ? 1u : 0u;
-            {
-                const uint4* kf4 = reinterpret_cast<const uint4*>(kf);
+        uint32_t any = p.amask ? 1u : 0u;             // warp-uniform: does this 32-key quarter need masking at all?
+        {
+            const uint4* kf4 = reinterpret_cast<const uint4*>(kf);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { const uint4 w = kf4[i]; any |= w.x | w.y | w.z | w.w; }
-            }
-            mbar_wait(sdp_full, t & 1);
+            for (int i = 0; i < 2; ++i) { const uint4 w = kf4[i]; any |= w.x | w.y | w.z | w.w; }
+        }
+
+        auto dq_readout = [&](int t) {   // dQ_part of pair t: 8 of its 32 columns per thread -> fp32 partial buffer
+            uint32_t v[8];
+            mbar_wait(dq_full + (t & 1), (t >> 1) & 1);
             tc_fence_after();
-            tmem_ld32(tmem_s + lane_addr + ch * 64, s0);
-            tmem_ld32(tmem_s + lane_addr + ch * 64 + 32, s1);
-            tmem_ld32(tmem_dp + lane_addr + ch * 64, d0);
-            tmem_ld32(tmem_dp + lane_addr + ch * 64 + 32, d1);
+            tmem_ld8(tmem_dq + (t & 1) * kD + lane_addr + kq * 8, v);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(sdp_empty);                         // score columns may be overwritten by the next tile
-            if (t > 0) mbar_wait(ds_empty, (t - 1) & 1);    // previous accumulation MMAs have consumed dS / P~
+            mbar_arrive(dq_empty + (t & 1));
+            const int q = t * kT + row;
+            if (q < p.L) {
+                float4* dst = reinterpret_cast<float4*>(dq_dst_base + (int64_t)q * C);
+                dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+                dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+            }
+        };
 
-            auto half_tile = [&](auto masked_c, auto drop_c, const uint32_t* sv, const uint32_t* dv, int hf) {
+        // per-row scalars of the NEXT tile are fetched one iteration ahead
+        float lse_n = CUDART_INF_F, dl_n = 0.f;
+        if (row < p.L) { lse_n = lse_bh[row]; dl_n = dl_bh[row]; }
+
+        uint32_t s[32], dp[32];
+        for (int t = 0; t < T; ++t) {
+            const int buf = t & 1;
+            const int q = t * kT + row;
+            // +inf (padding row / fully masked row) -> p = 0.  With dropout P comes out pre-scaled by 1/(1-p) and D is
+            // scaled by (1-p) instead:  dS = P/(1-p) o (keep o dP~ - (1-p) D)
+            const float nl = drop ? fmaf(-lse_n, 1.4426950408889634f, p.drop_log2_scale) : -lse_n * 1.4426950408889634f;
+            const float dlt = drop ? dl_n * p.drop_keep : dl_n;
+            {
+                const int qn = q + kT;
+                lse_n = CUDART_INF_F; dl_n = 0.f;
+                if (t + 1 < T && qn < p.L) { lse_n = lse_bh[qn]; dl_n = dl_bh[qn]; }
+            }
+            const uint32_t row_key = drop ? dropout_row_key(seed, bh, (uint32_t)q) : 0u;
+            const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S + key0 : nullptr;
+
+            mbar_wait(sdp_full, t & 1);
+            tc_fence_after();
+            tmem_ld32(tmem_s + lane_addr + kq * 32, s);
+            tmem_ld32(tmem_dp + lane_addr + kq * 32, dp);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(sdp_empty);                              // the score columns may be overwritten by the next pair
+            if (t >= 2) mbar_wait(ds_empty + buf, ((t >> 1) - 1) & 1);   // the MMAs of pair t-2 have consumed this buffer
+
+            uint8_t* ds_row = smem + Smem::ds + buf * (kT * kT * 2) + row_off;
+            uint8_t* pt_row = smem + Smem::pt + buf * (kT * kT * 2) + row_off;
+            auto quarter_tile = [&](auto masked_c, auto drop_c) {
                 constexpr bool MASKED = decltype(masked_c)::value, DROP = decltype(drop_c)::value;
-                const uint32_t th = p.drop_thresh << 24;
+                uint32_t rng = DROP ? dropout_group_state(row_key, (uint32_t)(key0 >> 5)) : 0u;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {               // 8 keys = one 16-byte chunk of the dS / P~ rows
-                    float pt[8], dsv[8];
-                    uint32_t b0 = 0, b1 = 0;
+                    float pr[8], dsv[8];
+                    uint32_t t0 = 0, t1 = 0;
+                    if (DROP) { t0 = dropout_quad(rng, thr4); t1 = dropout_quad(rng, thr4); }
+                    uint32_t m32[8];
                     if (DROP) {
-                        const uint32_t k4 = (uint32_t)((key0 + hf * 32 + g * 8) >> 2);
-                        b0 = dropout_bits4(row_key, k4); b1 = dropout_bits4(row_key, k4 + 1);
+                        m32[0] = dropout_mask_f32<0>(t0); m32[1] = dropout_mask_f32<1>(t0); m32[2] = dropout_mask_f32<2>(t0); m32[3] = dropout_mask_f32<3>(t0);
+                        m32[4] = dropout_mask_f32<0>(t1); m32[5] = dropout_mask_f32<1>(t1); m32[6] = dropout_mask_f32<2>(t1); m32[7] = dropout_mask_f32<3>(t1);
                     }
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int i = g * 8 + e;
-                        float pr = ex2(fmaf(__uint_as_float(sv[i]), p.scale_log2, -lse2));
+                        float x = ex2(fmaf(__uint_as_float(s[i]), p.scale_log2, nl));
                         if (MASKED) {
-                            const int c = hf * 32 + i;
-                            const bool m = kf[c] != 0 || (arow != nullptr && (key0 + c) < p.S && arow[c] != 0);
-                            pr = m ? 0.f : pr;
+                            const bool m = kf[i] != 0 || (arow != nullptr && (key0 + i) < p.S && arow[i] != 0);
+                            x = m ? 0.f : x;
                         }
-                        float keep = 1.f;
-                        if (DROP) keep = dropout_keep(e < 4 ? b0 : b1, e & 3, th) ? p.drop_scale : 0.f;
-                        pt[e] = DROP ? pr * keep : pr;
-                        // dS without the 1/sqrt(d) factor: it is applied once to the dQ / dK accumulators in the epilogue
-                        dsv[e] = pr * (DROP ? fmaf(__uint_as_float(dv[i]), keep, -dlt) : (__uint_as_float(dv[i]) - dlt));
+                        pr[e] = x;
+                        const float d = DROP ? __uint_as_float(dp[i] & m32[e]) : __uint_as_float(dp[i]);
+                        // dS without the 1/sqrt(d) factor: it is applied once to dK in the epilogue and to dQ in the reduction
+                        dsv[e] = x * (d - dlt);
                     }
-                    const uint32_t off = (uint32_t)(((hf * 4 + g) ^ (row & 7)) << 4);
+                    const uint32_t off = ((chunk0 + g) ^ (uint32_t)(row & 7)) << 4;
                     uint4 w;
                     w.x = pack_bf16x2(dsv[0], dsv[1]); w.y = pack_bf16x2(dsv[2], dsv[3]);
                     w.z = pack_bf16x2(dsv[4], dsv[5]); w.w = pack_bf16x2(dsv[6], dsv[7]);
                     *reinterpret_cast<uint4*>(ds_row + off) = w;
-                    if (!kDQ) {
-                        w.x = pack_bf16x2(pt[0], pt[1]); w.y = pack_bf16x2(pt[2], pt[3]);
-                        w.z = pack_bf16x2(pt[4], pt[5]); w.w = pack_bf16x2(pt[6], pt[7]);
-                        *reinterpret_cast<uint4*>(pt_row + off) = w;
+                    w.x = pack_bf16x2(pr[0], pr[1]); w.y = pack_bf16x2(pr[2], pr[3]);
+                    w.z = pack_bf16x2(pr[4], pr[5]); w.w = pack_bf16x2(pr[6], pr[7]);
+                    if (DROP) {
+                        w.x &= dropout_mask_bf16x2<0>(t0); w.y &= dropout_mask_bf16x2<1>(t0);
+                        w.z &= dropout_mask_bf16x2<0>(t1); w.w &= dropout_mask_bf16x2<1>(t1);
                     }
+                    *reinterpret_cast<uint4*>(pt_row + off) = w;
                 }
             };
             using TT = std::true_type; using FF = std::false_type;
             if (any) {
-                if (drop) { half_tile(TT{}, TT{}, s0, d0, 0); half_tile(TT{}, TT{}, s1, d1, 1); }
-                else      { half_tile(TT{}, FF{}, s0, d0, 0); half_tile(TT{}, FF{}, s1, d1, 1); }
+                if (drop) quarter_tile(TT{}, TT{}); else quarter_tile(TT{}, FF{});
             } else {
-                if (drop) { half_tile(FF{}, TT{}, s0, d0, 0); half_tile(FF{}, TT{}, s1, d1, 1); }
-                else      { half_tile(FF{}, FF{}, s0, d0, 0); half_tile(FF{}, FF{}, s1, d1, 1); }
+                if (drop) quarter_tile(FF{}, TT{}); else quarter_tile(FF{}, FF{});
             }
             fence_proxy_async_smem();
-            mbar_arrive(ds_full);
+            mbar_arrive(ds_full + buf);
+            if (t > 0) dq_readout(t - 1);
         }
-        // ---- epilogue: accumulators -> bf16 global ----
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int n_rows = kDQ ? p.L : p.S;
-        const int gr = t0 + row;
-        if (kDQ ? (ch == 0) : true) {
-            tmem_ld32((kDQ || ch == 0 ? tmem_a0 : tmem_a1) + lane_addr, s0);
+        dq_readout(T - 1);
+        // ---- epilogue: dK (key quarters 0,1: 16 columns each) and dV (quarters 2,3) -> bf16 global ----
+        // (dq_full of the last pair was committed after every MMA of the stream: the accumulators are complete)
+        {
+            const int gr = k0 + row;
+            const bool is_dk = kq < 2;
+            const int c0 = (kq & 1) * 16;
+            uint32_t a[16];
+            tc_fence_after();
+            tmem_ld16((is_dk ? tmem_dk : tmem_dv) + lane_addr + c0, a);
             tmem_ld_wait();
-            if (gr < n_rows) {
-                __nv_bfloat16* dst = (kDQ || ch == 0) ? p.out0 + b * p.o0_sb + (int64_t)gr * p.o0_sl + h * kD
-                                                      : p.out1 + b * p.o1_sb + (int64_t)gr * p.o1_sl + h * kD;
-                const float f = (kDQ || ch == 0) ? p.scale : 1.f;   // dQ and dK carry the 1/sqrt(d) of the scores; dV does not
+            if (gr < p.S) {
+                __nv_bfloat16* dst = is_dk ? p.dk + b * p.dk_sb + (int64_t)gr * p.dk_sl + h * kD + c0
+                                           : p.dv + b * p.dv_sb + (int64_t)gr * p.dv_sl + h * kD + c0;
+                const float f = is_dk ? p.scale : 1.f;   // dK carries the 1/sqrt(d) of the scores; dV does not
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < 2; ++g) {
                     uint4 w;
-                    w.x = pack_bf16x2(f * __uint_as_float(s0[g * 8 + 0]), f * __uint_as_float(s0[g * 8 + 1]));
-                    w.y = pack_bf16x2(f * __uint_as_float(s0[g * 8 + 2]), f * __uint_as_float(s0[g * 8 + 3]));
-                    w.z = pack_bf16x2(f * __uint_as_float(s0[g * 8 + 4]), f * __uint_as_float(s0[g * 8 + 5]));
-                    w.w = pack_bf16x2(f * __uint_as_float(s0[g * 8 + 6]), f * __uint_as_float(s0[g * 8 + 7]));
+                    w.x = pack_bf16x2(f * __uint_as_float(a[g * 8 + 0]), f * __uint_as_float(a[g * 8 + 1]));
+                    w.y = pack_bf16x2(f * __uint_as_float(a[g * 8 + 2]), f * __uint_as_float(a[g * 8 + 3]));
+                    w.z = pack_bf16x2(f * __uint_as_float(a[g * 8 + 4]), f * __uint_as_float(a[g * 8 + 5]));
+                    w.w = pack_bf16x2(f * __uint_as_float(a[g * 8 + 6]), f * __uint_as_float(a[g * 8 + 7]));
                     reinterpret_cast<uint4*>(dst)[g] = w;
                 }
             }
@@ -290,7 +331,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // D[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (one thread per (b,q,h), 64-byte vector loads)
@@ -320,15 +361,45 @@ __global__ void attention_delta_kernel(const __nv_bfloat16* __restrict__ dO, int
     delta[((int64_t)b * nh + h) * L + q] = acc;
 }
 
+// dQ[b,q,c] = scale * sum_kt part[kt][b][q][c]   (fixed summation order; 8 channels per thread)
+__global__ void attention_dq_reduce_kernel(const float* __restrict__ part, int KT, int64_t part_stride /* B*L*C */,
+                                           __nv_bfloat16* __restrict__ dq, int64_t dq_sb, int64_t dq_sl, int B, int L, int C, float scale) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*L*C/8
+    const int c8 = C >> 3;
+    if (idx >= (int64_t)B * L * c8) return;
+    const int c = (int)(idx % c8) * 8;
+    const int64_t bq = idx / c8;
+    const int q = (int)(bq % L), b = (int)(bq / L);
+    const float* src = part + ((int64_t)b * L + q) * C + c;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int kt = 0; kt < KT; ++kt) {
+        const float4 x = *reinterpret_cast<const float4*>(src + kt * part_stride);
+        const float4 y = *reinterpret_cast<const float4*>(src + kt * part_stride + 4);
+        acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
+        acc[4] += y.x; acc[5] += y.y; acc[6] += y.z; acc[7] += y.w;
+    }
+    uint4 w;
+    w.x = pack_bf16x2(scale * acc[0], scale * acc[1]); w.y = pack_bf16x2(scale * acc[2], scale * acc[3]);
+    w.z = pack_bf16x2(scale * acc[4], scale * acc[5]); w.w = pack_bf16x2(scale * acc[6], scale * acc[7]);
+    *reinterpret_cast<uint4*>(dq + b * dq_sb + (int64_t)q * dq_sl + c) = w;
+}
+
 }  // namespace bwd
 }  // namespace detr
 
 using namespace detr;
 
+extern "C" int64_t detr_attention_bwd_workspace_floats(int B, int nh, int L, int S) {
+    const int64_t kt = (S + bwd::kT - 1) / bwd::kT;
+    return kt * B * (int64_t)L * nh * bwd::kD;
+}
+
 extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
                                        const void* v, int64_t v_sb, int64_t v_sl, const void* o, int64_t o_sb, int64_t o_sl,
                                        const void* d_o, int64_t do_sb, int64_t do_sl, const float* lse, float* delta,
-                                       void* dq, int64_t dq_sb, int64_t dq_sl, void* dk, int64_t dk_sb, int64_t dk_sl,
+                                       float* dq_partial, void* dq, int64_t dq_sb, int64_t dq_sl, void* dk, int64_t dk_sb, int64_t dk_sl,
                                        void* dv, int64_t dv_sb, int64_t dv_sl, const uint8_t* key_padding_mask, int64_t kpm_sb,
                                        const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
                                        uint64_t seed, const uint64_t* seed_ptr, void* stream) {
@@ -336,6 +407,7 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     DETR_CHECK_ARG(B >= 1 && nh >= 1 && L >= 1 && S >= 1, "attention_bwd: bad sizes B=%d nh=%d L=%d S=%d", B, nh, L, S);
     DETR_CHECK_ARG(B <= 65535 && nh <= 65535, "attention_bwd: B and nh must fit the grid");
     DETR_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attention_bwd: dropout_p must be in [0,1)");
+    DETR_CHECK_ARG(dq_partial != nullptr && ((uintptr_t)dq_partial % 16) == 0, "attention_bwd: dq_partial workspace missing or misaligned");
     auto aligned = [](const void* ptr, int64_t sb, int64_t sl) { return ((uintptr_t)ptr % 16) == 0 && (sb % 8) == 0 && (sl % 8) == 0; };
     DETR_CHECK_ARG(aligned(dq, dq_sb, dq_sl) && aligned(dk, dk_sb, dk_sl) && aligned(dv, dv_sb, dv_sl) && aligned(o, o_sb, o_sl) &&
                        aligned(d_o, do_sb, do_sl),
@@ -354,31 +426,29 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     DETR_CHECK_LAUNCH("attention_delta");
 
     Params p;
+    p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dk_sb = dk_sb; p.dk_sl = dk_sl;
+    p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.dv_sb = dv_sb; p.dv_sl = dv_sl;
+    p.dq_part = dq_partial;
     p.lse = lse; p.delta = delta; p.kpm = key_padding_mask; p.kpm_sb = kpm_sb; p.amask = attention_mask;
     p.B = B; p.nh = nh; p.L = L; p.S = S;
     p.scale = 1.f / sqrtf((float)kD);
     p.scale_log2 = 1.4426950408889634f * p.scale;
-    p.drop_thresh = (uint32_t)lrintf(dropout_p * 256.f);
-    p.drop_scale = 256.f / (256.f - (float)p.drop_thresh);
+    p.drop_thresh = (uint32_t)lrintf(dropout_p * 128.f);
+    p.drop_keep = (128.f - (float)p.drop_thresh) / 128.f;
+    p.drop_log2_scale = -log2f(p.drop_keep);
     p.seed = seed; p.seed_ptr = seed_ptr;
-    const size_t smem_dq = Smem::flags + (size_t)((S + kT - 1) / kT) * kT + 1024, smem_dkv = Smem::flags + kT + 1024;
-    DETR_CHECK_ARG(smem_dq <= 200 * 1024, "attention_bwd: S=%d needs %zu B of shared memory", S, smem_dq);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e1 = cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaError_t e2 = cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("attention_bwd: cudaFuncSetAttribute failed"); return 2; }
+        cudaError_t e1 = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem::total);
+        if (e1 != cudaSuccess) { set_error("attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e1)); return 2; }
         attr_set = true;
     }
-    // dK, dV
-    p.out0 = reinterpret_cast<__nv_bfloat16*>(dk); p.o0_sb = dk_sb; p.o0_sl = dk_sl;
-    p.out1 = reinterpret_cast<__nv_bfloat16*>(dv); p.o1_sb = dv_sb; p.o1_sl = dv_sl;
-    attention_bwd_kernel<false><<<dim3((S + kT - 1) / kT, nh, B), kThreads, smem_dkv, st>>>(tq, tk, tv, tdo, p);
-    DETR_CHECK_LAUNCH("attention_bwd_dkv");
-    // dQ
-    p.out0 = reinterpret_cast<__nv_bfloat16*>(dq); p.o0_sb = dq_sb; p.o0_sl = dq_sl;
-    p.out1 = nullptr; p.o1_sb = p.o1_sl = 0;
-    attention_bwd_kernel<true><<<dim3((L + kT - 1) / kT, nh, B), kThreads, smem_dq, st>>>(tq, tk, tv, tdo, p);
-    DETR_CHECK_LAUNCH("attention_bwd_dq");
+    const int KT = (S + kT - 1) / kT;
+    attention_bwd_kernel<<<dim3(KT, nh, B), kThreads, Smem::total, st>>>(tq, tk, tv, tdo, p);
+    DETR_CHECK_LAUNCH("attention_bwd");
+    const int64_t n8 = (int64_t)B * L * (C / 8);
+    attention_dq_reduce_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
+        dq_partial, KT, (int64_t)B * L * C, reinterpret_cast<__nv_bfloat16*>(dq), dq_sb, dq_sl, B, L, C, p.scale);
+    DETR_CHECK_LAUNCH("attention_dq_reduce");
     return 0;
 }

@@ -45,8 +45,8 @@ struct AttnFwdParams {
     const uint8_t* amask;                  // attention mask (L, S) bytes, may be null
     int B, nh, L, S;
     float scale_log2;                      // log2(e) / sqrt(32)
-    uint32_t drop_thresh;                  // 0 = no dropout; drop key if byte < thresh
-    float drop_scale;                      // 256 / (256 - thresh)
+    uint32_t drop_thresh;                  // 0 = no dropout; a key is dropped if its 7 random bits < thresh
+    float drop_scale;                      // 128 / (128 - thresh)
     float drop_log2_scale;                 // log2(drop_scale): folded into the exponent
     uint64_t seed; const uint64_t* seed_ptr; // effective seed = seed + *seed_ptr (device side: CUDA-graph replays get fresh masks)
 };
@@ -67,7 +67,7 @@ template <bool MASKED, bool DROP>
 __device__ __forceinline__ void softmax_half_tile(uint32_t (&s)[64], const AttnFwdParams& p, const uint8_t* kf /*64 flags*/,
                                                   const uint8_t* arow /*attention-mask row at this tile's first key of the half, or null*/,
                                                   int keys_left /*S - first key of the half*/, float& m_run, float& l_run, float& alpha_out,
-                                                  float* xch_mine, const float* xch_other, uint32_t bar_id, uint32_t row_key, uint32_t k4_base,
+                                                  float* xch_mine, const float* xch_other, uint32_t bar_id, uint32_t row_key, uint32_t k32_base,
                                                   uint8_t* p_row /*this row inside the half's 64-key block*/, int row7) {
     const float sc = p.scale_log2;
     if (MASKED) {
@@ -91,7 +91,8 @@ __device__ __forceinline__ void softmax_half_tile(uint32_t (&s)[64], const AttnF
     const float m_new = fmaxf(m_run, mx);                 // finite: every tile has at least one in-range key
     alpha_out = ex2((m_run - m_new) * sc);                // first tile: exp2(-inf) = 0
     const float bias = DROP ? fmaf(-m_new, sc, p.drop_log2_scale) : -m_new * sc;   // kept entries come out pre-scaled by 1/(1-p)
-    const uint32_t th = p.drop_thresh << 24;
+    const uint32_t thr4 = p.drop_thresh * 0x01010101u;
+    uint32_t rng = 0;
     float rsum = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {                         // 8 values = one 16-byte chunk of the P row
@@ -101,16 +102,14 @@ __device__ __forceinline__ void softmax_half_tile(uint32_t (&s)[64], const AttnF
             e[i] = ex2(fmaf(__uint_as_float(s[g * 8 + i]), sc, bias));
             rsum += e[i];
         }
-        if (DROP) {
-            const uint32_t b0 = dropout_bits4(row_key, k4_base + 2 * g), b1 = dropout_bits4(row_key, k4_base + 2 * g + 1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                e[i] = dropout_keep(b0, i, th) ? e[i] : 0.f;
-                e[4 + i] = dropout_keep(b1, i, th) ? e[4 + i] : 0.f;
-            }
-        }
         uint4 w;
         w.x = pack_bf16x2(e[0], e[1]); w.y = pack_bf16x2(e[2], e[3]); w.z = pack_bf16x2(e[4], e[5]); w.w = pack_bf16x2(e[6], e[7]);
+        if (DROP) {   // the row sum above is of the un-dropped probabilities; dropped entries are cleared in the packed bf16 words
+            if ((g & 3) == 0) rng = dropout_group_state(row_key, k32_base + (g >> 2));
+            const uint32_t t0 = dropout_quad(rng, thr4), t1 = dropout_quad(rng, thr4);
+            w.x &= dropout_mask_bf16x2<0>(t0); w.y &= dropout_mask_bf16x2<1>(t0);
+            w.z &= dropout_mask_bf16x2<0>(t1); w.w &= dropout_mask_bf16x2<1>(t1);
+        }
         *reinterpret_cast<uint4*>(p_row + ((g ^ row7) << 4)) = w;
     }
     l_run = l_run * alpha_out + rsum;                     // (pre-scaled by 1/(1-p) when DROP; undone in the epilogue)
@@ -250,7 +249,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             float alpha;
             float* xm = xch + (j & 1) * 256 + half * 128 + row;
             const float* xo = xch + (j & 1) * 256 + (half ^ 1) * 128 + row;
-            const uint32_t k4 = (uint32_t)(key0 >> 2);
+            const uint32_t k4 = (uint32_t)(key0 >> 5);   // index of the first 32-key dropout group
             const uint8_t* ar = arow ? arow + key0 : nullptr;
             // previous tile's O columns (16 per thread) are loaded first so the TMEM read overlaps the row-max exchange
             uint32_t o_prev[16];
@@ -369,8 +368,8 @@ extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.kpm = key_padding_mask; p.kpm_sb = kpm_sb; p.amask = attention_mask;
     p.B = B; p.nh = nh; p.L = L; p.S = S;
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)kD);
-    p.drop_thresh = (uint32_t)lrintf(dropout_p * 256.f);
-    p.drop_scale = 256.f / (256.f - (float)p.drop_thresh);
+    p.drop_thresh = (uint32_t)lrintf(dropout_p * 128.f);
+    p.drop_scale = 128.f / (128.f - (float)p.drop_thresh);
     p.drop_log2_scale = log2f(p.drop_scale);
     p.seed = seed; p.seed_ptr = seed_ptr;
     const int T = (S + kBN - 1) / kBN;

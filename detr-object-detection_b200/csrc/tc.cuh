@@ -96,6 +96,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA ----------------------------------------------------------------------------------------------
@@ -145,10 +151,11 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-// ---- counter-based dropout bits ------------------------------------------------------------------------
-// One 32-bit hash yields keep/drop decisions for 4 consecutive keys (8-bit lanes): the dropout probability
-// is quantised to k/256.  The mask depends only on (seed, batch*head, query, key) so forward and both
-// backward kernels regenerate it identically whatever their tiling.
+// ---- counter-based dropout -------------------------------------------------------------------------------
+// Keep/drop decisions come in groups of 32 consecutive keys of one (batch*head, query) row: one seed hash per group,
+// then one multiply-with-carry step (IMAD.WIDE + LOP3) per 4 keys.  Each key owns 7 random bits, so the dropout
+// probability is quantised to k/128.  The mask depends only on (seed, batch*head, query, key): forward and backward
+// regenerate it identically whatever their tiling, as long as they walk a 32-key group in order.
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
@@ -157,15 +164,27 @@ __device__ __forceinline__ uint32_t dropout_row_key(uint64_t seed, uint32_t bh, 
     const uint32_t x = mix32((uint32_t)seed ^ (bh * 0x9E3779B1u)) ^ (q * 0x85EBCA77u);
     return mix32(x ^ (uint32_t)(seed >> 32));
 }
-__device__ __forceinline__ uint32_t dropout_bits4(uint32_t row_key, uint32_t k4) {
-    uint32_t x = row_key + k4 * 0x9E3779B1u;   // one IMAD
+__device__ __forceinline__ uint32_t dropout_group_state(uint32_t row_key, uint32_t k32 /* key / 32 */) {
+    uint32_t x = row_key + k32 * 0x9E3779B1u;
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15;
     return x;
 }
-// keep-test for key e (0..3) of the group: byte e of `bits` >= thresh, evaluated as one shift + one unsigned compare
-__device__ __forceinline__ bool dropout_keep(uint32_t bits, int e, uint32_t thresh_hi /* thresh << 24 */) {
-    return (bits << (24 - 8 * e)) >= thresh_hi;
+// Advance the group state by 4 keys.  Byte e of the result has bit 7 set iff key e of the quad is KEPT
+// (7 random bits r: (128 + r) - thresh keeps bit 7 iff r >= thresh; no borrow crosses a byte).
+__device__ __forceinline__ uint32_t dropout_quad(uint32_t& x, uint32_t thr4 /* thresh * 0x01010101 */) {
+    const uint64_t p = (uint64_t)x * 0x9E3779B1u + 0x7F4A7C15u;
+    x = (uint32_t)p;
+    return (((uint32_t)(p >> 32) ^ x) | 0x80808080u) - thr4;
 }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+    return d;
+}
+// selector nibbles with bit 3 set replicate the SIGN of the chosen byte over the whole output byte:
+// all-ones / all-zeros masks for a packed bf16 pair (keys 2*PAIR, 2*PAIR+1) and for one fp32 value (key E)
+template <int PAIR> __device__ __forceinline__ uint32_t dropout_mask_bf16x2(uint32_t t) { return prmt(t, PAIR == 0 ? 0x9988u : 0xBBAAu); }
+template <int E> __device__ __forceinline__ uint32_t dropout_mask_f32(uint32_t t) { return prmt(t, 0x8888u + 0x1111u * E); }
 
 }  // namespace tc
 }  // namespace detr

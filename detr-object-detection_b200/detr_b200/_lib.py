@@ -37,7 +37,8 @@ SIGNATURES = {
                                c_int, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P],
     "detr_attention_fwd_bf16": [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64,
                                 P, P, c_int64, P, c_int, c_int, c_int, c_int, c_float, ctypes.c_uint64, P, P],
-    "detr_attention_bwd_bf16": [P, c_int64, c_int64] * 5 + [P, P] + [P, c_int64, c_int64] * 3 +
+    "detr_attention_bwd_workspace_floats": [c_int, c_int, c_int, c_int],
+    "detr_attention_bwd_bf16": [P, c_int64, c_int64] * 5 + [P, P, P] + [P, c_int64, c_int64] * 3 +
                                [P, c_int64, P, c_int, c_int, c_int, c_int, c_float, ctypes.c_uint64, P, P],
     "detr_colsum_chunks": [c_int, c_int],
     "detr_colsum_bf16": [P, c_int64, c_int, c_int, P, P, P, P],
@@ -45,7 +46,7 @@ SIGNATURES = {
     "detr_layernorm_fwd": [P, c_int, c_int64, P, P, P, c_int, c_int64, c_int64, c_int, P, P, c_int, P, P, c_int, c_int, c_float, P],
     "detr_layernorm_bwd": [P, P, c_int, P, c_int, c_int64, P, P, P, P, P, P, P, P, c_int, c_int, P],
 }
-_RESTYPE = {"detr_matcher_smem_bytes": c_int64}
+_RESTYPE = {"detr_matcher_smem_bytes": c_int64, "detr_attention_bwd_workspace_floats": c_int64}
 
 
 def load() -> ctypes.CDLL:

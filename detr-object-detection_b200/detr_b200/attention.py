@@ -67,10 +67,11 @@ def attention_backward(d_out, q, k, v, out, lse, key_padding_mask=None, attentio
     dq = torch.empty(B, L, C, dtype=torch.bfloat16, device=q.device)
     dkv = torch.empty(2, B, S, C, dtype=torch.bfloat16, device=q.device)
     delta = torch.empty(B, nh, L, dtype=torch.float32, device=q.device)
+    dq_part = torch.empty(_lib.load().detr_attention_bwd_workspace_floats(B, nh, L, S), dtype=torch.float32, device=q.device)
     st = lambda t: (t.data_ptr(), t.stride(0), t.stride(1))
     _lib.call(
         "detr_attention_bwd_bf16",
-        *st(q), *st(k), *st(v), *st(out), *st(d_out), lse.data_ptr(), delta.data_ptr(), *st(dq), *st(dkv[0]), *st(dkv[1]),
+        *st(q), *st(k), *st(v), *st(out), *st(d_out), lse.data_ptr(), delta.data_ptr(), dq_part.data_ptr(), *st(dq), *st(dkv[0]), *st(dkv[1]),
         _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0, _lib.ptr(am), B, nh, L, S, float(dropout_p),
         int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_tensor), _lib.stream_ptr(), tag=(B, nh, L, S))
     return dq, dkv[0], dkv[1]

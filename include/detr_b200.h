@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DETR_B200_ABI_VERSION 1
+#define DETR_B200_ABI_VERSION 2
 
 /* status bits (device-side, sticky) -- mirror the reference's failure modes */
 #define DETR_ST_DEGENERATE_BOX 1 /* AssertionError at detr/utils.py:87-88 */
@@ -113,7 +113,7 @@ int detr_criterion_bwd_f32(const float* grad_losses,
  * detr/model.py:317-319,352 disappear.  lse float[B*nh*L] (natural log, saved for backward).
  * key_padding_mask: (B,S) bytes, non-zero = ignore (detr/model.py:326-330), row stride kpm_sb, may be NULL;
  * attention_mask: (L,S) bytes contiguous, non-zero = ignore (detr/model.py:332-334), may be NULL.
- * dropout_p is quantised to k/256 (in-kernel counter-based mask; 0 disables, as in eval()).  The mask seed is
+ * dropout_p is quantised to k/128 (in-kernel counter-based mask; 0 disables, as in eval()).  The mask seed is
  * `seed + *seed_ptr` (seed_ptr: optional DEVICE uint64, so that CUDA-graph replays draw fresh masks). */
 int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
                             const void* v, int64_t v_sb, int64_t v_sl, void* o, int64_t o_sb, int64_t o_sl,
@@ -122,12 +122,15 @@ int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const voi
                             uint64_t seed, const uint64_t* seed_ptr, void* stream);
 
 /* Backward of the call above: dq (B,L,C), dk/dv (B,S,C) bf16 from d_o (B,L,C) bf16, the forward's inputs, output
- * `o` and `lse`.  delta float[B*nh*L] is scratch (rowsum(dO o O)).  Same masks / dropout_p / seed as forward.
- * Three launches: delta, dK+dV (CTA per key tile), dQ (CTA per query tile); deterministic, no atomics. */
+ * `o` and `lse`.  Scratch: delta float[B*nh*L] (rowsum(dO o O)) and dq_partial
+ * float[detr_attention_bwd_workspace_floats(B,nh,L,S)] (one fp32 dQ partial per 128-key tile).  Same masks /
+ * dropout_p / seed as forward.  Three launches: delta, the fused dK+dV+dQ-partial kernel (CTA per key tile, every
+ * score tile recomputed once), the fixed-order dQ reduction; deterministic, no atomics. */
+int64_t detr_attention_bwd_workspace_floats(int B, int nh, int L, int S);
 int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
                             const void* v, int64_t v_sb, int64_t v_sl, const void* o, int64_t o_sb, int64_t o_sl,
                             const void* d_o, int64_t do_sb, int64_t do_sl, const float* lse, float* delta,
-                            void* dq, int64_t dq_sb, int64_t dq_sl, void* dk, int64_t dk_sb, int64_t dk_sl,
+                            float* dq_partial, void* dq, int64_t dq_sb, int64_t dq_sl, void* dk, int64_t dk_sb, int64_t dk_sl,
                             void* dv, int64_t dv_sb, int64_t dv_sl, const uint8_t* key_padding_mask, int64_t kpm_sb,
                             const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
                             uint64_t seed, const uint64_t* seed_ptr, void* stream);
