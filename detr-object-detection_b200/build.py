@@ -20,6 +20,8 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+# development switches, e.g. DETR_B200_DEFINES="-DDETR_BWD_TIMELINE" (clock64 stamps for tools/attn_timeline.py)
+FLAGS += [f for f in os.environ.get("DETR_B200_DEFINES", "").split() if f]
 
 
 def _stamp() -> str:

@@ -10,7 +10,9 @@
 //                                        partial per key tile; attention_dq_reduce_kernel sums the partials in a fixed
 //                                        order -> deterministic, no atomics.
 // 20 warps: 0-15 compute (warp w: TMEM lanes 32*(w%4).., key columns 32*(w/4)..+31 of the pair), 16 = TMA producer,
-// 17 = tcgen05.mma issuer, 18-19 complete the fifth warpgroup so that setmaxnreg can move its registers to the math.
+// 17 = tcgen05.mma issuer, 18 = dQ-partial store warp (TMA bulk tensor stores of tiles the math warps stage in shared
+// memory: per-row 32-byte global stores from 512 threads cost ~600 cycles per pair in the LSU), 19 idle (completes the
+// fifth warpgroup so that setmaxnreg can move its registers to the math).
 // TMEM (512 columns): S [0,128) | dP [128,256) | dK [256,288) | dV [288,320) | dQ_part x2 [320,384).
 // S / dP are copied to registers and released at once, so the next pair's score MMAs run under this pair's math;
 // the dS / P~ shared-memory tiles and the dQ_part columns are double buffered, so the math never waits for the MMAs.
@@ -29,6 +31,7 @@ using namespace tc;
 
 int make_head_tile_map(CUtensorMap* out, const void* base, int C, int rows, int B, int64_t row_stride_el, int64_t batch_stride_el,
                        int box_rows, const char* who);
+int make_f32_tile_map(CUtensorMap* out, const void* base, int C, int rows, int slabs, int box_c, int box_rows, const char* who);
 
 namespace bwd {
 
@@ -55,6 +58,7 @@ struct Params {
     float drop_log2_scale;     // log2(128 / (128 - thresh)): folded into the exponent, P comes out pre-scaled by 1/(1-p)
     float drop_keep;           // (128 - thresh) / 128
     uint64_t seed; const uint64_t* seed_ptr;
+    long long* dbg;            // optional timeline of CTA 0 (clock64 stamps; tools/attn_timeline.py), NULL in production
 };
 
 struct Smem {
@@ -62,15 +66,25 @@ struct Smem {
     static constexpr uint32_t ring = fixed + 2 * kTileBytes;               // kStages x (Q tile, dO tile)
     static constexpr uint32_t ds = 65536;                                  // 2 x (128x128 bf16, SWIZZLE_128B, two 64-key blocks)
     static constexpr uint32_t pt = ds + 2 * kT * kT * 2;                   // 2 x P~
-    static constexpr uint32_t bars = pt + 2 * kT * kT * 2;
+    static constexpr uint32_t dqs = pt + 2 * kT * kT * 2;                  // 2 x (128 queries x 32 fp32, SWIZZLE_128B) dQ_part staging
+    static constexpr uint32_t bars = dqs + 2 * kT * kD * 4;
     static constexpr uint32_t flags = bars + 256;                          // 128 key flags
     static constexpr uint32_t total = flags + kT + 1024;                   // + alignment slack
 };
 static_assert(Smem::ring + kStages * 2 * kTileBytes <= Smem::ds && Smem::ds % 1024 == 0 && Smem::pt % 1024 == 0, "smem layout");
 
+// debug timeline (build with DETR_B200_DEFINES=-DDETR_BWD_TIMELINE): slot = (warp, tile, event) of CTA (0,0,0) only
+#ifndef DETR_BWD_TIMELINE
+#define BWD_STAMP(ev, t) do {} while (0)
+#else
+#define BWD_STAMP(ev, t) do { if (p.dbg != nullptr && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t) < 16) \
+    p.dbg[(warp * 16 + (t)) * 8 + (ev)] = clock64(); } while (0)
+#endif
+
 __global__ void __launch_bounds__(kThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, const Params p) {
+                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                     const __grid_constant__ CUtensorMap tm_dqp, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -87,7 +101,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     uint64_t* ds_empty = sdp_full + 4;                 // [2]
     uint64_t* dq_full = sdp_full + 6;                  // [2]
     uint64_t* dq_empty = sdp_full + 8;                 // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 10);
+    uint64_t* dqs_full = sdp_full + 10;                // [2]
+    uint64_t* dqs_empty = sdp_full + 12;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 14);
     uint8_t* kflag = smem + Smem::flags;
 
     if (tid == 0) {
@@ -95,8 +111,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         for (int s = 0; s < kStages; ++s) { mbar_init(ring_full + s, 1); mbar_init(ring_empty + s, 1); }
         mbar_init(sdp_full, 1); mbar_init(sdp_empty, kComputeThreads);
         for (int s = 0; s < 2; ++s) {
-            mbar_init(ds_full + s, kComputeThreads); mbar_init(ds_empty + s, 1);
+            mbar_init(ds_full + s, kComputeThreads);
             mbar_init(dq_full + s, 1); mbar_init(dq_empty + s, kComputeThreads);
+            mbar_init(dqs_full + s, kComputeThreads); mbar_init(dqs_empty + s, 1);
         }
         fence_barrier_init();
     }
@@ -111,7 +128,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                    tmem_dq = tmem_base + 320;
 
     if (warp >= kComputeWarps) {
-        reg_dealloc<24>();   // the CTA's register pool is what its own warps release: 128 x (96-24) >= 512 x (112-96)
+        reg_dealloc<64>();   // the CTA register pool is what its own warps release: 128 x (96-64) == 512 x (104-96)
         if (warp == 16 && lane == 0) {
             // ================= TMA producer =================
             tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
@@ -126,19 +143,23 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 tma_load_3d(dst, &tm_q, ring_full + s, h * kD, t * kT, b);
                 tma_load_3d(dst + kTileBytes, &tm_do, ring_full + s, h * kD, t * kT, b);
             }
-        } else if (warp == 17 && lane == 0) {
+        } else if (warp == 17 && elect_one()) {
             // ================= MMA issuer =================
             constexpr uint32_t idesc_sc = make_idesc_bf16(kT, kT, false, false);   // scores: both operands K-major (contract over d)
             constexpr uint32_t idesc_dq = make_idesc_bf16(kT, kD, false, true);    // dS (K-major) x K (MN-major)
             constexpr uint32_t idesc_kv = make_idesc_bf16(kT, kD, true, true);     // P~^T / dS^T (MN-major) x dO / Q (MN-major)
-            const uint32_t sk = smem_u32(smem + Smem::fixed), sv = sk + kTileBytes;
-            auto kmaj64 = [](uint32_t a, int ks) { return make_smem_desc(a + ks * 32, 16, 512, SWZ_64B); };
+            // descriptor words (tc.cuh): high word per layout, low word = (address >> 4) + constant
+            constexpr uint32_t hi64 = desc_hi(512, SWZ_64B);      // Q/K/V/dO tiles: 64-byte rows, 8-row groups 512 B apart
+            constexpr uint32_t hi128 = desc_hi(1024, SWZ_128B);   // dS / P~ tiles: 128-byte rows, 8-row groups 1024 B apart
+            const uint32_t k_lo = smem_u32(smem + Smem::fixed) >> 4, v_lo = k_lo + (kTileBytes >> 4);
             auto issue_scores = [&](int t) {
-                const uint32_t sq = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes), sdo = sq + kTileBytes;
+                const uint32_t q_lo = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes) >> 4, do_lo = q_lo + (kTileBytes >> 4);
 #pragma unroll
-                for (int ks = 0; ks < kD / 16; ++ks) umma_bf16(tmem_s, kmaj64(sq, ks), kmaj64(sk, ks), idesc_sc, ks > 0);
+                for (int ks = 0; ks < kD / 16; ++ks)   // K-major operands: 32 B per 16-channel step, LBO 16
+                    umma_bf16_lh(tmem_s, q_lo + desc_lo(ks * 32, 16), hi64, k_lo + desc_lo(ks * 32, 16), hi64, idesc_sc, ks > 0);
 #pragma unroll
-                for (int ks = 0; ks < kD / 16; ++ks) umma_bf16(tmem_dp, kmaj64(sdo, ks), kmaj64(sv, ks), idesc_sc, ks > 0);
+                for (int ks = 0; ks < kD / 16; ++ks)
+                    umma_bf16_lh(tmem_dp, do_lo + desc_lo(ks * 32, 16), hi64, v_lo + desc_lo(ks * 32, 16), hi64, idesc_sc, ks > 0);
                 umma_commit(sdp_full);
             };
             mbar_wait_sleep(fixed_full, 0);
@@ -153,41 +174,58 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     tc_fence_after();
                     issue_scores(t + 1);
                 }
+                BWD_STAMP(0, t);
                 mbar_wait_sleep(ds_full + buf, (t >> 1) & 1);   // dS_t and P~_t are in shared memory
-                if (t >= 2) mbar_wait_sleep(dq_empty + buf, ((t >> 1) - 1) & 1);   // dQ_part of pair t-2 has been read out
+                BWD_STAMP(1, t);
+                if (t >= 2) {
+                    mbar_wait_sleep(dq_empty + buf, ((t >> 1) - 1) & 1);    // dQ_part of pair t-2 has been read out of TMEM
+                    mbar_wait_sleep(dqs_empty + buf, ((t >> 1) - 1) & 1);   // ... and its staging tile has been stored: dq_full(t)
+                }                                                            // tells the math warps that BOTH are free again
                 tc_fence_after();
-                const uint32_t sq = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes), sdo = sq + kTileBytes;
-                const uint32_t sds = smem_u32(smem + Smem::ds + buf * (kT * kT * 2)), spt = smem_u32(smem + Smem::pt + buf * (kT * kT * 2));
+                const uint32_t q_lo = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes) >> 4, do_lo = q_lo + (kTileBytes >> 4);
+                const uint32_t ds_lo = smem_u32(smem + Smem::ds + buf * (kT * kT * 2)) >> 4, pt_lo = smem_u32(smem + Smem::pt + buf * (kT * kT * 2)) >> 4;
+                const bool acc = t > 0;
 #pragma unroll
                 for (int ks = 0; ks < kT / 16; ++ks) {
                     // contraction over queries: A = [query][key] tiles read MN-major (keys = M): 16 queries = 2048 B per step,
-                    // the second 64-key block 16 KB further (LBO), 8-query groups 1024 B apart (SBO)
-                    const uint64_t b_do = make_smem_desc(sdo + ks * 1024, 512, 512, SWZ_64B);
-                    const uint64_t b_q = make_smem_desc(sq + ks * 1024, 512, 512, SWZ_64B);
-                    umma_bf16(tmem_dv, make_smem_desc(spt + ks * 2048, 16384, 1024, SWZ_128B), b_do, idesc_kv, t > 0 || ks > 0);
-                    umma_bf16(tmem_dk, make_smem_desc(sds + ks * 2048, 16384, 1024, SWZ_128B), b_q, idesc_kv, t > 0 || ks > 0);
+                    // the second 64-key block 16 KB further (LBO), 8-query groups 1024 B apart (SBO);
+                    // B = dO / Q tiles MN-major: 16 queries = 1024 B per step, LBO 512
+                    umma_bf16_lh(tmem_dv, pt_lo + desc_lo(ks * 2048, 16384), hi128, do_lo + desc_lo(ks * 1024, 512), hi64, idesc_kv, acc || ks > 0);
+                    umma_bf16_lh(tmem_dk, ds_lo + desc_lo(ks * 2048, 16384), hi128, q_lo + desc_lo(ks * 1024, 512), hi64, idesc_kv, acc || ks > 0);
                 }
 #pragma unroll
                 for (int ks = 0; ks < kT / 16; ++ks) {
-                    // dQ_part = dS K: A K-major SWIZZLE_128B (64-key blocks of 16 KB), B = K tile MN-major SWIZZLE_64B
-                    umma_bf16(tmem_dq + buf * kD, make_smem_desc(sds + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, SWZ_128B),
-                              make_smem_desc(sk + ks * 1024, 512, 512, SWZ_64B), idesc_dq, ks > 0);
+                    // dQ_part = dS K: A K-major SWIZZLE_128B (64-key blocks of 16 KB, 32 B per 16-key step), B = K tile MN-major
+                    umma_bf16_lh(tmem_dq + buf * kD, ds_lo + desc_lo((ks >> 2) * 16384 + (ks & 3) * 32, 16), hi128,
+                                 k_lo + desc_lo(ks * 1024, 512), hi64, idesc_dq, ks > 0);
                 }
-                umma_commit(ds_empty + buf);
                 umma_commit(ring_empty + (t % kStages));
                 umma_commit(dq_full + buf);                     // (also covers dK / dV of the last pair for the epilogue)
+                BWD_STAMP(2, t);
             }
+        }
+        else if (warp == 18 && elect_one()) {
+            // ================= dQ_part store warp =================
+            tma_prefetch_desc(&tm_dqp);
+            for (int t = 0; t < T; ++t) {
+                const int buf = t & 1;
+                mbar_wait_sleep(dqs_full + buf, (t >> 1) & 1);
+                tma_store_3d(&tm_dqp, smem + Smem::dqs + buf * (kT * kD * 4), h * kD, t * kT, kt * p.B + b);   // rows >= L are clipped
+                tma_store_commit();
+                tma_store_wait_read0();                 // the staging tile has been read: it may be overwritten
+                mbar_arrive(dqs_empty + buf);
+            }
+            tma_store_wait_all0();                      // the partials are in global memory before the CTA exits
         }
     } else {
         // ================= compute warps =================
-        reg_alloc<112>();
+        reg_alloc<104>();
         const int lq = warp & 3, kq = warp >> 2;      // TMEM lane quarter, 32-key quarter of the tile
         const int row = lq * 32 + lane;               // TMEM lane = query within the tile
         const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
         const uint32_t bh = (uint32_t)(b * p.nh + h);
         const float* lse_bh = p.lse + (int64_t)bh * p.L;
         const float* dl_bh = p.delta + (int64_t)bh * p.L;
-        const int C = p.nh * kD;
         const bool drop = p.drop_thresh != 0;
         const uint64_t seed = drop ? p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull) : 0ull;
         const uint32_t thr4 = p.drop_thresh * 0x01010101u;
@@ -196,7 +234,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         // byte offset of this thread's row inside a [query][64-key block] SWIZZLE_128B tile; its 4 chunks are (kq&1)*4 + g
         const uint32_t row_off = (uint32_t)((kq >> 1) * 16384 + (row >> 3) * 1024 + (row & 7) * 128);
         const uint32_t chunk0 = (uint32_t)((kq & 1) * 4);
-        float* dq_dst_base = p.dq_part + (((int64_t)kt * p.B + b) * p.L) * C + h * kD + kq * 8;
 
         uint32_t any = p.amask ? 1u : 0u;             // warp-uniform: does this 32-key quarter need masking at all?
         {
@@ -205,20 +242,23 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             for (int i = 0; i < 2; ++i) { const uint4 w = kf4[i]; any |= w.x | w.y | w.z | w.w; }
         }
 
-        auto dq_readout = [&](int t) {   // dQ_part of pair t: 8 of its 32 columns per thread -> fp32 partial buffer
+        // dQ_part of pair t: 8 of its 32 columns per thread, TMEM -> registers -> swizzled staging tile (row = 128 B,
+        // 16-byte chunk j of row r at ((j ^ (r & 7)) << 4): conflict-free stores, the layout TMA expects for SWIZZLE_128B)
+        uint8_t* dqs_row = smem + Smem::dqs + row * 128;
+        const uint32_t dqs_c0 = (uint32_t)(((2 * kq) ^ (row & 7)) << 4), dqs_c1 = (uint32_t)(((2 * kq + 1) ^ (row & 7)) << 4);
+        auto dq_readout = [&](int t) {
             uint32_t v[8];
-            mbar_wait(dq_full + (t & 1), (t >> 1) & 1);
+            mbar_wait(dq_full + (t & 1), (t >> 1) & 1);   // (also: staging tile t&1 has been stored, see the MMA warp)
             tc_fence_after();
             tmem_ld8(tmem_dq + (t & 1) * kD + lane_addr + kq * 8, v);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(dq_empty + (t & 1));
-            const int q = t * kT + row;
-            if (q < p.L) {
-                float4* dst = reinterpret_cast<float4*>(dq_dst_base + (int64_t)q * C);
-                dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-                dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-            }
+            uint8_t* dst = dqs_row + (t & 1) * (kT * kD * 4);
+            *reinterpret_cast<uint4*>(dst + dqs_c0) = make_uint4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint4*>(dst + dqs_c1) = make_uint4(v[4], v[5], v[6], v[7]);
+            fence_proxy_async_smem();
+            mbar_arrive(dqs_full + (t & 1));
         };
 
         // per-row scalars of the NEXT tile are fetched one iteration ahead
@@ -241,14 +281,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             const uint32_t row_key = drop ? dropout_row_key(seed, bh, (uint32_t)q) : 0u;
             const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S + key0 : nullptr;
 
+            BWD_STAMP(0, t);
             mbar_wait(sdp_full, t & 1);
+            BWD_STAMP(1, t);
             tc_fence_after();
             tmem_ld32(tmem_s + lane_addr + kq * 32, s);
             tmem_ld32(tmem_dp + lane_addr + kq * 32, dp);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(sdp_empty);                              // the score columns may be overwritten by the next pair
-            if (t >= 2) mbar_wait(ds_empty + buf, ((t >> 1) - 1) & 1);   // the MMAs of pair t-2 have consumed this buffer
+            // dS / P~ buffer `buf` is free: the MMAs of pair t-2 completed before dq_full(t-2), awaited in iteration t-1
+            BWD_STAMP(3, t);
 
             uint8_t* ds_row = smem + Smem::ds + buf * (kT * kT * 2) + row_off;
             uint8_t* pt_row = smem + Smem::pt + buf * (kT * kT * 2) + row_off;
@@ -300,7 +343,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             }
             fence_proxy_async_smem();
             mbar_arrive(ds_full + buf);
+            BWD_STAMP(4, t);
             if (t > 0) dq_readout(t - 1);
+            BWD_STAMP(5, t);
         }
         dq_readout(T - 1);
         // ---- epilogue: dK (key quarters 0,1: 16 columns each) and dV (quarters 2,3) -> bf16 global ----
@@ -391,6 +436,10 @@ __global__ void attention_dq_reduce_kernel(const float* __restrict__ part, int K
 
 using namespace detr;
 
+static long long* g_bwd_dbg = nullptr;
+/* debugging aid (not part of the drop-in surface): device buffer of 20*16*8 int64 that receives clock64 stamps of CTA 0 */
+extern "C" void detr_attention_bwd_set_debug(long long* buf) { g_bwd_dbg = buf; }
+
 extern "C" int64_t detr_attention_bwd_workspace_floats(int B, int nh, int L, int S) {
     const int64_t kt = (S + bwd::kT - 1) / bwd::kT;
     return kt * B * (int64_t)L * nh * bwd::kD;
@@ -407,7 +456,7 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     DETR_CHECK_ARG(B >= 1 && nh >= 1 && L >= 1 && S >= 1, "attention_bwd: bad sizes B=%d nh=%d L=%d S=%d", B, nh, L, S);
     DETR_CHECK_ARG(B <= 65535 && nh <= 65535, "attention_bwd: B and nh must fit the grid");
     DETR_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attention_bwd: dropout_p must be in [0,1)");
-    DETR_CHECK_ARG(dq_partial != nullptr && ((uintptr_t)dq_partial % 16) == 0, "attention_bwd: dq_partial workspace missing or misaligned");
+    DETR_CHECK_ARG(dq_partial != nullptr && ((uintptr_t)dq_partial % 128) == 0, "attention_bwd: dq_partial workspace missing or misaligned");
     auto aligned = [](const void* ptr, int64_t sb, int64_t sl) { return ((uintptr_t)ptr % 16) == 0 && (sb % 8) == 0 && (sl % 8) == 0; };
     DETR_CHECK_ARG(aligned(dq, dq_sb, dq_sl) && aligned(dk, dk_sb, dk_sl) && aligned(dv, dv_sb, dv_sl) && aligned(o, o_sb, o_sl) &&
                        aligned(d_o, do_sb, do_sl),
@@ -437,6 +486,7 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.drop_keep = (128.f - (float)p.drop_thresh) / 128.f;
     p.drop_log2_scale = -log2f(p.drop_keep);
     p.seed = seed; p.seed_ptr = seed_ptr;
+    p.dbg = g_bwd_dbg;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e1 = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem::total);
@@ -444,7 +494,9 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
         attr_set = true;
     }
     const int KT = (S + kT - 1) / kT;
-    attention_bwd_kernel<<<dim3(KT, nh, B), kThreads, Smem::total, st>>>(tq, tk, tv, tdo, p);
+    CUtensorMap tdqp;   // partials [KT*B][L][C] fp32, box = 32 channels x 128 queries, SWIZZLE_128B (128-byte rows)
+    if (int rc = make_f32_tile_map(&tdqp, dq_partial, C, L, KT * B, kD, kT, "attention_bwd(dQ partials)")) return rc;
+    attention_bwd_kernel<<<dim3(KT, nh, B), kThreads, Smem::total, st>>>(tq, tk, tv, tdo, tdqp, p);
     DETR_CHECK_LAUNCH("attention_bwd");
     const int64_t n8 = (int64_t)B * L * (C / 8);
     attention_dq_reduce_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(

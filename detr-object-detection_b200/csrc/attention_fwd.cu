@@ -166,17 +166,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 tma_load_3d(smem + FwdSmem::k + s * kTileBytes, &tm_k, kv_full + s, h * kD, j * kBN, b);
                 tma_load_3d(smem + FwdSmem::v + s * kTileBytes, &tm_v, kv_full + s, h * kD, j * kBN, b);
             }
-        } else if (warp == 9 && lane == 0) {
+        } else if (warp == 9 && elect_one()) {
             // ================= MMA issuer =================
             constexpr uint32_t idesc_s = make_idesc_bf16(kBM, kBN, false, false);
             constexpr uint32_t idesc_o = make_idesc_bf16(kBM, kD, false, true);
-            const uint32_t sq = smem_u32(smem + FwdSmem::q), sp = smem_u32(smem + FwdSmem::p);
+            // descriptor words (tc.cuh): high word per layout, low word = (address >> 4) + constant
+            constexpr uint32_t hi64 = desc_hi(512, SWZ_64B);      // Q/K/V tiles: 64-byte rows, 8-row groups 512 B apart
+            constexpr uint32_t hi128 = desc_hi(1024, SWZ_128B);   // P tile: 128-byte rows, 8-row groups 1024 B apart
+            const uint32_t q_lo = smem_u32(smem + FwdSmem::q) >> 4, p_lo = smem_u32(smem + FwdSmem::p) >> 4;
             auto issue_s = [&](int j) {
-                const uint32_t sk = smem_u32(smem + FwdSmem::k + (j % kStages) * kTileBytes);
+                const uint32_t k_lo = smem_u32(smem + FwdSmem::k + (j % kStages) * kTileBytes) >> 4;
 #pragma unroll
-                for (int ks = 0; ks < kD / 16; ++ks)  // K-major, 64-byte rows, SWIZZLE_64B: 8-row groups 512 B apart
-                    umma_bf16(tmem_s, make_smem_desc(sq + ks * 32, 16, 512, SWZ_64B), make_smem_desc(sk + ks * 32, 16, 512, SWZ_64B),
-                              idesc_s, ks > 0);
+                for (int ks = 0; ks < kD / 16; ++ks)  // K-major, 64-byte rows, SWIZZLE_64B: 32 B per 16-channel step
+                    umma_bf16_lh(tmem_s, q_lo + desc_lo(ks * 32, 16), hi64, k_lo + desc_lo(ks * 32, 16), hi64, idesc_s, ks > 0);
                 umma_commit(s_full);
             };
             mbar_wait_sleep(q_full, 0);
@@ -193,14 +195,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 mbar_wait_sleep(p_full, j & 1);             // P_j is in shared memory
                 if (j > 0) mbar_wait_sleep(o_empty, (j - 1) & 1);  // O_{j-1} has been read out of TMEM
                 tc_fence_after();
-                const uint32_t sv = smem_u32(smem + FwdSmem::v + (j % kStages) * kTileBytes);
+                const uint32_t v_lo = smem_u32(smem + FwdSmem::v + (j % kStages) * kTileBytes) >> 4;
 #pragma unroll
                 for (int ks = 0; ks < kBN / 16; ++ks) {
                     // A = P: K-major SWIZZLE_128B, 64-key blocks of 16 KB, 32 B per 16-key step inside a block
-                    const uint64_t da = make_smem_desc(sp + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, SWZ_128B);
                     // B = V: MN-major (d contiguous, 64-byte rows), SWIZZLE_64B, 16 keys = 1024 B per step
-                    const uint64_t db = make_smem_desc(sv + ks * 1024, 512, 512, SWZ_64B);
-                    umma_bf16(tmem_o, da, db, idesc_o, ks > 0);
+                    umma_bf16_lh(tmem_o, p_lo + desc_lo((ks >> 2) * 16384 + (ks & 3) * 32, 16), hi128,
+                                 v_lo + desc_lo(ks * 1024, 512), hi64, idesc_o, ks > 0);
                 }
                 umma_commit(o_full);
                 umma_commit(kv_empty + (j % kStages));
@@ -340,6 +341,22 @@ int make_head_tile_map(CUtensorMap* out, const void* base, int C, int rows, int 
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled failed (%d)", who, (int)r); return 2; }
+    return 0;
+}
+
+// contiguous fp32 (slabs, rows, C) tensor; box = box_c channels (128 bytes) x box_rows rows, SWIZZLE_128B; used for TMA stores
+int make_f32_tile_map(CUtensorMap* out, const void* base, int C, int rows, int slabs, int box_c, int box_rows, const char* who) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("%s: cuTensorMapEncodeTiled entry point not available", who); return 2; }
+    if (((uintptr_t)base % 128) || box_c * 4 != 128 || (C % 4)) { set_error("%s: needs a 128-byte aligned base and 128-byte box rows", who); return 1; }
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)slabs};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)rows * C * 4};
+    cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled failed (%d)", who, (int)r); return 2; }
     return 0;
