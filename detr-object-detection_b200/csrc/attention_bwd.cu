@@ -13,7 +13,7 @@
 // 17 = tcgen05.mma issuer, 18 = dQ-partial store warp (TMA bulk tensor stores of tiles the math warps stage in shared
 // memory: per-row 32-byte global stores from 512 threads cost ~600 cycles per pair in the LSU), 19 idle (completes the
 // fifth warpgroup so that setmaxnreg can move its registers to the math).
-// TMEM (512 columns): S [0,128) | dP [128,256) | dK [256,288) | dV [288,320) | dQ_part x2 [320,384).
+// TMEM (512 columns): S [0,128) | dP [128,256) | dK [256,288) | dV [288,320) | dQ_part x3 [320,416).
 // S / dP are copied to registers and released at once, so the next pair's score MMAs run under this pair's math;
 // the dS / P~ shared-memory tiles and the dQ_part columns are double buffered, so the math never waits for the MMAs.
 //
@@ -89,32 +89,40 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kt = blockIdx.x, k0 = kt * kT, h = blockIdx.y, b = blockIdx.z;
+#ifdef DETR_BWD_TIMELINE
+    const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (p.dbg != nullptr && tid == 0 && cta_lin < 1024) {
+        uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[2560 + cta_lin * 4 + 0] = gt; p.dbg[2560 + cta_lin * 4 + 3] = smid;
+        if (cta_lin == 0) p.dbg[(19 * 16 + 0) * 8 + 0] = clock64();
+    }
+#endif
     const int T = (p.L + kT - 1) / kT;    // number of streamed query tiles
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
     uint64_t* fixed_full = bars + 0;
     uint64_t* ring_full = bars + 1;                    // [kStages]
     uint64_t* ring_empty = ring_full + kStages;        // [kStages]
-    uint64_t* sdp_full = ring_empty + kStages;
-    uint64_t* sdp_empty = sdp_full + 1;
-    uint64_t* ds_full = sdp_full + 2;                  // [2]
-    uint64_t* ds_empty = sdp_full + 4;                 // [2]
-    uint64_t* dq_full = sdp_full + 6;                  // [2]
-    uint64_t* dq_empty = sdp_full + 8;                 // [2]
-    uint64_t* dqs_full = sdp_full + 10;                // [2]
-    uint64_t* dqs_empty = sdp_full + 12;               // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 14);
+    uint64_t* sdp_full = ring_empty + kStages;         // [2] one per 64-key half: the two math groups run out of phase
+    uint64_t* sdp_empty = sdp_full + 2;                // [2]
+    uint64_t* ds_full = sdp_full + 4;                  // [2]
+    uint64_t* dq_full = sdp_full + 6;                  // [3] dQ_part TMEM columns are triple buffered: read out two pairs late
+    uint64_t* dq_empty = sdp_full + 9;                 // [3]
+    uint64_t* dqs_full = sdp_full + 12;                // [2]
+    uint64_t* dqs_empty = sdp_full + 14;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 16);
     uint8_t* kflag = smem + Smem::flags;
 
     if (tid == 0) {
         mbar_init(fixed_full, 1);
         for (int s = 0; s < kStages; ++s) { mbar_init(ring_full + s, 1); mbar_init(ring_empty + s, 1); }
-        mbar_init(sdp_full, 1); mbar_init(sdp_empty, kComputeThreads);
         for (int s = 0; s < 2; ++s) {
+            mbar_init(sdp_full + s, 1); mbar_init(sdp_empty + s, kComputeThreads / 2);
             mbar_init(ds_full + s, kComputeThreads);
-            mbar_init(dq_full + s, 1); mbar_init(dq_empty + s, kComputeThreads);
             mbar_init(dqs_full + s, kComputeThreads); mbar_init(dqs_empty + s, 1);
         }
+        for (int s = 0; s < 3; ++s) { mbar_init(dq_full + s, 1); mbar_init(dq_empty + s, kComputeThreads); }
         fence_barrier_init();
     }
     if (warp == 17) tmem_alloc(tmem_slot, kTmemCols);
@@ -124,6 +132,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+#ifdef DETR_BWD_TIMELINE
+    if (p.dbg != nullptr && tid == 0 && cta_lin < 1024) {
+        long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[2560 + cta_lin * 4 + 1] = gt;
+    }
+#endif
     const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dk = tmem_base + 256, tmem_dv = tmem_base + 288,
                    tmem_dq = tmem_base + 320;
 
@@ -152,35 +166,41 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             constexpr uint32_t hi64 = desc_hi(512, SWZ_64B);      // Q/K/V/dO tiles: 64-byte rows, 8-row groups 512 B apart
             constexpr uint32_t hi128 = desc_hi(1024, SWZ_128B);   // dS / P~ tiles: 128-byte rows, 8-row groups 1024 B apart
             const uint32_t k_lo = smem_u32(smem + Smem::fixed) >> 4, v_lo = k_lo + (kTileBytes >> 4);
-            auto issue_scores = [&](int t) {
+            constexpr uint32_t idesc_half = make_idesc_bf16(kT, kT / 2, false, false);
+            // scores of one 64-key half: S_h = Q K_h^T, dP_h = dO V_h^T (keys 64h.. of the K / V tiles: 64 rows x 64 B further)
+            auto issue_scores = [&](int t, int hf) {
                 const uint32_t q_lo = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes) >> 4, do_lo = q_lo + (kTileBytes >> 4);
+                const uint32_t kh_lo = k_lo + hf * (64 * 64 >> 4), vh_lo = v_lo + hf * (64 * 64 >> 4);
 #pragma unroll
                 for (int ks = 0; ks < kD / 16; ++ks)   // K-major operands: 32 B per 16-channel step, LBO 16
-                    umma_bf16_lh(tmem_s, q_lo + desc_lo(ks * 32, 16), hi64, k_lo + desc_lo(ks * 32, 16), hi64, idesc_sc, ks > 0);
+                    umma_bf16_lh(tmem_s + hf * 64, q_lo + desc_lo(ks * 32, 16), hi64, kh_lo + desc_lo(ks * 32, 16), hi64, idesc_half, ks > 0);
 #pragma unroll
                 for (int ks = 0; ks < kD / 16; ++ks)
-                    umma_bf16_lh(tmem_dp, do_lo + desc_lo(ks * 32, 16), hi64, v_lo + desc_lo(ks * 32, 16), hi64, idesc_sc, ks > 0);
-                umma_commit(sdp_full);
+                    umma_bf16_lh(tmem_dp + hf * 64, do_lo + desc_lo(ks * 32, 16), hi64, vh_lo + desc_lo(ks * 32, 16), hi64, idesc_half, ks > 0);
+                umma_commit(sdp_full + hf);
             };
             mbar_wait_sleep(fixed_full, 0);
             mbar_wait_sleep(ring_full + 0, 0);
             tc_fence_after();
-            issue_scores(0);
+            issue_scores(0, 0);
+            issue_scores(0, 1);
             for (int t = 0; t < T; ++t) {
                 const int buf = t & 1;
                 if (t + 1 < T) {
                     mbar_wait_sleep(ring_full + ((t + 1) % kStages), ((t + 1) / kStages) & 1);
-                    mbar_wait_sleep(sdp_empty, t & 1);          // the compute warps hold S_t / dP_t in registers
-                    tc_fence_after();
-                    issue_scores(t + 1);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        mbar_wait_sleep(sdp_empty + hf, t & 1);     // that group holds its half of S_t / dP_t in registers
+                        tc_fence_after();
+                        issue_scores(t + 1, hf);
+                    }
                 }
                 BWD_STAMP(0, t);
                 mbar_wait_sleep(ds_full + buf, (t >> 1) & 1);   // dS_t and P~_t are in shared memory
                 BWD_STAMP(1, t);
-                if (t >= 2) {
-                    mbar_wait_sleep(dq_empty + buf, ((t >> 1) - 1) & 1);    // dQ_part of pair t-2 has been read out of TMEM
-                    mbar_wait_sleep(dqs_empty + buf, ((t >> 1) - 1) & 1);   // ... and its staging tile has been stored: dq_full(t)
-                }                                                            // tells the math warps that BOTH are free again
+                if (t >= 3) mbar_wait_sleep(dq_empty + t % 3, ((t / 3) - 1) & 1);   // dQ_part of pair t-3 has been read out of TMEM
+                if (t >= 2) mbar_wait_sleep(dqs_empty + buf, ((t >> 1) - 1) & 1);   // staging tile of pair t-2 has been stored: dq_full(t)
+                                                                                    // tells the math warps that it is free again
                 tc_fence_after();
                 const uint32_t q_lo = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes) >> 4, do_lo = q_lo + (kTileBytes >> 4);
                 const uint32_t ds_lo = smem_u32(smem + Smem::ds + buf * (kT * kT * 2)) >> 4, pt_lo = smem_u32(smem + Smem::pt + buf * (kT * kT * 2)) >> 4;
@@ -196,11 +216,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
                 for (int ks = 0; ks < kT / 16; ++ks) {
                     // dQ_part = dS K: A K-major SWIZZLE_128B (64-key blocks of 16 KB, 32 B per 16-key step), B = K tile MN-major
-                    umma_bf16_lh(tmem_dq + buf * kD, ds_lo + desc_lo((ks >> 2) * 16384 + (ks & 3) * 32, 16), hi128,
+                    umma_bf16_lh(tmem_dq + (t % 3) * kD, ds_lo + desc_lo((ks >> 2) * 16384 + (ks & 3) * 32, 16), hi128,
                                  k_lo + desc_lo(ks * 1024, 512), hi64, idesc_dq, ks > 0);
                 }
                 umma_commit(ring_empty + (t % kStages));
-                umma_commit(dq_full + buf);                     // (also covers dK / dV of the last pair for the epilogue)
+                umma_commit(dq_full + t % 3);                   // (also covers dK / dV of the last pair for the epilogue)
                 BWD_STAMP(2, t);
             }
         }
@@ -246,25 +266,40 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         // 16-byte chunk j of row r at ((j ^ (r & 7)) << 4): conflict-free stores, the layout TMA expects for SWIZZLE_128B)
         uint8_t* dqs_row = smem + Smem::dqs + row * 128;
         const uint32_t dqs_c0 = (uint32_t)(((2 * kq) ^ (row & 7)) << 4), dqs_c1 = (uint32_t)(((2 * kq + 1) ^ (row & 7)) << 4);
-        auto dq_readout = [&](int t) {
-            uint32_t v[8];
-            mbar_wait(dq_full + (t & 1), (t >> 1) & 1);   // (also: staging tile t&1 has been stored, see the MMA warp)
+        // The readout of pair u is split around the math of pair u+2: the TMEM load rides with the S / dP loads (its
+        // barrier completed long before), the staging stores share the fence of the dS / P~ stores.
+        uint32_t dqv[8];
+        auto dq_load = [&](int u) {
+            mbar_wait(dq_full + u % 3, (u / 3) & 1);   // (also: staging tile u&1 has been stored, see the MMA warp)
             tc_fence_after();
-            tmem_ld8(tmem_dq + (t & 1) * kD + lane_addr + kq * 8, v);
+            tmem_ld8(tmem_dq + (u % 3) * kD + lane_addr + kq * 8, dqv);
+        };
+        auto dq_stage = [&](int u) {
+            uint8_t* dst = dqs_row + (u & 1) * (kT * kD * 4);
+            *reinterpret_cast<uint4*>(dst + dqs_c0) = make_uint4(dqv[0], dqv[1], dqv[2], dqv[3]);
+            *reinterpret_cast<uint4*>(dst + dqs_c1) = make_uint4(dqv[4], dqv[5], dqv[6], dqv[7]);
+        };
+        auto dq_readout = [&](int u) {   // whole readout (the last two pairs, after the loop)
+            dq_load(u);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(dq_empty + (t & 1));
-            uint8_t* dst = dqs_row + (t & 1) * (kT * kD * 4);
-            *reinterpret_cast<uint4*>(dst + dqs_c0) = make_uint4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<uint4*>(dst + dqs_c1) = make_uint4(v[4], v[5], v[6], v[7]);
+            mbar_arrive(dq_empty + u % 3);
+            dq_stage(u);
             fence_proxy_async_smem();
-            mbar_arrive(dqs_full + (t & 1));
+            mbar_arrive(dqs_full + (u & 1));
         };
 
         // per-row scalars of the NEXT tile are fetched one iteration ahead
         float lse_n = CUDART_INF_F, dl_n = 0.f;
         if (row < p.L) { lse_n = lse_bh[row]; dl_n = dl_bh[row]; }
 
+        // The two 64-key halves of a pair are independent down to the accumulation MMAs: start the second group of 8
+        // warps about half a period late so that one group's latency-bound steps (barrier waits, TMEM loads, fences)
+        // run under the other group's issue-bound math.
+#ifndef DETR_BWD_SKEW_NS
+#define DETR_BWD_SKEW_NS 400
+#endif
+        if ((kq >> 1) && T > 1) __nanosleep(DETR_BWD_SKEW_NS);
         uint32_t s[32], dp[32];
         for (int t = 0; t < T; ++t) {
             const int buf = t & 1;
@@ -282,57 +317,58 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S + key0 : nullptr;
 
             BWD_STAMP(0, t);
-            mbar_wait(sdp_full, t & 1);
+            mbar_wait(sdp_full + (kq >> 1), t & 1);
             BWD_STAMP(1, t);
             tc_fence_after();
             tmem_ld32(tmem_s + lane_addr + kq * 32, s);
             tmem_ld32(tmem_dp + lane_addr + kq * 32, dp);
+            if (t >= 2) dq_load(t - 2);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(sdp_empty);                              // the score columns may be overwritten by the next pair
-            // dS / P~ buffer `buf` is free: the MMAs of pair t-2 completed before dq_full(t-2), awaited in iteration t-1
+            mbar_arrive(sdp_empty + (kq >> 1));                  // this half's score columns may be overwritten by the next pair
+            if (t >= 2) mbar_arrive(dq_empty + (t - 2) % 3);
+            // dS / P~ buffer `buf` is free: the MMAs of pair t-2 completed before dq_full(t-2), awaited just above
             BWD_STAMP(3, t);
 
             uint8_t* ds_row = smem + Smem::ds + buf * (kT * kT * 2) + row_off;
             uint8_t* pt_row = smem + Smem::pt + buf * (kT * kT * 2) + row_off;
+            // Packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2) halves the floating-point issue slots.  Dropout never
+            // touches an fp32 value: a dropped key's dS is -P*D', so both candidates x*(dP - D') and -x*D' are rounded
+            // to bf16 pairs and ONE bit-select per pair picks by the keep mask (the same mask clears P~).
             auto quarter_tile = [&](auto masked_c, auto drop_c) {
                 constexpr bool MASKED = decltype(masked_c)::value, DROP = decltype(drop_c)::value;
                 uint32_t rng = DROP ? dropout_group_state(row_key, (uint32_t)(key0 >> 5)) : 0u;
+                const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nl2 = make_float2(nl, nl), ndl2 = make_float2(-dlt, -dlt);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {               // 8 keys = one 16-byte chunk of the dS / P~ rows
-                    float pr[8], dsv[8];
                     uint32_t t0 = 0, t1 = 0;
                     if (DROP) { t0 = dropout_quad(rng, thr4); t1 = dropout_quad(rng, thr4); }
-                    uint32_t m32[8];
-                    if (DROP) {
-                        m32[0] = dropout_mask_f32<0>(t0); m32[1] = dropout_mask_f32<1>(t0); m32[2] = dropout_mask_f32<2>(t0); m32[3] = dropout_mask_f32<3>(t0);
-                        m32[4] = dropout_mask_f32<0>(t1); m32[5] = dropout_mask_f32<1>(t1); m32[6] = dropout_mask_f32<2>(t1); m32[7] = dropout_mask_f32<3>(t1);
-                    }
+                    uint32_t pk[4], dk[4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int i = g * 8 + e;
-                        float x = ex2(fmaf(__uint_as_float(s[i]), p.scale_log2, nl));
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = g * 8 + 2 * j;
+                        const float2 e = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nl2);
+                        float2 x = make_float2(ex2(e.x), ex2(e.y));
                         if (MASKED) {
-                            const bool m = kf[i] != 0 || (arow != nullptr && (key0 + i) < p.S && arow[i] != 0);
-                            x = m ? 0.f : x;
+                            const bool m0 = kf[i] != 0 || (arow != nullptr && (key0 + i) < p.S && arow[i] != 0);
+                            const bool m1 = kf[i + 1] != 0 || (arow != nullptr && (key0 + i + 1) < p.S && arow[i + 1] != 0);
+                            x.x = m0 ? 0.f : x.x; x.y = m1 ? 0.f : x.y;
                         }
-                        pr[e] = x;
-                        const float d = DROP ? __uint_as_float(dp[i] & m32[e]) : __uint_as_float(dp[i]);
                         // dS without the 1/sqrt(d) factor: it is applied once to dK in the epilogue and to dQ in the reduction
-                        dsv[e] = x * (d - dlt);
+                        const float2 a = __fmul2_rn(x, __fadd2_rn(make_float2(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1])), ndl2));
+                        pk[j] = pack_bf16x2(x.x, x.y);
+                        dk[j] = pack_bf16x2(a.x, a.y);
+                        if (DROP) {
+                            const float2 bb = __fmul2_rn(x, ndl2);
+                            const uint32_t bk = pack_bf16x2(bb.x, bb.y);
+                            const uint32_t m = (j & 1) ? dropout_mask_bf16x2<1>(j < 2 ? t0 : t1) : dropout_mask_bf16x2<0>(j < 2 ? t0 : t1);
+                            dk[j] = (dk[j] & m) | (bk & ~m);
+                            pk[j] &= m;
+                        }
                     }
                     const uint32_t off = ((chunk0 + g) ^ (uint32_t)(row & 7)) << 4;
-                    uint4 w;
-                    w.x = pack_bf16x2(dsv[0], dsv[1]); w.y = pack_bf16x2(dsv[2], dsv[3]);
-                    w.z = pack_bf16x2(dsv[4], dsv[5]); w.w = pack_bf16x2(dsv[6], dsv[7]);
-                    *reinterpret_cast<uint4*>(ds_row + off) = w;
-                    w.x = pack_bf16x2(pr[0], pr[1]); w.y = pack_bf16x2(pr[2], pr[3]);
-                    w.z = pack_bf16x2(pr[4], pr[5]); w.w = pack_bf16x2(pr[6], pr[7]);
-                    if (DROP) {
-                        w.x &= dropout_mask_bf16x2<0>(t0); w.y &= dropout_mask_bf16x2<1>(t0);
-                        w.z &= dropout_mask_bf16x2<0>(t1); w.w &= dropout_mask_bf16x2<1>(t1);
-                    }
-                    *reinterpret_cast<uint4*>(pt_row + off) = w;
+                    *reinterpret_cast<uint4*>(ds_row + off) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+                    *reinterpret_cast<uint4*>(pt_row + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             };
             using TT = std::true_type; using FF = std::false_type;
@@ -341,13 +377,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             } else {
                 if (drop) quarter_tile(FF{}, TT{}); else quarter_tile(FF{}, FF{});
             }
+            if (t >= 2) dq_stage(t - 2);
             fence_proxy_async_smem();
             mbar_arrive(ds_full + buf);
+            if (t >= 2) mbar_arrive(dqs_full + (t & 1));
             BWD_STAMP(4, t);
-            if (t > 0) dq_readout(t - 1);
             BWD_STAMP(5, t);
         }
+        BWD_STAMP(6, 0);
+        if (T >= 2) dq_readout(T - 2);
         dq_readout(T - 1);
+        BWD_STAMP(7, 0);
         // ---- epilogue: dK (key quarters 0,1: 16 columns each) and dV (quarters 2,3) -> bf16 global ----
         // (dq_full of the last pair was committed after every MMA of the stream: the accumulators are complete)
         {
@@ -374,9 +414,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             }
         }
         tc_fence_before();
+        BWD_STAMP(6, 1);
     }
+    BWD_STAMP(7, 1);
     __syncthreads();
     if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
+#ifdef DETR_BWD_TIMELINE
+    if (p.dbg != nullptr && tid == 0 && cta_lin < 1024) {
+        long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.dbg[2560 + cta_lin * 4 + 2] = gt;
+        if (cta_lin == 0) p.dbg[(19 * 16 + 0) * 8 + 1] = clock64();
+    }
+#endif
 }
 
 // D[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (one thread per (b,q,h), 64-byte vector loads)

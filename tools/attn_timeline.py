@@ -16,14 +16,15 @@ v = torch.randn(B, S, C, device=dev).bfloat16(); do = torch.randn(B, L, C, devic
 o, lse = attention_forward(q, k, v, dropout_p=0.1, seed=1)
 for _ in range(3):
     attention_backward(do, q, k, v, o, lse, dropout_p=0.1, seed=1)
-dbg = torch.zeros(20 * 16 * 8, dtype=torch.int64, device=dev)
+dbg = torch.zeros(20 * 16 * 8 + 1024 * 4, dtype=torch.int64, device=dev)
 lib = _lib.load()
 lib.detr_attention_bwd_set_debug.argtypes = [ctypes.c_void_p]; lib.detr_attention_bwd_set_debug.restype = None
 lib.detr_attention_bwd_set_debug(dbg.data_ptr())
 attention_backward(do, q, k, v, o, lse, dropout_p=0.1, seed=1)
 torch.cuda.synchronize()
 lib.detr_attention_bwd_set_debug(None)
-d = dbg.view(20, 16, 8).cpu()
+cta = dbg[2560:].view(1024, 4).cpu()
+d = dbg[:2560].view(20, 16, 8).cpu()
 t0 = int(d[d > 0].min())
 T = (L + 127) // 128
 print("cycles relative to the first stamp; compute warps: wait_sdp> <sdp_full | ld done> <ds_empty | math done | dq_readout done")
@@ -31,7 +32,30 @@ for w in (0, 5, 10, 15):
     for t in range(T):
         r = [int(x) - t0 if x > 0 else -1 for x in d[w, t, :6]]
         print(f"warp {w:2d} tile {t}: {r}   math={r[4]-r[3]} wait_sdp={r[1]-r[0]} wait_ds_empty={0} dq_readout={r[5]-r[4]}")
+print("all math warps, tile 3: [start, sdp_full, ld done, math done, dq done]  math duration per tile")
+for w in range(16):
+    r = [int(x) - t0 for x in (d[w, 3, 0], d[w, 3, 1], d[w, 3, 3], d[w, 3, 4], d[w, 3, 5])]
+    print(f"warp {w:2d} (smsp {w % 4}, kq {w // 4}): {r}  math/tile = {[int(d[w, t, 4] - d[w, t, 3]) for t in range(T)]}")
 print("MMA warp: before ds_full wait | after | issued")
 for t in range(T):
     r = [int(x) - t0 if x > 0 else -1 for x in d[17, t, :3]]
     print(f"tile {t}: {r}  waited={r[1]-r[0]}")
+
+rel = lambda x: int(x) - t0
+print(f"CTA 0: kernel entry {rel(d[19,0,0])}, exit {rel(d[19,0,1])}; warp 0: loop end {rel(d[0,0,6])}, last dQ readouts done {rel(d[0,0,7])}, dK/dV stored {rel(d[0,1,6])}")
+print("reached the final __syncthreads:", {w: rel(d[w,1,7]) for w in range(20)})
+n = (cta[:, 0] > 0).sum().item()
+if n:
+    c = cta[:n]
+    g0 = int(c[:, 0].min())
+    dur = (c[:, 2] - c[:, 0]).float()
+    setup = (c[:, 1] - c[:, 0]).float()
+    print(f"CTAs {n}: kernel span {(int(c[:, 2].max()) - g0) / 1e3:.1f} us; CTA duration ns mean {dur.mean():.0f} min {dur.min():.0f} max {dur.max():.0f}; setup (to TMEM alloc) mean {setup.mean():.0f} ns")
+    import collections
+    per = collections.defaultdict(list)
+    for i in range(n):
+        per[int(c[i, 3])].append((int(c[i, 0]) - g0, int(c[i, 2]) - g0))
+    for sm in sorted(per)[:4]:
+        print("SM", sm, sorted(per[sm]))
+    busy = sum(e - s_ for v in per.values() for s_, e in v)
+    print(f"SMs used {len(per)}, mean CTAs/SM {n / len(per):.2f}, sum of CTA time / (SMs x span) = {busy / (len(per) * (int(c[:, 2].max()) - g0)):.2f}")
