@@ -1,8 +1,9 @@
 // Row-wise helper kernels of the transformer blocks (HBM-bound, coalesced 16-byte accesses):
 //   colsum_bf16   bias gradient of nn.Linear: db[n] = sum_m g[m][n]  (detr/model.py:312-314,354,405-411 backward).
 //                 ATen's generic reduce_kernel needs ~27 us for a 6800 x 2048 bf16 matrix; this is one pass at
-//                 HBM speed: grid = column tiles x row chunks, fp32 partials; the last CTA of each column tile folds them
-//                 in a fixed order (deterministic, single launch).
+//                 HBM speed: grid = column tiles x row chunks, fp32 partials; a second small launch folds the partials in
+//                 a fixed order (deterministic).  (A "last CTA folds" tail in the same launch serialised up to 296
+//                 dependent L2 round trips in one CTA: 25-40 us per call, measured.)
 #include "common.cuh"
 #include <cuda_bf16.h>
 
@@ -11,11 +12,38 @@ namespace detr {
 constexpr int kColsPerCta = 256;   // 32 lanes x 8 bf16 (16 bytes)
 constexpr int kCsThreads = 256;    // 8 warps: each warp takes every 8th row of the chunk
 
+// out[c] = sum_k partial[k][c] (k < n_partials, row stride N), columns c < split go to out0, the rest to out1.
+// CTA = 32 columns; warp w adds partials w, w+8, ... (independent coalesced loads), then the 8 warps are combined.
+constexpr int kFoldThreads = 256;
+__global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(const float* __restrict__ partial, int n_partials, int N,
+                                                                     float* __restrict__ out0, float* __restrict__ out1, int split) {
+    __shared__ float red[kFoldThreads / 32][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (c < N) {
+        int k = warp;
+        for (; k + 24 < n_partials; k += 32) {
+            s0 += __ldcg(&partial[(int64_t)k * N + c]);
+            s1 += __ldcg(&partial[(int64_t)(k + 8) * N + c]);
+            s2 += __ldcg(&partial[(int64_t)(k + 16) * N + c]);
+            s3 += __ldcg(&partial[(int64_t)(k + 24) * N + c]);
+        }
+        for (; k < n_partials; k += 8) s0 += __ldcg(&partial[(int64_t)k * N + c]);
+    }
+    red[warp][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (warp == 0 && c < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kFoldThreads / 32; ++w) s += red[w][lane];
+        if (c < split) out0[c] = s; else out1[c - split] = s;
+    }
+}
+
 __global__ void __launch_bounds__(kCsThreads) colsum_kernel(const __nv_bfloat16* __restrict__ g, int64_t ld, int M, int N, int rows_per_cta,
-                                                              float* __restrict__ partial, float* __restrict__ out,
-                                                              unsigned* __restrict__ counters /* one per column tile, zero on entry and on exit */) {
+                                                              float* __restrict__ partial) {
     __shared__ float red[kCsThreads / 32][kColsPerCta];
-    __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * kColsPerCta + lane * 8;
     const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
@@ -41,19 +69,6 @@ __global__ void __launch_bounds__(kCsThreads) colsum_kernel(const __nv_bfloat16*
         for (int w = 0; w < kCsThreads / 32; ++w) s += red[w][c];
         partial[(int64_t)blockIdx.y * N + col] = s;
     }
-    // the last CTA of this column tile folds the row chunks in a fixed order (deterministic) -- no second launch
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(&counters[blockIdx.x], 1u) == gridDim.y - 1;
-    __syncthreads();
-    if (is_last) {
-        if (col < N) {
-            float s = 0.f;
-            for (int k = 0; k < (int)gridDim.y; ++k) s += __ldcg(&partial[(int64_t)k * N + col]);
-            out[col] = s;
-        }
-        if (threadIdx.x == 0) counters[blockIdx.x] = 0;
-    }
 }
 
 }  // namespace detr
@@ -62,22 +77,23 @@ using namespace detr;
 
 extern "C" int detr_colsum_chunks(int M, int N) {
     const int col_tiles = (N + kColsPerCta - 1) / kColsPerCta;
-    int chunks = (2 * 148 + col_tiles - 1) / col_tiles;          // ~2 CTAs per SM in flight
-    const int max_chunks = (M + 31) / 32;                        // at least 32 rows per CTA
+    int chunks = (4 * 148 + col_tiles - 1) / col_tiles;          // ~4 CTAs per SM in flight
+    const int max_chunks = (M + 15) / 16;                        // at least 16 rows (2 per warp) per CTA
     if (chunks > max_chunks) chunks = max_chunks;
-    if (chunks > 64) chunks = 64;                                // bounds the serial fold of the last CTA
     return chunks < 1 ? 1 : chunks;
 }
 
 extern "C" int detr_colsum_bf16(const void* g, int64_t ld, int M, int N, float* partial, float* out, uint32_t* counters, void* stream) {
     DETR_CHECK_ARG(M >= 1 && N >= 8 && (N % 8) == 0 && (ld % 8) == 0 && ((uintptr_t)g % 16) == 0,
                    "colsum: need N %% 8 == 0, ld %% 8 == 0 and a 16-byte aligned matrix (M=%d N=%d ld=%lld)", M, N, (long long)ld);
+    (void)counters;   // kept in the signature (ABI); the fold is a second launch now
     const int chunks = detr_colsum_chunks(M, N);
     const int rows_per_cta = (M + chunks - 1) / chunks;
     dim3 grid((N + kColsPerCta - 1) / kColsPerCta, chunks);
-    DETR_CHECK_ARG(counters != nullptr && N <= 64 * kColsPerCta, "colsum: counters required (64 zeroed uint32), N <= %d", 64 * kColsPerCta);
-    colsum_kernel<<<grid, kCsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(g), ld, M, N, rows_per_cta, partial, out, counters);
+    colsum_kernel<<<grid, kCsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(g), ld, M, N, rows_per_cta, partial);
     DETR_CHECK_LAUNCH("colsum");
+    fold_partials_kernel<<<(N + 31) / 32, kFoldThreads, 0, (cudaStream_t)stream>>>(partial, chunks, N, out, out, N);
+    DETR_CHECK_LAUNCH("colsum_fold");
     return 0;
 }
 
@@ -87,7 +103,7 @@ extern "C" int detr_colsum_bf16(const void* g, int64_t ld, int M, int N, float* 
 //   y2 = y + addend                                       (query/key input: + positional or query embedding)
 // one pass over x, both outputs written in the GEMM's input dtype (no fp32 round trip, no separate add / cast
 // kernels).  One warp per row, the row lives in registers, two-pass variance.  Backward: dx and per-CTA partial
-// dgamma / dbeta folded by the last CTA (single launch, deterministic).
+// dgamma / dbeta, folded by fold_partials_kernel (second launch, deterministic).
 // =========================================================================================================
 namespace detr {
 
@@ -187,7 +203,6 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const LnParams p) {
 template <typename TX, typename TG, int KT>
 __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnParams p) {
     extern __shared__ float sm[];   // [4 warps][2][C]
-    __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = KT ? KT : p.C / 32, C = p.C;
     constexpr int KA = KT ? KT : kLnMaxPerLane;
@@ -219,7 +234,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnParams p) {
         _Pragma("unroll") for (int i = 0; i < K; ++i) d[i] = rs * (d[i] - c2 - x[i] * c1);
         store_row<TX>(reinterpret_cast<TX*>(p.dx) + (int64_t)r * C, lane, K, d);
     }
-    // ---- dgamma / dbeta: warps -> CTA partial -> last CTA folds all partials ----
+    // ---- dgamma / dbeta: warps -> CTA partial; fold_partials_kernel adds the CTA partials ----
     _Pragma("unroll") for (int i = 0; i < K; ++i) { sm[(warp * 2 + 0) * C + lane * K + i] = dg[i]; sm[(warp * 2 + 1) * C + lane * K + i] = db[i]; }
     __syncthreads();
     for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) {
@@ -227,18 +242,6 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnParams p) {
         float s = 0.f;
         for (int w = 0; w < kLnThreads / 32; ++w) s += sm[(w * 2 + which) * C + col];
         p.partial[(int64_t)blockIdx.x * 2 * C + c] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(&p.counters[0], 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (is_last) {
-        for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) {
-            float s = 0.f;
-            for (int k = 0; k < (int)gridDim.x; ++k) s += __ldcg(&p.partial[(int64_t)k * 2 * C + c]);
-            if (c < C) p.dgamma[c] = s; else p.dbeta[c - C] = s;
-        }
-        if (threadIdx.x == 0) p.counters[0] = 0;
     }
 }
 
@@ -301,5 +304,8 @@ extern "C" int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, 
     else LN_BWD(__nv_bfloat16, __nv_bfloat16);
 #undef LN_BWD
     DETR_CHECK_LAUNCH("layernorm_bwd");
+    (void)counters;
+    fold_partials_kernel<<<(2 * C + 31) / 32, kFoldThreads, 0, st>>>(partial, grid, 2 * C, dgamma, dbeta, C);
+    DETR_CHECK_LAUNCH("layernorm_bwd_fold");
     return 0;
 }

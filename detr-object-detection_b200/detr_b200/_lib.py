@@ -69,7 +69,7 @@ def load() -> ctypes.CDLL:
 # kernels launched per C-ABI call (bench.py's gpu_launches is counted from this table)
 KERNELS_PER_CALL = {"detr_cost_matrix_f32": 1, "detr_hungarian_match_f32": 1, "detr_lsap_f32": 1, "detr_lsap_f64": 1,
                     "detr_criterion_fwd_f32": 2, "detr_criterion_bwd_f32": 1, "detr_attention_fwd_bf16": 1,
-                    "detr_attention_bwd_bf16": 3, "detr_colsum_bf16": 1, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 1}
+                    "detr_attention_bwd_bf16": 3, "detr_colsum_bf16": 2, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2}
 launch_count = 0          # kernels of libdetr_b200.so launched by this process
 _profile = None           # when a list: (name, tag, start_event, end_event) per call
 
