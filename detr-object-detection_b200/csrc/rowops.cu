@@ -309,3 +309,216 @@ extern "C" int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, 
     DETR_CHECK_LAUNCH("layernorm_bwd_fold");
     return 0;
 }
+
+// =========================================================================================================
+// Block epilogues of the pre-LN layers (detr/model.py:223-224,176-182 and the FFN 405-411), one pass each:
+//   MODE 0   out = x + dropout(y)                      residual add after the attention output / second FFN projection
+//   MODE 1   out = dropout(gelu_tanh(y))               between the two FFN projections
+// and their backward, which also produces the bias gradient of the Linear that made y (column sums of dy, as fp32
+// partials per row chunk folded by fold_partials_kernel), so ATen's dropout / masked_scale / gelu / gelu_backward /
+// add kernels and one colsum pass disappear:
+//   MODE 0   dy = dropout_mask(g) / (1-p)              (the residual branch's gradient is g itself)
+//   MODE 1   dy = dropout_mask(g) / (1-p) * gelu'(y)
+// The dropout mask is the 7-bit counter-based generator of the attention kernels (tc.cuh), indexed by the 8-element
+// chunk (row * N/8 + column/8): nothing is stored for backward, p is quantised to k/128.
+// =========================================================================================================
+#include "tc.cuh"
+
+namespace detr {
+
+struct EwParams {
+    const void* x;                 // MODE 0 forward: residual (TX), contiguous (M, N)
+    const __nv_bfloat16* y;        // forward: GEMM output; backward: the same tensor (MODE 1 needs it for gelu')
+    void* out;                     // forward: TX (MODE 0) / bf16 (MODE 1); backward: dy bf16
+    const void* g;                 // backward: incoming gradient, TG
+    float* partial;                // backward: [row chunks][N] column sums of dy
+    int M, N, rows_per_cta;
+    uint32_t thr4; float scale;    // dropout: thresh * 0x01010101 (0 = off), 1 / keep
+    uint64_t seed; const uint64_t* seed_ptr;
+};
+
+__device__ __forceinline__ float gelu_tanh_fwd(float a, float& t_out) {
+    const float u = 0.7978845608028654f * (a + 0.044715f * a * a * a);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    t_out = t;
+    return 0.5f * a * (1.f + t);
+}
+__device__ __forceinline__ float gelu_tanh_grad(float a) {
+    float t;
+    gelu_tanh_fwd(a, t);
+    const float du = 0.7978845608028654f * (1.f + 3.f * 0.044715f * a * a);
+    return 0.5f * (1.f + t) + 0.5f * a * (1.f - t * t) * du;
+}
+
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float* v);
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float* v);
+template <> __device__ __forceinline__ void st8<float>(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// keep[e] for the 8 elements of chunk `idx8`
+__device__ __forceinline__ void ew_keep8(uint32_t key, uint32_t idx8, uint32_t thr4, bool* keep) {
+    uint32_t st = tc::dropout_group_state(key, idx8);
+    const uint32_t t0 = tc::dropout_quad(st, thr4), t1 = tc::dropout_quad(st, thr4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { keep[e] = (t0 >> (8 * e + 7)) & 1u; keep[4 + e] = (t1 >> (8 * e + 7)) & 1u; }
+}
+__device__ __forceinline__ uint32_t ew_key(const EwParams& p) {
+    const uint64_t s = p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull);
+    return tc::mix32((uint32_t)s ^ tc::mix32((uint32_t)(s >> 32) + 0x9E3779B9u));
+}
+
+constexpr int kEwThreads = 256;
+
+template <int MODE, typename TX>
+__global__ void __launch_bounds__(kEwThreads) epilogue_fwd_kernel(const EwParams p) {
+    const int64_t n8 = (int64_t)p.M * (p.N >> 3);
+    const bool drop = p.thr4 != 0;
+    const uint32_t key = drop ? ew_key(p) : 0u;
+    for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < n8; i += (int64_t)gridDim.x * kEwThreads) {
+        float y[8], o[8];
+        ld8<__nv_bfloat16>(p.y + i * 8, y);
+        bool keep[8];
+        if (drop) ew_keep8(key, (uint32_t)i, p.thr4, keep);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float v = y[e];
+            if (MODE == 1) { float t; v = gelu_tanh_fwd(v, t); }
+            if (drop) v = keep[e] ? v * p.scale : 0.f;
+            o[e] = v;
+        }
+        if (MODE == 0) {
+            float x[8];
+            ld8<TX>(reinterpret_cast<const TX*>(p.x) + i * 8, x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += x[e];
+            st8<TX>(reinterpret_cast<TX*>(p.out) + i * 8, o);
+        } else {
+            st8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + i * 8, o);
+        }
+    }
+}
+
+// grid = (column tiles of 256, row chunks); warp w of the CTA takes rows r0 + w, r0 + w + 8, ...; lane = 8 columns
+template <int MODE, typename TG>
+__global__ void __launch_bounds__(kCsThreads) epilogue_bwd_kernel(const EwParams p) {
+    __shared__ float red[kCsThreads / 32][kColsPerCta];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * kColsPerCta + lane * 8;
+    const int r0 = blockIdx.y * p.rows_per_cta, r1 = min(p.M, r0 + p.rows_per_cta);
+    const bool drop = p.thr4 != 0;
+    const uint32_t key = drop ? ew_key(p) : 0u;
+    const int n8 = p.N >> 3;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c0 < p.N) {
+        for (int r = r0 + warp; r < r1; r += kCsThreads / 32) {
+            const int64_t off = (int64_t)r * p.N + c0;
+            float g[8], d[8];
+            ld8<TG>(reinterpret_cast<const TG*>(p.g) + off, g);
+            bool keep[8];
+            if (drop) ew_keep8(key, (uint32_t)((int64_t)r * n8 + (c0 >> 3)), p.thr4, keep);
+            float y[8];
+            if (MODE == 1) ld8<__nv_bfloat16>(p.y + off, y);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float v = g[e];
+                if (drop) v = keep[e] ? v * p.scale : 0.f;
+                if (MODE == 1) v *= gelu_tanh_grad(y[e]);
+                d[e] = v;
+            }
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                h[e] = __floats2bfloat162_rn(d[2 * e], d[2 * e + 1]);
+                const float2 f = __bfloat1622float2(h[e]);      // the bias gradient sums what the GEMMs will see
+                acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = u;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = acc[e];
+    __syncthreads();
+    const int c = threadIdx.x, col = blockIdx.x * kColsPerCta + c;
+    if (col < p.N) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kCsThreads / 32; ++w) s += red[w][c];
+        p.partial[(int64_t)blockIdx.y * p.N + col] = s;
+    }
+}
+
+static int ew_fill(EwParams& p, int M, int N, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, const char* who) {
+    if (!(M >= 1 && N >= 8 && N % 8 == 0)) { set_error("%s: need M >= 1 and N %% 8 == 0 (M=%d N=%d)", who, M, N); return 1; }
+    if (!((int64_t)M * (N / 8) < (1ll << 32))) { set_error("%s: tensor too large for the 32-bit chunk counter", who); return 1; }
+    if (!(dropout_p >= 0.f && dropout_p < 1.f)) { set_error("%s: dropout_p must be in [0,1)", who); return 1; }
+    const uint32_t th = (uint32_t)lrintf(dropout_p * 128.f);
+    p.M = M; p.N = N; p.thr4 = th * 0x01010101u; p.scale = 128.f / (128.f - (float)th); p.seed = seed; p.seed_ptr = seed_ptr;
+    return 0;
+}
+
+}  // namespace detr
+
+/* mode 0: out(TX) = x(TX) + dropout(y);  mode 1: out(bf16) = dropout(gelu_tanh(y)) (x unused).  x_dtype: 0 f32, 1 bf16. */
+extern "C" int detr_epilogue_fwd(int mode, const void* x, int x_dtype, const void* y, void* out, int M, int N, float dropout_p,
+                                 uint64_t seed, const uint64_t* seed_ptr, void* stream) {
+    EwParams p{};
+    if (int rc = ew_fill(p, M, N, dropout_p, seed, seed_ptr, "epilogue_fwd")) return rc;
+    DETR_CHECK_ARG(mode == 0 || mode == 1, "epilogue_fwd: mode must be 0 or 1");
+    DETR_CHECK_ARG(((uintptr_t)y % 16) == 0 && ((uintptr_t)out % 16) == 0 && (mode == 1 || ((uintptr_t)x % 16) == 0), "epilogue_fwd: 16-byte alignment");
+    p.x = x; p.y = reinterpret_cast<const __nv_bfloat16*>(y); p.out = out;
+    const int64_t n8 = (int64_t)M * (N / 8);
+    int grid = (int)((n8 + kEwThreads - 1) / kEwThreads);
+    if (grid > 148 * 16) grid = 148 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 1) epilogue_fwd_kernel<1, float><<<grid, kEwThreads, 0, st>>>(p);
+    else if (x_dtype == 0) epilogue_fwd_kernel<0, float><<<grid, kEwThreads, 0, st>>>(p);
+    else epilogue_fwd_kernel<0, __nv_bfloat16><<<grid, kEwThreads, 0, st>>>(p);
+    DETR_CHECK_LAUNCH("epilogue_fwd");
+    return 0;
+}
+
+extern "C" int detr_epilogue_chunks(int M, int N) { return detr_colsum_chunks(M, N); }
+
+/* dy(bf16) = dropout_mask(g)/(1-p) [* gelu'(y) in mode 1]; db[n] = sum_m dy[m][n].  g_dtype: 0 f32, 1 bf16.
+ * partial float[detr_epilogue_chunks(M,N) * N] scratch. */
+extern "C" int detr_epilogue_bwd(int mode, const void* g, int g_dtype, const void* y, void* dy, float* partial, float* db,
+                                 int M, int N, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream) {
+    EwParams p{};
+    if (int rc = ew_fill(p, M, N, dropout_p, seed, seed_ptr, "epilogue_bwd")) return rc;
+    DETR_CHECK_ARG(mode == 0 || mode == 1, "epilogue_bwd: mode must be 0 or 1");
+    DETR_CHECK_ARG(((uintptr_t)g % 16) == 0 && ((uintptr_t)dy % 16) == 0 && (mode == 0 || ((uintptr_t)y % 16) == 0), "epilogue_bwd: 16-byte alignment");
+    p.g = g; p.y = reinterpret_cast<const __nv_bfloat16*>(y); p.out = dy; p.partial = partial;
+    const int chunks = detr_colsum_chunks(M, N);
+    p.rows_per_cta = (M + chunks - 1) / chunks;
+    dim3 grid((N + kColsPerCta - 1) / kColsPerCta, chunks);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0 && g_dtype == 0) epilogue_bwd_kernel<0, float><<<grid, kCsThreads, 0, st>>>(p);
+    else if (mode == 0) epilogue_bwd_kernel<0, __nv_bfloat16><<<grid, kCsThreads, 0, st>>>(p);
+    else if (g_dtype == 0) epilogue_bwd_kernel<1, float><<<grid, kCsThreads, 0, st>>>(p);
+    else epilogue_bwd_kernel<1, __nv_bfloat16><<<grid, kCsThreads, 0, st>>>(p);
+    DETR_CHECK_LAUNCH("epilogue_bwd");
+    fold_partials_kernel<<<(N + 31) / 32, kFoldThreads, 0, st>>>(partial, chunks, N, db, db, N);
+    DETR_CHECK_LAUNCH("epilogue_bwd_fold");
+    return 0;
+}

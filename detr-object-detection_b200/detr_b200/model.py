@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .attention import HEAD_DIM, flash_attention
-from .rowops import ShadowedLinears, layer_norm_add, linear
+from .rowops import ShadowedLinears, fused_epilogues_enabled, layer_norm_add, linear, linear_dropout_add, linear_gelu_dropout
 
 
 @dataclass
@@ -95,7 +95,9 @@ class ScaledDotProductAttention(nn.Module):
 
     def forward(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
                 key_padding_mask: Optional[torch.BoolTensor] = None,
-                attention_mask: Optional[torch.BoolTensor] = None) -> torch.Tensor:
+                attention_mask: Optional[torch.BoolTensor] = None, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The reference's forward (detr/model.py:254-356).  `residual` is an extension used by this package's layers:
+        when given, the result is residual + dropout(output_proj(attention)), the tail running as one fused kernel."""
         C = self.hidden_size
         if key is query:
             # self-attention: one GEMM for both projections; q/k are strided views the TMA descriptors take as they are
@@ -106,10 +108,13 @@ class ScaledDotProductAttention(nn.Module):
         v = self._lin(value, "value")
         p_drop = self.dropout_attn.p if self.training else 0.0
         y = flash_attention(q, k, v, key_padding_mask, attention_mask, p_drop)
+        if residual is not None and fused_epilogues_enabled(y):
+            w16, b16 = self._shadows.get((self._skey, "output")) if self._shadows is not None else (None, None)
+            return linear_dropout_add(y, residual, self.output_proj, self.dropout.p if self.training else 0.0, w16, b16)
         if not torch.is_autocast_enabled():
             y = y.to(query.dtype)
-        y = self._lin(y, "output")
-        return self.dropout(y)
+        y = self.dropout(self._lin(y, "output"))
+        return y if residual is None else residual + y
 
 
 class FFN(nn.Module):
@@ -135,12 +140,18 @@ class FFN(nn.Module):
         sh.register((prefix, 0), (self.layers[0].weight,), (self.layers[0].bias,))
         sh.register((prefix, 3), (self.layers[3].weight,), (self.layers[3].bias,))
 
-    def forward(self, x):
+    def forward(self, x, residual: Optional[torch.Tensor] = None):
+        """The reference's forward (detr/model.py:413-424); with `residual` (this package's layers) the result is
+        residual + FFN(x), GELU+dropout and dropout+add each fused with the bias gradient into one kernel per pass."""
         fc1, act, drop1, fc2, drop2 = self.layers
         use = self._shadows is not None and torch.is_autocast_enabled()
         s1 = self._shadows.get((self._skey, 0)) if use else (None, None)
         s2 = self._shadows.get((self._skey, 3)) if use else (None, None)
-        return drop2(linear(drop1(act(linear(x, fc1.weight, fc1.bias, *s1))), fc2.weight, fc2.bias, *s2))
+        if residual is not None and fused_epilogues_enabled(x):
+            h = linear_gelu_dropout(x, fc1, drop1.p if self.training else 0.0, *s1)
+            return linear_dropout_add(h, residual, fc2, drop2.p if self.training else 0.0, *s2)
+        y = drop2(linear(drop1(act(linear(x, fc1.weight, fc1.bias, *s1))), fc2.weight, fc2.bias, *s2))
+        return y if residual is None else residual + y
 
 
 class EncoderLayer(nn.Module):
@@ -155,8 +166,8 @@ class EncoderLayer(nn.Module):
 
     def forward(self, x: torch.Tensor, position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
         x_attn, query = layer_norm_add(x, self.norm1, position_embedding)      # LN and "+ pos" in one kernel
-        x = x + self.self_attention(query, query, value=x_attn, key_padding_mask=key_padding_mask)
-        x = x + self.ffn(layer_norm_add(x, self.norm2)[0])
+        x = self.self_attention(query, query, value=x_attn, key_padding_mask=key_padding_mask, residual=x)
+        x = self.ffn(layer_norm_add(x, self.norm2)[0], residual=x)
         return x
 
 
@@ -194,11 +205,11 @@ class DecoderLayer(nn.Module):
                 position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor,
                 cross_key: Optional[torch.Tensor] = None):
         x_attn, query = layer_norm_add(x, self.norm1, object_query_embedding)
-        x = x + self.self_attention(query, query, value=x_attn)
+        x = self.self_attention(query, query, value=x_attn, residual=x)
         _, query = layer_norm_add(x, self.norm2, object_query_embedding, want_y=False)
         key = cross_key if cross_key is not None else encoded_image_tokens + position_embedding
-        x = x + self.cross_attention(query, key, value=encoded_image_tokens, key_padding_mask=key_padding_mask)
-        x = x + self.ffn(layer_norm_add(x, self.norm3)[0])
+        x = self.cross_attention(query, key, value=encoded_image_tokens, key_padding_mask=key_padding_mask, residual=x)
+        x = self.ffn(layer_norm_add(x, self.norm3)[0], residual=x)
         return x
 
 

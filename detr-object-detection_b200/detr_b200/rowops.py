@@ -6,6 +6,8 @@ import torch.nn.functional as F
 
 from . import _lib
 
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
 
 def colsum(g: torch.Tensor) -> torch.Tensor:
     """Column sums of a 2-D bf16 matrix -> fp32 (N,).  (Bias gradient of nn.Linear.)"""
@@ -69,6 +71,84 @@ def linear(x: torch.Tensor, weight, bias, w16=None, b16=None) -> torch.Tensor:
     return F.linear(x, w, b)
 
 
+def _ep_seed(p: float):
+    """(host seed, device step tensor) for an epilogue dropout mask: host draw (follows torch.manual_seed, no sync) plus
+    the device-side step counter registered for CUDA-graph replays (attention.set_dropout_step_tensor)."""
+    if p <= 0.0:
+        return 0, None
+    from . import attention
+    return int(torch.randint(0, 2 ** 62, (1,)).item()), attention._STEP_TENSOR
+
+
+class _LinearEpilogue(torch.autograd.Function):
+    """One pre-LN block tail on cuBLASLt + ONE elementwise kernel each way (csrc/rowops.cu, `detr_epilogue_*`):
+
+        mode 0:  out = residual + dropout(x W^T + b)        attention output projection, second FFN projection
+        mode 1:  out = dropout(gelu_tanh(x W^T + b))        first FFN projection
+
+    Backward regenerates the dropout mask, produces dy in bf16 for the two GEMMs and the bias gradient in the same
+    pass (no stored mask, no ATen dropout / masked_scale / gelu / gelu_backward / add launches, no separate colsum)."""
+
+    @staticmethod
+    def forward(ctx, mode, x, residual, w16, b16, weight, bias, p, seed, seed_t):
+        if w16 is None:
+            w16 = weight.to(torch.bfloat16)
+        if b16 is None:
+            b16 = bias.to(torch.bfloat16)
+        y = F.linear(x, w16, b16)
+        N = y.shape[-1]
+        M = y.numel() // N
+        if mode == 0:
+            res = residual if residual.is_contiguous() else residual.contiguous()
+            out = torch.empty_like(res)
+        else:
+            res = None
+            out = torch.empty_like(y)
+        _lib.call("detr_epilogue_fwd", mode, _lib.ptr(res), _DT[res.dtype] if res is not None else 1, y.data_ptr(), out.data_ptr(),
+                  M, N, float(p), seed & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_t), _lib.stream_ptr())
+        ctx.save_for_backward(x, w16, y if mode == 1 else None, seed_t)
+        ctx.mode, ctx.p, ctx.seed, ctx.MN = mode, p, seed, (M, N)
+        ctx.w_dtype = weight.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w16, y, seed_t = ctx.saved_tensors
+        M, N = ctx.MN
+        if g.dtype not in _DT:
+            g = g.float()
+        g = g if g.is_contiguous() else g.contiguous()
+        dy = torch.empty(M, N, dtype=torch.bfloat16, device=g.device)
+        chunks = _lib.load().detr_epilogue_chunks(M, N)
+        partial = torch.empty(chunks * N, dtype=torch.float32, device=g.device)
+        db = torch.empty(N, dtype=torch.float32, device=g.device)
+        _lib.call("detr_epilogue_bwd", ctx.mode, g.data_ptr(), _DT[g.dtype], _lib.ptr(y), dy.data_ptr(), partial.data_ptr(), db.data_ptr(),
+                  M, N, float(ctx.p), ctx.seed & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_t), _lib.stream_ptr())
+        x2 = x.reshape(M, -1)
+        dx = (dy @ w16).view(x.shape) if ctx.needs_input_grad[1] else None
+        dw = torch.mm(dy.t(), x2, out_dtype=torch.float32) if ctx.w_dtype == torch.float32 else (dy.t() @ x2).to(ctx.w_dtype)
+        d_res = g if (ctx.mode == 0 and ctx.needs_input_grad[2]) else None
+        return None, dx, d_res, None, None, dw, db.to(ctx.w_dtype) if ctx.w_dtype != torch.float32 else db, None, None, None
+
+
+def fused_epilogues_enabled(x: torch.Tensor) -> bool:
+    return x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
+
+
+def linear_dropout_add(x, residual, lin: torch.nn.Linear, p: float, w16=None, b16=None) -> torch.Tensor:
+    """residual + dropout(lin(x)) under bf16 autocast (result in the residual's dtype)."""
+    seed, seed_t = _ep_seed(p)
+    with torch.autocast("cuda", enabled=False):
+        return _LinearEpilogue.apply(0, x.to(torch.bfloat16), residual, w16, b16, lin.weight, lin.bias, p, seed, seed_t)
+
+
+def linear_gelu_dropout(x, lin: torch.nn.Linear, p: float, w16=None, b16=None) -> torch.Tensor:
+    """dropout(gelu_tanh(lin(x))) under bf16 autocast (bf16 result)."""
+    seed, seed_t = _ep_seed(p)
+    with torch.autocast("cuda", enabled=False):
+        return _LinearEpilogue.apply(1, x.to(torch.bfloat16), None, w16, b16, lin.weight, lin.bias, p, seed, seed_t)
+
+
 class ShadowedLinears:
     """bf16 shadows of a module tree's Linear weights and biases, refreshed with ONE multi-tensor copy per forward
     (instead of one cast kernel per weight per use under autocast).  Groups of parameters that are used stacked
@@ -107,7 +187,6 @@ class ShadowedLinears:
     def get(self, key):
         return self.shadow.get(key, (None, None))
 # ------------------------------------------------------------------------------------------------ fused LayerNorm
-_DT = {torch.float32: 0, torch.bfloat16: 1}
 
 
 class _LayerNormAdd(torch.autograd.Function):

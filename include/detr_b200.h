@@ -157,6 +157,21 @@ int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, const void*
                        const float* gamma, const float* mean, const float* rstd, void* dx, float* partial,
                        float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* stream);
 
+/* Block epilogues of the pre-LN layers, one pass each (detr/model.py:223-224, 176-182, FFN 405-411).
+ * mode 0: out(x's dtype) = x + dropout(y)  -- residual add after the attention output / second FFN projection;
+ * mode 1: out(bf16) = dropout(gelu_tanh(y)) -- between the FFN projections (x unused).
+ * y bf16 (M,N) contiguous = the producing Linear's output; x_dtype / g_dtype: 0 float32, 1 bfloat16.  The dropout mask
+ * is counter-based (7 bits per element, p quantised to k/128, seed + *seed_ptr as in the attention kernels) and is
+ * regenerated by the backward call, which also returns the producing Linear's bias gradient:
+ *   dy(bf16) = mask(g)/(1-p) [* gelu'(y) in mode 1],  db[n] = sum_m dy[m][n]
+ * partial float[detr_epilogue_chunks(M,N) * N] is scratch.  N % 8 == 0. */
+int detr_epilogue_fwd(int mode, const void* x, int x_dtype, const void* y, void* out, int M, int N, float dropout_p,
+                      uint64_t seed, const uint64_t* seed_ptr, void* stream);
+int detr_epilogue_chunks(int M, int N);
+int detr_epilogue_bwd(int mode, const void* g, int g_dtype, const void* y, void* dy, float* partial, float* db,
+                      int M, int N, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
+
+
 #ifdef __cplusplus
 }
 #endif

@@ -186,3 +186,64 @@ def test_fused_layernorm_add(cuda, xdt, odt, C):
     # y2-only variant (decoder cross-attention query)
     _, q = _LayerNormAdd.apply(x, ln.weight, ln.bias, emb[None].expand(B, -1, -1), ln.eps, odt, False)
     assert _ is None and (q.float() - y2r).abs().max().item() <= (3e-2 if lo else 2e-5) * y2r.abs().max().item()
+
+
+@pytest.mark.parametrize("mode,res_dtype", [(0, torch.float32), (0, torch.bfloat16), (1, None)])
+def test_fused_linear_epilogue_matches_torch(cuda, mode, res_dtype):
+    """residual + dropout(lin(x)) and dropout(gelu_tanh(lin(x))) with dropout OFF against the unfused autocast path
+    (detr/model.py:223-224, 405-411): values, dx, dW, db and the residual gradient."""
+    from detr_b200.rowops import linear_dropout_add, linear_gelu_dropout
+    torch.manual_seed(0)
+    K, N = (256, 256) if mode == 0 else (256, 2048)
+    lin = torch.nn.Linear(K, N).to(cuda)
+    x = torch.randn(3, 211, K, device=cuda).bfloat16().requires_grad_(True)
+    res = torch.randn(3, 211, N, device=cuda).to(res_dtype).requires_grad_(True) if mode == 0 else None
+    w = torch.randn(3, 211, N, device=cuda)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = linear_dropout_add(x, res, lin, 0.0) if mode == 0 else linear_gelu_dropout(x, lin, 0.0)
+    (out.float() * w).sum().backward()
+    got = (out, x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone(), res.grad.clone() if mode == 0 else None)
+    x.grad = None; lin.zero_grad()
+    if mode == 0:
+        res.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = torch.nn.functional.linear(x, lin.weight, lin.bias)
+        ref = res + y if mode == 0 else torch.nn.functional.gelu(y, approximate="tanh")
+    (ref.float() * w).sum().backward()
+    assert out.dtype == ref.dtype and out.shape == ref.shape
+    assert torch.allclose(out.float(), ref.float(), rtol=2e-2, atol=2e-2)
+    assert torch.allclose(got[1].float(), x.grad.float(), rtol=3e-2, atol=3e-2)
+    assert got[2].dtype == torch.float32 and torch.allclose(got[2], lin.weight.grad, rtol=3e-2, atol=3e-1)
+    ref_b = lin.bias.grad
+    assert torch.allclose(got[3], ref_b, rtol=3e-2, atol=0.5), (got[3] - ref_b).abs().max()
+    if mode == 0:
+        assert torch.allclose(got[4].float(), res.grad.float(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fused_linear_epilogue_dropout_consistency(cuda, mode):
+    """With dropout the backward must regenerate the forward's mask: dropped outputs get exactly zero gradient, kept
+    ones the 1/keep-scaled gradient; the keep rate is 1 - round(128 p)/128; same seed -> same mask."""
+    from detr_b200 import _lib
+    M, N, p = 999, 256, 0.25
+    y = (torch.randn(M, N, device=cuda) + 3.0).bfloat16()          # gelu(y) != 0 almost surely
+    x = torch.zeros(M, N, device=cuda)
+    outs = []
+    for seed in (7, 7, 8):
+        o = torch.empty(M, N, device=cuda, dtype=torch.float32 if mode == 0 else torch.bfloat16)
+        _lib.call("detr_epilogue_fwd", mode, x.data_ptr() if mode == 0 else None, 0, y.data_ptr(), o.data_ptr(), M, N, p, seed, None, _lib.stream_ptr())
+        outs.append(o.float())
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+    kept = outs[0] != 0
+    assert abs(kept.float().mean().item() - 0.75) < 0.01
+    g = torch.ones(M, N, device=cuda)
+    dy = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    chunks = _lib.load().detr_epilogue_chunks(M, N)
+    partial = torch.empty(chunks * N, device=cuda)
+    db = torch.empty(N, device=cuda)
+    _lib.call("detr_epilogue_bwd", mode, g.data_ptr(), 0, y.data_ptr(), dy.data_ptr(), partial.data_ptr(), db.data_ptr(), M, N, p, 7, None, _lib.stream_ptr())
+    assert torch.equal(dy.float() != 0, kept)
+    if mode == 0:
+        assert torch.allclose(dy.float()[kept], torch.full((), 1 / 0.75, device=cuda).expand(int(kept.sum())), rtol=1e-2)
+        assert torch.allclose(outs[0][kept], (y.float() / 0.75)[kept], rtol=1e-2)
+    assert torch.allclose(db, dy.float().sum(0), rtol=1e-3, atol=1e-2)
