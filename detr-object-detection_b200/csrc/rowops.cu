@@ -10,11 +10,11 @@
 namespace detr {
 
 constexpr int kColsPerCta = 256;   // 32 lanes x 8 bf16 (16 bytes)
-constexpr int kCsThreads = 256;    // 8 warps: each warp takes every 8th row of the chunk
+constexpr int kCsThreads = 256;    // 8 warps: each warp takes every 8th row of the chunk, 4 rows in flight
 
 // out[c] = sum_k partial[k][c] (k < n_partials, row stride N), columns c < split go to out0, the rest to out1.
 // CTA = 32 columns; warp w adds partials w, w+8, ... (independent coalesced loads), then the 8 warps are combined.
-constexpr int kFoldThreads = 256;
+constexpr int kFoldThreads = 1024;
 __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(const float* __restrict__ partial, int n_partials, int N,
                                                                      float* __restrict__ out0, float* __restrict__ out1, int split) {
     __shared__ float red[kFoldThreads / 32][32];
@@ -22,14 +22,15 @@ __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(const float
     const int c = blockIdx.x * 32 + lane;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (c < N) {
+        constexpr int W = kFoldThreads / 32;
         int k = warp;
-        for (; k + 24 < n_partials; k += 32) {
+        for (; k + 3 * W < n_partials; k += 4 * W) {   // four independent loads in flight per thread
             s0 += __ldcg(&partial[(int64_t)k * N + c]);
-            s1 += __ldcg(&partial[(int64_t)(k + 8) * N + c]);
-            s2 += __ldcg(&partial[(int64_t)(k + 16) * N + c]);
-            s3 += __ldcg(&partial[(int64_t)(k + 24) * N + c]);
+            s1 += __ldcg(&partial[(int64_t)(k + W) * N + c]);
+            s2 += __ldcg(&partial[(int64_t)(k + 2 * W) * N + c]);
+            s3 += __ldcg(&partial[(int64_t)(k + 3 * W) * N + c]);
         }
-        for (; k < n_partials; k += 8) s0 += __ldcg(&partial[(int64_t)k * N + c]);
+        for (; k < n_partials; k += W) s0 += __ldcg(&partial[(int64_t)k * N + c]);
     }
     red[warp][lane] = (s0 + s1) + (s2 + s3);
     __syncthreads();
@@ -49,13 +50,20 @@ __global__ void __launch_bounds__(kCsThreads) colsum_kernel(const __nv_bfloat16*
     const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (c0 < N) {   // N is a multiple of 8
-        for (int r = r0 + warp; r < r1; r += kCsThreads / 32) {
-            const uint4 v = *reinterpret_cast<const uint4*>(g + (int64_t)r * ld + c0);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+        constexpr int W = kCsThreads / 32;
+        for (int r = r0 + warp; r < r1; r += 4 * W) {    // four independent 16-byte loads in flight per lane
+            uint4 v[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h[e]);
-                acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+            for (int u = 0; u < 4; ++u)
+                v[u] = (r + u * W < r1) ? *reinterpret_cast<const uint4*>(g + (int64_t)(r + u * W) * ld + c0) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h[e]);
+                    acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+                }
             }
         }
     }
@@ -63,7 +71,7 @@ __global__ void __launch_bounds__(kCsThreads) colsum_kernel(const __nv_bfloat16*
     for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = acc[e];
     __syncthreads();
     const int c = threadIdx.x, col = blockIdx.x * kColsPerCta + c;
-    if (col < N) {
+    if (c < kColsPerCta && col < N) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kCsThreads / 32; ++w) s += red[w][c];
@@ -77,8 +85,9 @@ using namespace detr;
 
 extern "C" int detr_colsum_chunks(int M, int N) {
     const int col_tiles = (N + kColsPerCta - 1) / kColsPerCta;
-    int chunks = (4 * 148 + col_tiles - 1) / col_tiles;          // ~4 CTAs per SM in flight
-    const int max_chunks = (M + 15) / 16;                        // at least 16 rows (2 per warp) per CTA
+    int chunks = (4 * 148 + col_tiles - 1) / col_tiles;          // ~4 CTAs of 8 warps per SM
+    const int max_chunks = (M + 31) / 32;                        // at least 32 rows (one 4-row batch per warp) per CTA
+    if (chunks > 256) chunks = 256;                              // bounds the fold: 8 partials per fold warp
     if (chunks > max_chunks) chunks = max_chunks;
     return chunks < 1 ? 1 : chunks;
 }
@@ -107,7 +116,7 @@ extern "C" int detr_colsum_bf16(const void* g, int64_t ld, int M, int N, float* 
 // =========================================================================================================
 namespace detr {
 
-constexpr int kLnThreads = 128;
+constexpr int kLnThreads = 256;   // 8 warps, one row per warp at a time
 constexpr int kLnMaxPerLane = 32;   // C <= 1024
 
 template <typename T> __device__ __forceinline__ float ld1(const T* p);
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const LnParams p) {
 // dy / dy2: gradients w.r.t. y / y2 (type TG, row stride C, either may be null); dx in TX
 template <typename TX, typename TG, int KT>
 __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnParams p) {
-    extern __shared__ float sm[];   // [4 warps][2][C]
+    extern __shared__ float sm[];   // [warps][2][C]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = KT ? KT : p.C / 32, C = p.C;
     constexpr int KA = KT ? KT : kLnMaxPerLane;
@@ -245,9 +254,13 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnParams p) {
     }
 }
 
-static int ln_grid(int rows) {
+static int ln_grid(int rows) {   // backward: <= 296 CTA partials of dgamma / dbeta for the fold
     int g = (rows + kLnThreads / 32 - 1) / (kLnThreads / 32);
     return g > 2 * 148 ? 2 * 148 : (g < 1 ? 1 : g);
+}
+static int ln_grid_fwd(int rows) {
+    int g = (rows + kLnThreads / 32 - 1) / (kLnThreads / 32);
+    return g > 8 * 148 ? 8 * 148 : (g < 1 ? 1 : g);
 }
 
 }  // namespace detr
@@ -265,7 +278,7 @@ extern "C" int detr_layernorm_fwd(const void* x, int x_dtype, int64_t x_ld, cons
     LnParams p{};
     p.x = x; p.x_ld = x_ld; p.gamma = gamma; p.beta = beta; p.addend = addend; p.add_sb = add_sb; p.add_sr = add_sr;
     p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : rows; p.y = y; p.y2 = y2; p.mean = mean; p.rstd = rstd; p.rows = rows; p.C = C; p.eps = eps;
-    const int grid = ln_grid(rows);
+    const int grid = ln_grid_fwd(rows);
     cudaStream_t st = (cudaStream_t)stream;
     DETR_CHECK_ARG(!addend || add_dtype == 0, "layernorm: the addend must be float32");
 #define LN_FWD(TX, TO)                                                            \
@@ -460,7 +473,7 @@ __global__ void __launch_bounds__(kCsThreads) epilogue_bwd_kernel(const EwParams
     for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = acc[e];
     __syncthreads();
     const int c = threadIdx.x, col = blockIdx.x * kColsPerCta + c;
-    if (col < p.N) {
+    if (c < kColsPerCta && col < p.N) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kCsThreads / 32; ++w) s += red[w][c];
