@@ -115,23 +115,126 @@ def _bn_constants(bn):
     return c
 
 
-def _conv_bn_relu(x, conv: nn.Conv2d, bn, z=None) -> torch.Tensor:
-    """relu(conv_bn(x) [+ z]) through the fused cuDNN kernel (bf16, channels_last)."""
+def _conv_bn_relu(x, conv: nn.Conv2d, bn, z=None, w16=None, relu: bool = True) -> torch.Tensor:
+    """relu(conv_bn(x) [+ z]) through the fused cuDNN kernel (bf16, channels_last).  `w16`: the folded bf16 weight from
+    `FoldedConvWeights` (one launch for the whole network); folded here with three launches when absent."""
     scale, _, shift = _bn_constants(bn)
-    w = (conv.weight * scale).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = w16 if w16 is not None else (conv.weight * scale).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     x = x.to(torch.bfloat16)
     with torch.autocast("cuda", enabled=False):
+        if not relu:
+            return F.conv2d(x, w, shift, conv.stride, conv.padding, conv.dilation, conv.groups)
         return _ConvBiasAct.apply(x, w, shift, z, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
-def _bottleneck_forward(blk, x, fused: bool):
+def _hw_flat(t: torch.Tensor):
+    """(stride_o, stride_i, stride_hw) of a 4-D weight whose (h, w) dims can be walked with one stride, else None."""
+    O, I, H, W = t.shape
+    so, si, sh, sw = t.stride()
+    if H == 1 and W == 1:
+        return so, si, 1
+    if W == 1:
+        return so, si, sh
+    if H == 1 or sh == W * sw:
+        return so, si, sw
+    return None
+
+
+class _FoldFn(torch.autograd.Function):
+    """All frozen-BN folds of the network in one launch each way: w16_k = bf16(W_k * s_k) forward (OHWI storage, i.e.
+    channels_last weights for cuDNN), dW_k = fp32(dW16_k * s_k) backward."""
+
+    @staticmethod
+    def forward(ctx, pack, *weights):
+        ctx.pack = pack
+        pack.fold(weights)
+        return tuple(pack.views)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return (None, *ctx.pack.unfold(grads))
+
+
+class FoldedConvWeights:
+    """bf16 BN-folded shadows of every convolution weight of a backbone in ONE flat buffer (`detr_scale_cast_multi`)."""
+
+    def __init__(self, pairs):
+        from . import _lib
+        if len(pairs) > _lib.FOLD_MAX_TENSORS:
+            raise ValueError(f"at most {_lib.FOLD_MAX_TENSORS} convolutions per fold pack")
+        self.pairs = list(pairs)
+        self.views, self.flat, self._device = [], None, None
+
+    def _build(self, device):
+        total = sum(c.weight.numel() for c, _ in self.pairs)
+        self.flat = torch.empty(total, dtype=torch.bfloat16, device=device)
+        self.views, o = [], 0
+        for c, _ in self.pairs:
+            O, I, H, W = c.weight.shape
+            n = O * I * H * W
+            self.views.append(self.flat[o:o + n].view(O, H, W, I).permute(0, 3, 1, 2))   # logical OIHW, channels_last strides
+            o += n
+        self.scales = [_bn_constants(bn)[0].reshape(-1).contiguous() for _, bn in self.pairs]
+        self._device = device
+
+    def _launch(self, srcs, dsts, in_code, out_code):
+        from . import _lib
+        t = _lib.FoldTable()
+        t.n = len(srcs)
+        for k, (s_, d_) in enumerate(zip(srcs, dsts)):
+            O, I, H, W = s_.shape
+            t.src[k], t.dst[k], t.scale[k] = s_.data_ptr(), d_.data_ptr(), self.scales[k].data_ptr()
+            t.O[k], t.I[k], t.HW[k] = O, I, H * W
+            for j, v in enumerate(_hw_flat(s_)):
+                t.src_stride[k][j] = v
+            for j, v in enumerate(_hw_flat(d_)):
+                t.dst_stride[k][j] = v
+        _lib.call("detr_scale_cast_multi", ctypes_byref(t), in_code, out_code, _lib.stream_ptr())
+
+    def fold(self, weights):
+        dev = weights[0].device
+        if self._device != dev:
+            self._build(dev)
+        srcs = [w.detach() if _hw_flat(w) is not None else w.detach().contiguous() for w in weights]
+        self._launch(srcs, self.views, 0, 1)
+
+    def unfold(self, grads):
+        outs, srcs = [], []
+        for (c, _), g, v in zip(self.pairs, grads, self.views):
+            if g is None:
+                g = torch.zeros_like(v)
+            if g.dtype != torch.bfloat16:
+                g = g.to(torch.bfloat16)
+            if _hw_flat(g) is None:
+                g = g.contiguous(memory_format=torch.channels_last)
+            srcs.append(g)
+            outs.append(torch.empty_like(c.weight, dtype=torch.float32))
+        self._launch(srcs, outs, 1, 0)
+        return [o if c.weight.dtype == torch.float32 else o.to(c.weight.dtype) for o, (c, _) in zip(outs, self.pairs)]
+
+    def __call__(self):
+        """-> {conv module: folded bf16 weight}; differentiable w.r.t. the fp32 conv weights."""
+        ws = _FoldFn.apply(self, *[c.weight for c, _ in self.pairs])
+        return {c: w for (c, _), w in zip(self.pairs, ws)}
+
+
+def ctypes_byref(obj):
+    import ctypes
+    return ctypes.byref(obj)
+
+
+def _bottleneck_forward(blk, x, fused: bool, w16=None):
     identity = x
     if fused:
-        out = _conv_bn_relu(x, blk.conv1, blk.bn1)
-        out = _conv_bn_relu(out, blk.conv2, blk.bn2)
+        g = (lambda c: w16[c]) if w16 is not None else (lambda c: None)
+        out = _conv_bn_relu(x, blk.conv1, blk.bn1, w16=g(blk.conv1))
+        out = _conv_bn_relu(out, blk.conv2, blk.bn2, w16=g(blk.conv2))
         if blk.downsample is not None:
-            identity = _conv_bn(x, blk.downsample[0], blk.downsample[1])
-        return _conv_bn_relu(out, blk.conv3, blk.bn3, z=identity)
+            if w16 is not None:
+                identity = _conv_bn_relu(x, blk.downsample[0], blk.downsample[1], w16=g(blk.downsample[0]), relu=False)
+            else:
+                identity = _conv_bn(x, blk.downsample[0], blk.downsample[1])
+        return _conv_bn_relu(out, blk.conv3, blk.bn3, z=identity, w16=g(blk.conv3))
     out = F.relu(_conv_bn(x, blk.conv1, blk.bn1), inplace=True)
     out = F.relu(_conv_bn(out, blk.conv2, blk.bn2), inplace=True)
     out = _conv_bn(out, blk.conv3, blk.bn3)
@@ -155,20 +258,37 @@ class _Backbone(nn.Module):
         self.scale = 32
         self.fold_bn = fold_bn
         self.fuse_relu = True   # cuDNN conv+bias(+add)+ReLU epilogues; needs CUDA bf16 autocast, else plain path
+        self._fold = None       # FoldedConvWeights packs, built on first fused forward
+        self.use_fold_pack = True   # False: fold each weight where it is used (3 launches per convolution each way)
 
     def forward(self, x):
         if not self.fold_bn:
             return self.backbone(x)["final_feature_map"]
         m = self.backbone
         fused = (self.fuse_relu and x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16)
-        if fused:
+        w16 = None
+        if fused and not self.use_fold_pack:
             x = _conv_bn_relu(x.contiguous(memory_format=torch.channels_last), m.conv1, m.bn1)
+        elif fused:
+            if self._fold is None:
+                pairs = [(m.conv1, m.bn1)]
+                for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
+                    for blk in layer:
+                        pairs += [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2), (blk.conv3, blk.bn3)]
+                        if blk.downsample is not None:
+                            pairs.append((blk.downsample[0], blk.downsample[1]))
+                # R101 has 104 convolutions: several packs of <= 64
+                object.__setattr__(self, "_fold", [FoldedConvWeights(pairs[i:i + 64]) for i in range(0, len(pairs), 64)])
+            w16 = {}
+            for pack in self._fold:
+                w16.update(pack())
+            x = _conv_bn_relu(x.contiguous(memory_format=torch.channels_last), m.conv1, m.bn1, w16=w16[m.conv1])
         else:
             x = F.relu(_conv_bn(x, m.conv1, m.bn1), inplace=True)
         x = m.maxpool(x)
         for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
             for blk in layer:
-                x = _bottleneck_forward(blk, x, fused)
+                x = _bottleneck_forward(blk, x, fused, w16)
         return x
 
 

@@ -171,6 +171,24 @@ int detr_epilogue_chunks(int M, int N);
 int detr_epilogue_bwd(int mode, const void* g, int g_dtype, const void* y, void* dy, float* partial, float* db,
                       int M, int N, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
 
+/* ---- caller-side glue: frozen-BatchNorm fold of the backbone weights (detr/model.py:427-438) ----------------- */
+/* dst[o][i][hw] = (out dtype)(src[o][i][hw] * scale[o]) for up to 64 (O, I, H*W) tensors in ONE launch; element strides
+ * are given per tensor for (o, i, hw) on both sides (hw must be flattenable: stride_h == W * stride_w).  Used forward
+ * (fp32 conv weights -> bf16 folded weights) and backward (bf16 weight gradients -> fp32 parameter gradients).
+ * dtype codes: 0 float32, 1 bfloat16.  The table is read on the host during the call. */
+#define DETR_FOLD_MAX_TENSORS 64
+typedef struct DetrFoldTable {
+    const void* src[DETR_FOLD_MAX_TENSORS];
+    void* dst[DETR_FOLD_MAX_TENSORS];
+    const float* scale[DETR_FOLD_MAX_TENSORS];
+    int O[DETR_FOLD_MAX_TENSORS], I[DETR_FOLD_MAX_TENSORS], HW[DETR_FOLD_MAX_TENSORS];
+    int src_stride[DETR_FOLD_MAX_TENSORS][3];
+    int dst_stride[DETR_FOLD_MAX_TENSORS][3];
+    int n;
+} DetrFoldTable;
+int detr_scale_cast_multi(const DetrFoldTable* table, int in_dtype, int out_dtype, void* stream);
+
+
 
 #ifdef __cplusplus
 }

@@ -247,3 +247,31 @@ def test_fused_linear_epilogue_dropout_consistency(cuda, mode):
         assert torch.allclose(dy.float()[kept], torch.full((), 1 / 0.75, device=cuda).expand(int(kept.sum())), rtol=1e-2)
         assert torch.allclose(outs[0][kept], (y.float() / 0.75)[kept], rtol=1e-2)
     assert torch.allclose(db, dy.float().sum(0), rtol=1e-3, atol=1e-2)
+
+
+def test_backbone_fold_pack_matches_per_conv_fold(cuda):
+    """One-launch BN fold of all convolution weights (detr_scale_cast_multi) against folding each weight where it is
+    used: same activations, same parameter gradients (both paths feed cuDNN the same bf16 weights)."""
+    from detr_b200.harness import _Backbone
+    torch.manual_seed(0)
+    bb = _Backbone("resnet50").to(cuda).to(memory_format=torch.channels_last).train()
+    for m in bb.modules():   # non-trivial frozen statistics
+        if hasattr(m, "running_var"):
+            m.running_var.uniform_(0.5, 1.5); m.running_mean.normal_(0, 0.1); m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.1)
+    x = torch.randn(2, 3, 96, 128, device=cuda)
+    res = []
+    for use in (True, False):
+        bb.use_fold_pack = use
+        bb.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = bb(x)
+        y.float().square().mean().backward()
+        gs = {n: p.grad.clone() for n, p in bb.named_parameters() if p.grad is not None}
+        res.append((y.float(), gs))
+    (y1, g1), (y0, g0) = res
+    assert torch.allclose(y1, y0, rtol=2e-2, atol=2e-2)
+    assert set(g1) == set(g0) and len(g1) >= 53
+    for n in g0:
+        assert g1[n].dtype == g0[n].dtype and g1[n].shape == g0[n].shape
+        scale = g0[n].abs().max().item() + 1e-12
+        assert (g1[n] - g0[n]).abs().max().item() <= 5e-2 * scale, n
