@@ -140,6 +140,40 @@ def _hw_flat(t: torch.Tensor):
     return None
 
 
+class _MaxPool3x3s2(torch.autograd.Function):
+    """torchvision's stem `maxpool` (kernel 3, stride 2, padding 1) on channels_last bf16 through the gather kernels of
+    csrc/pool.cu (ATen's nhwc kernels run at a tenth of HBM speed on the 8 x 64 x 400 x 544 activation)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        from . import _lib
+        B, C, H, W = x.shape
+        Ho, Wo = _lib.load().detr_maxpool3x3s2_out(H), _lib.load().detr_maxpool3x3s2_out(W)
+        y = torch.empty((B, C, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        idx = torch.empty((B, Ho, Wo, C), dtype=torch.uint8, device=x.device)
+        _lib.call("detr_maxpool3x3s2_fwd_bf16", x.data_ptr(), y.data_ptr(), idx.data_ptr(), B, H, W, C, _lib.stream_ptr())
+        ctx.save_for_backward(idx)
+        ctx.shape = (B, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        (idx,) = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        g = g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=g.device, memory_format=torch.channels_last)
+        _lib.call("detr_maxpool3x3s2_bwd_bf16", g.data_ptr(), idx.data_ptr(), dx.data_ptr(), B, H, W, C, _lib.stream_ptr())
+        return dx
+
+
+def _stem_maxpool(pool: nn.MaxPool2d, x: torch.Tensor) -> torch.Tensor:
+    ok = (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] % 8 == 0 and x.is_contiguous(memory_format=torch.channels_last)
+          and pool.kernel_size in (3, (3, 3)) and pool.stride in (2, (2, 2)) and pool.padding in (1, (1, 1))
+          and pool.dilation in (1, (1, 1)) and not pool.ceil_mode)
+    return _MaxPool3x3s2.apply(x) if ok else pool(x)
+
+
 class _FoldFn(torch.autograd.Function):
     """All frozen-BN folds of the network in one launch each way: w16_k = bf16(W_k * s_k) forward (OHWI storage, i.e.
     channels_last weights for cuDNN), dW_k = fp32(dW16_k * s_k) backward."""
@@ -285,7 +319,7 @@ class _Backbone(nn.Module):
             x = _conv_bn_relu(x.contiguous(memory_format=torch.channels_last), m.conv1, m.bn1, w16=w16[m.conv1])
         else:
             x = F.relu(_conv_bn(x, m.conv1, m.bn1), inplace=True)
-        x = m.maxpool(x)
+        x = _stem_maxpool(m.maxpool, x) if fused else m.maxpool(x)
         for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
             for blk in layer:
                 x = _bottleneck_forward(blk, x, fused, w16)

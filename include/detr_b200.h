@@ -188,6 +188,14 @@ typedef struct DetrFoldTable {
 } DetrFoldTable;
 int detr_scale_cast_multi(const DetrFoldTable* table, int in_dtype, int out_dtype, void* stream);
 
+/* Channels-last (B,H,W,C physical) bf16 max pooling, kernel 3 / stride 2 / padding 1 -- the ResNet stem's `maxpool`
+ * (torchvision, called from detr/model.py:437).  idx (B,Ho,Wo,C) uint8 receives the window position (0..8) of the
+ * first maximum (ATen's tie rule) for the backward gather.  C % 8 == 0; Ho = detr_maxpool3x3s2_out(H). */
+int detr_maxpool3x3s2_out(int n);
+int detr_maxpool3x3s2_fwd_bf16(const void* x, void* y, uint8_t* idx, int B, int H, int W, int C, void* stream);
+int detr_maxpool3x3s2_bwd_bf16(const void* dy, const uint8_t* idx, void* dx, int B, int H, int W, int C, void* stream);
+
+
 
 
 #ifdef __cplusplus

@@ -275,3 +275,20 @@ def test_backbone_fold_pack_matches_per_conv_fold(cuda):
         assert g1[n].dtype == g0[n].dtype and g1[n].shape == g0[n].shape
         scale = g0[n].abs().max().item() + 1e-12
         assert (g1[n] - g0[n]).abs().max().item() <= 5e-2 * scale, n
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 50, 68), (1, 8, 7, 9), (2, 64, 33, 31)])
+def test_stem_maxpool_kernels_match_aten(cuda, B, C, H, W):
+    """3x3 / stride 2 / pad 1 channels_last bf16 max pooling: values bit-exact, gradients equal to ATen's (including its
+    first-maximum tie rule: the input is ReLU-like with many exact ties)."""
+    from detr_b200.harness import _stem_maxpool
+    torch.manual_seed(0)
+    pool = torch.nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+    x0 = torch.randn(B, C, H, W, device=cuda).relu().bfloat16().contiguous(memory_format=torch.channels_last)
+    xa, xb = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+    ya, yb = _stem_maxpool(pool, xa), pool(xb)
+    assert ya.shape == yb.shape and torch.equal(ya, yb)
+    w = torch.randn_like(yb)
+    (ya * w).sum().backward(); (yb * w).sum().backward()
+    assert torch.allclose(xa.grad.float(), xb.grad.float(), rtol=1e-2, atol=1e-2)
+    assert ((xa.grad != 0) != (xb.grad != 0)).float().mean().item() < 1e-4   # same arg-max choice everywhere (ties included)
