@@ -28,6 +28,34 @@ __global__ void __launch_bounds__(256) scale_cast_multi_kernel(const DetrFoldTab
     const float* scale = t.scale[k];
     const int s_o = t.src_stride[k][0], s_i = t.src_stride[k][1], s_hw = t.src_stride[k][2];
     const int d_o = t.dst_stride[k][0], d_i = t.dst_stride[k][1], d_hw = t.dst_stride[k][2];
+    const int row = I * HW;   // elements per output channel
+    if (s_i == 1 && d_i == 1 && s_hw == I && d_hw == I && s_o == row && d_o == row && (row & 3) == 0 &&
+        ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0) {
+        // both sides dense in (o, hw, i) order (channels_last weights): 4 elements per thread, one division per group
+        for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t idx = q * 4;
+            const float sc = scale[(int)(idx / row)];
+            float v[4];
+            if (sizeof(TIn) == 4) {
+                const float4 a = reinterpret_cast<const float4*>(src)[q];
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            } else {
+                const uint2 a = reinterpret_cast<const uint2*>(src)[q];
+                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a.x));
+                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a.y));
+                v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+            }
+            if (sizeof(TOut) == 4) {
+                reinterpret_cast<float4*>(dst)[q] = make_float4(v[0] * sc, v[1] * sc, v[2] * sc, v[3] * sc);
+            } else {
+                uint2 o;
+                *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v[0] * sc, v[1] * sc);
+                *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v[2] * sc, v[3] * sc);
+                reinterpret_cast<uint2*>(dst)[q] = o;
+            }
+        }
+        return;
+    }
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
         const int i = (int)(idx % I);
         const int64_t r = idx / I;

@@ -80,26 +80,37 @@ def _conv_bn(x, conv: nn.Conv2d, bn) -> torch.Tensor:
 
 class _ConvBiasAct(torch.autograd.Function):
     """cuDNN fused conv + bias (+ residual) + ReLU forward (`cudnn_convolution_relu` / `_add_relu`, one kernel instead of
-    conv, bias add, residual add and ReLU) with the standard convolution backward.  Library calls only (out of scope)."""
+    conv, bias add, residual add and ReLU) with the standard convolution backward; `relu=False` (the downsample branch)
+    is a plain conv + bias whose backward takes the same route, so that both gradients of a block input come out of
+    `convolution_backward` in the same memory format and add with a vectorised kernel.  Library calls only (out of scope)."""
 
     @staticmethod
-    def forward(ctx, x, w, shift, z, stride, padding, dilation, groups):
-        if z is None:
+    def forward(ctx, x, w, shift, z, stride, padding, dilation, groups, relu=True):
+        if not relu:
+            y = F.conv2d(x, w, shift, stride, padding, dilation, groups)
+        elif z is None:
             y = torch.cudnn_convolution_relu(x, w, shift, stride, padding, dilation, groups)
         else:
             y = torch.cudnn_convolution_add_relu(x, w, z, 1.0, shift, stride, padding, dilation, groups)
-        ctx.save_for_backward(x, w, y)
-        ctx.conf = (stride, padding, dilation, groups, z is not None)
+        if relu:
+            ctx.save_for_backward(x, w, y)
+        else:
+            ctx.save_for_backward(x, w)
+        ctx.conf = (stride, padding, dilation, groups, z is not None, relu)
         return y
 
     @staticmethod
     def backward(ctx, g):
-        x, w, y = ctx.saved_tensors
-        stride, padding, dilation, groups, has_z = ctx.conf
-        g = torch.ops.aten.threshold_backward(g, y, 0)
+        stride, padding, dilation, groups, has_z, relu = ctx.conf
+        if relu:
+            x, w, y = ctx.saved_tensors
+            g = torch.ops.aten.threshold_backward(g, y, 0)
+        else:
+            x, w = ctx.saved_tensors
+            g = g.contiguous(memory_format=torch.channels_last) if x.is_contiguous(memory_format=torch.channels_last) else g
         dx, dw, _ = torch.ops.aten.convolution_backward(g, x, w, None, stride, padding, dilation, False, [0, 0], groups,
                                                         [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
-        return dx, dw, None, (g if has_z else None), None, None, None, None
+        return dx, dw, None, (g if has_z else None), None, None, None, None, None
 
 
 def _bn_constants(bn):
@@ -122,9 +133,7 @@ def _conv_bn_relu(x, conv: nn.Conv2d, bn, z=None, w16=None, relu: bool = True) -
     w = w16 if w16 is not None else (conv.weight * scale).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     x = x.to(torch.bfloat16)
     with torch.autocast("cuda", enabled=False):
-        if not relu:
-            return F.conv2d(x, w, shift, conv.stride, conv.padding, conv.dilation, conv.groups)
-        return _ConvBiasAct.apply(x, w, shift, z, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return _ConvBiasAct.apply(x, w, shift, z, conv.stride, conv.padding, conv.dilation, conv.groups, relu)
 
 
 def _hw_flat(t: torch.Tensor):
