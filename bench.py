@@ -256,11 +256,16 @@ def run_b200(args):
             # algorithmic FLOPs per call: backward = 2.5 x forward core, forward core = 4*L*S*C per image
             flops = 2.5 * 4.0 * SP * SP * 256 * PER_GPU_BATCH
             ach = flops / (tot / calls * 1e-3) / 1e12
-            roof = {"kernel": "attention_bwd (delta + dK/dV + dQ), encoder self-attention B=8 nh=8 L=S=850", "bound": "tensor",
+            roof = {"kernel": "attention_bwd (delta + fused dK/dV/dQ-partial + dQ reduction), encoder self-attention B=8 nh=8 L=S=850", "bound": "tensor",
                     "achieved": round(ach, 2), "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops_sustained"], 4),
-                    "peak_source": pk["src"] + " sustained (kernel timed inside a long step)", "traffic": None,
+                    "peak_source": pk["src"] + " sustained (kernel timed inside a long step)",
+                    # dram__bytes_read.sum + dram__bytes_write.sum of the call's three kernels, one `ncu --set full` capture
+                    # (profiles/r01_attention_ncu_full_v3.md; ncu flushes L2 between kernels, so the 48.8 MB the dQ reduction
+                    # re-reads from L2 in a real step counts as DRAM traffic here)
+                    "traffic": 75.4e6, "traffic_algorithmic": 14.1e6,
                     "ms_per_launch": round(tot / calls, 4), "flops_per_launch": flops,
-                    "note": "head_dim 32 makes the core MUFU(exp)-bound, not tensor-bound (SURVEY.md 7.1)"}
+                    "note": "head_dim 32: one MUFU exp per 128 tensor FLOPs caps the tensor pipe at ~25% (SURVEY.md 7.1); measured "
+                            "limiter now is per-CTA fixed cost + 3.03-wave quantisation (profiles/r01_attention_ncu_full_v3.md)"}
             if key_f in rows:
                 c2, t2 = rows[key_f]
                 f2 = 4.0 * SP * SP * 256 * PER_GPU_BATCH
