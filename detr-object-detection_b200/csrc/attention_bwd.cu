@@ -1,21 +1,25 @@
 // Flash attention backward for head_dim = 32 (gradient of detr/model.py:317-352), tcgen05 + TMA + TMEM.
 //
-// ONE pass over the (query tile, key tile) pairs.  CTA = (batch, head, 128-key tile); it streams the query tiles and,
-// per 128x128 pair, recomputes
+// ONE pass over the (query tile, key tile) pairs, PERSISTENT: min(#SMs, #items) CTAs, each walking a contiguous range of
+// pairs in (batch, head, key tile, query tile) order -- whole (b, h, key tile) items plus at most one partial item at each
+// end, so the SMs finish together (448 items on 148 SMs used to cost 4 waves for 3.03 waves of work) and TMEM
+// allocation, barrier setup and pipeline fill/drain are paid once per SM instead of once per item.  Per 128x128 pair:
 //     S = Q K^T,  dP~ = dO V^T,  P = exp(S/sqrt(d) - LSE),  P~ = dropout(P),
 //     dS = P o (dropout(dP~) - D) / sqrt(d),     D = rowsum(dO o O)
-// exactly once, with queries on the TMEM lanes (so LSE, D and the dropout key are per-thread scalars, as in forward):
-//     dV += P~^T dO,  dK += dS^T Q      accumulate in TMEM over the whole stream (P~, dS consumed as MN-major A operands)
+// computed exactly once, with queries on the TMEM lanes (LSE, D and the dropout key are per-thread scalars, as in forward):
+//     dV += P~^T dO,  dK += dS^T Q      accumulate in TMEM over an item's pairs (P~, dS consumed as MN-major A operands);
+//                                        double-buffered accumulators: the read-out of item i runs under the math of i+1
 //     dQ_part = dS K                     per pair (the SAME dS tile consumed as a K-major A operand), written as an fp32
 //                                        partial per key tile; attention_dq_reduce_kernel sums the partials in a fixed
-//                                        order -> deterministic, no atomics.
+//                                        order -> deterministic, no atomics.  Items split between two CTAs leave fp32
+//                                        dK / dV partials that attention_dkv_reduce_kernel folds.
 // 20 warps: 0-15 compute (warp w: TMEM lanes 32*(w%4).., key columns 32*(w/4)..+31 of the pair), 16 = TMA producer,
 // 17 = tcgen05.mma issuer, 18 = dQ-partial store warp (TMA bulk tensor stores of tiles the math warps stage in shared
 // memory: per-row 32-byte global stores from 512 threads cost ~600 cycles per pair in the LSU), 19 idle (completes the
 // fifth warpgroup so that setmaxnreg can move its registers to the math).
-// TMEM (512 columns): S [0,128) | dP [128,256) | dK [256,288) | dV [288,320) | dQ_part x3 [320,416).
+// TMEM (512 columns): S [0,128) | dP [128,256) | (dK | dV) x2 [256,384) | dQ_part x3 [384,480).
 // S / dP are copied to registers and released at once, so the next pair's score MMAs run under this pair's math;
-// the dS / P~ shared-memory tiles and the dQ_part columns are double buffered, so the math never waits for the MMAs.
+// the dS / P~ shared-memory tiles and the dQ_part columns are multi-buffered, so the math never waits for the MMAs.
 //
 // Masked keys (key_padding_mask / attention_mask) receive zero gradient as in the reference (masked_fill);
 // a query row whose keys are ALL masked is stored with LSE = +inf by the forward kernel and contributes nothing.
@@ -48,6 +52,7 @@ struct Params {
     __nv_bfloat16* dk; int64_t dk_sb, dk_sl;
     __nv_bfloat16* dv; int64_t dv_sb, dv_sl;
     float* dq_part;       // [key tiles][B][L][nh*32] fp32 partial dQ (without the 1/sqrt(d) factor)
+    float* kv_part;       // [items][2 slots][128 keys][dK 32 | dV 32] fp32 partials of items split between two CTAs
     const float* lse;     // (B, nh, L) natural log
     const float* delta;   // (B, nh, L) rowsum(dO o O)
     const uint8_t* kpm; int64_t kpm_sb;
@@ -73,13 +78,36 @@ struct Smem {
 };
 static_assert(Smem::ring + kStages * 2 * kTileBytes <= Smem::ds && Smem::ds % 1024 == 0 && Smem::pt % 1024 == 0, "smem layout");
 
-// debug timeline (build with DETR_B200_DEFINES=-DDETR_BWD_TIMELINE): slot = (warp, tile, event) of CTA (0,0,0) only
+// debug timeline (build with DETR_B200_DEFINES=-DDETR_BWD_TIMELINE): slot = (warp, local pair index, event) of CTA 0 only
 #ifndef DETR_BWD_TIMELINE
-#define BWD_STAMP(ev, t) do {} while (0)
+#define BWD_STAMP(ev, j) do {} while (0)
 #else
-#define BWD_STAMP(ev, t) do { if (p.dbg != nullptr && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (t) < 16) \
-    p.dbg[(warp * 16 + (t)) * 8 + (ev)] = clock64(); } while (0)
+#define BWD_STAMP(ev, j) do { if (p.dbg != nullptr && lane == 0 && blockIdx.x == 0 && (j) < 32) \
+    p.dbg[(warp * 32 + (j)) * 8 + (ev)] = clock64(); } while (0)
 #endif
+
+// ---- persistent schedule --------------------------------------------------------------------------------------------
+// item = (batch, head, key tile) in the order ((b * nh + h) * KT + kt); an item has T (query tile, key tile) pairs.  CTA c
+// of G walks the contiguous pair range [c * I*T / G, (c+1) * I*T / G): whole items in the middle, at most one partial
+// item at each end (G <= I, so a range is never shorter than T).  A partial item leaves fp32 dK / dV partials in slot 0
+// (the part holding query tile 0) or slot 1 of `kv_part`; attention_dkv_reduce_kernel folds the two slots.
+struct Sched {
+    int T, KT, nh, NT;     // pairs per item, key tiles, heads, pairs of this CTA
+    int item0, t0;         // first pair of this CTA
+    __device__ __forceinline__ void init(const Params& p, int c, int G) {
+        T = (p.L + kT - 1) / kT; KT = (p.S + kT - 1) / kT; nh = p.nh;
+        const long long total = (long long)KT * p.nh * p.B * T;
+        const long long n0 = total * c / G, n1 = total * (c + 1) / G;
+        NT = (int)(n1 - n0); item0 = (int)(n0 / T); t0 = (int)(n0 - (long long)item0 * T);
+    }
+    __device__ __forceinline__ void split(int item, int& b, int& h, int& kt) const { kt = item % KT; const int bh = item / KT; h = bh % nh; b = bh / nh; }
+};
+// walks the CTA's pairs in order without divisions: (item, t) of local pair j
+struct Cursor {
+    int item, t;
+    __device__ __forceinline__ explicit Cursor(const Sched& sc) : item(sc.item0), t(sc.t0) {}
+    __device__ __forceinline__ void next(const Sched& sc) { if (++t == sc.T) { t = 0; ++item; } }
+};
 
 __global__ void __launch_bounds__(kThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -88,21 +116,21 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int kt = blockIdx.x, k0 = kt * kT, h = blockIdx.y, b = blockIdx.z;
+    Sched sc;
+    sc.init(p, blockIdx.x, gridDim.x);
+    const int NT = sc.NT;
 #ifdef DETR_BWD_TIMELINE
-    const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    if (p.dbg != nullptr && tid == 0 && cta_lin < 1024) {
+    if (p.dbg != nullptr && tid == 0 && blockIdx.x < 1024) {
         uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.dbg[2560 + cta_lin * 4 + 0] = gt; p.dbg[2560 + cta_lin * 4 + 3] = smid;
-        if (cta_lin == 0) p.dbg[(19 * 16 + 0) * 8 + 0] = clock64();
+        p.dbg[20 * 32 * 8 + blockIdx.x * 4 + 0] = gt; p.dbg[20 * 32 * 8 + blockIdx.x * 4 + 3] = smid;
     }
 #endif
-    const int T = (p.L + kT - 1) / kT;    // number of streamed query tiles
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
-    uint64_t* fixed_full = bars + 0;
-    uint64_t* ring_full = bars + 1;                    // [kStages]
+    uint64_t* kv_full = bars + 0;
+    uint64_t* k_empty = bars + 1;                      // K tile: free after the segment's last dQ_part MMAs
+    uint64_t* ring_full = bars + 2;                    // [kStages]
     uint64_t* ring_empty = ring_full + kStages;        // [kStages]
     uint64_t* sdp_full = ring_empty + kStages;         // [2] one per 64-key half: the two math groups run out of phase
     uint64_t* sdp_empty = sdp_full + 2;                // [2]
@@ -111,65 +139,71 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     uint64_t* dq_empty = sdp_full + 9;                 // [3]
     uint64_t* dqs_full = sdp_full + 12;                // [2]
     uint64_t* dqs_empty = sdp_full + 14;               // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 16);
-    uint8_t* kflag = smem + Smem::flags;
+    uint64_t* acc_full = sdp_full + 16;                // [2] dK / dV accumulators of a finished segment
+    uint64_t* acc_empty = sdp_full + 18;               // [2]
+    uint64_t* v_empty = sdp_full + 20;                 // V tile: free after the segment's last score MMAs
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 21);
 
     if (tid == 0) {
-        mbar_init(fixed_full, 1);
+        mbar_init(kv_full, 1); mbar_init(k_empty, 1); mbar_init(v_empty, 1);
         for (int s = 0; s < kStages; ++s) { mbar_init(ring_full + s, 1); mbar_init(ring_empty + s, 1); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(sdp_full + s, 1); mbar_init(sdp_empty + s, kComputeThreads / 2);
             mbar_init(ds_full + s, kComputeThreads);
             mbar_init(dqs_full + s, kComputeThreads); mbar_init(dqs_empty + s, 1);
+            mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, kComputeThreads);
         }
         for (int s = 0; s < 3; ++s) { mbar_init(dq_full + s, 1); mbar_init(dq_empty + s, kComputeThreads); }
         fence_barrier_init();
     }
     if (warp == 17) tmem_alloc(tmem_slot, kTmemCols);
-    if (tid < kT)   // key flags of the CTA's own 128 keys: 0 normal, 1 masked, 2 beyond S
-        kflag[tid] = (k0 + tid) >= p.S ? 2 : ((p.kpm && p.kpm[b * p.kpm_sb + k0 + tid]) ? 1 : 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-#ifdef DETR_BWD_TIMELINE
-    if (p.dbg != nullptr && tid == 0 && cta_lin < 1024) {
-        long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.dbg[2560 + cta_lin * 4 + 1] = gt;
-    }
-#endif
-    const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_dk = tmem_base + 256, tmem_dv = tmem_base + 288,
-                   tmem_dq = tmem_base + 320;
+    const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_acc = tmem_base + 256 /* 2 x (dK 32 | dV 32) */,
+                   tmem_dq = tmem_base + 384 /* 3 x 32 */;
 
     if (warp >= kComputeWarps) {
         reg_dealloc<64>();   // the CTA register pool is what its own warps release: 128 x (96-64) == 512 x (104-96)
         if (warp == 16 && lane == 0) {
             // ================= TMA producer =================
             tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
-            mbar_expect_tx(fixed_full, 2 * kTileBytes);
-            tma_load_3d(smem + Smem::fixed, &tm_k, fixed_full, h * kD, k0, b);
-            tma_load_3d(smem + Smem::fixed + kTileBytes, &tm_v, fixed_full, h * kD, k0, b);
-            for (int t = 0; t < T; ++t) {
-                const int s = t % kStages;
-                if (t >= kStages) mbar_wait_sleep(ring_empty + s, ((t / kStages) - 1) & 1);
-                mbar_expect_tx(ring_full + s, 2 * kTileBytes);
-                uint8_t* dst = smem + Smem::ring + s * 2 * kTileBytes;
-                tma_load_3d(dst, &tm_q, ring_full + s, h * kD, t * kT, b);
-                tma_load_3d(dst + kTileBytes, &tm_do, ring_full + s, h * kD, t * kT, b);
+            int seg = -1, b = 0, h = 0, kt = 0;
+            Cursor cur(sc);
+            for (int j = 0; j < NT; ++j, cur.next(sc)) {
+                const int t = cur.t;
+                const bool first = j == 0 || t == 0;
+                if (first) sc.split(cur.item, b, h, kt);
+                const int st = j % kStages;
+                if (j >= kStages) mbar_wait_sleep(ring_empty + st, ((j / kStages) - 1) & 1);
+                mbar_expect_tx(ring_full + st, 2 * kTileBytes);
+                uint8_t* dst = smem + Smem::ring + st * 2 * kTileBytes;
+                tma_load_3d(dst, &tm_q, ring_full + st, h * kD, t * kT, b);
+                tma_load_3d(dst + kTileBytes, &tm_do, ring_full + st, h * kD, t * kT, b);
+                if (first) {   // new segment: its K / V tiles, once every MMA of the previous segment has read the old ones
+                    ++seg;
+                    // V is last read by the previous segment's final score MMAs, K by its final dQ_part MMAs (issued before the
+                    // dK / dV accumulation of that pair): both loads start long before the previous segment has drained
+                    if (seg >= 1) mbar_wait_sleep(v_empty, (seg - 1) & 1);   // (the previous kv_full phase completed long before)
+                    mbar_expect_tx(kv_full, 2 * kTileBytes);
+                    tma_load_3d(smem + Smem::fixed + kTileBytes, &tm_v, kv_full, h * kD, kt * kT, b);
+                    if (seg >= 1) mbar_wait_sleep(k_empty, (seg - 1) & 1);
+                    tma_load_3d(smem + Smem::fixed, &tm_k, kv_full, h * kD, kt * kT, b);
+                }
             }
         } else if (warp == 17 && elect_one()) {
             // ================= MMA issuer =================
-            constexpr uint32_t idesc_sc = make_idesc_bf16(kT, kT, false, false);   // scores: both operands K-major (contract over d)
             constexpr uint32_t idesc_dq = make_idesc_bf16(kT, kD, false, true);    // dS (K-major) x K (MN-major)
             constexpr uint32_t idesc_kv = make_idesc_bf16(kT, kD, true, true);     // P~^T / dS^T (MN-major) x dO / Q (MN-major)
+            constexpr uint32_t idesc_half = make_idesc_bf16(kT, kT / 2, false, false);   // scores: both operands K-major
             // descriptor words (tc.cuh): high word per layout, low word = (address >> 4) + constant
             constexpr uint32_t hi64 = desc_hi(512, SWZ_64B);      // Q/K/V/dO tiles: 64-byte rows, 8-row groups 512 B apart
             constexpr uint32_t hi128 = desc_hi(1024, SWZ_128B);   // dS / P~ tiles: 128-byte rows, 8-row groups 1024 B apart
             const uint32_t k_lo = smem_u32(smem + Smem::fixed) >> 4, v_lo = k_lo + (kTileBytes >> 4);
-            constexpr uint32_t idesc_half = make_idesc_bf16(kT, kT / 2, false, false);
             // scores of one 64-key half: S_h = Q K_h^T, dP_h = dO V_h^T (keys 64h.. of the K / V tiles: 64 rows x 64 B further)
-            auto issue_scores = [&](int t, int hf) {
-                const uint32_t q_lo = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes) >> 4, do_lo = q_lo + (kTileBytes >> 4);
+            auto issue_scores = [&](int j, int hf) {
+                const uint32_t q_lo = smem_u32(smem + Smem::ring + (j % kStages) * 2 * kTileBytes) >> 4, do_lo = q_lo + (kTileBytes >> 4);
                 const uint32_t kh_lo = k_lo + hf * (64 * 64 >> 4), vh_lo = v_lo + hf * (64 * 64 >> 4);
 #pragma unroll
                 for (int ks = 0; ks < kD / 16; ++ks)   // K-major operands: 32 B per 16-channel step, LBO 16
@@ -179,57 +213,78 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     umma_bf16_lh(tmem_dp + hf * 64, do_lo + desc_lo(ks * 32, 16), hi64, vh_lo + desc_lo(ks * 32, 16), hi64, idesc_half, ks > 0);
                 umma_commit(sdp_full + hf);
             };
-            mbar_wait_sleep(fixed_full, 0);
-            mbar_wait_sleep(ring_full + 0, 0);
-            tc_fence_after();
-            issue_scores(0, 0);
-            issue_scores(0, 1);
-            for (int t = 0; t < T; ++t) {
-                const int buf = t & 1;
-                if (t + 1 < T) {
-                    mbar_wait_sleep(ring_full + ((t + 1) % kStages), ((t + 1) / kStages) & 1);
+            // scores of pair j (j >= 1: once both math groups hold pair j-1's halves in registers)
+            auto scores = [&](int j, bool last_of_segment) {
+                mbar_wait_sleep(ring_full + (j % kStages), (j / kStages) & 1);
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        mbar_wait_sleep(sdp_empty + hf, t & 1);     // that group holds its half of S_t / dP_t in registers
-                        tc_fence_after();
-                        issue_scores(t + 1, hf);
-                    }
+                for (int hf = 0; hf < 2; ++hf) {
+                    if (j >= 1) mbar_wait_sleep(sdp_empty + hf, (j - 1) & 1);
+                    tc_fence_after();
+                    issue_scores(j, hf);
                 }
-                BWD_STAMP(0, t);
-                mbar_wait_sleep(ds_full + buf, (t >> 1) & 1);   // dS_t and P~_t are in shared memory
-                BWD_STAMP(1, t);
-                if (t >= 3) mbar_wait_sleep(dq_empty + t % 3, ((t / 3) - 1) & 1);   // dQ_part of pair t-3 has been read out of TMEM
-                if (t >= 2) mbar_wait_sleep(dqs_empty + buf, ((t >> 1) - 1) & 1);   // staging tile of pair t-2 has been stored: dq_full(t)
-                                                                                    // tells the math warps that it is free again
+                if (last_of_segment) umma_commit(v_empty);   // no later MMA of this segment reads the V tile
+            };
+            int seg = 0;
+            if (NT > 0) {
+                mbar_wait_sleep(kv_full, 0);
+                scores(0, NT == 1 || sc.t0 == sc.T - 1);
+            }
+            Cursor cur(sc);
+            for (int j = 0; j < NT; ++j, cur.next(sc)) {
+                const bool first = j == 0 || cur.t == 0, last = j == NT - 1 || cur.t == sc.T - 1;
+                const bool has_next = j + 1 < NT;
+                const int buf = j & 1, ab = seg & 1;
+                if (has_next && !last) scores(j + 1, j + 2 == NT || cur.t + 1 == sc.T - 1);   // same K / V: run under the math of pair j
+                BWD_STAMP(0, j);
+                mbar_wait_sleep(ds_full + buf, (j >> 1) & 1);   // dS_j and P~_j are in shared memory
+                BWD_STAMP(1, j);
+                if (j >= 3) mbar_wait_sleep(dq_empty + j % 3, ((j / 3) - 1) & 1);    // dQ_part of pair j-3 has been read out of TMEM
+                if (j >= 2) mbar_wait_sleep(dqs_empty + buf, ((j >> 1) - 1) & 1);    // staging tile of pair j-2 has been stored: dq_full(j)
+                                                                                     // tells the math warps that it is free again
+                if (first && seg >= 2) mbar_wait_sleep(acc_empty + ab, ((seg >> 1) - 1) & 1);   // accumulators of segment seg-2 read out
                 tc_fence_after();
-                const uint32_t q_lo = smem_u32(smem + Smem::ring + (t % kStages) * 2 * kTileBytes) >> 4, do_lo = q_lo + (kTileBytes >> 4);
+                const uint32_t q_lo = smem_u32(smem + Smem::ring + (j % kStages) * 2 * kTileBytes) >> 4, do_lo = q_lo + (kTileBytes >> 4);
                 const uint32_t ds_lo = smem_u32(smem + Smem::ds + buf * (kT * kT * 2)) >> 4, pt_lo = smem_u32(smem + Smem::pt + buf * (kT * kT * 2)) >> 4;
-                const bool acc = t > 0;
+                const bool acc = !first;
+                const uint32_t t_dk = tmem_acc + ab * 64, t_dv = t_dk + 32;
+                // dQ_part first: on the last pair of a segment the K tile is handed back to the producer right after it
+#pragma unroll
+                for (int ks = 0; ks < kT / 16; ++ks) {
+                    // dQ_part = dS K: A K-major SWIZZLE_128B (64-key blocks of 16 KB, 32 B per 16-key step), B = K tile MN-major
+                    umma_bf16_lh(tmem_dq + (j % 3) * kD, ds_lo + desc_lo((ks >> 2) * 16384 + (ks & 3) * 32, 16), hi128,
+                                 k_lo + desc_lo(ks * 1024, 512), hi64, idesc_dq, ks > 0);
+                }
+                if (last) umma_commit(k_empty);
 #pragma unroll
                 for (int ks = 0; ks < kT / 16; ++ks) {
                     // contraction over queries: A = [query][key] tiles read MN-major (keys = M): 16 queries = 2048 B per step,
                     // the second 64-key block 16 KB further (LBO), 8-query groups 1024 B apart (SBO);
                     // B = dO / Q tiles MN-major: 16 queries = 1024 B per step, LBO 512
-                    umma_bf16_lh(tmem_dv, pt_lo + desc_lo(ks * 2048, 16384), hi128, do_lo + desc_lo(ks * 1024, 512), hi64, idesc_kv, acc || ks > 0);
-                    umma_bf16_lh(tmem_dk, ds_lo + desc_lo(ks * 2048, 16384), hi128, q_lo + desc_lo(ks * 1024, 512), hi64, idesc_kv, acc || ks > 0);
+                    umma_bf16_lh(t_dv, pt_lo + desc_lo(ks * 2048, 16384), hi128, do_lo + desc_lo(ks * 1024, 512), hi64, idesc_kv, acc || ks > 0);
+                    umma_bf16_lh(t_dk, ds_lo + desc_lo(ks * 2048, 16384), hi128, q_lo + desc_lo(ks * 1024, 512), hi64, idesc_kv, acc || ks > 0);
                 }
-#pragma unroll
-                for (int ks = 0; ks < kT / 16; ++ks) {
-                    // dQ_part = dS K: A K-major SWIZZLE_128B (64-key blocks of 16 KB, 32 B per 16-key step), B = K tile MN-major
-                    umma_bf16_lh(tmem_dq + (t % 3) * kD, ds_lo + desc_lo((ks >> 2) * 16384 + (ks & 3) * 32, 16), hi128,
-                                 k_lo + desc_lo(ks * 1024, 512), hi64, idesc_dq, ks > 0);
+                umma_commit(ring_empty + (j % kStages));
+                umma_commit(dq_full + j % 3);
+                if (last) {
+                    umma_commit(acc_full + ab);                  // dK / dV of this segment are complete
+                    if (has_next) {                              // next segment: new K / V, then its first scores
+                        ++seg;
+                        mbar_wait_sleep(kv_full, seg & 1);
+                        scores(j + 1, j + 2 == NT || sc.T == 1);
+                    }
                 }
-                umma_commit(ring_empty + (t % kStages));
-                umma_commit(dq_full + t % 3);                   // (also covers dK / dV of the last pair for the epilogue)
-                BWD_STAMP(2, t);
+                BWD_STAMP(2, j);
             }
-        }
-        else if (warp == 18 && elect_one()) {
+        } else if (warp == 18 && elect_one()) {
             // ================= dQ_part store warp =================
             tma_prefetch_desc(&tm_dqp);
-            for (int t = 0; t < T; ++t) {
-                const int buf = t & 1;
-                mbar_wait_sleep(dqs_full + buf, (t >> 1) & 1);
+            Cursor cur(sc);
+            int b = 0, h = 0, kt = 0;
+            for (int j = 0; j < NT; ++j, cur.next(sc)) {
+                const int t = cur.t;
+                if (j == 0 || t == 0) sc.split(cur.item, b, h, kt);
+                const int buf = j & 1;
+                mbar_wait_sleep(dqs_full + buf, (j >> 1) & 1);
                 tma_store_3d(&tm_dqp, smem + Smem::dqs + buf * (kT * kD * 4), h * kD, t * kT, kt * p.B + b);   // rows >= L are clipped
                 tma_store_commit();
                 tma_store_wait_read0();                 // the staging tile has been read: it may be overwritten
@@ -243,31 +298,19 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int lq = warp & 3, kq = warp >> 2;      // TMEM lane quarter, 32-key quarter of the tile
         const int row = lq * 32 + lane;               // TMEM lane = query within the tile
         const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
-        const uint32_t bh = (uint32_t)(b * p.nh + h);
-        const float* lse_bh = p.lse + (int64_t)bh * p.L;
-        const float* dl_bh = p.delta + (int64_t)bh * p.L;
         const bool drop = p.drop_thresh != 0;
         const uint64_t seed = drop ? p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull) : 0ull;
         const uint32_t thr4 = p.drop_thresh * 0x01010101u;
-        const int key0 = k0 + kq * 32;                // first key of this thread's 32 columns
-        const uint8_t* kf = kflag + kq * 32;
         // byte offset of this thread's row inside a [query][64-key block] SWIZZLE_128B tile; its 4 chunks are (kq&1)*4 + g
         const uint32_t row_off = (uint32_t)((kq >> 1) * 16384 + (row >> 3) * 1024 + (row & 7) * 128);
         const uint32_t chunk0 = (uint32_t)((kq & 1) * 4);
+        const int C = p.nh * kD;
 
-        uint32_t any = p.amask ? 1u : 0u;             // warp-uniform: does this 32-key quarter need masking at all?
-        {
-            const uint4* kf4 = reinterpret_cast<const uint4*>(kf);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) { const uint4 w = kf4[i]; any |= w.x | w.y | w.z | w.w; }
-        }
-
-        // dQ_part of pair t: 8 of its 32 columns per thread, TMEM -> registers -> swizzled staging tile (row = 128 B,
-        // 16-byte chunk j of row r at ((j ^ (r & 7)) << 4): conflict-free stores, the layout TMA expects for SWIZZLE_128B)
+        // The readout of pair u is split around the math of pair u+2: the TMEM load rides with the S / dP loads (its
+        // barrier completed long before), the staging stores share the fence of the dS / P~ stores.  Staging tile:
+        // row = 128 B, 16-byte chunk c of row r at ((c ^ (r & 7)) << 4): conflict-free stores, TMA's SWIZZLE_128B layout.
         uint8_t* dqs_row = smem + Smem::dqs + row * 128;
         const uint32_t dqs_c0 = (uint32_t)(((2 * kq) ^ (row & 7)) << 4), dqs_c1 = (uint32_t)(((2 * kq + 1) ^ (row & 7)) << 4);
-        // The readout of pair u is split around the math of pair u+2: the TMEM load rides with the S / dP loads (its
-        // barrier completed long before), the staging stores share the fence of the dS / P~ stores.
         uint32_t dqv[8];
         auto dq_load = [&](int u) {
             mbar_wait(dq_full + u % 3, (u / 3) & 1);   // (also: staging tile u&1 has been stored, see the MMA warp)
@@ -288,47 +331,101 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             fence_proxy_async_smem();
             mbar_arrive(dqs_full + (u & 1));
         };
-
-        // per-row scalars of the NEXT tile are fetched one iteration ahead
-        float lse_n = CUDART_INF_F, dl_n = 0.f;
-        if (row < p.L) { lse_n = lse_bh[row]; dl_n = dl_bh[row]; }
+        // dK (key quarters 0,1: 16 columns each) and dV (quarters 2,3) of a finished segment: bf16 to dk / dv when the
+        // segment covered the whole item, fp32 partials to kv_part otherwise
+        auto acc_readout = [&](int sg, int item, bool whole, int slot) {
+            int b, h, kt;
+            sc.split(item, b, h, kt);
+            const bool is_dk = kq < 2;
+            const int c0 = (kq & 1) * 16;
+            uint32_t a[16];
+            mbar_wait(acc_full + (sg & 1), (sg >> 1) & 1);
+            tc_fence_after();
+            tmem_ld16(tmem_acc + (sg & 1) * 64 + (is_dk ? 0 : 32) + lane_addr + c0, a);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(acc_empty + (sg & 1));
+            const int gr = kt * kT + row;
+            if (whole) {
+                if (gr < p.S) {
+                    __nv_bfloat16* dst = is_dk ? p.dk + b * p.dk_sb + (int64_t)gr * p.dk_sl + h * kD + c0
+                                               : p.dv + b * p.dv_sb + (int64_t)gr * p.dv_sl + h * kD + c0;
+                    const float f = is_dk ? p.scale : 1.f;   // dK carries the 1/sqrt(d) of the scores; dV does not
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        uint4 w;
+                        w.x = pack_bf16x2(f * __uint_as_float(a[g * 8 + 0]), f * __uint_as_float(a[g * 8 + 1]));
+                        w.y = pack_bf16x2(f * __uint_as_float(a[g * 8 + 2]), f * __uint_as_float(a[g * 8 + 3]));
+                        w.z = pack_bf16x2(f * __uint_as_float(a[g * 8 + 4]), f * __uint_as_float(a[g * 8 + 5]));
+                        w.w = pack_bf16x2(f * __uint_as_float(a[g * 8 + 6]), f * __uint_as_float(a[g * 8 + 7]));
+                        reinterpret_cast<uint4*>(dst)[g] = w;
+                    }
+                }
+            } else {
+                uint4* dst = reinterpret_cast<uint4*>(p.kv_part + (((int64_t)item * 2 + slot) * kT + row) * 64 + (is_dk ? 0 : 32) + c0);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) dst[g] = make_uint4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
+            }
+        };
 
         // The two 64-key halves of a pair are independent down to the accumulation MMAs: start the second group of 8
-        // warps about half a period late so that one group's latency-bound steps (barrier waits, TMEM loads, fences)
-        // run under the other group's issue-bound math.
+        // warps a little late so that one group's latency-bound steps (barrier waits, TMEM loads, fences) can run under the
+        // other group's math.
 #ifndef DETR_BWD_SKEW_NS
 #define DETR_BWD_SKEW_NS 400
 #endif
-        if ((kq >> 1) && T > 1) __nanosleep(DETR_BWD_SKEW_NS);
+        if ((kq >> 1) && NT > 1) __nanosleep(DETR_BWD_SKEW_NS);
+
+        // per-segment state (kept small: the math loop runs at the register limit)
+        int seg = -1, seg_t0 = 0, key0 = 0;
+        uint32_t bh = 0, kmask = 0;       // kmask bit i: key key0+i is masked (key_padding_mask) or beyond S
+        Cursor cur(sc);
+
         uint32_t s[32], dp[32];
-        for (int t = 0; t < T; ++t) {
-            const int buf = t & 1;
+        for (int j = 0; j < NT; ++j, cur.next(sc)) {
+            const int t = cur.t;
+            const bool first = j == 0 || t == 0;
+            const int prev_t0 = seg_t0;
+            if (first) {
+                ++seg; seg_t0 = t;
+                int b, h, kt;
+                sc.split(cur.item, b, h, kt);
+                key0 = kt * kT + kq * 32;
+                bh = (uint32_t)(b * p.nh + h);
+                const int key = key0 + lane;
+                const bool m = key >= p.S || (p.kpm != nullptr && p.kpm[b * p.kpm_sb + key] != 0);
+                kmask = __ballot_sync(FULL_MASK, m);
+            }
+            const float* lse_bh = p.lse + (int64_t)bh * p.L;
+            const float* dl_bh = p.delta + (int64_t)bh * p.L;
+            const uint32_t any = kmask | (p.amask ? 1u : 0u);   // warp-uniform: does this 32-key quarter need masking at all?
+            const int buf = j & 1;
             const int q = t * kT + row;
             // +inf (padding row / fully masked row) -> p = 0.  With dropout P comes out pre-scaled by 1/(1-p) and D is
             // scaled by (1-p) instead:  dS = P/(1-p) o (keep o dP~ - (1-p) D)
-            const float nl = drop ? fmaf(-lse_n, 1.4426950408889634f, p.drop_log2_scale) : -lse_n * 1.4426950408889634f;
-            const float dlt = drop ? dl_n * p.drop_keep : dl_n;
-            {
-                const int qn = q + kT;
-                lse_n = CUDART_INF_F; dl_n = 0.f;
-                if (t + 1 < T && qn < p.L) { lse_n = lse_bh[qn]; dl_n = dl_bh[qn]; }
-            }
+            float lse_q = CUDART_INF_F, dl_q = 0.f;
+            if (q < p.L) { lse_q = lse_bh[q]; dl_q = dl_bh[q]; }
             const uint32_t row_key = drop ? dropout_row_key(seed, bh, (uint32_t)q) : 0u;
             const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S + key0 : nullptr;
 
-            BWD_STAMP(0, t);
-            mbar_wait(sdp_full + (kq >> 1), t & 1);
-            BWD_STAMP(1, t);
+            BWD_STAMP(0, j);
+            mbar_wait(sdp_full + (kq >> 1), j & 1);
+            BWD_STAMP(1, j);
             tc_fence_after();
             tmem_ld32(tmem_s + lane_addr + kq * 32, s);
             tmem_ld32(tmem_dp + lane_addr + kq * 32, dp);
-            if (t >= 2) dq_load(t - 2);
+            if (j >= 2) dq_load(j - 2);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(sdp_empty + (kq >> 1));                  // this half's score columns may be overwritten by the next pair
-            if (t >= 2) mbar_arrive(dq_empty + (t - 2) % 3);
-            // dS / P~ buffer `buf` is free: the MMAs of pair t-2 completed before dq_full(t-2), awaited just above
-            BWD_STAMP(3, t);
+            if (j >= 2) {
+                mbar_arrive(dq_empty + (j - 2) % 3);
+                dq_stage(j - 2);                                 // (made visible to TMA by the fence after the dS / P~ stores)
+            }
+            // dS / P~ buffer `buf` is free: the MMAs of pair j-2 completed before dq_full(j-2), awaited just above
+            BWD_STAMP(3, j);
+            const float nl = drop ? fmaf(-lse_q, 1.4426950408889634f, p.drop_log2_scale) : -lse_q * 1.4426950408889634f;
+            const float dlt = drop ? dl_q * p.drop_keep : dl_q;
 
             uint8_t* ds_row = smem + Smem::ds + buf * (kT * kT * 2) + row_off;
             uint8_t* pt_row = smem + Smem::pt + buf * (kT * kT * 2) + row_off;
@@ -345,25 +442,25 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     if (DROP) { t0 = dropout_quad(rng, thr4); t1 = dropout_quad(rng, thr4); }
                     uint32_t pk[4], dk[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = g * 8 + 2 * j;
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int i = g * 8 + 2 * jj;
                         const float2 e = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, nl2);
                         float2 x = make_float2(ex2(e.x), ex2(e.y));
                         if (MASKED) {
-                            const bool m0 = kf[i] != 0 || (arow != nullptr && (key0 + i) < p.S && arow[i] != 0);
-                            const bool m1 = kf[i + 1] != 0 || (arow != nullptr && (key0 + i + 1) < p.S && arow[i + 1] != 0);
+                            const bool m0 = ((kmask >> i) & 1u) || (arow != nullptr && (key0 + i) < p.S && arow[i] != 0);
+                            const bool m1 = ((kmask >> (i + 1)) & 1u) || (arow != nullptr && (key0 + i + 1) < p.S && arow[i + 1] != 0);
                             x.x = m0 ? 0.f : x.x; x.y = m1 ? 0.f : x.y;
                         }
-                        // dS without the 1/sqrt(d) factor: it is applied once to dK in the epilogue and to dQ in the reduction
+                        // dS without the 1/sqrt(d) factor: it is applied once to dK in the read-out and to dQ in the reduction
                         const float2 a = __fmul2_rn(x, __fadd2_rn(make_float2(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1])), ndl2));
-                        pk[j] = pack_bf16x2(x.x, x.y);
-                        dk[j] = pack_bf16x2(a.x, a.y);
+                        pk[jj] = pack_bf16x2(x.x, x.y);
+                        dk[jj] = pack_bf16x2(a.x, a.y);
                         if (DROP) {
                             const float2 bb = __fmul2_rn(x, ndl2);
                             const uint32_t bk = pack_bf16x2(bb.x, bb.y);
-                            const uint32_t m = (j & 1) ? dropout_mask_bf16x2<1>(j < 2 ? t0 : t1) : dropout_mask_bf16x2<0>(j < 2 ? t0 : t1);
-                            dk[j] = (dk[j] & m) | (bk & ~m);
-                            pk[j] &= m;
+                            const uint32_t m = (jj & 1) ? dropout_mask_bf16x2<1>(jj < 2 ? t0 : t1) : dropout_mask_bf16x2<0>(jj < 2 ? t0 : t1);
+                            dk[jj] = (dk[jj] & m) | (bk & ~m);
+                            pk[jj] &= m;
                         }
                     }
                     const uint32_t off = ((chunk0 + g) ^ (uint32_t)(row & 7)) << 4;
@@ -377,53 +474,30 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             } else {
                 if (drop) quarter_tile(FF{}, TT{}); else quarter_tile(FF{}, FF{});
             }
-            if (t >= 2) dq_stage(t - 2);
             fence_proxy_async_smem();
             mbar_arrive(ds_full + buf);
-            if (t >= 2) mbar_arrive(dqs_full + (t & 1));
-            BWD_STAMP(4, t);
-            BWD_STAMP(5, t);
+            if (j >= 2) mbar_arrive(dqs_full + (j & 1));
+            BWD_STAMP(4, j);
+            // the previous segment's accumulators are read out after this pair's math has been handed to the MMA warp
+            // (its last MMAs were issued one pair ago)
+            if (first && seg >= 1) acc_readout(seg - 1, cur.item - 1, prev_t0 == 0 /* and it ended at T-1: t == 0 here */, prev_t0 == 0 ? 0 : 1);
+            BWD_STAMP(5, j);
         }
-        BWD_STAMP(6, 0);
-        if (T >= 2) dq_readout(T - 2);
-        dq_readout(T - 1);
-        BWD_STAMP(7, 0);
-        // ---- epilogue: dK (key quarters 0,1: 16 columns each) and dV (quarters 2,3) -> bf16 global ----
-        // (dq_full of the last pair was committed after every MMA of the stream: the accumulators are complete)
-        {
-            const int gr = k0 + row;
-            const bool is_dk = kq < 2;
-            const int c0 = (kq & 1) * 16;
-            uint32_t a[16];
-            tc_fence_after();
-            tmem_ld16((is_dk ? tmem_dk : tmem_dv) + lane_addr + c0, a);
-            tmem_ld_wait();
-            if (gr < p.S) {
-                __nv_bfloat16* dst = is_dk ? p.dk + b * p.dk_sb + (int64_t)gr * p.dk_sl + h * kD + c0
-                                           : p.dv + b * p.dv_sb + (int64_t)gr * p.dv_sl + h * kD + c0;
-                const float f = is_dk ? p.scale : 1.f;   // dK carries the 1/sqrt(d) of the scores; dV does not
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    uint4 w;
-                    w.x = pack_bf16x2(f * __uint_as_float(a[g * 8 + 0]), f * __uint_as_float(a[g * 8 + 1]));
-                    w.y = pack_bf16x2(f * __uint_as_float(a[g * 8 + 2]), f * __uint_as_float(a[g * 8 + 3]));
-                    w.z = pack_bf16x2(f * __uint_as_float(a[g * 8 + 4]), f * __uint_as_float(a[g * 8 + 5]));
-                    w.w = pack_bf16x2(f * __uint_as_float(a[g * 8 + 6]), f * __uint_as_float(a[g * 8 + 7]));
-                    reinterpret_cast<uint4*>(dst)[g] = w;
-                }
-            }
+        if (NT >= 2) dq_readout(NT - 2);
+        if (NT >= 1) {
+            dq_readout(NT - 1);
+            // `cur` has stepped past the last pair: it sits on (item + 1, 0) iff the last segment ended at T-1
+            const bool ended = cur.t == 0;
+            acc_readout(seg, ended ? cur.item - 1 : cur.item, seg_t0 == 0 && ended, seg_t0 == 0 ? 0 : 1);
         }
         tc_fence_before();
-        BWD_STAMP(6, 1);
     }
-    BWD_STAMP(7, 1);
     __syncthreads();
     if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
 #ifdef DETR_BWD_TIMELINE
-    if (p.dbg != nullptr && tid == 0 && cta_lin < 1024) {
+    if (p.dbg != nullptr && tid == 0 && blockIdx.x < 1024) {
         long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.dbg[2560 + cta_lin * 4 + 2] = gt;
-        if (cta_lin == 0) p.dbg[(19 * 16 + 0) * 8 + 1] = clock64();
+        p.dbg[20 * 32 * 8 + blockIdx.x * 4 + 2] = gt;
     }
 #endif
 }
@@ -480,6 +554,36 @@ __global__ void attention_dq_reduce_kernel(const float* __restrict__ part, int K
     *reinterpret_cast<uint4*>(dq + b * dq_sb + (int64_t)q * dq_sl + c) = w;
 }
 
+// dK / dV of the items that were split between two CTAs: sum of the two fp32 partial slots, dK scaled, bf16.
+// CTA c handles the boundary between persistent CTAs c and c+1 (nothing to do when it falls on an item edge).
+__global__ void __launch_bounds__(256) attention_dkv_reduce_kernel(const float* __restrict__ kv_part, __nv_bfloat16* __restrict__ dk,
+                                                                   int64_t dk_sb, int64_t dk_sl, __nv_bfloat16* __restrict__ dv,
+                                                                   int64_t dv_sb, int64_t dv_sl, int B, int nh, int L, int S, int G, float scale) {
+    const int T = (L + kT - 1) / kT, KT = (S + kT - 1) / kT;
+    const long long total = (long long)KT * nh * B * T;
+    const long long n = total * (blockIdx.x + 1) / G;
+    if (n % T == 0) return;
+    const int item = (int)(n / T);
+    const int kt = item % KT, bh = item / KT, h = bh % nh, b = bh / nh;
+    for (int w = threadIdx.x; w < kT * 4; w += 256) {
+        const int row = w >> 2, g = w & 3;
+        const int key = kt * kT + row;
+        if (key >= S) continue;
+        const float4* s0 = reinterpret_cast<const float4*>(kv_part + (((int64_t)item * 2 + 0) * kT + row) * 64 + g * 16);
+        const float4* s1 = reinterpret_cast<const float4*>(kv_part + (((int64_t)item * 2 + 1) * kT + row) * 64 + g * 16);
+        const float f = g < 2 ? scale : 1.f;
+        __nv_bfloat16* dst = g < 2 ? dk + b * dk_sb + (int64_t)key * dk_sl + h * kD + g * 16 : dv + b * dv_sb + (int64_t)key * dv_sl + h * kD + (g - 2) * 16;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float4 a0 = s0[2 * e], a1 = s0[2 * e + 1], b0 = s1[2 * e], b1 = s1[2 * e + 1];
+            uint4 o;
+            o.x = pack_bf16x2(f * (a0.x + b0.x), f * (a0.y + b0.y)); o.y = pack_bf16x2(f * (a0.z + b0.z), f * (a0.w + b0.w));
+            o.z = pack_bf16x2(f * (a1.x + b1.x), f * (a1.y + b1.y)); o.w = pack_bf16x2(f * (a1.z + b1.z), f * (a1.w + b1.w));
+            reinterpret_cast<uint4*>(dst)[e] = o;
+        }
+    }
+}
+
 }  // namespace bwd
 }  // namespace detr
 
@@ -489,9 +593,14 @@ static long long* g_bwd_dbg = nullptr;
 /* debugging aid (not part of the drop-in surface): device buffer of 20*16*8 int64 that receives clock64 stamps of CTA 0 */
 extern "C" void detr_attention_bwd_set_debug(long long* buf) { g_bwd_dbg = buf; }
 
-extern "C" int64_t detr_attention_bwd_workspace_floats(int B, int nh, int L, int S) {
+static int64_t bwd_dq_part_floats(int B, int nh, int L, int S) {
     const int64_t kt = (S + bwd::kT - 1) / bwd::kT;
     return kt * B * (int64_t)L * nh * bwd::kD;
+}
+/* dQ partials [key tiles][B][L][C] followed by the dK/dV partial slots [items][2][128][64] */
+extern "C" int64_t detr_attention_bwd_workspace_floats(int B, int nh, int L, int S) {
+    const int64_t kt = (S + bwd::kT - 1) / bwd::kT;
+    return bwd_dq_part_floats(B, nh, L, S) + kt * nh * B * 2 * bwd::kT * 64;
 }
 
 extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
@@ -527,6 +636,7 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dk_sb = dk_sb; p.dk_sl = dk_sl;
     p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.dv_sb = dv_sb; p.dv_sl = dv_sl;
     p.dq_part = dq_partial;
+    p.kv_part = dq_partial + bwd_dq_part_floats(B, nh, L, S);
     p.lse = lse; p.delta = delta; p.kpm = key_padding_mask; p.kpm_sb = kpm_sb; p.amask = attention_mask;
     p.B = B; p.nh = nh; p.L = L; p.S = S;
     p.scale = 1.f / sqrtf((float)kD);
@@ -545,8 +655,20 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     const int KT = (S + kT - 1) / kT;
     CUtensorMap tdqp;   // partials [KT*B][L][C] fp32, box = 32 channels x 128 queries, SWIZZLE_128B (128-byte rows)
     if (int rc = make_f32_tile_map(&tdqp, dq_partial, C, L, KT * B, kD, kT, "attention_bwd(dQ partials)")) return rc;
-    attention_bwd_kernel<<<dim3(KT, nh, B), kThreads, Smem::total, st>>>(tq, tk, tv, tdo, tdqp, p);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    const int64_t items = (int64_t)KT * nh * B;
+    const int G = (int)(items < num_sms ? items : num_sms);   // G <= items: a CTA's pair range is never shorter than one item
+    attention_bwd_kernel<<<G, kThreads, Smem::total, st>>>(tq, tk, tv, tdo, tdqp, p);
     DETR_CHECK_LAUNCH("attention_bwd");
+    if (items > G) {   // only then can a boundary between two CTAs fall inside an item
+        attention_dkv_reduce_kernel<<<G - 1, 256, 0, st>>>(p.kv_part, p.dk, dk_sb, dk_sl, p.dv, dv_sb, dv_sl, B, nh, L, S, G, p.scale);
+        DETR_CHECK_LAUNCH("attention_dkv_reduce");
+    }
     const int64_t n8 = (int64_t)B * L * (C / 8);
     attention_dq_reduce_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
         dq_partial, KT, (int64_t)B * L * C, reinterpret_cast<__nv_bfloat16*>(dq), dq_sb, dq_sl, B, L, C, p.scale);

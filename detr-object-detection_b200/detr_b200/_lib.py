@@ -86,7 +86,7 @@ class FoldTable(ctypes.Structure):
 # kernels launched per C-ABI call (bench.py's gpu_launches is counted from this table)
 KERNELS_PER_CALL = {"detr_cost_matrix_f32": 1, "detr_hungarian_match_f32": 1, "detr_lsap_f32": 1, "detr_lsap_f64": 1,
                     "detr_criterion_fwd_f32": 2, "detr_criterion_bwd_f32": 1, "detr_attention_fwd_bf16": 1,
-                    "detr_attention_bwd_bf16": 3, "detr_colsum_bf16": 2, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2,
+                    "detr_attention_bwd_bf16": 4, "detr_colsum_bf16": 2, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2,
                     "detr_epilogue_fwd": 1, "detr_epilogue_bwd": 2, "detr_scale_cast_multi": 1,
                     "detr_maxpool3x3s2_fwd_bf16": 1, "detr_maxpool3x3s2_bwd_bf16": 1}
 launch_count = 0          # kernels of libdetr_b200.so launched by this process

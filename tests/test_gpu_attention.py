@@ -109,7 +109,9 @@ def _check_backward(q, k, v, nh, kpm=None, am=None):
         assert err <= 3e-2 and err <= 2 * err_ref + 4e-3, (name, err, err_ref)
 
 
-@pytest.mark.parametrize("B,L,S,nh", [(1, 128, 128, 1), (2, 256, 384, 2), (2, 100, 100, 8), (2, 100, 850, 8), (1, 850, 850, 8), (1, 37, 5, 1)])
+@pytest.mark.parametrize("B,L,S,nh", [(1, 128, 128, 1), (2, 256, 384, 2), (2, 100, 100, 8), (2, 100, 850, 8), (1, 850, 850, 8), (1, 37, 5, 1),
+                                      # more (batch, head, key tile) items than SMs: persistent CTAs walk several items and split some
+                                      (3, 300, 850, 8), (2, 200, 1200, 8), (24, 100, 100, 8), (3, 850, 850, 8)])
 def test_attention_backward_shapes(cuda, B, L, S, nh):
     g = torch.Generator(device="cpu").manual_seed(L * 1000 + S + 1)
     C = nh * 32
@@ -131,6 +133,15 @@ def test_attention_backward_masks(cuda):
     kpm[1, ::3] = True
     _check_backward(q, k, v, nh, kpm=kpm)
     am = torch.rand(L, S, generator=g).to(cuda) < 0.3
+    _check_backward(q, k, v, nh, kpm=kpm, am=am)
+    # 288 (batch, head, key tile) items on 148 persistent CTAs: per-item key masks must follow the item a CTA is working on
+    B = 24
+    q = torch.randn(B, L, C, generator=g).to(cuda, torch.bfloat16)
+    k = torch.randn(B, S, C, generator=g).to(cuda, torch.bfloat16)
+    v = torch.randn(B, S, C, generator=g).to(cuda, torch.bfloat16)
+    kpm = torch.rand(B, S, generator=g).to(cuda) < 0.2
+    kpm[3, 130:] = True
+    _check_backward(q, k, v, nh, kpm=kpm)
     _check_backward(q, k, v, nh, kpm=kpm, am=am)
 
 
