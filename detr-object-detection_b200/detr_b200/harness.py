@@ -470,6 +470,7 @@ class GraphedTrainStep:
         attention.set_dropout_step_tensor(self.step_counter)
         self.loss = torch.zeros((), device=self.dev)
         self.params = [p for p in model.parameters() if p.requires_grad]
+        self.flat, self.flat_views = None, None
         self.load(example)
         # warm-up on a side stream (allocator, cuDNN autotune, lazy attribute setup), then capture
         side = torch.cuda.Stream()
@@ -494,6 +495,8 @@ class GraphedTrainStep:
 
     # -- pieces -------------------------------------------------------------------------------------------
     def _forward_backward(self):
+        for q in self.params:          # fresh gradient tensors (no accumulation kernels); Python-only, nothing is launched
+            q.grad = None
         self.step_counter.add_(1)
         with torch.autocast(device_type="cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
             out = self.model(self.images, self.heights, self.widths)
@@ -503,7 +506,15 @@ class GraphedTrainStep:
         loss.backward()
         self.loss.copy_(loss.detach())
         if self.world > 1:
-            self.flat = torch.cat([p.grad.reshape(-1) for p in self.params])
+            # one multi-tensor copy into the flat all-reduce buffer (torch.cat over ~330 gradients costs 0.8 ms, measured)
+            if self.flat is None:
+                self.flat = torch.empty(sum(q.numel() for q in self.params), dtype=torch.float32, device=self.dev)
+                self.flat_views, o = [], 0
+                for q in self.params:
+                    # the view must look like the parameter (channels_last conv weights included) for the fused optimizer
+                    self.flat_views.append(torch.as_strided(self.flat, q.shape, q.stride(), o))
+                    o += q.numel()
+            torch._foreach_copy_(self.flat_views, [q.grad if q.grad is not None else torch.zeros_like(q) for q in self.params])
 
     def _allreduce(self):
         if self.world > 1:
@@ -512,10 +523,10 @@ class GraphedTrainStep:
 
     def _update(self):
         if self.world > 1:
-            grads = [p.grad for p in self.params]
-            views = torch.split(self.flat, [g.numel() for g in grads])
-            torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(views, grads)])
-            torch._foreach_div_(grads, float(self.world))
+            # the reduced gradients are consumed in place: .grad becomes a view of the flat buffer, averaged by ONE kernel
+            self.flat.div_(float(self.world))
+            for q, v in zip(self.params, self.flat_views):
+                q.grad = v
         torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm)
         self.opt.step()
 
