@@ -308,8 +308,12 @@ def build_cpu_reference():
     def dec_fn(dec, mem, pos, qe, mask):
         return O.decoder(dict(dec.named_parameters()), mem, pos, qe, mask, cfg.num_decoder_layers, cfg.num_attention_heads, cfg.layer_norm_eps)
 
+    def posenc_fn(eh, ew, heights, widths, scale, feats, temperature):
+        pos = O.positional_encoding(eh, ew, heights, widths, scale, feats, temperature)
+        return pos.flatten(2).permute(0, 2, 1), O.padding_mask(eh, ew, heights, widths, scale).flatten(1)
+
     torch.manual_seed(0)
-    model = DetrHarness(cfg, encoder_fn=enc_fn, decoder_fn=dec_fn).train()
+    model = DetrHarness(cfg, encoder_fn=enc_fn, decoder_fn=dec_fn, posenc_fn=posenc_fn).train()
     model.backbone.fold_bn = False   # the reference's stock path: FrozenBatchNorm2d modules, unfused
 
     class OracleCriterion(torch.nn.Module):

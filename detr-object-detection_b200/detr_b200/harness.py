@@ -18,35 +18,36 @@ from torch import nn
 from .model import DETRConfig, Decoder, Encoder
 
 
+def positional_encoding_tokens(embed_h: int, embed_w: int, heights: torch.Tensor, widths: torch.Tensor, scale: int = 32,
+                               num_pos_feats: int = 128, temperature: float = 10000.0):
+    """-> (pos (B, H'*W', 2F) fp32 contiguous, mask (B, H'*W') bool): detr/position_encoding.py:5-97 and
+    detr/model.py:96-114 in ONE kernel (`detr_positional_encoding_f32`), already in the layout Encoder / Decoder consume
+    (no per-image host loop, no `.item()` syncs, no permuted views that every LayerNorm launch would have to copy)."""
+    from . import _lib
+    _lib.require_cuda(heights, "positional_encoding")
+    B = heights.shape[0]
+    h32 = heights.to(torch.int32).contiguous()
+    w32 = widths.to(torch.int32).contiguous()
+    pos = torch.empty(B, embed_h * embed_w, 2 * num_pos_feats, dtype=torch.float32, device=heights.device)
+    mask = torch.empty(B, embed_h * embed_w, dtype=torch.uint8, device=heights.device)
+    _lib.call("detr_positional_encoding_f32", h32.data_ptr(), w32.data_ptr(), B, embed_h, embed_w, int(scale), int(num_pos_feats),
+              float(temperature), pos.data_ptr(), mask.data_ptr(), _lib.stream_ptr())
+    return pos, mask.view(torch.bool)
+
+
 def positional_encoding_device(embed_h: int, embed_w: int, heights: torch.Tensor, widths: torch.Tensor, scale: int = 32,
                                num_pos_feats: int = 128, temperature: float = 10000.0) -> torch.Tensor:
-    """(B, 2*num_pos_feats, H', W') fp32, same values as detr/position_encoding.py:5-97 without its per-image loop:
-    coordinates are linspace(0,1,n) inside the valid ceil(h/scale) x ceil(w/scale) window and 0 in the padding."""
-    dev = heights.device
-    hs = torch.ceil(heights.float() / scale)
-    ws = torch.ceil(widths.float() / scale)
-    iy = torch.arange(embed_h, device=dev, dtype=torch.float32)[None, :, None]
-    ix = torch.arange(embed_w, device=dev, dtype=torch.float32)[None, None, :]
-    inside = (iy < hs[:, None, None]) & (ix < ws[:, None, None])
-    gy = torch.where(inside, iy / (hs[:, None, None] - 1).clamp(min=1), torch.zeros((), device=dev))
-    gx = torch.where(inside, ix / (ws[:, None, None] - 1).clamp(min=1), torch.zeros((), device=dev))
-    freq = temperature ** (torch.arange(0, num_pos_feats, 2, device=dev, dtype=torch.float32) / num_pos_feats)
-    ay = (gy * (2 * math.pi))[..., None] / freq
-    ax = (gx * (2 * math.pi))[..., None] / freq
-    py = torch.stack((ay.sin(), ay.cos()), dim=-1).flatten(-2)
-    px = torch.stack((ax.sin(), ax.cos()), dim=-1).flatten(-2)
-    return torch.cat((py, px), dim=-1).permute(0, 3, 1, 2)
+    """(B, 2*num_pos_feats, H', W') fp32 -- the reference's `PositionalEncoding.forward` result (a view of the token-major
+    tensor `positional_encoding_tokens` produces)."""
+    pos, _ = positional_encoding_tokens(embed_h, embed_w, heights, widths, scale, num_pos_feats, temperature)
+    return pos.permute(0, 2, 1).reshape(heights.shape[0], 2 * num_pos_feats, embed_h, embed_w)
 
 
 def padding_mask_device(embed_h: int, embed_w: int, heights: torch.Tensor, widths: torch.Tensor, scale: int = 32) -> torch.Tensor:
     """(B, H', W') bool, True only on the bottom-right corner [ceil(h/s):, ceil(w/s):] -- the reference's own rule
     (detr/model.py:96-114)."""
-    dev = heights.device
-    hs = torch.ceil(heights.float() / scale)[:, None, None]
-    ws = torch.ceil(widths.float() / scale)[:, None, None]
-    iy = torch.arange(embed_h, device=dev, dtype=torch.float32)[None, :, None]
-    ix = torch.arange(embed_w, device=dev, dtype=torch.float32)[None, None, :]
-    return (iy >= hs) & (ix >= ws)
+    _, mask = positional_encoding_tokens(embed_h, embed_w, heights, widths, scale, 2)
+    return mask.view(heights.shape[0], embed_h, embed_w)
 
 
 class _MLP(nn.Module):
@@ -338,7 +339,8 @@ class _Backbone(nn.Module):
 class DetrHarness(nn.Module):
     """DETR.forward (detr/model.py:68-94) around pluggable encoder/decoder implementations."""
 
-    def __init__(self, config: DETRConfig, encoder_fn: Optional[Callable] = None, decoder_fn: Optional[Callable] = None):
+    def __init__(self, config: DETRConfig, encoder_fn: Optional[Callable] = None, decoder_fn: Optional[Callable] = None,
+                 posenc_fn: Optional[Callable] = None):
         super().__init__()
         self.config = config
         self.backbone = _Backbone(config.backbone)
@@ -357,14 +359,14 @@ class DetrHarness(nn.Module):
         # optional functional replacements (the CPU oracle plugs in here for the reference arm of bench.py)
         self._encoder_fn = encoder_fn
         self._decoder_fn = decoder_fn
+        self._posenc_fn = posenc_fn   # (H', W', heights, widths, scale, F, T) -> (pos (B,S,C), mask (B,S)); default: the CUDA kernel
 
     def forward(self, images: torch.Tensor, heights: torch.Tensor, widths: torch.Tensor) -> Dict[str, torch.Tensor]:
         x = self.input_proj(self.backbone(images))
         B, C, H, W = x.shape
-        pos = positional_encoding_device(H, W, heights, widths, self.backbone.scale, C // 2, self.config.temperature)
-        mask = padding_mask_device(H, W, heights, widths, self.backbone.scale).flatten(1)
+        posenc = self._posenc_fn or positional_encoding_tokens
+        pos, mask = posenc(H, W, heights, widths, self.backbone.scale, C // 2, self.config.temperature)
         x = x.flatten(2).permute(0, 2, 1)
-        pos = pos.flatten(2).permute(0, 2, 1)
         query_embed = self.object_query_embedding.weight.unsqueeze(0).expand(B, -1, -1)
         if self._encoder_fn is None:
             memory = self.encoder(x, position_embedding=pos, key_padding_mask=mask)

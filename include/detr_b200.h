@@ -195,6 +195,14 @@ int detr_maxpool3x3s2_out(int n);
 int detr_maxpool3x3s2_fwd_bf16(const void* x, void* y, uint8_t* idx, int B, int H, int W, int C, void* stream);
 int detr_maxpool3x3s2_bwd_bf16(const void* dy, const uint8_t* idx, void* dx, int B, int H, int W, int C, void* stream);
 
+/* Sine positional encoding + padding mask of DETR.forward (detr/position_encoding.py:5-97, detr/model.py:96-114) in one
+ * launch, token-major: pos float[B][H'*W'][2F] (channel order of the reference: F y-channels then F x-channels, sin/cos
+ * interleaved), mask uint8[B][H'*W'] (1 = the reference's bottom-right padding corner), heights/widths DEVICE int32[B]
+ * image sizes before padding; scale = backbone stride.  mask may be NULL. */
+int detr_positional_encoding_f32(const int32_t* heights, const int32_t* widths, int B, int embed_h, int embed_w, int scale,
+                                 int num_pos_feats, float temperature, float* pos, uint8_t* mask, void* stream);
+
+
 
 
 
