@@ -1,20 +1,20 @@
 // Flash attention forward for DETR's head_dim = 32 (detr/model.py:317-352): TMA-fed tcgen05 with TMEM accumulators.
 //
-//   O[b,q,h,:] = dropout(softmax(Q K^T / sqrt(32) + mask)) V        LSE[b,h,q] saved for the backward kernels
+//   O[b,q,h,:] = dropout(softmax(Q K^T / sqrt(32) + mask)) V        LSE[b,h,q] saved for the backward kernel
 //
-// One CTA = one (batch, head, 128-query tile); 12 warps in 3 warpgroups:
-//   warps 0-7   softmax.  Warp w owns TMEM lanes (query rows) 32*(w%4).. and the key columns 64*(w/4)..+63 of each
-//               128x128 fp32 score tile: ONE TMEM read into 64 registers, local row max, a 64-thread named barrier
-//               to exchange the max with the warp holding the other half of the row, exp2 / row sum / dropout /
-//               bf16 P into SWIZZLE_128B shared memory (the K-major A operand of P V), and 16 of the 32 running
-//               O columns in registers (rescaled on-line).
-//   warp 8      TMA producer: Q once, then K/V tiles of 128 keys through a 3-stage ring (SWIZZLE_64B boxes).
-//   warp 9      TMEM allocation + single-thread tcgen05.mma issue: S = Q K^T (M128 N128 K32) and
-//               O_tile = P V (M128 N32 K128, V consumed MN-major straight from its natural [key][d] layout).
-//   warps 10-11 idle (complete the third warpgroup so that setmaxnreg can move its registers to the softmax warps).
-// The score columns are released right after they are copied to registers, so S_{j+1} = Q K_{j+1}^T runs under the
-// exponentials of tile j.  Two CTAs are resident per SM (256 TMEM columns, ~92 KB shared memory each): with d = 32
-// the kernel is bound by MUFU/issue slots, not by the tensor pipe, and needs the warps.
+// PERSISTENT: min(#SMs, #items) CTAs; an item is a (batch, head, 128-query tile) and has KT (query tile, key tile)
+// pairs; CTA c walks the contiguous pair range [c*N/G, (c+1)*N/G) in (b, h, query tile, key tile) order -- whole items
+// plus at most one partial item at each end, so all SMs finish together (448 items on 296 CTA slots used to cost 2 waves
+// for 1.51 waves of work).  A partial item leaves (unnormalised O, row max, row sum) in one of two fp32 slots and
+// attention_fwd_combine_kernel merges the two parts.
+// 20 warps: 0-15 softmax (warp w: TMEM lanes = query rows 32*(w%4).., key columns 32*(w/4)..+31 of each 128x128 score tile,
+// and 8 of the 32 output columns), 16 = TMA producer, 17 = tcgen05.mma issuer, 18-19 idle (fifth warpgroup for setmaxnreg).
+// Per pair j (global counter across items) the only barrier a softmax warp waits on is s_full[j&1]:
+//   MMA warp:  wait p_full[j&1] -> O_tile[j&1] = P_j V_j -> S[(j+2)&1] = Q K_{j+2}^T -> commit s_full[(j+2)&1]
+//   so "S_{j+2} is ready" also means "P V of pair j is complete": the P buffer and the O_tile columns of pair j are free /
+//   readable, and S_j had been copied to registers before p_full(j) was signalled.  The output accumulates in registers
+//   two pairs late:  acc = (acc + O_tile(j-2) * alpha(j-1)) * alpha(j).
+// TMEM: S x2 [0,256) | O_tile x2 [256,320).  Shared memory: Q 8 KB | K/V ring 4 x 16 KB | P x2 64 KB | row-max exchange.
 //
 // Masking follows the reference: key_padding_mask / attention_mask entries get a huge FINITE negative score
 // (detr/model.py:326-334 uses finfo.min, so a fully masked row is uniform, not NaN); keys beyond S (tile
@@ -27,13 +27,15 @@
 namespace detr {
 using namespace tc;
 
-constexpr int kBM = 128;          // queries per CTA
-constexpr int kBN = 128;          // keys per tile
+constexpr int kBM = 128;          // queries per item
+constexpr int kBN = 128;          // keys per pair
 constexpr int kD = 32;            // head dim
-constexpr int kStages = 3;
-constexpr int kFwdThreads = 384;
+constexpr int kStages = 4;
+constexpr int kSoftmaxWarps = 16;
+constexpr int kSoftmaxThreads = kSoftmaxWarps * 32;
+constexpr int kFwdThreads = 640;
 constexpr uint32_t kTileBytes = kBN * kD * 2;  // 8 KB: one Q, K or V tile
-constexpr uint32_t kTmemCols = 256;            // S: [0,128)  O: [128,160)
+constexpr uint32_t kTmemCols = 512;
 // Masked score: huge, finite, and a POWER OF TWO (-2^126) so that score*scale is exact and the fused
 // multiply-add s*scale - m*scale cancels to exactly 0 when a whole row is masked (-> uniform probabilities).
 constexpr float kMaskedScore = -8.507059173023462e37f;
@@ -41,6 +43,7 @@ constexpr float kMaskedScore = -8.507059173023462e37f;
 struct AttnFwdParams {
     __nv_bfloat16* O; int64_t o_sb, o_sl;  // (B, L, nh*32): element strides of batch and row
     float* lse;                            // (B, nh, L)
+    float* part;                           // [items][2 slots][128 rows][36]: unnormalised O (32), row max, row sum of split items
     const uint8_t* kpm; int64_t kpm_sb;    // key padding mask (B, S) bytes, may be null
     const uint8_t* amask;                  // attention mask (L, S) bytes, may be null
     int B, nh, L, S;
@@ -50,263 +53,341 @@ struct AttnFwdParams {
     float drop_log2_scale;                 // log2(drop_scale): folded into the exponent
     uint64_t seed; const uint64_t* seed_ptr; // effective seed = seed + *seed_ptr (device side: CUDA-graph replays get fresh masks)
 };
+constexpr int kPartRow = 36;   // 32 output columns, row max, row sum, padding to a 16-byte multiple
 
 struct FwdSmem {
     static constexpr uint32_t q = 0;
-    static constexpr uint32_t k = q + kTileBytes;
-    static constexpr uint32_t v = k + kStages * kTileBytes;
-    static constexpr uint32_t p = 57344;                          // 128 x 128 bf16, two 64-key blocks, SWIZZLE_128B
-    static constexpr uint32_t xch = p + kBM * kBN * 2;            // float[2 parity][2 halves][128 rows] row-max exchange
-    static constexpr uint32_t bars = xch + 2 * 2 * kBM * 4;
-    static constexpr uint32_t flags = bars + 128;
+    static constexpr uint32_t kv = q + kTileBytes;                       // kStages x (K tile, V tile)
+    static constexpr uint32_t p = 73728;                                 // 2 x (128 x 128 bf16, two 64-key blocks, SWIZZLE_128B)
+    static constexpr uint32_t xch = p + 2 * kBM * kBN * 2;               // float[2 parity + 1 (row sums)][4 key quarters][128 rows]
+    static constexpr uint32_t bars = xch + 3 * 4 * kBM * 4;
+    static constexpr uint32_t total = bars + 256 + 1024;                 // + alignment slack
 };
-static_assert(FwdSmem::v + kStages * kTileBytes <= FwdSmem::p && FwdSmem::p % 1024 == 0, "smem layout");
+static_assert(FwdSmem::kv + kStages * 2 * kTileBytes <= FwdSmem::p && FwdSmem::p % 1024 == 0, "smem layout");
 
-// One 64-column half of a score tile for one query row: max, exponentials, P store.  MASKED / DROP are warp-uniform.
-template <bool MASKED, bool DROP>
-__device__ __forceinline__ void softmax_half_tile(uint32_t (&s)[64], const AttnFwdParams& p, const uint8_t* kf /*64 flags*/,
-                                                  const uint8_t* arow /*attention-mask row at this tile's first key of the half, or null*/,
-                                                  int keys_left /*S - first key of the half*/, float& m_run, float& l_run, float& alpha_out,
-                                                  float* xch_mine, const float* xch_other, uint32_t bar_id, uint32_t row_key, uint32_t k32_base,
-                                                  uint8_t* p_row /*this row inside the half's 64-key block*/, int row7) {
-    const float sc = p.scale_log2;
-    if (MASKED) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-            const uint32_t f = kf[i];
-            const bool am = arow != nullptr && i < keys_left && arow[i] != 0;
-            float v = __uint_as_float(s[i]);
-            v = (f == 1u || am) ? kMaskedScore : v;
-            v = (f == 2u) ? -CUDART_INF_F : v;
-            s[i] = __float_as_uint(v);
-        }
+// persistent schedule (same scheme as the backward kernel): item = ((b * nh + h) * QT + qt), T = KT pairs per item
+struct FwdSched {
+    int T, QT, nh, NT, item0, t0;
+    __device__ __forceinline__ void init(const AttnFwdParams& p, int c, int G) {
+        T = (p.S + kBN - 1) / kBN; QT = (p.L + kBM - 1) / kBM; nh = p.nh;
+        const long long total = (long long)QT * p.nh * p.B * T;
+        const long long n0 = total * c / G, n1 = total * (c + 1) / G;
+        NT = (int)(n1 - n0); item0 = (int)(n0 / T); t0 = (int)(n0 - (long long)item0 * T);
     }
-    float mx = fmaxf(__uint_as_float(s[0]), __uint_as_float(s[1]));
-#pragma unroll
-    for (int i = 2; i < 64; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
-    // exchange with the warp that holds the other 64 columns of this row
-    *xch_mine = mx;
-    named_bar_sync(bar_id, 64);
-    mx = fmaxf(mx, *xch_other);
-    const float m_new = fmaxf(m_run, mx);                 // finite: every tile has at least one in-range key
-    alpha_out = ex2((m_run - m_new) * sc);                // first tile: exp2(-inf) = 0
-    const float bias = DROP ? fmaf(-m_new, sc, p.drop_log2_scale) : -m_new * sc;   // kept entries come out pre-scaled by 1/(1-p)
-    const uint32_t thr4 = p.drop_thresh * 0x01010101u;
-    uint32_t rng = 0;
-    float rsum = 0.f;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {                         // 8 values = one 16-byte chunk of the P row
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            e[i] = ex2(fmaf(__uint_as_float(s[g * 8 + i]), sc, bias));
-            rsum += e[i];
-        }
-        uint4 w;
-        w.x = pack_bf16x2(e[0], e[1]); w.y = pack_bf16x2(e[2], e[3]); w.z = pack_bf16x2(e[4], e[5]); w.w = pack_bf16x2(e[6], e[7]);
-        if (DROP) {   // the row sum above is of the un-dropped probabilities; dropped entries are cleared in the packed bf16 words
-            if ((g & 3) == 0) rng = dropout_group_state(row_key, k32_base + (g >> 2));
-            const uint32_t t0 = dropout_quad(rng, thr4), t1 = dropout_quad(rng, thr4);
-            w.x &= dropout_mask_bf16x2<0>(t0); w.y &= dropout_mask_bf16x2<1>(t0);
-            w.z &= dropout_mask_bf16x2<0>(t1); w.w &= dropout_mask_bf16x2<1>(t1);
-        }
-        *reinterpret_cast<uint4*>(p_row + ((g ^ row7) << 4)) = w;
-    }
-    l_run = l_run * alpha_out + rsum;                     // (pre-scaled by 1/(1-p) when DROP; undone in the epilogue)
-    m_run = m_new;
-}
+    __device__ __forceinline__ void split(int item, int& b, int& h, int& qt) const { qt = item % QT; const int bh = item / QT; h = bh % nh; b = bh / nh; }
+};
+struct FwdCursor {
+    int item, t;
+    __device__ __forceinline__ explicit FwdCursor(const FwdSched& sc) : item(sc.item0), t(sc.t0) {}
+    __device__ __forceinline__ void next(const FwdSched& sc) { if (++t == sc.T) { t = 0; ++item; } }
+};
 
-__global__ void __launch_bounds__(kFwdThreads, 2)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                      const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzled tiles need 1024-byte alignment
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.x * kBM, h = blockIdx.y, b = blockIdx.z;
-    const int T = (p.S + kBN - 1) / kBN;
+    FwdSched sc;
+    sc.init(p, blockIdx.x, gridDim.x);
+    const int NT = sc.NT;
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::bars);
     uint64_t* q_full = bars + 0;
-    uint64_t* kv_full = bars + 1;              // [kStages]
-    uint64_t* kv_empty = bars + 1 + kStages;   // [kStages]
-    uint64_t* s_full = bars + 1 + 2 * kStages;
-    uint64_t* s_empty = s_full + 1;
-    uint64_t* p_full = s_full + 2;
-    uint64_t* o_full = s_full + 3;
-    uint64_t* o_empty = s_full + 4;
+    uint64_t* q_empty = bars + 1;
+    uint64_t* kv_full = bars + 2;               // [kStages]
+    uint64_t* kv_empty = kv_full + kStages;     // [kStages]
+    uint64_t* s_full = kv_empty + kStages;      // [2]
+    uint64_t* p_full = s_full + 2;              // [2]
+    uint64_t* o_done = s_full + 4;              // all P V of a segment complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
-    uint8_t* kflag = smem + FwdSmem::flags;    // per key: 0 normal, 1 masked (finite), 2 beyond S (-inf)
 
     if (tid == 0) {
-        mbar_init(q_full, 1);
+        mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(o_done, 1);
         for (int s = 0; s < kStages; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
-        mbar_init(s_full, 1); mbar_init(s_empty, 256); mbar_init(p_full, 256); mbar_init(o_full, 1); mbar_init(o_empty, 256);
+        for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(p_full + s, kSoftmaxThreads); }
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, kTmemCols);
-    for (int k = tid; k < T * kBN; k += kFwdThreads)
-        kflag[k] = k >= p.S ? 2 : ((p.kpm && p.kpm[b * p.kpm_sb + k]) ? 1 : 0);
+    if (warp == 17) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 256;
 
-    if (warp >= 8) {
-        reg_dealloc<24>();
-        if (warp == 8 && lane == 0) {
+    if (warp >= kSoftmaxWarps) {
+        reg_dealloc<64>();
+        if (warp == 16 && lane == 0) {
             // ================= TMA producer =================
             tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
-            mbar_expect_tx(q_full, kTileBytes);
-            tma_load_3d(smem + FwdSmem::q, &tm_q, q_full, h * kD, q0, b);
-            for (int j = 0; j < T; ++j) {
-                const int s = j % kStages;
-                if (j >= kStages) mbar_wait_sleep(kv_empty + s, ((j / kStages) - 1) & 1);
-                mbar_expect_tx(kv_full + s, 2 * kTileBytes);
-                tma_load_3d(smem + FwdSmem::k + s * kTileBytes, &tm_k, kv_full + s, h * kD, j * kBN, b);
-                tma_load_3d(smem + FwdSmem::v + s * kTileBytes, &tm_v, kv_full + s, h * kD, j * kBN, b);
+            int seg = -1, b = 0, h = 0, qt = 0;
+            FwdCursor cur(sc);
+            for (int j = 0; j < NT; ++j, cur.next(sc)) {
+                if (j == 0 || cur.t == 0) {   // new segment: its Q tile, once the previous segment's last score MMAs have read the old one
+                    ++seg;
+                    sc.split(cur.item, b, h, qt);
+                    if (seg >= 1) mbar_wait_sleep(q_empty, (seg - 1) & 1);
+                    mbar_expect_tx(q_full, kTileBytes);
+                    tma_load_3d(smem + FwdSmem::q, &tm_q, q_full, h * kD, qt * kBM, b);
+                }
+                const int st = j % kStages;
+                if (j >= kStages) mbar_wait_sleep(kv_empty + st, ((j / kStages) - 1) & 1);
+                mbar_expect_tx(kv_full + st, 2 * kTileBytes);
+                uint8_t* dst = smem + FwdSmem::kv + st * 2 * kTileBytes;
+                tma_load_3d(dst, &tm_k, kv_full + st, h * kD, cur.t * kBN, b);
+                tma_load_3d(dst + kTileBytes, &tm_v, kv_full + st, h * kD, cur.t * kBN, b);
             }
-        } else if (warp == 9 && elect_one()) {
+        } else if (warp == 17 && elect_one()) {
             // ================= MMA issuer =================
             constexpr uint32_t idesc_s = make_idesc_bf16(kBM, kBN, false, false);
             constexpr uint32_t idesc_o = make_idesc_bf16(kBM, kD, false, true);
             // descriptor words (tc.cuh): high word per layout, low word = (address >> 4) + constant
             constexpr uint32_t hi64 = desc_hi(512, SWZ_64B);      // Q/K/V tiles: 64-byte rows, 8-row groups 512 B apart
             constexpr uint32_t hi128 = desc_hi(1024, SWZ_128B);   // P tile: 128-byte rows, 8-row groups 1024 B apart
-            const uint32_t q_lo = smem_u32(smem + FwdSmem::q) >> 4, p_lo = smem_u32(smem + FwdSmem::p) >> 4;
-            auto issue_s = [&](int j) {
-                const uint32_t k_lo = smem_u32(smem + FwdSmem::k + (j % kStages) * kTileBytes) >> 4;
+            const uint32_t q_lo = smem_u32(smem + FwdSmem::q) >> 4;
+            // `seg_of_scores`: segment of the last score MMA issued; scores of a new segment wait for its Q tile
+            int seg_scores = -1;
+            FwdCursor sc_cur(sc);   // cursor of the NEXT pair whose scores will be issued
+            int js = 0;             // its local index
+            auto scores = [&]() {
+                const int j = js;
+                const bool first = j == 0 || sc_cur.t == 0, last = j == NT - 1 || sc_cur.t == sc.T - 1;
+                if (first) { ++seg_scores; mbar_wait_sleep(q_full, seg_scores & 1); }
+                mbar_wait_sleep(kv_full + (j % kStages), (j / kStages) & 1);
+                tc_fence_after();
+                const uint32_t k_lo = smem_u32(smem + FwdSmem::kv + (j % kStages) * 2 * kTileBytes) >> 4;
 #pragma unroll
                 for (int ks = 0; ks < kD / 16; ++ks)  // K-major, 64-byte rows, SWIZZLE_64B: 32 B per 16-channel step
-                    umma_bf16_lh(tmem_s, q_lo + desc_lo(ks * 32, 16), hi64, k_lo + desc_lo(ks * 32, 16), hi64, idesc_s, ks > 0);
-                umma_commit(s_full);
+                    umma_bf16_lh(tmem_s + (j & 1) * kBN, q_lo + desc_lo(ks * 32, 16), hi64, k_lo + desc_lo(ks * 32, 16), hi64, idesc_s, ks > 0);
+                umma_commit(s_full + (j & 1));
+                if (last) umma_commit(q_empty);   // no later MMA of this segment reads the Q tile
+                ++js; sc_cur.next(sc);
             };
-            mbar_wait_sleep(q_full, 0);
-            mbar_wait_sleep(kv_full + 0, 0);
-            tc_fence_after();
-            issue_s(0);
-            for (int j = 0; j < T; ++j) {
-                if (j + 1 < T) {
-                    mbar_wait_sleep(kv_full + ((j + 1) % kStages), ((j + 1) / kStages) & 1);
-                    mbar_wait_sleep(s_empty, j & 1);        // the softmax warps hold S_j in registers
-                    tc_fence_after();
-                    issue_s(j + 1);
-                }
-                mbar_wait_sleep(p_full, j & 1);             // P_j is in shared memory
-                if (j > 0) mbar_wait_sleep(o_empty, (j - 1) & 1);  // O_{j-1} has been read out of TMEM
+            if (NT > 0) scores();
+            if (NT > 1) scores();
+            FwdCursor cur(sc);
+            for (int j = 0; j < NT; ++j, cur.next(sc)) {
+                const bool last = j == NT - 1 || cur.t == sc.T - 1;
+                mbar_wait_sleep(p_full + (j & 1), (j >> 1) & 1);     // P_j is in shared memory (and S_j, O_tile(j-2) are in registers)
                 tc_fence_after();
-                const uint32_t v_lo = smem_u32(smem + FwdSmem::v + (j % kStages) * kTileBytes) >> 4;
+                const uint32_t v_lo = (smem_u32(smem + FwdSmem::kv + (j % kStages) * 2 * kTileBytes) + kTileBytes) >> 4;
+                const uint32_t p_lo = smem_u32(smem + FwdSmem::p + (j & 1) * (kBM * kBN * 2)) >> 4;
 #pragma unroll
                 for (int ks = 0; ks < kBN / 16; ++ks) {
                     // A = P: K-major SWIZZLE_128B, 64-key blocks of 16 KB, 32 B per 16-key step inside a block
                     // B = V: MN-major (d contiguous, 64-byte rows), SWIZZLE_64B, 16 keys = 1024 B per step
-                    umma_bf16_lh(tmem_o, p_lo + desc_lo((ks >> 2) * 16384 + (ks & 3) * 32, 16), hi128,
+                    umma_bf16_lh(tmem_o + (j & 1) * kD, p_lo + desc_lo((ks >> 2) * 16384 + (ks & 3) * 32, 16), hi128,
                                  v_lo + desc_lo(ks * 1024, 512), hi64, idesc_o, ks > 0);
                 }
-                umma_commit(o_full);
                 umma_commit(kv_empty + (j % kStages));
+                if (last) umma_commit(o_done);
+                if (j + 2 < NT) scores();                          // S_{j+2}: its commit also covers P V of pair j
             }
         }
     } else {
         // ================= softmax warps =================
-        reg_alloc<104>();   // 384 x 80 launch registers: 128 x 24 stay with warps 8-11, 256 x 104 <= the rest
-        const int wq = warp & 3, half = warp >> 2;
-        const int row = wq * 32 + lane;
-        const int q = q0 + row;
-        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        const uint32_t bh = (uint32_t)(b * p.nh + h);
+        reg_alloc<104>();
+        const int lq = warp & 3, kq = warp >> 2;      // TMEM lane quarter, 32-key quarter of the pair
+        const int row = lq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
         const bool drop = p.drop_thresh != 0;
-        const uint32_t row_key = drop ? dropout_row_key(p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull), bh, (uint32_t)q) : 0u;
-        const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S : nullptr;
-        uint8_t* p_row = smem + FwdSmem::p + half * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
+        const uint64_t seed = drop ? p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull) : 0ull;
+        const uint32_t thr4 = p.drop_thresh * 0x01010101u;
+        const float sc_l2 = p.scale_log2;
+        // this thread's row inside a [query][64-key block] SWIZZLE_128B tile; its 4 chunks are (kq&1)*4 + g
+        const uint32_t row_off = (uint32_t)((kq >> 1) * 16384 + (row >> 3) * 1024 + (row & 7) * 128);
+        const uint32_t chunk0 = (uint32_t)((kq & 1) * 4);
         float* xch = reinterpret_cast<float*>(smem + FwdSmem::xch);
-        float m_run = -CUDART_INF_F, l_run = 0.f;
-        float acc[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-        uint32_t s[64];
 
-        for (int j = 0; j < T; ++j) {
-            const int key0 = j * kBN + half * 64;
-            const uint8_t* kf = kflag + key0;
-            uint32_t any = p.amask ? 1u : 0u;                 // warp-uniform: does this half tile need masking at all?
-            {
-                const uint4* kf4 = reinterpret_cast<const uint4*>(kf);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { const uint4 w = kf4[i]; any |= w.x | w.y | w.z | w.w; }
-            }
-            mbar_wait(s_full, j & 1);
+        int seg = -1, seg_t0 = 0, b = 0, h = 0, q = 0;
+        uint32_t bh = 0, row_key = 0;
+        float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 1.f;
+        float acc[8];
+        uint8_t pad_next = 0;
+        FwdCursor cur(sc);
+
+        // finish a segment: the last two O tiles, total row sum, then either the normalised output + LSE or the partial slot
+        auto finish = [&](int j_last, int item, bool whole, int slot, int n_tiles) {
+            mbar_wait(o_done, seg & 1);
             tc_fence_after();
-            tmem_ld32(tmem_s + lane_addr + half * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-            tmem_ld32(tmem_s + lane_addr + half * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+            uint32_t o0[8], o1[8];
+            if (n_tiles >= 2) tmem_ld8(tmem_o + ((j_last - 1) & 1) * kD + lane_addr + kq * 8, o0);
+            tmem_ld8(tmem_o + (j_last & 1) * kD + lane_addr + kq * 8, o1);
+            // total row sum = sum over the 4 key quarters (same running max, same alpha history)
+            // (third exchange buffer: a fast warp may already be writing the next pair's row max into either parity buffer)
+            float* xm = xch + 2 * 512 + kq * 128 + row;
+            *xm = l_run;
+            named_bar_sync(1 + lq, 128);
+            const float* xr = xch + 2 * 512 + row;
+            float l_tot = (xr[0] + xr[128]) + (xr[256] + xr[384]);
+            if (drop) l_tot *= 1.f / p.drop_scale;              // the exponentials were pre-scaled by 1/(1-p)
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(s_empty);                             // S_{j+1} may now overwrite the score columns
-
-            if (j > 0) {   // the P buffer is free once P V of the previous tile has completed (o_full)
-                mbar_wait(o_full, (j - 1) & 1);
-                tc_fence_after();
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float v = acc[e];
+                if (n_tiles >= 2) v += __uint_as_float(o0[e]) * alpha_prev;   // O_tile(last-1) is relative to the max before the last pair
+                o[e] = v + __uint_as_float(o1[e]);
             }
-            float alpha;
-            float* xm = xch + (j & 1) * 256 + half * 128 + row;
-            const float* xo = xch + (j & 1) * 256 + (half ^ 1) * 128 + row;
-            const uint32_t k4 = (uint32_t)(key0 >> 5);   // index of the first 32-key dropout group
-            const uint8_t* ar = arow ? arow + key0 : nullptr;
-            // previous tile's O columns (16 per thread) are loaded first so the TMEM read overlaps the row-max exchange
-            uint32_t o_prev[16];
-            if (j > 0) tmem_ld16(tmem_o + lane_addr + half * 16, o_prev);
+            if (q < p.L) {
+                if (whole) {
+                    const float inv = 1.f / l_tot;
+                    uint4 w;
+                    w.x = pack_bf16x2(o[0] * inv, o[1] * inv); w.y = pack_bf16x2(o[2] * inv, o[3] * inv);
+                    w.z = pack_bf16x2(o[4] * inv, o[5] * inv); w.w = pack_bf16x2(o[6] * inv, o[7] * inv);
+                    *reinterpret_cast<uint4*>(p.O + b * p.o_sb + (int64_t)q * p.o_sl + h * kD + kq * 8) = w;
+                    // natural-log LSE of the scaled scores: m/sqrt(d) + ln(l).  A row whose keys are all masked is flagged
+                    // with +inf: the backward kernel then skips it.
+                    if (kq == 0)
+                        p.lse[((int64_t)b * p.nh + h) * p.L + q] =
+                            m_run == kMaskedScore ? CUDART_INF_F : (m_run * sc_l2 + log2f(l_tot)) * 0.6931471805599453f;
+                } else {
+                    float* dst = p.part + (((int64_t)item * 2 + slot) * kBM + row) * kPartRow;
+                    *reinterpret_cast<float4*>(dst + kq * 8) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(dst + kq * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                    if (kq == 0) { dst[32] = m_run; dst[33] = l_tot; }
+                }
+            }
+        };
+
+        uint32_t s[32];
+        for (int j = 0; j < NT; ++j, cur.next(sc)) {
+            const int t = cur.t;
+            if (j == 0 || t == 0) {
+                ++seg; seg_t0 = t;
+                int qt;
+                sc.split(cur.item, b, h, qt);
+                q = qt * kBM + row;
+                bh = (uint32_t)(b * p.nh + h);
+                row_key = drop ? dropout_row_key(seed, bh, (uint32_t)q) : 0u;
+                m_run = -CUDART_INF_F; l_run = 0.f; alpha_prev = 1.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+            }
+            const int jt = j - (t - seg_t0);                       // local index of the segment's first pair
+            const int key0 = t * kBN + kq * 32;
+            // key flags of this thread's 32 columns: bit i of `oob` = beyond S (-inf), of `pad` = key_padding_mask (finite).
+            // The mask byte of the NEXT pair is fetched one iteration ahead (its L2 latency would sit on the critical path).
+            const int n_valid = p.S - key0;
+            const uint32_t oob = n_valid >= 32 ? 0u : (n_valid <= 0 ? 0xffffffffu : (0xffffffffu << n_valid));
+            if (p.kpm != nullptr && (j == 0 || t == 0)) pad_next = (key0 + lane < p.S) ? p.kpm[b * p.kpm_sb + key0 + lane] : (uint8_t)0;
+            const uint32_t pad = p.kpm ? __ballot_sync(FULL_MASK, pad_next != 0) : 0u;
+            if (p.kpm != nullptr && t + 1 < sc.T) {
+                const int kn = key0 + kBN + lane;
+                pad_next = kn < p.S ? p.kpm[b * p.kpm_sb + kn] : (uint8_t)0;
+            }
+            const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S + key0 : nullptr;
+            const bool any = (oob | pad) != 0u || p.amask != nullptr;
+
+            mbar_wait(s_full + (j & 1), (j >> 1) & 1);            // S_j ready; P V of pair j-2 complete
+            tc_fence_after();
+            tmem_ld32(tmem_s + (j & 1) * kBN + lane_addr + kq * 32, s);
+            uint32_t o_old[8];
+            const bool have_old = j - 2 >= jt;                     // O_tile(j-2) belongs to this segment
+            if (have_old) tmem_ld8(tmem_o + (j & 1) * kD + lane_addr + kq * 8, o_old);
+            tmem_ld_wait();
+            tc_fence_before();
+
             if (any) {
-                if (drop) softmax_half_tile<true, true>(s, p, kf, ar, p.S - key0, m_run, l_run, alpha, xm, xo, 1 + wq, row_key, k4, p_row, row & 7);
-                else softmax_half_tile<true, false>(s, p, kf, ar, p.S - key0, m_run, l_run, alpha, xm, xo, 1 + wq, row_key, k4, p_row, row & 7);
-            } else {
-                if (drop) softmax_half_tile<false, true>(s, p, kf, ar, p.S - key0, m_run, l_run, alpha, xm, xo, 1 + wq, row_key, k4, p_row, row & 7);
-                else softmax_half_tile<false, false>(s, p, kf, ar, p.S - key0, m_run, l_run, alpha, xm, xo, 1 + wq, row_key, k4, p_row, row & 7);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const bool am = arow != nullptr && (key0 + i) < p.S && arow[i] != 0;
+                    float v = __uint_as_float(s[i]);
+                    v = (((pad >> i) & 1u) || am) ? kMaskedScore : v;
+                    v = ((oob >> i) & 1u) ? -CUDART_INF_F : v;
+                    s[i] = __float_as_uint(v);
+                }
+            }
+            float mx = fmaxf(__uint_as_float(s[0]), __uint_as_float(s[1]));
+#pragma unroll
+            for (int i = 2; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+            // exchange with the three warps that hold the other columns of this row
+            xch[(j & 1) * 512 + kq * 128 + row] = mx;
+#ifndef DETR_FWD_EXP_NOXCH
+            named_bar_sync(1 + lq, 128);
+#endif
+            {
+                const float* xr = xch + (j & 1) * 512 + row;
+                mx = fmaxf(fmaxf(xr[0], xr[128]), fmaxf(xr[256], xr[384]));
+            }
+            const float m_new = fmaxf(m_run, mx);                 // finite: every pair has at least one in-range key
+            const float alpha = ex2((m_run - m_new) * sc_l2);     // first pair: exp2(-inf) = 0
+            const float bias = drop ? fmaf(-m_new, sc_l2, p.drop_log2_scale) : -m_new * sc_l2;   // kept entries come out pre-scaled by 1/(1-p)
+            uint8_t* p_row = smem + FwdSmem::p + (j & 1) * (kBM * kBN * 2) + row_off;
+            uint32_t rng = drop ? dropout_group_state(row_key, (uint32_t)(key0 >> 5)) : 0u;
+            const float2 sc2 = make_float2(sc_l2, sc_l2), bias2 = make_float2(bias, bias);
+            float2 rs = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {                         // 8 values = one 16-byte chunk of the P row
+                uint32_t w[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int i = g * 8 + 2 * jj;
+                    const float2 e = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, bias2);
+                    const float2 x = make_float2(ex2(e.x), ex2(e.y));
+                    rs = __fadd2_rn(rs, x);
+                    w[jj] = pack_bf16x2(x.x, x.y);
+                }
+                if (drop) {   // the row sum is of the un-dropped probabilities; dropped entries are cleared in the packed bf16 words
+                    const uint32_t t0 = dropout_quad(rng, thr4), t1 = dropout_quad(rng, thr4);
+                    w[0] &= dropout_mask_bf16x2<0>(t0); w[1] &= dropout_mask_bf16x2<1>(t0);
+                    w[2] &= dropout_mask_bf16x2<0>(t1); w[3] &= dropout_mask_bf16x2<1>(t1);
+                }
+                *reinterpret_cast<uint4*>(p_row + (((chunk0 + g) ^ (uint32_t)(row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
             fence_proxy_async_smem();
-            mbar_arrive(p_full);
-            if (j > 0) {
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(o_empty);
+            mbar_arrive(p_full + (j & 1));
+            // output accumulation, two pairs late: acc = (acc + O_tile(j-2) * alpha(j-1)) * alpha(j)
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = (acc[i] + __uint_as_float(o_prev[i])) * alpha;
+            for (int e = 0; e < 8; ++e) {
+                float v = acc[e];
+                if (have_old) v = fmaf(__uint_as_float(o_old[e]), alpha_prev, v);
+                acc[e] = v * alpha;
+            }
+            l_run = l_run * alpha + (rs.x + rs.y);                // (pre-scaled by 1/(1-p) when dropping; undone in `finish`)
+            m_run = m_new;
+            alpha_prev = alpha;
+            if (j == NT - 1 || t == sc.T - 1) {
+                const int n_tiles = j - jt + 1;
+                finish(j, cur.item, seg_t0 == 0 && t == sc.T - 1, seg_t0 == 0 ? 0 : 1, n_tiles);
             }
         }
-        // ---- epilogue: last P V, normalise, store ----
-        mbar_wait(o_full, (T - 1) & 1);
-        tc_fence_after();
-        uint32_t o_last[16];
-        tmem_ld16(tmem_o + lane_addr + half * 16, o_last);
-        // total row sum = sum of the two halves (same running max, same alpha history)
-        float* xm = xch + (T & 1) * 256 + half * 128 + row;
-        const float* xo = xch + (T & 1) * 256 + (half ^ 1) * 128 + row;
-        *xm = l_run;
-        named_bar_sync(1 + wq, 64);
-        float l_tot = l_run + *xo;
-        if (drop) l_tot *= 1.f / p.drop_scale;              // the exponentials were pre-scaled by 1/(1-p)
-        tmem_ld_wait();
         tc_fence_before();
-        if (q < p.L) {
-            const float inv = 1.f / l_tot;
-            __nv_bfloat16* dst = p.O + b * p.o_sb + (int64_t)q * p.o_sl + h * kD + half * 16;
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                uint4 w;
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = (acc[g * 8 + e] + __uint_as_float(o_last[g * 8 + e])) * inv;
-                w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]); w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-                reinterpret_cast<uint4*>(dst)[g] = w;
-            }
-            // natural-log LSE of the scaled scores: m/sqrt(d) + ln(l).  A row whose keys are all masked is flagged
-            // with +inf: the backward kernels then skip it.
-            if (half == 0)
-                p.lse[((int64_t)b * p.nh + h) * p.L + q] =
-                    m_run == kMaskedScore ? CUDART_INF_F : (m_run * p.scale_log2 + log2f(l_tot)) * 0.6931471805599453f;
-        }
     }
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 17) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// Merge the two parts of the items that were split between two persistent CTAs:
+//   m = max(m0, m1), l = l0 2^{(m0-m) s} + l1 2^{(m1-m) s}, O = (O0 2^{(m0-m) s} + O1 2^{(m1-m) s}) / l
+// CTA c handles the boundary between persistent CTAs c and c+1 (nothing to do when it falls on an item edge).
+__global__ void __launch_bounds__(512) attention_fwd_combine_kernel(const AttnFwdParams p, int G) {
+    const int T = (p.S + kBN - 1) / kBN, QT = (p.L + kBM - 1) / kBM;
+    const long long total = (long long)QT * p.nh * p.B * T;
+    const long long n = total * (blockIdx.x + 1) / G;
+    if (n % T == 0) return;
+    const int item = (int)(n / T);
+    const int qt = item % QT, bh = item / QT, h = bh % p.nh, b = bh / p.nh;
+    const int row = threadIdx.x >> 2, g = threadIdx.x & 3, q = qt * kBM + row;   // 4 threads per row, 8 output columns each
+    if (q >= p.L) return;
+    const float* s0 = p.part + (((int64_t)item * 2 + 0) * kBM + row) * kPartRow;
+    const float* s1 = s0 + (int64_t)kBM * kPartRow;
+    const float m0 = s0[32], l0 = s0[33], m1 = s1[32], l1 = s1[33];
+    const float m = fmaxf(m0, m1);
+    const float a0 = ex2((m0 - m) * p.scale_log2), a1 = ex2((m1 - m) * p.scale_log2);
+    const float l = l0 * a0 + l1 * a1;
+    const float inv = 1.f / l;
+    const float4 x0 = *reinterpret_cast<const float4*>(s0 + g * 8), x1 = *reinterpret_cast<const float4*>(s0 + g * 8 + 4);
+    const float4 y0 = *reinterpret_cast<const float4*>(s1 + g * 8), y1 = *reinterpret_cast<const float4*>(s1 + g * 8 + 4);
+    uint4 w;
+    w.x = pack_bf16x2((x0.x * a0 + y0.x * a1) * inv, (x0.y * a0 + y0.y * a1) * inv);
+    w.y = pack_bf16x2((x0.z * a0 + y0.z * a1) * inv, (x0.w * a0 + y0.w * a1) * inv);
+    w.z = pack_bf16x2((x1.x * a0 + y1.x * a1) * inv, (x1.y * a0 + y1.y * a1) * inv);
+    w.w = pack_bf16x2((x1.z * a0 + y1.z * a1) * inv, (x1.w * a0 + y1.w * a1) * inv);
+    *reinterpret_cast<uint4*>(p.O + b * p.o_sb + (int64_t)q * p.o_sl + h * kD + g * 8) = w;
+    if (g == 0)
+        p.lse[((int64_t)b * p.nh + h) * p.L + q] = m == kMaskedScore ? CUDART_INF_F : (m * p.scale_log2 + log2f(l)) * 0.6931471805599453f;
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -366,22 +447,28 @@ int make_f32_tile_map(CUtensorMap* out, const void* base, int C, int rows, int s
 
 using namespace detr;
 
+extern "C" int64_t detr_attention_fwd_workspace_floats(int B, int nh, int L, int S) {
+    (void)S;
+    const int64_t items = (int64_t)((L + kBM - 1) / kBM) * nh * B;
+    return items * 2 * kBM * kPartRow;
+}
+
 extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
                                        const void* v, int64_t v_sb, int64_t v_sl, void* o, int64_t o_sb, int64_t o_sl,
-                                       float* lse, const uint8_t* key_padding_mask, int64_t kpm_sb,
+                                       float* lse, float* workspace, const uint8_t* key_padding_mask, int64_t kpm_sb,
                                        const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
                                        uint64_t seed, const uint64_t* seed_ptr, void* stream) {
     DETR_CHECK_ARG(B >= 1 && nh >= 1 && L >= 1 && S >= 1, "attention_fwd: bad sizes B=%d nh=%d L=%d S=%d", B, nh, L, S);
-    DETR_CHECK_ARG(B <= 65535 && nh <= 65535, "attention_fwd: B and nh must fit the grid");
     DETR_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "attention_fwd: dropout_p must be in [0,1)");
     DETR_CHECK_ARG(((uintptr_t)o % 16) == 0 && (o_sb % 8) == 0 && (o_sl % 8) == 0, "attention_fwd: O must be 16-byte aligned rows");
+    DETR_CHECK_ARG(workspace != nullptr && ((uintptr_t)workspace % 16) == 0, "attention_fwd: workspace missing or misaligned");
     const int C = nh * kD;
     CUtensorMap tq, tk, tv;
     if (int rc = make_head_tile_map(&tq, q, C, L, B, q_sl, q_sb, kBM, "attention_fwd(Q)")) return rc;
     if (int rc = make_head_tile_map(&tk, k, C, S, B, k_sl, k_sb, kBN, "attention_fwd(K)")) return rc;
     if (int rc = make_head_tile_map(&tv, v, C, S, B, v_sl, v_sb, kBN, "attention_fwd(V)")) return rc;
     AttnFwdParams p;
-    p.O = reinterpret_cast<__nv_bfloat16*>(o); p.o_sb = o_sb; p.o_sl = o_sl; p.lse = lse;
+    p.O = reinterpret_cast<__nv_bfloat16*>(o); p.o_sb = o_sb; p.o_sl = o_sl; p.lse = lse; p.part = workspace;
     p.kpm = key_padding_mask; p.kpm_sb = kpm_sb; p.amask = attention_mask;
     p.B = B; p.nh = nh; p.L = L; p.S = S;
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)kD);
@@ -389,17 +476,26 @@ extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.drop_scale = 128.f / (128.f - (float)p.drop_thresh);
     p.drop_log2_scale = log2f(p.drop_scale);
     p.seed = seed; p.seed_ptr = seed_ptr;
-    const int T = (S + kBN - 1) / kBN;
-    const size_t smem = FwdSmem::flags + (size_t)T * kBN + 1024;  // +1024: manual alignment slack
-    DETR_CHECK_ARG(smem <= 110 * 1024, "attention_fwd: S=%d needs %zu B of shared memory", S, smem);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem::total);
         if (e != cudaSuccess) { set_error("attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 2; }
         attr_set = true;
     }
-    dim3 grid((L + kBM - 1) / kBM, nh, B);
-    attention_fwd_kernel<<<grid, kFwdThreads, smem, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    const int64_t items = (int64_t)((L + kBM - 1) / kBM) * nh * B;
+    const int G = (int)(items < num_sms ? items : num_sms);   // G <= items: a CTA's pair range is never shorter than one item
+    cudaStream_t st = (cudaStream_t)stream;
+    attention_fwd_kernel<<<G, kFwdThreads, FwdSmem::total, st>>>(tq, tk, tv, p);
     DETR_CHECK_LAUNCH("attention_fwd");
+    if (items > G) {   // only then can a boundary between two CTAs fall inside an item
+        attention_fwd_combine_kernel<<<G - 1, 512, 0, st>>>(p, G);
+        DETR_CHECK_LAUNCH("attention_fwd_combine");
+    }
     return 0;
 }

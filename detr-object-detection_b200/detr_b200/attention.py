@@ -46,10 +46,11 @@ def attention_forward(q, k, v, key_padding_mask=None, attention_mask=None, dropo
     am = _mask_bytes(attention_mask, (L, S), "attention_mask")
     out = torch.empty(B, L, C, dtype=torch.bfloat16, device=q.device)
     lse = torch.empty(B, nh, L, dtype=torch.float32, device=q.device)
+    ws = torch.empty(_lib.load().detr_attention_fwd_workspace_floats(B, nh, L, S), dtype=torch.float32, device=q.device)
     _lib.call(
         "detr_attention_fwd_bf16",
         q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0), v.stride(1),
-        out.data_ptr(), out.stride(0), out.stride(1), lse.data_ptr(), _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0,
+        out.data_ptr(), out.stride(0), out.stride(1), lse.data_ptr(), ws.data_ptr(), _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0,
         _lib.ptr(am), B, nh, L, S, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_tensor), _lib.stream_ptr(),
         tag=(B, nh, L, S))
     return out, lse

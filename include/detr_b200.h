@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DETR_B200_ABI_VERSION 2
+#define DETR_B200_ABI_VERSION 3
 
 /* status bits (device-side, sticky) -- mirror the reference's failure modes */
 #define DETR_ST_DEGENERATE_BOX 1 /* AssertionError at detr/utils.py:87-88 */
@@ -114,10 +114,13 @@ int detr_criterion_bwd_f32(const float* grad_losses,
  * key_padding_mask: (B,S) bytes, non-zero = ignore (detr/model.py:326-330), row stride kpm_sb, may be NULL;
  * attention_mask: (L,S) bytes contiguous, non-zero = ignore (detr/model.py:332-334), may be NULL.
  * dropout_p is quantised to k/128 (in-kernel counter-based mask; 0 disables, as in eval()).  The mask seed is
- * `seed + *seed_ptr` (seed_ptr: optional DEVICE uint64, so that CUDA-graph replays draw fresh masks). */
+ * `seed + *seed_ptr` (seed_ptr: optional DEVICE uint64, so that CUDA-graph replays draw fresh masks).
+ * workspace float[detr_attention_fwd_workspace_floats(B,nh,L,S)]: partial results of the (batch, head, query tile) items
+ * that the persistent kernel splits between two CTAs (merged by a second small launch). */
+int64_t detr_attention_fwd_workspace_floats(int B, int nh, int L, int S);
 int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
                             const void* v, int64_t v_sb, int64_t v_sl, void* o, int64_t o_sb, int64_t o_sl,
-                            float* lse, const uint8_t* key_padding_mask, int64_t kpm_sb,
+                            float* lse, float* workspace, const uint8_t* key_padding_mask, int64_t kpm_sb,
                             const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
                             uint64_t seed, const uint64_t* seed_ptr, void* stream);
 

@@ -45,7 +45,9 @@ def _check(q, k, v, nh, kpm=None, am=None):
     return err
 
 
-@pytest.mark.parametrize("B,L,S,nh", [(2, 128, 128, 2), (1, 256, 384, 8), (2, 100, 100, 8), (2, 100, 850, 8), (2, 850, 850, 8), (1, 37, 5, 1)])
+@pytest.mark.parametrize("B,L,S,nh", [(2, 128, 128, 2), (1, 256, 384, 8), (2, 100, 100, 8), (2, 100, 850, 8), (2, 850, 850, 8), (1, 37, 5, 1),
+                                      # more (batch, head, query tile) items than SMs: persistent CTAs split items between them
+                                      (3, 850, 850, 8), (24, 100, 300, 8), (5, 600, 130, 8)])
 def test_attention_forward_shapes(cuda, B, L, S, nh):
     g = torch.Generator(device="cpu").manual_seed(L * 1000 + S)
     C = nh * 32
