@@ -1,9 +1,10 @@
 // Row-wise helper kernels of the transformer blocks (HBM-bound, coalesced 16-byte accesses):
 //   colsum_bf16   bias gradient of nn.Linear: db[n] = sum_m g[m][n]  (detr/model.py:312-314,354,405-411 backward).
 //                 ATen's generic reduce_kernel needs ~27 us for a 6800 x 2048 bf16 matrix; this is one pass at
-//                 HBM speed: grid = column tiles x row chunks, fp32 partials; a second small launch folds the partials in
-//                 a fixed order (deterministic).  (A "last CTA folds" tail in the same launch serialised up to 296
-//                 dependent L2 round trips in one CTA: 25-40 us per call, measured.)
+//                 HBM speed: grid = column tiles x (<= 64) row chunks, fp32 partials; the last CTA of a column tile folds
+//                 them in a fixed order with its 8 warps in parallel (deterministic, one launch).  (A serial fold of
+//                 hundreds of partials by one thread per column cost 25-40 us per call, measured; LayerNorm's 296 CTA
+//                 partials go through fold_partials_kernel instead.)
 #include "common.cuh"
 #include <cuda_bf16.h>
 
@@ -42,8 +43,47 @@ __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(const float
     }
 }
 
+// Tail of the column-sum kernels: the last CTA of a column tile (grid.y <= 64 row chunks) folds the chunk partials in a
+// fixed order -- 8 warps take every 8th chunk with independent 32-byte loads, then combine through shared memory -- so
+// the bias gradient needs no second launch.  counter: one uint32 per column tile, zero on entry and on exit.
+__device__ __forceinline__ void colsum_fold_tail(const float* __restrict__ partial, int N, float* __restrict__ out,
+                                                 unsigned* __restrict__ counter, float (*red)[kColsPerCta]) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.y - 1;
+    __syncthreads();
+    if (!is_last) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * kColsPerCta + lane * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c0 < N) {
+        constexpr int W = kCsThreads / 32;
+        for (int k = warp; k < (int)gridDim.y; k += 2 * W) {
+            const float* r0 = partial + (int64_t)k * N + c0;
+            const bool two = k + W < (int)gridDim.y;
+            const float* r1 = two ? r0 + (int64_t)W * N : r0;
+            const float4 a0 = __ldcg(reinterpret_cast<const float4*>(r0)), a1 = __ldcg(reinterpret_cast<const float4*>(r0) + 1);
+            const float4 b0 = __ldcg(reinterpret_cast<const float4*>(r1)), b1 = __ldcg(reinterpret_cast<const float4*>(r1) + 1);
+            acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w; acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+            if (two) { acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w; acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w; }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[warp][lane * 8 + e] = acc[e];
+    __syncthreads();
+    const int c = threadIdx.x, col = blockIdx.x * kColsPerCta + c;
+    if (c < kColsPerCta && col < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kCsThreads / 32; ++w) s += red[w][c];
+        out[col] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+}
+
 __global__ void __launch_bounds__(kCsThreads) colsum_kernel(const __nv_bfloat16* __restrict__ g, int64_t ld, int M, int N, int rows_per_cta,
-                                                              float* __restrict__ partial) {
+                                                              float* __restrict__ partial, float* __restrict__ out, unsigned* __restrict__ counters) {
     __shared__ float red[kCsThreads / 32][kColsPerCta];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c0 = blockIdx.x * kColsPerCta + lane * 8;
@@ -77,6 +117,7 @@ __global__ void __launch_bounds__(kCsThreads) colsum_kernel(const __nv_bfloat16*
         for (int w = 0; w < kCsThreads / 32; ++w) s += red[w][c];
         partial[(int64_t)blockIdx.y * N + col] = s;
     }
+    colsum_fold_tail(partial, N, out, counters + blockIdx.x, red);
 }
 
 }  // namespace detr
@@ -87,7 +128,7 @@ extern "C" int detr_colsum_chunks(int M, int N) {
     const int col_tiles = (N + kColsPerCta - 1) / kColsPerCta;
     int chunks = (4 * 148 + col_tiles - 1) / col_tiles;          // ~4 CTAs of 8 warps per SM
     const int max_chunks = (M + 31) / 32;                        // at least 32 rows (one 4-row batch per warp) per CTA
-    if (chunks > 256) chunks = 256;                              // bounds the fold: 8 partials per fold warp
+    if (chunks > 64) chunks = 64;                                // bounds the in-kernel fold: 8 partials per warp of the last CTA
     if (chunks > max_chunks) chunks = max_chunks;
     return chunks < 1 ? 1 : chunks;
 }
@@ -95,14 +136,12 @@ extern "C" int detr_colsum_chunks(int M, int N) {
 extern "C" int detr_colsum_bf16(const void* g, int64_t ld, int M, int N, float* partial, float* out, uint32_t* counters, void* stream) {
     DETR_CHECK_ARG(M >= 1 && N >= 8 && (N % 8) == 0 && (ld % 8) == 0 && ((uintptr_t)g % 16) == 0,
                    "colsum: need N %% 8 == 0, ld %% 8 == 0 and a 16-byte aligned matrix (M=%d N=%d ld=%lld)", M, N, (long long)ld);
-    (void)counters;   // kept in the signature (ABI); the fold is a second launch now
+    DETR_CHECK_ARG(counters != nullptr && N <= 64 * kColsPerCta, "colsum: counters required (64 zeroed uint32), N <= %d", 64 * kColsPerCta);
     const int chunks = detr_colsum_chunks(M, N);
     const int rows_per_cta = (M + chunks - 1) / chunks;
     dim3 grid((N + kColsPerCta - 1) / kColsPerCta, chunks);
-    colsum_kernel<<<grid, kCsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(g), ld, M, N, rows_per_cta, partial);
+    colsum_kernel<<<grid, kCsThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(g), ld, M, N, rows_per_cta, partial, out, counters);
     DETR_CHECK_LAUNCH("colsum");
-    fold_partials_kernel<<<(N + 31) / 32, kFoldThreads, 0, (cudaStream_t)stream>>>(partial, chunks, N, out, out, N);
-    DETR_CHECK_LAUNCH("colsum_fold");
     return 0;
 }
 
@@ -345,6 +384,7 @@ struct EwParams {
     void* out;                     // forward: TX (MODE 0) / bf16 (MODE 1); backward: dy bf16
     const void* g;                 // backward: incoming gradient, TG
     float* partial;                // backward: [row chunks][N] column sums of dy
+    float* db; unsigned* counters; // backward: bias gradient, per-column-tile counters (zero on entry and exit)
     int M, N, rows_per_cta;
     uint32_t thr4; float scale;    // dropout: thresh * 0x01010101 (0 = off), 1 / keep
     uint64_t seed; const uint64_t* seed_ptr;
@@ -479,6 +519,7 @@ __global__ void __launch_bounds__(kCsThreads) epilogue_bwd_kernel(const EwParams
         for (int w = 0; w < kCsThreads / 32; ++w) s += red[w][c];
         p.partial[(int64_t)blockIdx.y * p.N + col] = s;
     }
+    colsum_fold_tail(p.partial, p.N, p.db, p.counters + blockIdx.x, red);
 }
 
 static int ew_fill(EwParams& p, int M, int N, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, const char* who) {
@@ -516,12 +557,13 @@ extern "C" int detr_epilogue_chunks(int M, int N) { return detr_colsum_chunks(M,
 /* dy(bf16) = dropout_mask(g)/(1-p) [* gelu'(y) in mode 1]; db[n] = sum_m dy[m][n].  g_dtype: 0 f32, 1 bf16.
  * partial float[detr_epilogue_chunks(M,N) * N] scratch. */
 extern "C" int detr_epilogue_bwd(int mode, const void* g, int g_dtype, const void* y, void* dy, float* partial, float* db,
-                                 int M, int N, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream) {
+                                 uint32_t* counters, int M, int N, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream) {
     EwParams p{};
     if (int rc = ew_fill(p, M, N, dropout_p, seed, seed_ptr, "epilogue_bwd")) return rc;
     DETR_CHECK_ARG(mode == 0 || mode == 1, "epilogue_bwd: mode must be 0 or 1");
     DETR_CHECK_ARG(((uintptr_t)g % 16) == 0 && ((uintptr_t)dy % 16) == 0 && (mode == 0 || ((uintptr_t)y % 16) == 0), "epilogue_bwd: 16-byte alignment");
-    p.g = g; p.y = reinterpret_cast<const __nv_bfloat16*>(y); p.out = dy; p.partial = partial;
+    DETR_CHECK_ARG(counters != nullptr && N <= 64 * kColsPerCta, "epilogue_bwd: counters required (64 zeroed uint32), N <= %d", 64 * kColsPerCta);
+    p.g = g; p.y = reinterpret_cast<const __nv_bfloat16*>(y); p.out = dy; p.partial = partial; p.db = db; p.counters = counters;
     const int chunks = detr_colsum_chunks(M, N);
     p.rows_per_cta = (M + chunks - 1) / chunks;
     dim3 grid((N + kColsPerCta - 1) / kColsPerCta, chunks);
@@ -531,7 +573,5 @@ extern "C" int detr_epilogue_bwd(int mode, const void* g, int g_dtype, const voi
     else if (g_dtype == 0) epilogue_bwd_kernel<1, float><<<grid, kCsThreads, 0, st>>>(p);
     else epilogue_bwd_kernel<1, __nv_bfloat16><<<grid, kCsThreads, 0, st>>>(p);
     DETR_CHECK_LAUNCH("epilogue_bwd");
-    fold_partials_kernel<<<(N + 31) / 32, kFoldThreads, 0, st>>>(partial, chunks, N, db, db, N);
-    DETR_CHECK_LAUNCH("epilogue_bwd_fold");
     return 0;
 }

@@ -53,7 +53,7 @@ SIGNATURES = {
     "detr_maxpool3x3s2_out": [c_int],
     "detr_maxpool3x3s2_fwd_bf16": [P, P, P, c_int, c_int, c_int, c_int, P],
     "detr_maxpool3x3s2_bwd_bf16": [P, P, P, c_int, c_int, c_int, c_int, P],
-    "detr_epilogue_bwd": [c_int, P, c_int, P, P, P, P, c_int, c_int, c_float, ctypes.c_uint64, P, P],
+    "detr_epilogue_bwd": [c_int, P, c_int, P, P, P, P, P, c_int, c_int, c_float, ctypes.c_uint64, P, P],
 }
 _RESTYPE = {"detr_matcher_smem_bytes": c_int64, "detr_attention_bwd_workspace_floats": c_int64,
             "detr_attention_fwd_workspace_floats": c_int64}
@@ -89,8 +89,8 @@ class FoldTable(ctypes.Structure):
 # kernels launched per C-ABI call (bench.py's gpu_launches is counted from this table)
 KERNELS_PER_CALL = {"detr_cost_matrix_f32": 1, "detr_hungarian_match_f32": 1, "detr_lsap_f32": 1, "detr_lsap_f64": 1,
                     "detr_criterion_fwd_f32": 2, "detr_criterion_bwd_f32": 1, "detr_attention_fwd_bf16": 2,
-                    "detr_attention_bwd_bf16": 4, "detr_colsum_bf16": 2, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2,
-                    "detr_epilogue_fwd": 1, "detr_epilogue_bwd": 2, "detr_scale_cast_multi": 1,
+                    "detr_attention_bwd_bf16": 4, "detr_colsum_bf16": 1, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2,
+                    "detr_epilogue_fwd": 1, "detr_epilogue_bwd": 1, "detr_scale_cast_multi": 1,
                     "detr_maxpool3x3s2_fwd_bf16": 1, "detr_maxpool3x3s2_bwd_bf16": 1,
                     "detr_positional_encoding_f32": 1}
 launch_count = 0          # kernels of libdetr_b200.so launched by this process

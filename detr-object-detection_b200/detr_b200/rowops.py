@@ -123,7 +123,7 @@ class _LinearEpilogue(torch.autograd.Function):
         partial = torch.empty(chunks * N, dtype=torch.float32, device=g.device)
         db = torch.empty(N, dtype=torch.float32, device=g.device)
         _lib.call("detr_epilogue_bwd", ctx.mode, g.data_ptr(), _DT[g.dtype], _lib.ptr(y), dy.data_ptr(), partial.data_ptr(), db.data_ptr(),
-                  M, N, float(ctx.p), ctx.seed & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_t), _lib.stream_ptr())
+                  _lib.zero_counters(g.device).data_ptr(), M, N, float(ctx.p), ctx.seed & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_t), _lib.stream_ptr())
         x2 = x.reshape(M, -1)
         dx = (dy @ w16).view(x.shape) if ctx.needs_input_grad[1] else None
         dw = torch.mm(dy.t(), x2, out_dtype=torch.float32) if ctx.w_dtype == torch.float32 else (dy.t() @ x2).to(ctx.w_dtype)

@@ -167,12 +167,12 @@ int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, const void*
  * is counter-based (7 bits per element, p quantised to k/128, seed + *seed_ptr as in the attention kernels) and is
  * regenerated by the backward call, which also returns the producing Linear's bias gradient:
  *   dy(bf16) = mask(g)/(1-p) [* gelu'(y) in mode 1],  db[n] = sum_m dy[m][n]
- * partial float[detr_epilogue_chunks(M,N) * N] is scratch.  N % 8 == 0. */
+ * partial float[detr_epilogue_chunks(M,N) * N] is scratch; counters as for detr_colsum_bf16.  N % 8 == 0. */
 int detr_epilogue_fwd(int mode, const void* x, int x_dtype, const void* y, void* out, int M, int N, float dropout_p,
                       uint64_t seed, const uint64_t* seed_ptr, void* stream);
 int detr_epilogue_chunks(int M, int N);
 int detr_epilogue_bwd(int mode, const void* g, int g_dtype, const void* y, void* dy, float* partial, float* db,
-                      int M, int N, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
+                      uint32_t* counters, int M, int N, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
 
 /* ---- caller-side glue: frozen-BatchNorm fold of the backbone weights (detr/model.py:427-438) ----------------- */
 /* dst[o][i][hw] = (out dtype)(src[o][i][hw] * scale[o]) for up to 64 (O, I, H*W) tensors in ONE launch; element strides

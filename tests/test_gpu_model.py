@@ -241,7 +241,8 @@ def test_fused_linear_epilogue_dropout_consistency(cuda, mode):
     chunks = _lib.load().detr_epilogue_chunks(M, N)
     partial = torch.empty(chunks * N, device=cuda)
     db = torch.empty(N, device=cuda)
-    _lib.call("detr_epilogue_bwd", mode, g.data_ptr(), 0, y.data_ptr(), dy.data_ptr(), partial.data_ptr(), db.data_ptr(), M, N, p, 7, None, _lib.stream_ptr())
+    _lib.call("detr_epilogue_bwd", mode, g.data_ptr(), 0, y.data_ptr(), dy.data_ptr(), partial.data_ptr(), db.data_ptr(),
+              _lib.zero_counters(g.device).data_ptr(), M, N, p, 7, None, _lib.stream_ptr())
     assert torch.equal(dy.float() != 0, kept)
     if mode == 0:
         assert torch.allclose(dy.float()[kept], torch.full((), 1 / 0.75, device=cuda).expand(int(kept.sum())), rtol=1e-2)
