@@ -52,6 +52,7 @@ struct AttnFwdParams {
     float drop_scale;                      // 128 / (128 - thresh)
     float drop_log2_scale;                 // log2(drop_scale): folded into the exponent
     uint64_t seed; const uint64_t* seed_ptr; // effective seed = seed + *seed_ptr (device side: CUDA-graph replays get fresh masks)
+    long long* dbg;                        // optional clock64 timeline of CTA 0 (DETR_FWD_TIMELINE builds), NULL in production
 };
 constexpr int kPartRow = 36;   // 32 output columns, row max, row sum, padding to a 16-byte multiple
 
@@ -81,6 +82,13 @@ struct FwdCursor {
     __device__ __forceinline__ explicit FwdCursor(const FwdSched& sc) : item(sc.item0), t(sc.t0) {}
     __device__ __forceinline__ void next(const FwdSched& sc) { if (++t == sc.T) { t = 0; ++item; } }
 };
+
+#ifndef DETR_FWD_TIMELINE
+#define FWD_STAMP(ev, j) do {} while (0)
+#else
+#define FWD_STAMP(ev, j) do { if (p.dbg != nullptr && lane == 0 && blockIdx.x == 0 && (j) < 32) \
+    p.dbg[(warp * 32 + (j)) * 8 + (ev)] = clock64(); } while (0)
+#endif
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -168,7 +176,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             FwdCursor cur(sc);
             for (int j = 0; j < NT; ++j, cur.next(sc)) {
                 const bool last = j == NT - 1 || cur.t == sc.T - 1;
+                FWD_STAMP(0, j);
                 mbar_wait_sleep(p_full + (j & 1), (j >> 1) & 1);     // P_j is in shared memory (and S_j, O_tile(j-2) are in registers)
+                FWD_STAMP(1, j);
                 tc_fence_after();
                 const uint32_t v_lo = (smem_u32(smem + FwdSmem::kv + (j % kStages) * 2 * kTileBytes) + kTileBytes) >> 4;
                 const uint32_t p_lo = smem_u32(smem + FwdSmem::p + (j & 1) * (kBM * kBN * 2)) >> 4;
@@ -182,6 +192,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 umma_commit(kv_empty + (j % kStages));
                 if (last) umma_commit(o_done);
                 if (j + 2 < NT) scores();                          // S_{j+2}: its commit also covers P V of pair j
+                FWD_STAMP(2, j);
             }
         }
     } else {
@@ -280,7 +291,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             const uint8_t* arow = (p.amask && q < p.L) ? p.amask + (int64_t)q * p.S + key0 : nullptr;
             const bool any = (oob | pad) != 0u || p.amask != nullptr;
 
+            FWD_STAMP(0, j);
             mbar_wait(s_full + (j & 1), (j >> 1) & 1);            // S_j ready; P V of pair j-2 complete
+            FWD_STAMP(1, j);
             tc_fence_after();
             tmem_ld32(tmem_s + (j & 1) * kBN + lane_addr + kq * 32, s);
             uint32_t o_old[8];
@@ -288,6 +301,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             if (have_old) tmem_ld8(tmem_o + (j & 1) * kD + lane_addr + kq * 8, o_old);
             tmem_ld_wait();
             tc_fence_before();
+            FWD_STAMP(2, j);
 
             if (any) {
 #pragma unroll
@@ -311,6 +325,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 const float* xr = xch + (j & 1) * 512 + row;
                 mx = fmaxf(fmaxf(xr[0], xr[128]), fmaxf(xr[256], xr[384]));
             }
+            FWD_STAMP(3, j);
             const float m_new = fmaxf(m_run, mx);                 // finite: every pair has at least one in-range key
             const float alpha = ex2((m_run - m_new) * sc_l2);     // first pair: exp2(-inf) = 0
             const float bias = drop ? fmaf(-m_new, sc_l2, p.drop_log2_scale) : -m_new * sc_l2;   // kept entries come out pre-scaled by 1/(1-p)
@@ -336,8 +351,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 }
                 *reinterpret_cast<uint4*>(p_row + (((chunk0 + g) ^ (uint32_t)(row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
+            FWD_STAMP(4, j);
             fence_proxy_async_smem();
             mbar_arrive(p_full + (j & 1));
+            FWD_STAMP(5, j);
             // output accumulation, two pairs late: acc = (acc + O_tile(j-2) * alpha(j-1)) * alpha(j)
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -447,6 +464,10 @@ int make_f32_tile_map(CUtensorMap* out, const void* base, int C, int rows, int s
 
 using namespace detr;
 
+static long long* g_fwd_dbg = nullptr;
+/* debugging aid (not part of the drop-in surface): device buffer of 20*32*8 int64 that receives clock64 stamps of CTA 0 */
+extern "C" void detr_attention_fwd_set_debug(long long* buf) { g_fwd_dbg = buf; }
+
 extern "C" int64_t detr_attention_fwd_workspace_floats(int B, int nh, int L, int S) {
     (void)S;
     const int64_t items = (int64_t)((L + kBM - 1) / kBM) * nh * B;
@@ -476,6 +497,7 @@ extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.drop_scale = 128.f / (128.f - (float)p.drop_thresh);
     p.drop_log2_scale = log2f(p.drop_scale);
     p.seed = seed; p.seed_ptr = seed_ptr;
+    p.dbg = g_fwd_dbg;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem::total);
