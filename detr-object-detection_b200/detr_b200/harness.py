@@ -556,6 +556,42 @@ class GraphedTrainStep:
             self.targets.num_boxes.copy_((t / self.world).clamp_(min=1.0))
         return (batch["image"].numel() * batch["image"].element_size() + 8 * self.heights.numel() + self.targets.bytes_per_update())
 
+    # double-buffered input pipeline: the H2D copy of batch i+1 runs on a copy stream under the compute of step i
+    _copy_stream = None
+
+    def prefetch(self, batch: Dict) -> None:
+        """Start copying a (pinned) host batch's images into a staging buffer on a side stream; `commit()` makes it the
+        current input.  The previous staging contents must have been committed."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = torch.empty_like(self.images)
+            self._ready, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream())
+        self._copy_stream.wait_event(self._consumed)          # the last commit's device copy has read the staging buffer
+        with torch.cuda.stream(self._copy_stream):
+            self._stage.copy_(batch["image"], non_blocking=True)
+            self._ready.record(self._copy_stream)
+        self._pending = batch
+
+    def commit(self) -> int:
+        """Make the prefetched batch the input of the next `step()`: wait for its H2D copy, move it into the graph's static
+        image buffer (device-to-device), upload sizes and repacked ground truth.  Returns the bytes moved host->device."""
+        import torch.distributed as dist
+        batch = self._pending
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready)
+        self.images.copy_(self._stage, non_blocking=True)
+        self._consumed.record(cur)
+        self.heights.copy_(batch["height"], non_blocking=True)
+        self.widths.copy_(batch["width"], non_blocking=True)
+        n = self.targets.update(batch["class_idx"], batch["boxes_normalized"])
+        self.targets.set_num_boxes(float(n))
+        if self.world > 1 and getattr(self.criterion, "sync_num_boxes", True):
+            t = self.targets.num_boxes.clone()
+            dist.all_reduce(t)
+            self.targets.num_boxes.copy_((t / self.world).clamp_(min=1.0))
+        return (batch["image"].numel() * batch["image"].element_size() + 8 * self.heights.numel() + self.targets.bytes_per_update())
+
     def step(self) -> torch.Tensor:
         """One optimizer step on whatever `load()` put in the static buffers. Returns the (device) loss scalar."""
         self.graph_a.replay()
