@@ -58,3 +58,25 @@ def test_graph_replays_draw_fresh_dropout_masks(cuda):
     losses = [float(g.step()) for _ in range(4)]
     assert len(set(round(l, 6) for l in losses)) > 1, losses
     assert int(g.step_counter.item()) >= 6
+
+
+def test_prefetch_commit_equals_load(cuda):
+    """The double-buffered input path (prefetch on a copy stream + commit) feeds the captured step the same inputs as the
+    blocking load(): with frozen weights (lr 0, eval) the loss of a batch is identical either way, in any order."""
+    from detr_b200.harness import GraphedTrainStep, make_optimizer, synthetic_batch
+    m, c = _make(cuda, train=False)
+    opt = make_optimizer(m, lr=0.0, weight_decay=0.0, capturable=True)
+    batches = [synthetic_batch(2, 160, 200, 11, 6, seed=s, pin=True) for s in (5, 6, 7)]
+    g = GraphedTrainStep(m, c, opt, batches[0], gt_cap=8, warmup=2)
+    ref = []
+    for b in batches:
+        g.load(b)
+        ref.append(float(g.step()))
+    got = []
+    g.prefetch(batches[0])
+    for i in range(len(batches)):
+        g.commit()
+        if i + 1 < len(batches):
+            g.prefetch(batches[i + 1])
+        got.append(float(g.step()))
+    assert got == ref, (got, ref)
