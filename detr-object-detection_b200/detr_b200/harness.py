@@ -450,6 +450,60 @@ def batch_bytes(batch: Dict) -> int:
     return n
 
 
+class FlatAdamW:
+    """clip_grad_norm_ + AdamW (detr/train.py:265-267, torch.optim.AdamW semantics) on flat fp32 buffers: the parameters of
+    `torch_optimizer`'s groups are re-homed into ONE buffer (each `p.data` becomes a view with its original shape and
+    strides), the moments live in two more, and a step is `detr_sumsq_f32` + one `detr_adamw_clip_f32` per group instead of
+    ~28 ATen launches over ~330 tensors.  Hyper-parameters are read from the torch optimizer's param_groups at every step
+    (LR schedulers keep working); its own state is not used."""
+
+    def __init__(self, torch_optimizer, device):
+        self.opt = torch_optimizer
+        self.params, self.ranges, o = [], [], 0
+        for g in torch_optimizer.param_groups:
+            ps = [q for q in g["params"] if q.requires_grad]
+            n = sum(q.numel() for q in ps)
+            n_pad = (n + 3) // 4 * 4                     # every group starts 16-byte aligned
+            self.ranges.append((o, n))
+            self.params += ps
+            o += n_pad
+        self.total = o
+        self.flat_p = torch.zeros(o, dtype=torch.float32, device=device)
+        self.flat_m, self.flat_v = torch.zeros_like(self.flat_p), torch.zeros_like(self.flat_p)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.grad_views, self.offsets, o = [], [], 0
+        with torch.no_grad():
+            for g, (start, n) in zip(torch_optimizer.param_groups, self.ranges):
+                o = start
+                for q in (q for q in g["params"] if q.requires_grad):
+                    view = torch.as_strided(self.flat_p, q.shape, q.stride(), o)
+                    view.copy_(q)
+                    q.data = view                                  # the parameter now lives in the flat buffer
+                    self.grad_views.append(torch.as_strided(self.flat_g, q.shape, q.stride(), o))
+                    o += q.numel()
+        from . import _lib
+        self.step_t = torch.zeros(1, dtype=torch.float32, device=device)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=device)
+        self.partial = torch.empty(_lib.load().detr_sumsq_grid(self.total), dtype=torch.float32, device=device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def step(self, max_norm: float, grad_div: float = 1.0) -> None:
+        """One update from the gradients in `flat_g` (scaled by grad_div, e.g. 1 / world size, then clipped to max_norm)."""
+        from . import _lib
+        self.step_t.add_(1.0)
+        st = _lib.stream_ptr()
+        _lib.call("detr_sumsq_f32", self.flat_g.data_ptr(), self.total, self.partial.data_ptr(), self.sumsq.data_ptr(),
+                  self.counter.data_ptr(), st)
+        for g, (start, n) in zip(self.opt.param_groups, self.ranges):
+            if n == 0:
+                continue
+            b1, b2 = g["betas"]
+            off = start * 4
+            _lib.call("detr_adamw_clip_f32", self.flat_p.data_ptr() + off, self.flat_g.data_ptr() + off, self.flat_m.data_ptr() + off,
+                      self.flat_v.data_ptr() + off, n, float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
+                      self.step_t.data_ptr(), self.sumsq.data_ptr(), float(max_norm), float(grad_div), st)
+
+
 class GraphedTrainStep:
     """The reference's step body (detr/train.py:258-267) captured ONCE in CUDA graphs and replayed: the eager step is
     host-launch-bound (~2 500 launches), the replay is GPU-bound.
@@ -464,7 +518,7 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model: nn.Module, criterion: nn.Module, optimizer, example: Dict, gt_cap: int = 100,
-                 autocast_dtype=torch.bfloat16, max_grad_norm: float = 1.0, warmup: int = 3):
+                 autocast_dtype=torch.bfloat16, max_grad_norm: float = 1.0, warmup: int = 3, flat_optimizer: bool = True):
         from . import attention
         from .targets import StaticTargets
         import torch.distributed as dist
@@ -482,6 +536,12 @@ class GraphedTrainStep:
         self.loss = torch.zeros((), device=self.dev)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.flat, self.flat_views = None, None
+        # default: clip + AdamW as two HBM-speed launches on flat buffers (`optimizer` supplies groups and hyper-parameters)
+        self.fopt = None
+        if flat_optimizer and isinstance(optimizer, torch.optim.AdamW) and all(not g.get("amsgrad", False) for g in optimizer.param_groups):
+            self.fopt = FlatAdamW(optimizer, self.dev)
+            self.params = self.fopt.params
+            self.flat, self.flat_views = self.fopt.flat_g, self.fopt.grad_views
         self.load(example)
         # warm-up on a side stream (allocator, cuDNN autotune, lazy attribute setup), then capture
         side = torch.cuda.Stream()
@@ -499,10 +559,10 @@ class GraphedTrainStep:
         self.graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_a):
             self._forward_backward()
-        self.own_launches_per_step = _lib.launch_count - l0   # kernels of libdetr_b200.so inside one replay
         self.graph_b = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
             self._update()
+        self.own_launches_per_step = _lib.launch_count - l0   # kernels of libdetr_b200.so inside one replay of both graphs
 
     # -- pieces -------------------------------------------------------------------------------------------
     def _forward_backward(self):
@@ -516,8 +576,8 @@ class GraphedTrainStep:
         loss = sum(v for k, v in losses.items() if k.startswith("loss"))
         loss.backward()
         self.loss.copy_(loss.detach())
-        if self.world > 1:
-            # one multi-tensor copy into the flat all-reduce buffer (torch.cat over ~330 gradients costs 0.8 ms, measured)
+        if self.world > 1 or self.fopt is not None:
+            # one multi-tensor copy into the flat gradient / all-reduce buffer (torch.cat over ~330 gradients costs 0.8 ms, measured)
             if self.flat is None:
                 self.flat = torch.empty(sum(q.numel() for q in self.params), dtype=torch.float32, device=self.dev)
                 self.flat_views, o = [], 0
@@ -533,6 +593,9 @@ class GraphedTrainStep:
             dist.all_reduce(self.flat)
 
     def _update(self):
+        if self.fopt is not None:
+            self.fopt.step(self.max_grad_norm, 1.0 / self.world)   # the data-parallel mean rides in the clip coefficient
+            return
         if self.world > 1:
             # the reduced gradients are consumed in place: .grad becomes a view of the flat buffer, averaged by ONE kernel
             self.flat.div_(float(self.world))
@@ -555,6 +618,15 @@ class GraphedTrainStep:
             dist.all_reduce(t)                         # the num_boxes all-reduce: 1 scalar, no host sync
             self.targets.num_boxes.copy_((t / self.world).clamp_(min=1.0))
         return (batch["image"].numel() * batch["image"].element_size() + 8 * self.heights.numel() + self.targets.bytes_per_update())
+
+    def reset_optimizer_state(self) -> None:
+        """Zero the moments and the step count (the constructor's warm-up iterations have advanced them)."""
+        if self.fopt is not None:
+            self.fopt.flat_m.zero_(); self.fopt.flat_v.zero_(); self.fopt.step_t.zero_()
+        for st in self.opt.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()
 
     # double-buffered input pipeline: the H2D copy of batch i+1 runs on a copy stream under the compute of step i
     _copy_stream = None

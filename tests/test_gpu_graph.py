@@ -33,10 +33,7 @@ def test_graphed_step_matches_eager(cuda):
     g = GraphedTrainStep(m2, c2, o2, batches[0], gt_cap=8, warmup=2)
     # warm-up inside the constructor already stepped the weights: rewind model and optimizer state, then replay
     m2.load_state_dict(snapshot)
-    for st in o2.state.values():
-        for k, v in st.items():
-            if torch.is_tensor(v):
-                v.zero_()
+    g.reset_optimizer_state()
     graphed = []
     for b in batches:
         g.load(b)
@@ -80,3 +77,33 @@ def test_prefetch_commit_equals_load(cuda):
             g.prefetch(batches[i + 1])
         got.append(float(g.step()))
     assert got == ref, (got, ref)
+
+
+def test_flat_adamw_matches_torch(cuda):
+    """clip_grad_norm_(1.0) + torch.optim.AdamW against the flat two-launch optimizer (detr_sumsq_f32 + detr_adamw_clip_f32):
+    same parameters after several steps, two groups with different learning rates, channels_last conv weights included."""
+    from detr_b200.harness import FlatAdamW
+    torch.manual_seed(0)
+    def make():
+        torch.manual_seed(1)
+        a = torch.nn.Conv2d(8, 16, 3).to(cuda).to(memory_format=torch.channels_last)
+        b = torch.nn.Linear(37, 19).to(cuda)
+        return a, b
+    (a1, b1), (a2, b2) = make(), make()
+    groups = lambda a, b: [{"params": list(b.parameters()), "lr": 3e-3}, {"params": list(a.parameters()), "lr": 3e-4}]
+    o1 = torch.optim.AdamW(groups(a1, b1), lr=3e-3, weight_decay=1e-2)
+    o2 = torch.optim.AdamW(groups(a2, b2), lr=3e-3, weight_decay=1e-2)
+    f = FlatAdamW(o2, cuda)
+    p1 = [q for g in o1.param_groups for q in g["params"]]
+    for it in range(5):
+        gs = [torch.randn_like(q) * (3.0 if it % 2 else 0.01) for q in p1]     # clipped and unclipped steps
+        for q, g in zip(p1, gs):
+            q.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(p1, 1.0)
+        o1.step()
+        for v, g in zip(f.grad_views, gs):
+            v.copy_(g)
+        f.step(1.0)
+    for q1, q2 in zip(p1, f.params):
+        assert q1.shape == q2.shape and q1.stride() == q2.stride()
+        assert torch.allclose(q1, q2, rtol=1e-4, atol=1e-6), (q1 - q2).abs().max()
