@@ -266,12 +266,12 @@ def run_b200(args):
                     "achieved": round(ach, 2), "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops_sustained"], 4),
                     "peak_source": pk["src"] + " sustained (kernel timed inside a long step)",
                     # dram__bytes_read.sum + dram__bytes_write.sum of the call's three kernels, one `ncu --set full` capture
-                    # (profiles/r01_attention_ncu_full_v3.md; ncu flushes L2 between kernels, so the 48.8 MB the dQ reduction
+                    # (profiles/r01_attention_ncu_full_v4.md; ncu flushes L2 between kernels, so the 48.8 MB the dQ reduction
                     # re-reads from L2 in a real step counts as DRAM traffic here)
-                    "traffic": 75.4e6, "traffic_algorithmic": 14.1e6,
+                    "traffic": 82.0e6, "traffic_algorithmic": 14.1e6,
                     "ms_per_launch": round(tot / calls, 4), "flops_per_launch": flops,
-                    "note": "head_dim 32: one MUFU exp per 128 tensor FLOPs caps the tensor pipe at ~25% (SURVEY.md 7.1); measured "
-                            "limiter now is per-CTA fixed cost + 3.03-wave quantisation (profiles/r01_attention_ncu_full_v3.md)"}
+                    "note": "head_dim 32: one MUFU exp per 128 tensor FLOPs caps the tensor pipe at ~25% (SURVEY.md 7.1); the persistent "
+                            "kernel is bound by per-warp latency chains and issue slots, not by a pipe (profiles/r01_attention_ncu_full_v4.md)"}
             if key_f in rows:
                 c2, t2 = rows[key_f]
                 f2 = 4.0 * SP * SP * 256 * PER_GPU_BATCH
