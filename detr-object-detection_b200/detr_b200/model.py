@@ -23,7 +23,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from .attention import HEAD_DIM, flash_attention
-from .rowops import ShadowedLinears, fused_epilogues_enabled, layer_norm_add, linear, linear_dropout_add, linear_gelu_dropout
+from .rowops import (ShadowedLinears, fused_epilogues_enabled, layer_norm_add, linear, linear_dropout_add, linear_gelu_dropout,
+                     stacked_linear)
 
 
 @dataclass
@@ -95,17 +96,24 @@ class ScaledDotProductAttention(nn.Module):
 
     def forward(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
                 key_padding_mask: Optional[torch.BoolTensor] = None,
-                attention_mask: Optional[torch.BoolTensor] = None, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """The reference's forward (detr/model.py:254-356).  `residual` is an extension used by this package's layers:
-        when given, the result is residual + dropout(output_proj(attention)), the tail running as one fused kernel."""
+                attention_mask: Optional[torch.BoolTensor] = None, residual: Optional[torch.Tensor] = None,
+                projected_kv: Optional[tuple] = None) -> torch.Tensor:
+        """The reference's forward (detr/model.py:254-356).  Extensions used by this package's layers: `residual` -- the
+        result is residual + dropout(output_proj(attention)), the tail running as one fused kernel; `projected_kv` --
+        (key_proj(key), value_proj(value)) computed by the caller (the decoder projects the encoder memory for all its
+        layers in one GEMM), `key` / `value` are then ignored."""
         C = self.hidden_size
-        if key is query:
+        if projected_kv is not None:
+            q = self._lin(query, "query")
+            k, v = projected_kv
+        elif key is query:
             # self-attention: one GEMM for both projections; q/k are strided views the TMA descriptors take as they are
             qk = self._lin(query, "qk")
             q, k = qk[..., :C], qk[..., C:]
         else:
             q, k = self._lin(query, "query"), self._lin(key, "key")
-        v = self._lin(value, "value")
+        if projected_kv is None:
+            v = self._lin(value, "value")
         p_drop = self.dropout_attn.p if self.training else 0.0
         y = flash_attention(q, k, v, key_padding_mask, attention_mask, p_drop)
         if residual is not None and fused_epilogues_enabled(y):
@@ -203,12 +211,13 @@ class DecoderLayer(nn.Module):
 
     def forward(self, x: torch.Tensor, encoded_image_tokens: torch.Tensor, object_query_embedding: torch.Tensor,
                 position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor,
-                cross_key: Optional[torch.Tensor] = None):
+                cross_key: Optional[torch.Tensor] = None, cross_kv: Optional[tuple] = None):
         x_attn, query = layer_norm_add(x, self.norm1, object_query_embedding)
         x = self.self_attention(query, query, value=x_attn, residual=x)
         _, query = layer_norm_add(x, self.norm2, object_query_embedding, want_y=False)
-        key = cross_key if cross_key is not None else encoded_image_tokens + position_embedding
-        x = self.cross_attention(query, key, value=encoded_image_tokens, key_padding_mask=key_padding_mask, residual=x)
+        key = cross_key if (cross_key is not None or cross_kv is not None) else encoded_image_tokens + position_embedding
+        x = self.cross_attention(query, key, value=encoded_image_tokens, key_padding_mask=key_padding_mask, residual=x,
+                                 projected_kv=cross_kv)
         x = self.ffn(layer_norm_add(x, self.norm3)[0], residual=x)
         return x
 
@@ -230,10 +239,18 @@ class Decoder(nn.Module):
         _refresh_shadows(self, encoded_image_tokens)
         x = torch.zeros_like(object_query_embedding)
         cross_key = encoded_image_tokens + position_embedding   # layer-invariant: computed once, not 6 times
+        # ... and so are the cross-attention key / value projections' INPUTS: all layers' projections run as two wide GEMMs
+        # (n_layers*C outputs each) whose column slices feed the per-layer attention kernels as strided views
+        kvs = [None] * len(self.layers)
+        if fused_epilogues_enabled(encoded_image_tokens):
+            sh = self._shadows
+            ks = stacked_linear(cross_key, [l.cross_attention.key_proj for l in self.layers], *sh.get(("", "cross_keys")))
+            vs = stacked_linear(encoded_image_tokens, [l.cross_attention.value_proj for l in self.layers], *sh.get(("", "cross_values")))
+            kvs = list(zip(ks, vs))
         outputs = []
-        for layer in self.layers:
+        for layer, kv in zip(self.layers, kvs):
             x = layer(x, encoded_image_tokens, object_query_embedding, position_embedding, key_padding_mask,
-                      cross_key=cross_key)
+                      cross_key=cross_key, cross_kv=kv)
             outputs.append(x)
         # one LayerNorm launch over all layers' outputs instead of one per layer
         stacked = torch.stack(outputs, dim=1)
@@ -248,6 +265,10 @@ def _attach_shadows(root: nn.Module) -> None:
     for name, m in root.named_modules():
         if isinstance(m, (ScaledDotProductAttention, FFN)):
             m.register_shadows(sh, name)
+    if isinstance(root, Decoder):   # stacked shadows of all layers' cross-attention key / value projections (one GEMM each)
+        ca = [l.cross_attention for l in root.layers]
+        sh.register(("", "cross_keys"), [a.key_proj.weight for a in ca], [a.key_proj.bias for a in ca])
+        sh.register(("", "cross_values"), [a.value_proj.weight for a in ca], [a.value_proj.bias for a in ca])
     object.__setattr__(root, "_shadows", sh)
 
 

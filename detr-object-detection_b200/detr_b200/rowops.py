@@ -58,6 +58,48 @@ class _LinearFn(torch.autograd.Function):
         return (dx, None, None, None, *dws, *dbs)
 
 
+class _StackedLinearFn(torch.autograd.Function):
+    """Several nn.Linear layers applied to the SAME input as one GEMM: y_l = x W_l^T + b_l for l = 0..n-1, returned as n
+    tensors that are column slices of one (.., n*N) buffer (the attention kernels take the strided views as they are).
+    Backward concatenates the n incoming gradients once and runs ONE dgrad GEMM, ONE wgrad GEMM and ONE colsum instead of n of
+    each plus n-1 gradient accumulations on x.  Used for the decoder's cross-attention key / value projections, which read
+    the same encoder memory in every layer (detr/model.py:179-180 executes them six times)."""
+
+    @staticmethod
+    def forward(ctx, x, w16, b16, n, *params):
+        weights, biases = params[:n], params[n:]
+        if w16 is None:
+            w16 = torch.cat(weights, 0).to(x.dtype)
+        if b16 is None:
+            b16 = torch.cat(biases, 0).to(x.dtype)
+        ctx.save_for_backward(x, w16)
+        ctx.n, ctx.N, ctx.w_dtype = n, weights[0].shape[0], weights[0].dtype
+        y = F.linear(x, w16, b16)
+        return tuple(y[..., i * ctx.N:(i + 1) * ctx.N] for i in range(n))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, w16 = ctx.saved_tensors
+        n, N = ctx.n, ctx.N
+        gs = [g if g is not None else x.new_zeros(x.shape[:-1] + (N,)) for g in grads]
+        g2 = torch.cat([g.reshape(-1, N) for g in gs], dim=1)          # (M, n*N) bf16
+        x2 = x.reshape(-1, x.shape[-1])
+        dx = (g2 @ w16).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = torch.mm(g2.t(), x2, out_dtype=torch.float32) if ctx.w_dtype == torch.float32 else (g2.t() @ x2).to(ctx.w_dtype)
+        db = colsum(g2)
+        if ctx.w_dtype != torch.float32:
+            db = db.to(ctx.w_dtype)
+        return (dx, None, None, None, *torch.split(dw, N, 0), *torch.split(db, N, 0))
+
+
+def stacked_linear(x: torch.Tensor, linears, w16=None, b16=None):
+    """[lin(x) for lin in linears] as one GEMM under bf16 autocast (strided views of one buffer); plain loop otherwise."""
+    if torch.is_autocast_enabled() and x.is_cuda and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        with torch.autocast("cuda", enabled=False):
+            return _StackedLinearFn.apply(x.to(torch.bfloat16), w16, b16, len(linears), *[l.weight for l in linears], *[l.bias for l in linears])
+    return tuple(F.linear(x, l.weight, l.bias) for l in linears)
+
+
 def linear(x: torch.Tensor, weight, bias, w16=None, b16=None) -> torch.Tensor:
     """nn.functional.linear under bf16 autocast through `_LinearFn`; plain F.linear otherwise (fp32 mode).
     `weight` / `bias` may be tuples of parameters stacked along the output dimension."""
