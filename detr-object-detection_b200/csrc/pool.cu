@@ -130,3 +130,39 @@ extern "C" int detr_maxpool3x3s2_bwd_bf16(const void* dy, const uint8_t* idx, vo
     DETR_CHECK_LAUNCH("maxpool_bwd");
     return 0;
 }
+
+// ---- residual-gradient add fused with the preceding block's ReLU backward (caller-side glue of the ResNet harness) ----
+// out = (a + b) * (x > 0): the gradient w.r.t. a bottleneck block's input is the sum of its first convolution's dgrad and the
+// identity branch's gradient; when that input is the previous block's ReLU output, the previous block's threshold_backward can be
+// applied in the same pass (ATen runs add and threshold_backward as two kernels: 6 tensor passes instead of 4).
+namespace detr {
+__global__ void __launch_bounds__(256) add_relu_mask_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                            const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t n8) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 va = reinterpret_cast<const uint4*>(a)[i], vb = reinterpret_cast<const uint4*>(b)[i], vx = reinterpret_cast<const uint4*>(x)[i];
+        const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&va);
+        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&vb);
+        const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&vx);
+        uint4 o;
+        __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]), fx = __bfloat1622float2(hx[e]);
+            ho[e] = __floats2bfloat162_rn(fx.x > 0.f ? fa.x + fb.x : 0.f, fx.y > 0.f ? fa.y + fb.y : 0.f);
+        }
+        reinterpret_cast<uint4*>(out)[i] = o;
+    }
+}
+}  // namespace detr
+
+/* out = (a + b) * (x > 0), bf16, n elements (n % 8 == 0), all four buffers with the same dense layout. */
+extern "C" int detr_add_relu_mask_bf16(const void* a, const void* b, const void* x, void* out, long long n, void* stream) {
+    DETR_CHECK_ARG(n >= 8 && n % 8 == 0, "add_relu_mask: n must be a positive multiple of 8 (n=%lld)", n);
+    DETR_CHECK_ARG(((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0, "add_relu_mask: alignment");
+    const int64_t n8 = n / 8;
+    detr::add_relu_mask_kernel<<<detr::pool_grid(n8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), reinterpret_cast<const __nv_bfloat16*>(x),
+        reinterpret_cast<__nv_bfloat16*>(out), n8);
+    DETR_CHECK_LAUNCH("add_relu_mask");
+    return 0;
+}

@@ -269,6 +269,77 @@ def ctypes_byref(obj):
     return ctypes.byref(obj)
 
 
+def _conv_conf(conv: nn.Conv2d):
+    return (tuple(conv.stride), tuple(conv.padding), tuple(conv.dilation), conv.groups)
+
+
+class _BottleneckFn(torch.autograd.Function):
+    """One torchvision Bottleneck (frozen BN folded) as a single autograd node: three / four cuDNN fused convolutions forward,
+    a hand-ordered backward in which the residual-gradient add of the block input is fused with the PREVIOUS block's ReLU
+    backward (`detr_add_relu_mask_bf16`: (dx_conv1 + g_identity) * (x > 0), 4 tensor passes instead of ATen's 6).
+    premask_out: this block multiplies the gradient it returns by (x > 0) -- legal when x is the previous block's ReLU output;
+    premasked_in: the consumer of y already applied (y > 0) to the incoming gradient, so conv3's threshold_backward is skipped.
+    Library calls + one glue kernel (out of scope of the hot path; it serves the headline step time)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2, w3, wd, s1, s2, s3, confs, premask_out, premasked_in):
+        c1, c2, c3, cd = confs
+        o1 = torch.cudnn_convolution_relu(x, w1, s1, *c1)
+        o2 = torch.cudnn_convolution_relu(o1, w2, s2, *c2)
+        idn = x if wd is None else F.conv2d(x, wd, None, *cd)
+        y = torch.cudnn_convolution_add_relu(o2, w3, idn, 1.0, s3, *c3)
+        ctx.save_for_backward(x, w1, w2, w3, wd, o1, o2, y)
+        ctx.confs, ctx.premask_out, ctx.premasked_in = confs, premask_out, premasked_in
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        x, w1, w2, w3, wd, o1, o2, y = ctx.saved_tensors
+        c1, c2, c3, cd = ctx.confs
+        tb, cb = torch.ops.aten.threshold_backward, torch.ops.aten.convolution_backward
+        cl = torch.channels_last
+        g = g.contiguous(memory_format=cl)
+        g3 = g if ctx.premasked_in else tb(g, y, 0)
+        d2, dw3, _ = cb(g3, o2, w3, None, c3[0], c3[1], c3[2], False, [0, 0], c3[3], [True, True, False])
+        g2 = tb(d2, o2, 0)
+        d1, dw2, _ = cb(g2, o1, w2, None, c2[0], c2[1], c2[2], False, [0, 0], c2[3], [True, True, False])
+        g1 = tb(d1, o1, 0)
+        need_dx = ctx.needs_input_grad[0]
+        dx1, dw1, _ = cb(g1, x, w1, None, c1[0], c1[1], c1[2], False, [0, 0], c1[3], [need_dx, True, False])
+        dwd, b = None, g3
+        if wd is not None:
+            b, dwd, _ = cb(g3, x, wd, None, cd[0], cd[1], cd[2], False, [0, 0], cd[3], [need_dx, True, False])
+        dx = None
+        if need_dx:
+            same = (dx1.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dx1.stride() == x.stride()
+                    and b.stride() == x.stride() and x.is_contiguous(memory_format=cl) and x.numel() % 8 == 0)
+            if ctx.premask_out and same:
+                dx = torch.empty_like(x)
+                _lib.call("detr_add_relu_mask_bf16", dx1.data_ptr(), b.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), _lib.stream_ptr())
+            else:
+                dx = dx1 + b
+                if ctx.premask_out:
+                    dx = tb(dx, x, 0)
+        return dx, dw1, dw2, dw3, dwd, None, None, None, None, None, None
+
+
+def _bottleneck_fused(blk, x, w16, premask_out: bool, premasked_in: bool):
+    s1, s2 = _bn_constants(blk.bn1)[2], _bn_constants(blk.bn2)[2]
+    s3 = _bn_constants(blk.bn3)[2]
+    wd, cd = None, None
+    if blk.downsample is not None:
+        s3 = blk.__dict__.get("_detr_shift3")
+        if s3 is None or s3.device != x.device:
+            s3 = (_bn_constants(blk.bn3)[1] + _bn_constants(blk.downsample[1])[1]).to(torch.bfloat16)
+            blk.__dict__["_detr_shift3"] = s3
+        wd, cd = w16[blk.downsample[0]], _conv_conf(blk.downsample[0])
+    confs = (_conv_conf(blk.conv1), _conv_conf(blk.conv2), _conv_conf(blk.conv3), cd)
+    with torch.autocast("cuda", enabled=False):
+        return _BottleneckFn.apply(x.to(torch.bfloat16), w16[blk.conv1], w16[blk.conv2], w16[blk.conv3], wd, s1, s2, s3, confs,
+                                   premask_out, premasked_in)
+
+
 def _bottleneck_forward(blk, x, fused: bool, w16=None):
     identity = x
     if fused:
@@ -313,6 +384,7 @@ class _Backbone(nn.Module):
         self.fuse_relu = True   # cuDNN conv+bias(+add)+ReLU epilogues; needs CUDA bf16 autocast, else plain path
         self._fold = None       # FoldedConvWeights packs, built on first fused forward
         self.use_fold_pack = True   # False: fold each weight where it is used (3 launches per convolution each way)
+        self.fuse_block_backward = True   # one autograd node per bottleneck (ReLU backward fused with the residual-gradient add)
 
     def forward(self, x):
         if not self.fold_bn:
@@ -339,9 +411,14 @@ class _Backbone(nn.Module):
         else:
             x = F.relu(_conv_bn(x, m.conv1, m.bn1), inplace=True)
         x = _stem_maxpool(m.maxpool, x) if fused else m.maxpool(x)
-        for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
-            for blk in layer:
-                x = _bottleneck_forward(blk, x, fused, w16)
+        blocks = [blk for layer in (m.layer1, m.layer2, m.layer3, m.layer4) for blk in layer]
+        if w16 is not None and self.fuse_block_backward and all(type(b).__name__ == "Bottleneck" for b in blocks):
+            for i, blk in enumerate(blocks):
+                # the first block's input is the max-pool output (no ReLU to fold); the last block's output leaves the backbone
+                x = _bottleneck_fused(blk, x, w16, premask_out=i > 0, premasked_in=i + 1 < len(blocks))
+            return x
+        for blk in blocks:
+            x = _bottleneck_forward(blk, x, fused, w16)
         return x
 
 

@@ -197,6 +197,10 @@ int detr_scale_cast_multi(const DetrFoldTable* table, int in_dtype, int out_dtyp
 int detr_maxpool3x3s2_out(int n);
 int detr_maxpool3x3s2_fwd_bf16(const void* x, void* y, uint8_t* idx, int B, int H, int W, int C, void* stream);
 int detr_maxpool3x3s2_bwd_bf16(const void* dy, const uint8_t* idx, void* dx, int B, int H, int W, int C, void* stream);
+/* out = (a + b) * (x > 0) on dense bf16 buffers of n elements (n % 8 == 0): residual-gradient accumulation of a ResNet
+ * bottleneck fused with the previous block's ReLU backward (harness glue). */
+int detr_add_relu_mask_bf16(const void* a, const void* b, const void* x, void* out, long long n, void* stream);
+
 
 /* Sine positional encoding + padding mask of DETR.forward (detr/position_encoding.py:5-97, detr/model.py:96-114) in one
  * launch, token-major: pos float[B][H'*W'][2F] (channel order of the reference: F y-channels then F x-channels, sin/cos

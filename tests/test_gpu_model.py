@@ -300,3 +300,26 @@ def test_stem_maxpool_kernels_match_aten(cuda, B, C, H, W):
     (ya * w).sum().backward(); (yb * w).sum().backward()
     assert torch.allclose(xa.grad.float(), xb.grad.float(), rtol=1e-2, atol=1e-2)
     assert ((xa.grad != 0) != (xb.grad != 0)).float().mean().item() < 1e-4   # same arg-max choice everywhere (ties included)
+
+
+def test_backbone_block_backward_fusion_matches_unfused(cuda):
+    """One autograd node per bottleneck with (dx + g_identity) * (x > 0) fused (detr_add_relu_mask_bf16) against the per-convolution
+    autograd path: same activations (identical cuDNN calls), parameter gradients equal up to bf16 accumulation order."""
+    from detr_b200.harness import _Backbone
+    torch.manual_seed(0)
+    bb = _Backbone("resnet50").to(cuda).to(memory_format=torch.channels_last).train()
+    x = torch.randn(2, 3, 96, 128, device=cuda)
+    res = []
+    for fuse in (True, False):
+        bb.fuse_block_backward = fuse
+        bb.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = bb(x)
+        y.float().square().mean().backward()
+        res.append((y.float(), {n: p.grad.clone() for n, p in bb.named_parameters() if p.grad is not None}))
+    (y1, g1), (y0, g0) = res
+    assert torch.equal(y1, y0)
+    assert set(g1) == set(g0)
+    for n in g0:
+        rel = ((g1[n] - g0[n]).norm() / (g0[n].norm() + 1e-12)).item()
+        assert rel <= 2e-2, (n, rel)
