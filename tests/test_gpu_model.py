@@ -323,3 +323,23 @@ def test_backbone_block_backward_fusion_matches_unfused(cuda):
     for n in g0:
         rel = ((g1[n] - g0[n]).norm() / (g0[n].norm() + 1e-12)).item()
         assert rel <= 2e-2, (n, rel)
+
+
+def test_stem_space_to_depth_matches_direct_conv(cuda):
+    """The 4x4 stride-1 convolution over the space-to-depth image equals the 7x7 stride-2 stem (same bf16 products, different
+    summation order), forward and weight gradient."""
+    from detr_b200.harness import _Backbone
+    torch.manual_seed(0)
+    bb = _Backbone("resnet50").to(cuda).to(memory_format=torch.channels_last).train()
+    x = torch.randn(2, 3, 64, 96, device=cuda)
+    res = []
+    for s2d in (True, False):
+        bb.stem_space_to_depth = s2d
+        bb.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = bb(x)
+        y.float().square().mean().backward()
+        res.append((y.float(), bb.backbone.conv1.weight.grad.clone()))
+    (y1, g1), (y0, g0) = res
+    assert (y1 - y0).abs().max().item() <= 3e-2 * y0.abs().max().item()
+    assert ((g1 - g0).norm() / g0.norm()).item() <= 5e-2
