@@ -166,3 +166,46 @@ extern "C" int detr_add_relu_mask_bf16(const void* a, const void* b, const void*
     DETR_CHECK_LAUNCH("add_relu_mask");
     return 0;
 }
+
+// ---- stem input: pad 3 + 2x2 space-to-depth + bf16 cast + channel padding, one pass (harness glue) --------------------
+// out[b][i][j][c*4 + r*2 + s] = x[b][c][2i + r - 3][2j + s - 3] (0 outside the image), channels 4*Cin..Cout-1 zero.
+// x: fp32, any strides (element units); out: bf16 NHWC-dense (B, Hs, Ws, Cout), Hs = (H+6)/2, Ws = (W+6)/2.
+namespace detr {
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int B, int Cin,
+                                                       int H, int W, __nv_bfloat16* __restrict__ out, int Hs, int Ws, int Cout) {
+    const int64_t n = (int64_t)B * Hs * Ws;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % Ws);
+        int64_t r0 = t / Ws;
+        const int i = (int)(r0 % Hs);
+        const int b = (int)(r0 / Hs);
+        __nv_bfloat16* o = out + t * Cout;
+        for (int c8 = 0; c8 < Cout; c8 += 8) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ch = c8 + e;
+                const int c = ch >> 2, r = (ch >> 1) & 1, s = ch & 1;
+                const int h = 2 * i + r - 3, w = 2 * j + s - 3;
+                v[e] = (c < Cin && h >= 0 && h < H && w >= 0 && w < W) ? x[b * sb + c * sc + h * sh + w * sw] : 0.f;
+            }
+            uint4 u;
+            __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            *reinterpret_cast<uint4*>(o + c8) = u;
+        }
+    }
+}
+}  // namespace detr
+
+extern "C" int detr_stem_s2d_bf16(const float* x, long long sb, long long sc, long long sh, long long sw, int B, int Cin, int H, int W,
+                                  void* out, int Cout, void* stream) {
+    DETR_CHECK_ARG(B >= 1 && Cin >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "stem_s2d: need even H, W (B=%d Cin=%d H=%d W=%d)", B, Cin, H, W);
+    DETR_CHECK_ARG(Cout >= 4 * Cin && Cout % 8 == 0 && ((uintptr_t)out % 16) == 0, "stem_s2d: Cout must be a multiple of 8 >= 4*Cin, out 16-byte aligned");
+    const int Hs = (H + 6) / 2, Ws = (W + 6) / 2;
+    const int64_t n = (int64_t)B * Hs * Ws;
+    detr::stem_s2d_kernel<<<detr::pool_grid(n), 256, 0, (cudaStream_t)stream>>>(x, sb, sc, sh, sw, B, Cin, H, W, reinterpret_cast<__nv_bfloat16*>(out), Hs, Ws, Cout);
+    DETR_CHECK_LAUNCH("stem_s2d");
+    return 0;
+}

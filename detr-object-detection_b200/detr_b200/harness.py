@@ -276,10 +276,17 @@ def _stem_s2d(x: torch.Tensor, conv: nn.Conv2d, w16: torch.Tensor, shift: torch.
         out[o,i,j] = sum_{c,u,v} w[o,c,u,v] xp[c,2i+u,2j+v],  u = 2a+r, v = 2b+s  =>  sum_{(c,r,s),a,b} w'[o,(c,r,s),a,b] S[(c,r,s),i+a,j+b]
     with xp = x zero-padded by 3, S = pixel_unshuffle(xp, 2), w' = the 7x7 kernel zero-padded to 8x8 and regrouped.  The weight
     regrouping is differentiable torch code on the folded bf16 weight (64 x 147 values), so autograd carries dW back."""
+    from . import _lib
     O, Cin = w16.shape[0], w16.shape[1]
-    xs = F.pixel_unshuffle(F.pad(x.to(torch.bfloat16), (3, 3, 3, 3)), 2)                # (B, 4*Cin, (H+6)/2, (W+6)/2)
-    pad_c = (-xs.shape[1]) % 8
-    xs = F.pad(xs, (0, 0, 0, 0, 0, pad_c)).contiguous(memory_format=torch.channels_last)
+    pad_c = (-4 * Cin) % 8
+    if x.dtype == torch.float32 and not x.requires_grad:
+        # one pass: pad + space-to-depth + bf16 cast + channel padding (`detr_stem_s2d_bf16`), channels_last output
+        B, _, H, W = x.shape
+        xs = torch.empty((B, 4 * Cin + pad_c, (H + 6) // 2, (W + 6) // 2), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        _lib.call("detr_stem_s2d_bf16", x.data_ptr(), *x.stride(), B, Cin, H, W, xs.data_ptr(), 4 * Cin + pad_c, _lib.stream_ptr())
+    else:
+        xs = F.pixel_unshuffle(F.pad(x.to(torch.bfloat16), (3, 3, 3, 3)), 2)            # (B, 4*Cin, (H+6)/2, (W+6)/2)
+        xs = F.pad(xs, (0, 0, 0, 0, 0, pad_c)).contiguous(memory_format=torch.channels_last)
     w = F.pad(w16, (0, 1, 0, 1)).reshape(O, Cin, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4).reshape(O, 4 * Cin, 4, 4)
     w = F.pad(w, (0, 0, 0, 0, 0, pad_c)).contiguous(memory_format=torch.channels_last)
     with torch.autocast("cuda", enabled=False):

@@ -200,6 +200,12 @@ int detr_maxpool3x3s2_bwd_bf16(const void* dy, const uint8_t* idx, void* dx, int
 /* out = (a + b) * (x > 0) on dense bf16 buffers of n elements (n % 8 == 0): residual-gradient accumulation of a ResNet
  * bottleneck fused with the previous block's ReLU backward (harness glue). */
 int detr_add_relu_mask_bf16(const void* a, const void* b, const void* x, void* out, long long n, void* stream);
+/* Stem input of the ResNet harness in one pass: zero-pad by 3, 2x2 space-to-depth, cast to bf16, pad channels.
+ * x fp32 (B,Cin,H,W) with element strides (sb,sc,sh,sw); out bf16 dense (B,(H+6)/2,(W+6)/2,Cout) i.e. channels_last,
+ * out[b][i][j][c*4+r*2+s] = x[b][c][2i+r-3][2j+s-3].  H, W even; Cout % 8 == 0, Cout >= 4*Cin. */
+int detr_stem_s2d_bf16(const float* x, long long sb, long long sc, long long sh, long long sw, int B, int Cin, int H, int W,
+                       void* out, int Cout, void* stream);
+
 
 
 /* Sine positional encoding + padding mask of DETR.forward (detr/position_encoding.py:5-97, detr/model.py:96-114) in one
