@@ -47,7 +47,9 @@ def _check(q, k, v, nh, kpm=None, am=None):
 
 @pytest.mark.parametrize("B,L,S,nh", [(2, 128, 128, 2), (1, 256, 384, 8), (2, 100, 100, 8), (2, 100, 850, 8), (2, 850, 850, 8), (1, 37, 5, 1),
                                       # more (batch, head, query tile) items than SMs: persistent CTAs split items between them
-                                      (3, 850, 850, 8), (24, 100, 300, 8), (5, 600, 130, 8)])
+                                      (3, 850, 850, 8), (24, 100, 300, 8), (5, 600, 130, 8),
+                                      # BASELINE config 4: DC5 encoder self-attention (stride 16, 50 x 67 = 3 350 tokens)
+                                      (1, 3350, 3350, 8)])
 def test_attention_forward_shapes(cuda, B, L, S, nh):
     g = torch.Generator(device="cpu").manual_seed(L * 1000 + S)
     C = nh * 32
@@ -113,7 +115,9 @@ def _check_backward(q, k, v, nh, kpm=None, am=None):
 
 @pytest.mark.parametrize("B,L,S,nh", [(1, 128, 128, 1), (2, 256, 384, 2), (2, 100, 100, 8), (2, 100, 850, 8), (1, 850, 850, 8), (1, 37, 5, 1),
                                       # more (batch, head, key tile) items than SMs: persistent CTAs walk several items and split some
-                                      (3, 300, 850, 8), (2, 200, 1200, 8), (24, 100, 100, 8), (3, 850, 850, 8)])
+                                      (3, 300, 850, 8), (2, 200, 1200, 8), (24, 100, 100, 8), (3, 850, 850, 8),
+                                      # BASELINE config 4 (DC5, 3 350 tokens) and config 5 (300 object queries)
+                                      (1, 3350, 3350, 8), (2, 300, 850, 8), (2, 300, 300, 8)])
 def test_attention_backward_shapes(cuda, B, L, S, nh):
     g = torch.Generator(device="cpu").manual_seed(L * 1000 + S + 1)
     C = nh * 32
