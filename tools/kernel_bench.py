@@ -15,7 +15,26 @@ import torch  # noqa: E402
 
 from detr_b200 import HungarianMatcher, SetCriterion, _lib, pack_targets  # noqa: E402
 from detr_b200.attention import attention_backward, attention_forward  # noqa: E402
-from oracle import detr_oracle as O  # noqa: E402
+
+
+def synth_predictions(batch, layers, queries, num_classes, seed):
+    """SURVEY.md 8(d) config 3 inputs (same generator as the test fixtures use)."""
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(batch, layers, queries, num_classes + 1, generator=g)
+    boxes = torch.randn(batch, layers, queries, 4, generator=g).sigmoid()
+    return logits, boxes
+
+
+def synth_targets(batch, max_gt, num_classes, seed, min_gt=1):
+    g = torch.Generator().manual_seed(seed)
+    n = torch.randint(min_gt, max_gt + 1, (batch,), generator=g).tolist()
+    labels, boxes = [], []
+    for m in n:
+        c = torch.rand(m, 2, generator=g) * 0.6 + 0.2
+        s = torch.rand(m, 2, generator=g) * 0.30 + 0.02
+        boxes.append(torch.cat([c - s / 2, c + s / 2], dim=1).float())
+        labels.append(torch.randint(0, num_classes, (m,), generator=g, dtype=torch.int64))
+    return labels, boxes
 
 
 def peaks():
@@ -75,8 +94,8 @@ def main():
     if not args.only or "matcher" in args.only:
         for (B, L, maxm, tag) in ((256, 6, 100, "config 3"), (8, 6, 20, "config 2")):
             Q, NC = 100, 91
-            logits, boxes = O.synth_predictions(B, L, Q, NC, seed=0)
-            labels, gts = O.synth_targets(B, maxm, NC, seed=1)
+            logits, boxes = synth_predictions(B, L, Q, NC, seed=0)
+            labels, gts = synth_targets(B, maxm, NC, seed=1)
             logits, boxes = logits.to(dev), boxes.to(dev)
             pt = pack_targets([l.to(dev) for l in labels], [g.to(dev) for g in gts], Q, dev)
             m = HungarianMatcher(1.0, 5.0, 2.0)
