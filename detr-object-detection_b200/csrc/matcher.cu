@@ -33,6 +33,7 @@ struct MatchParams {
     float* cost_out;          // optional export (required when the work matrix does not fit shared memory)
     int64_t* idx_q; int64_t* idx_gt;   // null => cost only
     int32_t* status;
+    const int32_t* order;     // optional: images sorted by descending GT count (largest assignment problems first)
 };
 
 struct LsapParams {
@@ -230,7 +231,8 @@ template <int SLOTS, bool W_SMEM>
 __global__ void __launch_bounds__(kMatchThreads) hungarian_match_kernel(const MatchParams p) {
     extern __shared__ __align__(16) char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
+    const int bi = blockIdx.x / p.L, l = blockIdx.x % p.L;
+    const int b = p.order ? p.order[bi] : bi;
     const int g0 = p.gt_off[b];
     const int M = p.gt_off[b + 1] - g0;
     if (M == 0) return;
@@ -495,8 +497,22 @@ extern "C" int detr_cost_matrix_f32(const float* logits, int64_t lg_sb, int64_t 
                                     float* cost_out, int32_t* status, void* stream) {
     DETR_CHECK_ARG(cost_out != nullptr && status != nullptr, "cost_matrix: cost_out and status are required");
     MatchParams p{logits, lg_sb, lg_sl, lg_sq, boxes, bx_sb, bx_sl, bx_sq, gt_labels, gt_boxes, gt_off, nullptr,
-                  B, L, Q, K, max_m, w_class, w_bbox, w_giou, cost_out, nullptr, nullptr, status};
+                  B, L, Q, K, max_m, w_class, w_bbox, w_giou, cost_out, nullptr, nullptr, status, nullptr};
     return run_match(p, (cudaStream_t)stream);
+}
+
+// order[rank] = image index, rank by descending GT count (ties by index): the assignment phase of a problem costs ~M^2
+// serial steps, so a launch with more problems than resident CTAs finishes sooner when the big ones start first.
+__global__ void match_order_kernel(const int32_t* __restrict__ gt_off, int B, int32_t* __restrict__ order) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        const int m = gt_off[b + 1] - gt_off[b];
+        int rank = 0;
+        for (int c = 0; c < B; ++c) {
+            const int mc = gt_off[c + 1] - gt_off[c];
+            rank += (mc > m) || (mc == m && c < b);
+        }
+        order[rank] = b;
+    }
 }
 
 extern "C" int detr_hungarian_match_f32(const float* logits, int64_t lg_sb, int64_t lg_sl, int64_t lg_sq,
@@ -504,12 +520,18 @@ extern "C" int detr_hungarian_match_f32(const float* logits, int64_t lg_sb, int6
                                         const int64_t* gt_labels, const float* gt_boxes, const int32_t* gt_off,
                                         const int32_t* match_off, int B, int L, int Q, int K, int max_m,
                                         float w_class, float w_bbox, float w_giou, float* cost_out,
-                                        int64_t* idx_q, int64_t* idx_gt, int32_t* status, void* stream) {
+                                        int64_t* idx_q, int64_t* idx_gt, int32_t* status, int32_t* order_ws, void* stream) {
     DETR_CHECK_ARG(idx_q != nullptr && idx_gt != nullptr && status != nullptr && match_off != nullptr,
                    "hungarian_match: idx_q, idx_gt, match_off and status are required");
     DETR_CHECK_ARG(!(w_class == 0.f && w_bbox == 0.f && w_giou == 0.f), "all costs can't be 0");  // detr/matcher.py:38
     MatchParams p{logits, lg_sb, lg_sl, lg_sq, boxes, bx_sb, bx_sl, bx_sq, gt_labels, gt_boxes, gt_off, match_off,
-                  B, L, Q, K, max_m, w_class, w_bbox, w_giou, cost_out, idx_q, idx_gt, status};
+                  B, L, Q, K, max_m, w_class, w_bbox, w_giou, cost_out, idx_q, idx_gt, status, nullptr};
+    // more problems than CTA slots of one wave (~4 per SM): run the largest first
+    if (order_ws != nullptr && (int64_t)B * L > 4 * 148 && B <= 4096) {
+        match_order_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gt_off, B, order_ws);
+        DETR_CHECK_LAUNCH("match_order");
+        p.order = order_ws;
+    }
     return run_match(p, (cudaStream_t)stream);
 }
 

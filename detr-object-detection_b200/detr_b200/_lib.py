@@ -28,7 +28,7 @@ SIGNATURES = {
     "detr_cost_matrix_f32": [P, *_STRIDES3, P, *_STRIDES3, P, P, P, c_int, c_int, c_int, c_int, c_int,
                              c_float, c_float, c_float, P, P, P],
     "detr_hungarian_match_f32": [P, *_STRIDES3, P, *_STRIDES3, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
-                                 c_float, c_float, c_float, P, P, P, P, P],
+                                 c_float, c_float, c_float, P, P, P, P, P, P],
     "detr_lsap_f32": [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P],
     "detr_lsap_f64": [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P],
     "detr_criterion_fwd_f32": [P, *_STRIDES3, P, *_STRIDES3, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int,

@@ -82,13 +82,14 @@ class HungarianMatcher(nn.Module):
         need_ws = _lib.load().detr_matcher_smem_bytes(Q, pt.max_count, 4) < 0
         cost = torch.empty(max(Q * L * pt.total, 1), dtype=torch.float32, device=dev) if (export_cost or need_ws) else None
         st = self.status_tensor(dev)
+        order_ws = torch.empty(B, dtype=torch.int32, device=dev) if B * L > 4 * 148 else None   # largest problems first
         _lib.call(
             "detr_hungarian_match_f32",
             logits.data_ptr(), logits.stride(0), logits.stride(1), logits.stride(2),
             boxes.data_ptr(), boxes.stride(0), boxes.stride(1), boxes.stride(2),
             pt.labels.data_ptr(), pt.boxes.data_ptr(), pt.gt_off.data_ptr(), pt.match_off.data_ptr(),
             B, L, Q, K, pt.max_count, float(self.cost_class), float(self.cost_bbox), float(self.cost_giou),
-            _lib.ptr(cost), idx[0].data_ptr(), idx[1].data_ptr(), st.data_ptr(), _lib.stream_ptr())
+            _lib.ptr(cost), idx[0].data_ptr(), idx[1].data_ptr(), st.data_ptr(), _lib.ptr(order_ws), _lib.stream_ptr())
         return (idx[0][:n_out], idx[1][:n_out], cost) if export_cost else (idx[0][:n_out], idx[1][:n_out])
 
     @torch.no_grad()

@@ -57,14 +57,16 @@ int detr_cost_matrix_f32(const float* logits, int64_t lg_sb, int64_t lg_sl, int6
 
 /* Fused matcher: cost matrix kept in shared memory + assignment, one CTA per problem.
  * Replaces the per-image loop + `.cpu()` + scipy call of detr/matcher.py:69-97 for all images and all
- * decoder layers (detr/loss.py:213-217) in ONE launch.  cost_out may be NULL (not exported). */
+ * decoder layers (detr/loss.py:213-217) in ONE launch.  cost_out may be NULL (not exported).  order_ws: optional
+ * int32[B] scratch; when given and the launch has more problems than one wave of CTAs, a tiny pre-kernel ranks the images by
+ * descending GT count and the largest assignment problems are started first (results are unaffected). */
 int detr_hungarian_match_f32(const float* logits, int64_t lg_sb, int64_t lg_sl, int64_t lg_sq,
                              const float* boxes, int64_t bx_sb, int64_t bx_sl, int64_t bx_sq,
                              const int64_t* gt_labels, const float* gt_boxes, const int32_t* gt_off,
                              const int32_t* match_off, int B, int L, int Q, int K, int max_m,
                              float w_class, float w_bbox, float w_giou,
                              float* cost_out, int64_t* idx_q, int64_t* idx_gt, int32_t* status,
-                             void* stream);
+                             int32_t* order_ws, void* stream);
 
 /* Batched rectangular linear-sum assignment on caller-provided cost matrices: the drop-in for
  * scipy.optimize.linear_sum_assignment at detr/matcher.py:94 (bit-exact indices).
