@@ -97,34 +97,61 @@ __global__ void __launch_bounds__(kCritThreads) criterion_fwd_kernel(const CritP
     float wnll = 0.f, wsum = 0.f, nonempty = 0.f, correct = 0.f;
     float* lse_out = p.lse + (int64_t)blockIdx.x * Q;
     int32_t* tgt_out = p.tgt + (int64_t)blockIdx.x * Q;
-    for (int q = warp; q < Q; q += kCritThreads / 32) {
-        const float* row = lg + (int64_t)q * p.lg_sq;
-        float mx = -CUDART_INF_F;
-        int am = 0x7fffffff;
-        for (int k = lane; k < K; k += 32) {
-            const float v = row[k];
-            if (v > mx) { mx = v; am = k; }
-        }
-        // warp arg-max, lowest index wins ties (torch.argmax / topk behaviour on distinct values is unaffected)
+    // kRows rows per warp at a time: every lane first issues the loads of all of them (a row is only 368 bytes; one row at a
+    // time leaves a single dependent memory round trip in flight per warp), then the reductions run interleaved
+    constexpr int kRows = 4, kW = kCritThreads / 32, kMaxK = 4;   // K <= 128 logits per row on the register path
+    for (int q0 = warp; q0 < Q; q0 += kW * kRows) {
+        float v[kRows][kMaxK];
+        const bool reg_path = K <= 32 * kMaxK;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float omx = __shfl_xor_sync(FULL_MASK, mx, o);
-            const int oam = __shfl_xor_sync(FULL_MASK, am, o);
-            if (omx > mx || (omx == mx && oam < am)) { mx = omx; am = oam; }
+        for (int r = 0; r < kRows; ++r) {
+            const int q = q0 + r * kW;
+            const float* row = lg + (int64_t)q * p.lg_sq;
+#pragma unroll
+            for (int c = 0; c < kMaxK; ++c) {
+                const int k = lane + 32 * c;
+                v[r][c] = (reg_path && q < Q && k < K) ? row[k] : -CUDART_INF_F;
+            }
         }
-        float sum = 0.f;
-        for (int k = lane; k < K; k += 32) sum += expf(row[k] - mx);
-        sum = warp_sum(sum);
-        if (lane == 0) {
-            const int t = s_tgt[q];
-            const float lse = mx + logf(sum);
-            const float w = p.class_weight[t];
-            wnll += w * (lse - row[t]);
-            wsum += w;
-            nonempty += (am != K - 1) ? 1.f : 0.f;
-            if (s_matched[q]) correct += (am == t) ? 1.f : 0.f;
-            lse_out[q] = lse;
-            tgt_out[q] = t;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const int q = q0 + r * kW;
+            if (q >= Q) break;
+            const float* row = lg + (int64_t)q * p.lg_sq;
+            float mx = -CUDART_INF_F;
+            int am = 0x7fffffff;
+            if (reg_path) {
+#pragma unroll
+                for (int c = 0; c < kMaxK; ++c) if (v[r][c] > mx) { mx = v[r][c]; am = lane + 32 * c; }
+            } else {
+                for (int k = lane; k < K; k += 32) { const float x = row[k]; if (x > mx) { mx = x; am = k; } }
+            }
+            // warp arg-max, lowest index wins ties (torch.argmax / topk behaviour on distinct values is unaffected)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float omx = __shfl_xor_sync(FULL_MASK, mx, o);
+                const int oam = __shfl_xor_sync(FULL_MASK, am, o);
+                if (omx > mx || (omx == mx && oam < am)) { mx = omx; am = oam; }
+            }
+            float sum = 0.f;
+            if (reg_path) {
+#pragma unroll
+                for (int c = 0; c < kMaxK; ++c) if (lane + 32 * c < K) sum += expf(v[r][c] - mx);
+            } else {
+                for (int k = lane; k < K; k += 32) sum += expf(row[k] - mx);
+            }
+            sum = warp_sum(sum);
+            if (lane == 0) {
+                const int t = s_tgt[q];
+                const float lse = mx + logf(sum);
+                const float w = p.class_weight[t];
+                wnll += w * (lse - row[t]);
+                wsum += w;
+                nonempty += (am != K - 1) ? 1.f : 0.f;
+                if (s_matched[q]) correct += (am == t) ? 1.f : 0.f;
+                lse_out[q] = lse;
+                tgt_out[q] = t;
+            }
         }
     }
     float* out = p.partials + (int64_t)blockIdx.x * kPartials;
@@ -181,12 +208,42 @@ __global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritP
     const float* lse = p.lse + (int64_t)blockIdx.x * Q;
     const int32_t* tgt = p.tgt + (int64_t)blockIdx.x * Q;
     float* dlg = p.grad_logits + (int64_t)blockIdx.x * Q * K;
-    for (int q = warp; q < Q; q += kCritThreads / 32) {
-        const float* row = lg + (int64_t)q * p.lg_sq;
-        const int t = tgt[q];
-        const float c = ce_scale * p.class_weight[t];
-        const float ls = lse[q];
-        for (int k = lane; k < K; k += 32) dlg[(int64_t)q * K + k] = c * (expf(row[k] - ls) - (k == t ? 1.f : 0.f));
+    {
+        constexpr int kRows = 4, kW = kCritThreads / 32, kMaxK = 4;
+        const bool reg_path = K <= 32 * kMaxK;
+        for (int q0 = warp; q0 < Q; q0 += kW * kRows) {   // loads of 4 rows in flight per warp (see criterion_fwd_kernel)
+            float v[kRows][kMaxK], ls[kRows], cc[kRows];
+            int tt[kRows];
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                const int q = q0 + r * kW;
+                const float* row = lg + (int64_t)q * p.lg_sq;
+                tt[r] = q < Q ? tgt[q] : 0;
+                ls[r] = q < Q ? lse[q] : 0.f;
+#pragma unroll
+                for (int c = 0; c < kMaxK; ++c) {
+                    const int k = lane + 32 * c;
+                    v[r][c] = (reg_path && q < Q && k < K) ? row[k] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) cc[r] = ce_scale * p.class_weight[tt[r]];
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                const int q = q0 + r * kW;
+                if (q >= Q) break;
+                if (reg_path) {
+#pragma unroll
+                    for (int c = 0; c < kMaxK; ++c) {
+                        const int k = lane + 32 * c;
+                        if (k < K) dlg[(int64_t)q * K + k] = cc[r] * (expf(v[r][c] - ls[r]) - (k == tt[r] ? 1.f : 0.f));
+                    }
+                } else {
+                    const float* row = lg + (int64_t)q * p.lg_sq;
+                    for (int k = lane; k < K; k += 32) dlg[(int64_t)q * K + k] = cc[r] * (expf(row[k] - ls[r]) - (k == tt[r] ? 1.f : 0.f));
+                }
+            }
+        }
     }
     // ---- d boxes: zero everywhere, analytic L1 + GIoU on matched queries ----
     float4* dbx = reinterpret_cast<float4*>(p.grad_boxes + (int64_t)blockIdx.x * Q * 4);
