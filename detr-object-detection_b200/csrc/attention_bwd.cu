@@ -73,8 +73,7 @@ struct Smem {
     static constexpr uint32_t pt = ds + 2 * kT * kT * 2;                   // 2 x P~
     static constexpr uint32_t dqs = pt + 2 * kT * kT * 2;                  // 2 x (128 queries x 32 fp32, SWIZZLE_128B) dQ_part staging
     static constexpr uint32_t bars = dqs + 2 * kT * kD * 4;
-    static constexpr uint32_t flags = bars + 256;                          // 128 key flags
-    static constexpr uint32_t total = flags + kT + 1024;                   // + alignment slack
+    static constexpr uint32_t total = bars + 256 + 1024;                   // + alignment slack
 };
 static_assert(Smem::ring + kStages * 2 * kTileBytes <= Smem::ds && Smem::ds % 1024 == 0 && Smem::pt % 1024 == 0, "smem layout");
 
