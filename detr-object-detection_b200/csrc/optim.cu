@@ -50,10 +50,10 @@ __global__ void __launch_bounds__(kOptThreads) sumsq_kernel(const float* __restr
 }
 
 __global__ void __launch_bounds__(kOptThreads) adamw_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                                 float* __restrict__ v, int64_t n, float lr, float beta1, float beta2,
+                                                                 float* __restrict__ v, int64_t n, const float* __restrict__ lr_ptr, float beta1, float beta2,
                                                                  float eps, float weight_decay, const float* __restrict__ step,
                                                                  const float* __restrict__ sumsq, float max_norm, float grad_div) {
-    const float t = *step;
+    const float t = *step, lr = *lr_ptr;   // both in device memory: a captured CUDA graph follows the LR schedule and the step count
     const float bc1 = 1.f - powf(beta1, t), bc2_sqrt = sqrtf(1.f - powf(beta2, t));
     float coef = grad_div;                                      // 1 / world size folded in (data-parallel mean)
     if (sumsq != nullptr && max_norm > 0.f) {
@@ -102,9 +102,9 @@ extern "C" int detr_sumsq_f32(const float* g, long long n, float* partial, float
     return 0;
 }
 
-extern "C" int detr_adamw_clip_f32(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+extern "C" int detr_adamw_clip_f32(float* p, const float* g, float* m, float* v, long long n, const float* lr, float beta1, float beta2, float eps,
                                    float weight_decay, const float* step, const float* sumsq, float max_norm, float grad_div, void* stream) {
-    DETR_CHECK_ARG(p && g && m && v && step && n >= 1, "adamw_clip: null pointer or empty range");
+    DETR_CHECK_ARG(p && g && m && v && step && lr && n >= 1, "adamw_clip: null pointer or empty range");
     DETR_CHECK_ARG(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0, "adamw_clip: 16-byte alignment");
     long long grid = (n / 4 + kOptThreads * 4 - 1) / (kOptThreads * 4);
     if (grid > 148 * 16) grid = 148 * 16;

@@ -52,7 +52,7 @@ SIGNATURES = {
     "detr_positional_encoding_f32": [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P],
     "detr_sumsq_grid": [ctypes.c_longlong],
     "detr_sumsq_f32": [P, ctypes.c_longlong, P, P, P, P],
-    "detr_adamw_clip_f32": [P, P, P, P, ctypes.c_longlong, c_float, c_float, c_float, c_float, c_float, P, P, c_float, c_float, P],
+    "detr_adamw_clip_f32": [P, P, P, P, ctypes.c_longlong, P, c_float, c_float, c_float, c_float, P, P, c_float, c_float, P],
     "detr_add_relu_mask_bf16": [P, P, P, P, ctypes.c_longlong, P],
     "detr_stem_s2d_bf16": [P, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, c_int, P, c_int, P],
     "detr_maxpool3x3s2_out": [c_int],

@@ -590,9 +590,19 @@ class FlatAdamW:
                     o += q.numel()
         from . import _lib
         self.step_t = torch.zeros(1, dtype=torch.float32, device=device)
+        self.lr_t = torch.tensor([float(g["lr"]) for g in torch_optimizer.param_groups], dtype=torch.float32, device=device)
+        self._lr_host = [float(g["lr"]) for g in torch_optimizer.param_groups]
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=device)
         self.partial = torch.empty(_lib.load().detr_sumsq_grid(self.total), dtype=torch.float32, device=device)
         self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def sync_lr(self) -> None:
+        """Upload the groups' current learning rates if an LR scheduler changed them (the kernels read them from device
+        memory, so a captured graph needs this call -- not a re-capture -- to follow the schedule)."""
+        cur = [float(g["lr"]) for g in self.opt.param_groups]
+        if cur != self._lr_host:
+            self.lr_t.copy_(torch.tensor(cur, dtype=torch.float32), non_blocking=True)
+            self._lr_host = cur
 
     def step(self, max_norm: float, grad_div: float = 1.0) -> None:
         """One update from the gradients in `flat_g` (scaled by grad_div, e.g. 1 / world size, then clipped to max_norm)."""
@@ -601,13 +611,13 @@ class FlatAdamW:
         st = _lib.stream_ptr()
         _lib.call("detr_sumsq_f32", self.flat_g.data_ptr(), self.total, self.partial.data_ptr(), self.sumsq.data_ptr(),
                   self.counter.data_ptr(), st)
-        for g, (start, n) in zip(self.opt.param_groups, self.ranges):
+        for gi, (g, (start, n)) in enumerate(zip(self.opt.param_groups, self.ranges)):
             if n == 0:
                 continue
             b1, b2 = g["betas"]
             off = start * 4
             _lib.call("detr_adamw_clip_f32", self.flat_p.data_ptr() + off, self.flat_g.data_ptr() + off, self.flat_m.data_ptr() + off,
-                      self.flat_v.data_ptr() + off, n, float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
+                      self.flat_v.data_ptr() + off, n, self.lr_t.data_ptr() + 4 * gi, float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
                       self.step_t.data_ptr(), self.sumsq.data_ptr(), float(max_norm), float(grad_div), st)
 
 
@@ -775,5 +785,7 @@ class GraphedTrainStep:
         """One optimizer step on whatever `load()` put in the static buffers. Returns the (device) loss scalar."""
         self.graph_a.replay()
         self._allreduce()
+        if self.fopt is not None:
+            self.fopt.sync_lr()
         self.graph_b.replay()
         return self.loss

@@ -220,11 +220,11 @@ int detr_positional_encoding_f32(const int32_t* heights, const int32_t* widths, 
 /* Caller-side glue of the benchmark harness: clip_grad_norm_(max_norm) + AdamW.step (detr/train.py:265-267) on FLAT fp32
  * buffers.  detr_sumsq_f32: out[0] = sum g^2 (partial float[detr_sumsq_grid(n)] scratch, counter: one zeroed uint32,
  * left zero).  detr_adamw_clip_f32 updates p, m, v in place with g scaled by grad_div * min(1, max_norm /
- * (grad_div * sqrt(*sumsq) + 1e-6)) (sumsq NULL or max_norm <= 0: no clipping); `step` is a DEVICE float holding the
- * 1-based step count (bias correction), so both launches are CUDA-graph replayable. */
+ * (grad_div * sqrt(*sumsq) + 1e-6)) (sumsq NULL or max_norm <= 0: no clipping); `step` (1-based step count, for the bias
+ * correction) and `lr` are DEVICE floats, so a captured CUDA graph follows the step count and the LR schedule. */
 int detr_sumsq_grid(long long n);
 int detr_sumsq_f32(const float* g, long long n, float* partial, float* out, uint32_t* counter, void* stream);
-int detr_adamw_clip_f32(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+int detr_adamw_clip_f32(float* p, const float* g, float* m, float* v, long long n, const float* lr, float beta1, float beta2, float eps,
                         float weight_decay, const float* step, const float* sumsq, float max_norm, float grad_div, void* stream);
 
 

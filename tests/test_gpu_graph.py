@@ -96,6 +96,10 @@ def test_flat_adamw_matches_torch(cuda):
     f = FlatAdamW(o2, cuda)
     p1 = [q for g in o1.param_groups for q in g["params"]]
     for it in range(5):
+        if it == 3:   # an LR scheduler step: both optimizers must follow it
+            for o in (o1, o2):
+                for grp in o.param_groups:
+                    grp["lr"] *= 0.5
         gs = [torch.randn_like(q) * (3.0 if it % 2 else 0.01) for q in p1]     # clipped and unclipped steps
         for q, g in zip(p1, gs):
             q.grad = g.clone()
@@ -103,6 +107,7 @@ def test_flat_adamw_matches_torch(cuda):
         o1.step()
         for v, g in zip(f.grad_views, gs):
             v.copy_(g)
+        f.sync_lr()
         f.step(1.0)
     for q1, q2 in zip(p1, f.params):
         assert q1.shape == q2.shape and q1.stride() == q2.stride()
