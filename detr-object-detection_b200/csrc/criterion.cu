@@ -13,8 +13,10 @@
 
 namespace detr {
 
-constexpr int kCritThreads = 128;
+constexpr int kCritThreads = 256;
+constexpr int kCritWarps = kCritThreads / 32;
 constexpr int kPartials = 8;  // {sum w*nll, sum w, n_pred_nonempty, n_correct, l1_sum, giou_sum, n_pairs, unused}
+constexpr int kFwdRows = 13;  // query rows a warp keeps in registers at once: 8 warps x 13 rows cover Q = 100 in one batch
 
 struct CritParams {
     const float* logits; int64_t lg_sb, lg_sl, lg_sq;
@@ -41,125 +43,147 @@ __device__ __forceinline__ Box4 cxcywh_to_xyxy(float4 c) {
     return r;
 }
 
-__device__ __forceinline__ float block_sum(float v, float* red /*[4]*/, int tid) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((tid & 31) == 0) red[tid >> 5] = v;
-    __syncthreads();
-    return (red[0] + red[1]) + (red[2] + red[3]);
+__device__ __forceinline__ float redux_max_f32(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));   // CREDUX.MAX.F32: one instruction per warp
+    return r;
 }
 
-__global__ void __launch_bounds__(kCritThreads) criterion_fwd_kernel(const CritParams p) {
-    extern __shared__ int s_tgt[];  // [Q] target class per query, then [Q] matched flag
-    __shared__ float red[4];
+// One CTA per (image, layer).  kC = 32-wide column chunks of a logits row held in registers (K <= 32 * kC); kC == 0 is the
+// generic path for wider rows (one row per warp at a time, logits re-read from L1/L2).
+//
+// The problem is 36.8 KB of logits (Q=100, K=92) and finishes in a handful of dependent memory round trips, so the kernel
+// is written to put ALL of its logits loads in flight first (13 rows x kC registers per lane), resolve the matched pairs
+// (offsets -> indices -> labels / boxes: three dependent trips) underneath them, and only then reduce the rows.
+template <int kC>
+__global__ void __launch_bounds__(kCritThreads, 3) criterion_fwd_kernel(const CritParams p) {
+    extern __shared__ int s_dyn[];  // [Q] target class | [Q] matched flag | [Q] row log-sum-exp | [Q] row arg-max
+    __shared__ float red[kCritWarps][kPartials];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
     const int Q = p.Q, K = p.K;
-    int* s_matched = s_tgt + Q;
-    const int g0 = p.gt_off[b], M = p.gt_off[b + 1] - g0;
-    const int n = min(Q, M);
-    const int64_t moff = (int64_t)p.L * p.match_off[b] + (int64_t)l * n;
+    int* s_tgt = s_dyn;
+    int* s_matched = s_dyn + Q;
+    float* s_lse = reinterpret_cast<float*>(s_dyn + 2 * Q);
+    int* s_am = s_dyn + 3 * Q;
     const float* lg = p.logits + b * p.lg_sb + l * p.lg_sl;
     const float* bx = p.boxes + b * p.bx_sb + l * p.bx_sl;
+    constexpr int kCr = kC > 0 ? kC : 1;
 
-    for (int q = tid; q < Q; q += kCritThreads) { s_tgt[q] = K - 1; s_matched[q] = 0; }
-    __syncthreads();
-    // scatter the matched labels (detr/loss.py:79-85) and accumulate the box losses of the matched pairs
     float l1 = 0.f, gi = 0.f, npairs = 0.f;
-    for (int k = tid; k < n; k += kCritThreads) {
-        const int64_t q = p.idx_q[moff + k], g = p.idx_gt[moff + k];
-        if (q < 0 || q >= Q || g < 0 || g >= M) continue;  // poisoned by a failed assignment: status already set
-        int64_t lab = p.gt_labels[g0 + g];
-        if (lab < 0 || lab >= K) { atomicOr(p.status, DETR_ST_BAD_LABEL); lab = K - 1; }
-        s_tgt[q] = (int)lab;
-        s_matched[q] = 1;
-        npairs += 1.f;
-        const float4 s = *reinterpret_cast<const float4*>(bx + q * p.bx_sq);
-        const float4 t = *reinterpret_cast<const float4*>(p.gt_boxes + (int64_t)(g0 + g) * 4);
-        // L1 against cxcywh(target) (detr/loss.py:149-156)
-        const float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
-        const float tcx = __fdiv_rn(__fadd_rn(__fmul_rn(t.x, 2.f), tw), 2.f);
-        const float tcy = __fdiv_rn(__fadd_rn(__fmul_rn(t.y, 2.f), th), 2.f);
-        l1 += fabsf(s.x - tcx) + fabsf(s.y - tcy) + fabsf(s.z - tw) + fabsf(s.w - th);
-        // GIoU loss with eps (torchvision giou_loss.py:47-62, _utils.py:87-106)
-        const Box4 a = cxcywh_to_xyxy(s);
-        const float eps = 1e-7f;
-        const float ix1 = fmaxf(a.x1, t.x), iy1 = fmaxf(a.y1, t.y), ix2 = fminf(a.x2, t.z), iy2 = fminf(a.y2, t.w);
-        const float inter = (iy2 > iy1 && ix2 > ix1) ? __fmul_rn(ix2 - ix1, iy2 - iy1) : 0.f;
-        const float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.x2 - a.x1, a.y2 - a.y1), __fmul_rn(t.z - t.x, t.w - t.y)), inter);
-        const float iou = __fdiv_rn(inter, uni + eps);
-        const float hull = __fmul_rn(fmaxf(a.x2, t.z) - fminf(a.x1, t.x), fmaxf(a.y2, t.w) - fminf(a.y1, t.y));
-        gi += 1.f - (iou - __fdiv_rn(hull - uni, hull + eps));
+    for (int base = 0; base < Q; base += kCritWarps * kFwdRows) {
+        float v[kFwdRows][kCr];
+        if (kC > 0) {
+#pragma unroll
+            for (int r = 0; r < kFwdRows; ++r) {
+                const int q = base + r * kCritWarps + warp;
+                const float* row = lg + (int64_t)q * p.lg_sq;
+#pragma unroll
+                for (int c = 0; c < kCr; ++c) {
+                    const int k = lane + 32 * c;
+                    v[r][c] = (q < Q && k < K) ? __ldg(row + k) : -CUDART_INF_F;
+                }
+            }
+        }
+        if (base == 0) {
+            const int g0 = p.gt_off[b], M = p.gt_off[b + 1] - g0;
+            const int n = min(Q, M);
+            const int64_t moff = (int64_t)p.L * p.match_off[b] + (int64_t)l * n;
+            for (int q = tid; q < Q; q += kCritThreads) { s_tgt[q] = K - 1; s_matched[q] = 0; }
+            __syncthreads();
+            // scatter the matched labels (detr/loss.py:79-85) and accumulate the box losses of the matched pairs
+            for (int k = tid; k < n; k += kCritThreads) {
+                const int64_t q = p.idx_q[moff + k], g = p.idx_gt[moff + k];
+                if (q < 0 || q >= Q || g < 0 || g >= M) continue;  // poisoned by a failed assignment: status already set
+                int64_t lab = p.gt_labels[g0 + g];
+                const float4 s = *reinterpret_cast<const float4*>(bx + q * p.bx_sq);
+                const float4 t = *reinterpret_cast<const float4*>(p.gt_boxes + (int64_t)(g0 + g) * 4);
+                if (lab < 0 || lab >= K) { atomicOr(p.status, DETR_ST_BAD_LABEL); lab = K - 1; }
+                s_tgt[q] = (int)lab;
+                s_matched[q] = 1;
+                npairs += 1.f;
+                // L1 against cxcywh(target) (detr/loss.py:149-156)
+                const float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
+                const float tcx = __fdiv_rn(__fadd_rn(__fmul_rn(t.x, 2.f), tw), 2.f);
+                const float tcy = __fdiv_rn(__fadd_rn(__fmul_rn(t.y, 2.f), th), 2.f);
+                l1 += fabsf(s.x - tcx) + fabsf(s.y - tcy) + fabsf(s.z - tw) + fabsf(s.w - th);
+                // GIoU loss with eps (torchvision giou_loss.py:47-62, _utils.py:87-106)
+                const Box4 a = cxcywh_to_xyxy(s);
+                const float eps = 1e-7f;
+                const float ix1 = fmaxf(a.x1, t.x), iy1 = fmaxf(a.y1, t.y), ix2 = fminf(a.x2, t.z), iy2 = fminf(a.y2, t.w);
+                const float inter = (iy2 > iy1 && ix2 > ix1) ? __fmul_rn(ix2 - ix1, iy2 - iy1) : 0.f;
+                const float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.x2 - a.x1, a.y2 - a.y1), __fmul_rn(t.z - t.x, t.w - t.y)), inter);
+                const float iou = __fdiv_rn(inter, uni + eps);
+                const float hull = __fmul_rn(fmaxf(a.x2, t.z) - fminf(a.x1, t.x), fmaxf(a.y2, t.w) - fminf(a.y1, t.y));
+                gi += 1.f - (iou - __fdiv_rn(hull - uni, hull + eps));
+            }
+        }
+        // row log-sum-exp and arg-max (lowest index wins ties: torch.argmax / topk on distinct values is unaffected)
+#pragma unroll
+        for (int r = 0; r < kFwdRows; ++r) {
+            const int q = base + r * kCritWarps + warp;
+            if (q >= Q) break;   // warp-uniform
+            float mx = -CUDART_INF_F, sum = 0.f;
+            int am = 0x7fffffff;
+            if (kC > 0) {
+#pragma unroll
+                for (int c = 0; c < kCr; ++c) mx = fmaxf(mx, v[r][c]);
+                mx = redux_max_f32(mx);
+#pragma unroll
+                for (int c = 0; c < kCr; ++c) {
+                    const int k = lane + 32 * c;
+                    if (k < K) {
+                        if (v[r][c] == mx) am = min(am, k);
+                        sum += expf(v[r][c] - mx);
+                    }
+                }
+            } else {
+                const float* row = lg + (int64_t)q * p.lg_sq;
+                for (int k = lane; k < K; k += 32) mx = fmaxf(mx, row[k]);
+                mx = redux_max_f32(mx);
+                for (int k = lane; k < K; k += 32) {
+                    const float x = row[k];
+                    if (x == mx) am = min(am, k);
+                    sum += expf(x - mx);
+                }
+            }
+            am = __reduce_min_sync(FULL_MASK, am);
+            sum = warp_sum(sum);
+            if (lane == 0) { s_lse[q] = mx + logf(sum); s_am[q] = am; }
+        }
     }
     __syncthreads();
 
-    // one query row per warp: log-sum-exp, weighted NLL, arg-max
+    // one thread per query row: weighted NLL of its target class, cardinality and class_error counts
     float wnll = 0.f, wsum = 0.f, nonempty = 0.f, correct = 0.f;
     float* lse_out = p.lse + (int64_t)blockIdx.x * Q;
     int32_t* tgt_out = p.tgt + (int64_t)blockIdx.x * Q;
-    // kRows rows per warp at a time: every lane first issues the loads of all of them (a row is only 368 bytes; one row at a
-    // time leaves a single dependent memory round trip in flight per warp), then the reductions run interleaved
-    constexpr int kRows = 4, kW = kCritThreads / 32, kMaxK = 4;   // K <= 128 logits per row on the register path
-    for (int q0 = warp; q0 < Q; q0 += kW * kRows) {
-        float v[kRows][kMaxK];
-        const bool reg_path = K <= 32 * kMaxK;
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-            const int q = q0 + r * kW;
-            const float* row = lg + (int64_t)q * p.lg_sq;
-#pragma unroll
-            for (int c = 0; c < kMaxK; ++c) {
-                const int k = lane + 32 * c;
-                v[r][c] = (reg_path && q < Q && k < K) ? row[k] : -CUDART_INF_F;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-            const int q = q0 + r * kW;
-            if (q >= Q) break;
-            const float* row = lg + (int64_t)q * p.lg_sq;
-            float mx = -CUDART_INF_F;
-            int am = 0x7fffffff;
-            if (reg_path) {
-#pragma unroll
-                for (int c = 0; c < kMaxK; ++c) if (v[r][c] > mx) { mx = v[r][c]; am = lane + 32 * c; }
-            } else {
-                for (int k = lane; k < K; k += 32) { const float x = row[k]; if (x > mx) { mx = x; am = k; } }
-            }
-            // warp arg-max, lowest index wins ties (torch.argmax / topk behaviour on distinct values is unaffected)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float omx = __shfl_xor_sync(FULL_MASK, mx, o);
-                const int oam = __shfl_xor_sync(FULL_MASK, am, o);
-                if (omx > mx || (omx == mx && oam < am)) { mx = omx; am = oam; }
-            }
-            float sum = 0.f;
-            if (reg_path) {
-#pragma unroll
-                for (int c = 0; c < kMaxK; ++c) if (lane + 32 * c < K) sum += expf(v[r][c] - mx);
-            } else {
-                for (int k = lane; k < K; k += 32) sum += expf(row[k] - mx);
-            }
-            sum = warp_sum(sum);
-            if (lane == 0) {
-                const int t = s_tgt[q];
-                const float lse = mx + logf(sum);
-                const float w = p.class_weight[t];
-                wnll += w * (lse - row[t]);
-                wsum += w;
-                nonempty += (am != K - 1) ? 1.f : 0.f;
-                if (s_matched[q]) correct += (am == t) ? 1.f : 0.f;
-                lse_out[q] = lse;
-                tgt_out[q] = t;
-            }
-        }
+    for (int q = tid; q < Q; q += kCritThreads) {
+        const int t = s_tgt[q], am = s_am[q];
+        const float lse = s_lse[q];
+        const float w = p.class_weight[t];
+        const float xt = lg[(int64_t)q * p.lg_sq + t];
+        wnll += w * (lse - xt);
+        wsum += w;
+        nonempty += (am != K - 1) ? 1.f : 0.f;
+        if (s_matched[q]) correct += (am == t) ? 1.f : 0.f;
+        lse_out[q] = lse;
+        tgt_out[q] = t;
     }
-    float* out = p.partials + (int64_t)blockIdx.x * kPartials;
-    const float r0 = block_sum(wnll, red, tid), r1 = block_sum(wsum, red, tid), r2 = block_sum(nonempty, red, tid),
-                r3 = block_sum(correct, red, tid), r4 = block_sum(l1, red, tid), r5 = block_sum(gi, red, tid),
-                r6 = block_sum(npairs, red, tid);
-    if (tid == 0) {
-        out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3; out[4] = r4; out[5] = r5; out[6] = r6; out[7] = 0.f;
+    const float vals[7] = {wnll, wsum, nonempty, correct, l1, gi, npairs};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const float s = warp_sum(vals[k]);
+        if (lane == 0) red[warp][k] = s;
+    }
+    __syncthreads();
+    if (tid < kPartials) {
+        float s = 0.f;
+        if (tid < 7) {
+#pragma unroll
+            for (int w = 0; w < kCritWarps; ++w) s += red[w][tid];   // fixed order: deterministic
+        }
+        p.partials[(int64_t)blockIdx.x * kPartials + tid] = s;
     }
 }
 
@@ -191,15 +215,31 @@ __global__ void criterion_finalize_kernel(const CritParams p) {
 
 __device__ __forceinline__ float step_gt(float a, float b) { return a > b ? 1.f : (a == b ? 0.5f : 0.f); }
 
+constexpr int kBwdVec = 9;  // float4 per thread in flight on the dense path: 256 x 9 x 4 covers Q*K = 9 200 in one batch
+
+// kVec: the (Q, K) logits block of a problem is dense, 16-byte aligned and K % 4 == 0 -> walked as flat float4 with every
+// load of the block in flight before the first use; otherwise 4 rows per warp at a time.
+template <bool kVec>
 __global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritParams p) {
+    extern __shared__ int s_dyn[];  // kVec: [Q] coefficient | [Q] row log-sum-exp | [Q] target class
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
     const int Q = p.Q, K = p.K;
+    const float* lg = p.logits + b * p.lg_sb + l * p.lg_sl;
+    const float* bx = p.boxes + b * p.bx_sb + l * p.bx_sl;
+    float* dlg = p.grad_logits + (int64_t)blockIdx.x * Q * K;
+    const int n4 = (Q * K) >> 2;
+    float4 x[kBwdVec];
+    if (kVec) {
+#pragma unroll
+        for (int i = 0; i < kBwdVec; ++i) {
+            const int e = tid + i * kCritThreads;
+            if (e < n4) x[i] = __ldg(reinterpret_cast<const float4*>(lg) + e);
+        }
+    }
     const int g0 = p.gt_off[b], M = p.gt_off[b + 1] - g0;
     const int n = min(Q, M);
     const int64_t moff = (int64_t)p.L * p.match_off[b] + (int64_t)l * n;
-    const float* lg = p.logits + b * p.lg_sb + l * p.lg_sl;
-    const float* bx = p.boxes + b * p.bx_sb + l * p.bx_sl;
     const float g_ce = p.grad_losses[l * 5 + 0], g_l1 = p.grad_losses[l * 5 + 2], g_gi = p.grad_losses[l * 5 + 3];
     const float nb = p.num_boxes ? *p.num_boxes : fmaxf((float)p.gt_off[p.B], 1.f);
 
@@ -207,16 +247,26 @@ __global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritP
     const float ce_scale = g_ce * p.w_ce / p.wsum[l];
     const float* lse = p.lse + (int64_t)blockIdx.x * Q;
     const int32_t* tgt = p.tgt + (int64_t)blockIdx.x * Q;
-    float* dlg = p.grad_logits + (int64_t)blockIdx.x * Q * K;
-    {
-        constexpr int kRows = 4, kW = kCritThreads / 32, kMaxK = 4;
+    float4* dbx = reinterpret_cast<float4*>(p.grad_boxes + (int64_t)blockIdx.x * Q * 4);
+    if (kVec) {
+        float* s_cc = reinterpret_cast<float*>(s_dyn);
+        float* s_ls = s_cc + Q;
+        int* s_tt = s_dyn + 2 * Q;
+        for (int q = tid; q < Q; q += kCritThreads) {
+            const int t = tgt[q];
+            s_tt[q] = t;
+            s_ls[q] = lse[q];
+            s_cc[q] = ce_scale * p.class_weight[t];
+        }
+    } else {
+        constexpr int kRows = 4, kMaxK = 4;
         const bool reg_path = K <= 32 * kMaxK;
-        for (int q0 = warp; q0 < Q; q0 += kW * kRows) {   // loads of 4 rows in flight per warp (see criterion_fwd_kernel)
+        for (int q0 = warp; q0 < Q; q0 += kCritWarps * kRows) {   // loads of 4 rows in flight per warp
             float v[kRows][kMaxK], ls[kRows], cc[kRows];
             int tt[kRows];
 #pragma unroll
             for (int r = 0; r < kRows; ++r) {
-                const int q = q0 + r * kW;
+                const int q = q0 + r * kCritWarps;
                 const float* row = lg + (int64_t)q * p.lg_sq;
                 tt[r] = q < Q ? tgt[q] : 0;
                 ls[r] = q < Q ? lse[q] : 0.f;
@@ -230,7 +280,7 @@ __global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritP
             for (int r = 0; r < kRows; ++r) cc[r] = ce_scale * p.class_weight[tt[r]];
 #pragma unroll
             for (int r = 0; r < kRows; ++r) {
-                const int q = q0 + r * kW;
+                const int q = q0 + r * kCritWarps;
                 if (q >= Q) break;
                 if (reg_path) {
 #pragma unroll
@@ -246,7 +296,6 @@ __global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritP
         }
     }
     // ---- d boxes: zero everywhere, analytic L1 + GIoU on matched queries ----
-    float4* dbx = reinterpret_cast<float4*>(p.grad_boxes + (int64_t)blockIdx.x * Q * 4);
     for (int q = tid; q < Q; q += kCritThreads) dbx[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     const float s_l1 = g_l1 * p.w_l1 / nb, s_gi = g_gi * p.w_giou / nb;
@@ -294,6 +343,34 @@ __global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritP
         dw += 0.5f * (dxy[2] - dxy[0]); dh += 0.5f * (dxy[3] - dxy[1]);
         dbx[q] = make_float4(dcx, dcy, dw, dh);
     }
+    if (kVec) {
+        const float* s_cc = reinterpret_cast<const float*>(s_dyn);
+        const float* s_ls = s_cc + Q;
+        const int* s_tt = s_dyn + 2 * Q;
+        for (int base = 0; base < n4; base += kBwdVec * kCritThreads) {
+            if (base > 0) {
+#pragma unroll
+                for (int i = 0; i < kBwdVec; ++i) {
+                    const int e = base + tid + i * kCritThreads;
+                    if (e < n4) x[i] = __ldg(reinterpret_cast<const float4*>(lg) + e);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kBwdVec; ++i) {
+                const int e = base + tid + i * kCritThreads;
+                if (e >= n4) break;
+                const int q = (4 * e) / K, k = 4 * e - q * K;   // K % 4 == 0: the four elements share a row
+                const float c = s_cc[q], ls = s_ls[q];
+                const int t = s_tt[q] - k;
+                float4 o;
+                o.x = c * (expf(x[i].x - ls) - (t == 0 ? 1.f : 0.f));
+                o.y = c * (expf(x[i].y - ls) - (t == 1 ? 1.f : 0.f));
+                o.z = c * (expf(x[i].z - ls) - (t == 2 ? 1.f : 0.f));
+                o.w = c * (expf(x[i].w - ls) - (t == 3 ? 1.f : 0.f));
+                reinterpret_cast<float4*>(dlg)[e] = o;
+            }
+        }
+    }
 }
 
 static int check_common(const CritParams& p, const char* who) {
@@ -324,7 +401,14 @@ extern "C" int detr_criterion_fwd_f32(const float* logits, int64_t lg_sb, int64_
     if (check_common(p, "criterion_fwd")) return 1;
     DETR_CHECK_ARG(partials && lse && tgt && wsum && losses && status, "criterion_fwd: null output/workspace");
     cudaStream_t st = (cudaStream_t)stream;
-    criterion_fwd_kernel<<<B * L, kCritThreads, 2 * Q * sizeof(int), st>>>(p);
+    const size_t smem = 4 * (size_t)Q * sizeof(int);
+    DETR_CHECK_ARG(smem <= 48 * 1024, "criterion_fwd: Q=%d too large (<= 3072)", Q);
+    const int chunks = (K + 31) / 32;
+    if (chunks == 1) criterion_fwd_kernel<1><<<B * L, kCritThreads, smem, st>>>(p);
+    else if (chunks == 2) criterion_fwd_kernel<2><<<B * L, kCritThreads, smem, st>>>(p);
+    else if (chunks == 3) criterion_fwd_kernel<3><<<B * L, kCritThreads, smem, st>>>(p);
+    else if (chunks == 4) criterion_fwd_kernel<4><<<B * L, kCritThreads, smem, st>>>(p);
+    else criterion_fwd_kernel<0><<<B * L, kCritThreads, smem, st>>>(p);
     DETR_CHECK_LAUNCH("criterion_fwd");
     criterion_finalize_kernel<<<L, 32, 0, st>>>(p);
     DETR_CHECK_LAUNCH("criterion_finalize");
@@ -349,7 +433,10 @@ extern "C" int detr_criterion_bwd_f32(const float* grad_losses, const float* log
     if (check_common(p, "criterion_bwd")) return 1;
     DETR_CHECK_ARG(grad_losses && grad_logits && grad_boxes && lse && tgt && wsum, "criterion_bwd: null pointer");
     DETR_CHECK_ARG(((uintptr_t)grad_boxes % 16) == 0, "criterion_bwd: grad_boxes must be 16-byte aligned");
-    criterion_bwd_kernel<<<B * L, kCritThreads, 0, (cudaStream_t)stream>>>(p);
+    const bool vec = (K % 4) == 0 && lg_sq == K && (lg_sb % 4) == 0 && (lg_sl % 4) == 0 && ((uintptr_t)logits % 16) == 0 &&
+                     ((uintptr_t)grad_logits % 16) == 0 && 3 * (size_t)Q * sizeof(int) <= 48 * 1024;
+    if (vec) criterion_bwd_kernel<true><<<B * L, kCritThreads, 3 * (size_t)Q * sizeof(int), (cudaStream_t)stream>>>(p);
+    else criterion_bwd_kernel<false><<<B * L, kCritThreads, 0, (cudaStream_t)stream>>>(p);
     DETR_CHECK_LAUNCH("criterion_bwd");
     return 0;
 }

@@ -127,6 +127,13 @@ class profile:
             out[(name, tag)] = (n + 1, t + a.elapsed_time(b))
         return out
 
+    def median(self):
+        """{(name, tag): median ms per call}"""
+        per = {}
+        for name, tag, a, b in self.records:
+            per.setdefault((name, tag), []).append(a.elapsed_time(b))
+        return {k: sorted(v)[len(v) // 2] for k, v in per.items()}
+
 
 def call(name: str, *args, tag=None) -> None:
     """Invoke a launcher of the C ABI, count its kernels, raise on a non-zero return code."""

@@ -111,3 +111,38 @@ def test_criterion_fault_poisons_losses(cuda):
     assert torch.isnan(out["loss_label_ce"]) and torch.isnan(out["loss_giou"])
     with pytest.raises(ValueError):
         crit.check_status()
+
+
+@pytest.mark.parametrize("B,L,Q,NC,pad", [(2, 2, 300, 91, 0),    # config 5: 300 queries -> three register batches per warp
+                                          (3, 2, 30, 10, 0),     # K = 11: rows that are not a multiple of 4 floats
+                                          (2, 1, 20, 149, 0),    # K = 150: wider than the register path
+                                          (2, 3, 100, 91, 5),    # logits are a strided view (row stride K + 5)
+                                          (2, 2, 40, 63, 0)])    # K = 64: two full 32-wide chunks
+def test_criterion_kernel_paths_vs_oracle(cuda, B, L, Q, NC, pad):
+    """Every template instance of the criterion kernels (register chunks 1-4, generic rows, dense float4 / row-wise
+    backward) against the oracle."""
+    logits, boxes = O.synth_predictions(B, L, Q, NC, seed=11)
+    labels, gts = O.synth_targets(B, min(Q, 40), NC, seed=12)
+    tg = {"class_idx": [l.to(cuda) for l in labels], "boxes_normalized": [g.to(cuda) for g in gts]}
+    from detr_b200 import HungarianMatcher, SetCriterion
+    crit = SetCriterion(NC, HungarianMatcher(1.0, 5.0, 2.0)).to(cuda)
+    if pad:
+        big = torch.randn(B, L, Q, NC + 1 + pad, device=cuda)
+        big[..., :NC + 1] = logits.to(cuda)
+        big.requires_grad_(True)
+        lg_in = big[..., :NC + 1]
+        assert not lg_in.is_contiguous()
+    else:
+        big = logits.to(cuda).requires_grad_(True)
+        lg_in = big
+    bx = boxes.to(cuda).requires_grad_(True)
+    out = crit({"pred_logits": lg_in, "pred_boxes": bx}, tg)
+    sum(v for k, v in out.items() if k.startswith("loss")).backward()
+    crit.check_status()
+    lg2 = logits.clone().requires_grad_(True); bx2 = boxes.clone().requires_grad_(True)
+    ref = O.set_criterion({"pred_logits": lg2, "pred_boxes": bx2}, {"class_idx": labels, "boxes_normalized": gts}, NC, (1.0, 5.0, 2.0))
+    sum(v for k, v in ref.items() if k.startswith("loss")).backward()
+    for k in ref:
+        assert float(out[k]) == pytest.approx(float(ref[k]), rel=1e-5, abs=1e-6), k
+    np.testing.assert_allclose(big.grad[..., :NC + 1].cpu().numpy(), lg2.grad.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(bx.grad.cpu().numpy(), bx2.grad.numpy(), rtol=1e-4, atol=1e-6)

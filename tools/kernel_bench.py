@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Stand-alone timing of every kernel of libdetr_b200.so at the BASELINE shapes (CUDA events on the launching
-stream, >=3 warm-ups, L2 flushed between timed iterations by writing a 256 MB buffer).  Prints one JSON line per
+stream, >=3 warm-ups, L2 flushed between timed iterations: --flush read (default) streams a 256 MB buffer through L2
+with loads, leaving it full of CLEAN foreign lines; --flush write fills the buffer, which leaves up to 126 MB of DIRTY
+lines whose write-back is then charged to the kernel under test -- tens of microseconds for the HBM-bound kernels).  Prints one JSON line per
 kernel with its algorithmic work and roofline fraction (peaks: MEASURED_PEAKS.json, burst figure -- kernels timed
 alone).  Also the command `ncu` is pointed at (tools/kernel_bench.py --only attention --iters 1)."""
 import argparse
@@ -45,13 +47,25 @@ def peaks():
         return 1590.0, 6650.0, "fallback"
 
 
+class Flush:
+    def __init__(self, dev, mode):
+        self.buf = torch.ones(64 * 1024 * 1024, device=dev)
+        self.mode = mode
+
+    def __call__(self):
+        if self.mode == "write":
+            self.buf.fill_(1.0)
+        else:
+            self.sink = self.buf.sum()
+
+
 def timeit(fn, iters, flush):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
-        flush.fill_(1.0)
+        flush()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record()
         torch.cuda.synchronize()
@@ -65,10 +79,11 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--flush", choices=("read", "write"), default="read")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     tf, hbm, src = peaks()
-    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    flush = Flush(dev, args.flush)
     out = []
 
     def attn(name, B, nh, L, S):
@@ -107,21 +122,25 @@ def main():
             crit = SetCriterion(NC, m).to(dev)
             lg = logits.clone().requires_grad_(True); bx = boxes.clone().requires_grad_(True)
             tg = {"class_idx": [l.to(dev) for l in labels], "boxes_normalized": [g.to(dev) for g in gts]}
+            def crit_step():
+                flush()
+                loss = sum(v for k, v in crit({"pred_logits": lg, "pred_boxes": bx}, tg).items() if k.startswith("loss"))
+                flush()
+                loss.backward()
+            for _ in range(3):
+                crit_step()
             with _lib.profile() as prof:
-                for _ in range(5):
-                    flush.fill_(1.0)
-                    loss = sum(v for k, v in crit({"pred_logits": lg, "pred_boxes": bx}, tg).items() if k.startswith("loss"))
-                    flush.fill_(1.0)
-                    loss.backward()
+                for _ in range(args.iters):
+                    crit_step()
             torch.cuda.synchronize()
-            for (n, _), (c, t) in prof.summary().items():
+            for (n, _), ms_c in prof.median().items():
                 if "criterion" in n:
-                    ms_c = t / c
                     byt_c = sum((36800 + 40 * cc) if "fwd" in n else (36800 * 2 + 1600 + 40 * cc) for cc in pt.counts) * L
                     out.append({"kernel": f"{n} {tag}", "ms": round(ms_c, 4), "bytes_algorithmic": byt_c, "achieved_gbs": round(byt_c / ms_c / 1e6, 2),
                                 "frac_of_hbm_peak": round(byt_c / ms_c / 1e6 / hbm, 5), "bound": "hbm"})
     for r in out:
         r["peak_source"] = src
+        r["l2_flush"] = args.flush
         print(json.dumps(r))
 
 
