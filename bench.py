@@ -240,8 +240,8 @@ def run_b200(args):
         eager_opt = make_optimizer(model)
         resident = batch_to(host, dev)
         prof_step = lambda: train_step(model, crit, eager_opt, resident)
-        if world > 1:
-            prof_step = lambda: None   # ranks would diverge without the gradient all-reduce: profile at N=1 only
+        # (at N > 1 these three untimed steps skip the gradient all-reduce: the replicas diverge AFTER every timed region
+        #  has ended, which is harmless; every rank runs them so that the num_boxes all-reduce stays collective)
     with _lib.profile() as prof:
         for _ in range(3):
             prof_step()

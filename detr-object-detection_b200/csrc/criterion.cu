@@ -43,6 +43,17 @@ __device__ __forceinline__ Box4 cxcywh_to_xyxy(float4 c) {
     return r;
 }
 
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float redux_max_f32(float v) {
     float r;
     asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));   // CREDUX.MAX.F32: one instruction per warp
@@ -57,15 +68,16 @@ __device__ __forceinline__ float redux_max_f32(float v) {
 // (offsets -> indices -> labels / boxes: three dependent trips) underneath them, and only then reduce the rows.
 template <int kC>
 __global__ void __launch_bounds__(kCritThreads, 3) criterion_fwd_kernel(const CritParams p) {
-    extern __shared__ int s_dyn[];  // [Q] target class | [Q] matched flag | [Q] row log-sum-exp | [Q] row arg-max
+    extern __shared__ int s_dyn[];  // [Q] target class | [Q] matched flag | [Q] row max | [Q] row arg-max | [Q] row sum of exp
     __shared__ float red[kCritWarps][kPartials];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
     const int Q = p.Q, K = p.K;
     int* s_tgt = s_dyn;
     int* s_matched = s_dyn + Q;
-    float* s_lse = reinterpret_cast<float*>(s_dyn + 2 * Q);
+    float* s_mx = reinterpret_cast<float*>(s_dyn + 2 * Q);
     int* s_am = s_dyn + 3 * Q;
+    float* s_sum = reinterpret_cast<float*>(s_dyn + 4 * Q);
     const float* lg = p.logits + b * p.lg_sb + l * p.lg_sl;
     const float* bx = p.boxes + b * p.bx_sb + l * p.bx_sl;
     constexpr int kCr = kC > 0 ? kC : 1;
@@ -118,38 +130,49 @@ __global__ void __launch_bounds__(kCritThreads, 3) criterion_fwd_kernel(const Cr
                 gi += 1.f - (iou - __fdiv_rn(hull - uni, hull + eps));
             }
         }
-        // row log-sum-exp and arg-max (lowest index wins ties: torch.argmax / topk on distinct values is unaffected)
+        // row max, arg-max (lowest index wins ties: torch.argmax / topk on distinct values is unaffected) and sum of
+        // exp(x - max).  Straight-line over the 13 rows (out-of-range rows and columns hold -inf and only cost issue slots):
+        // the compiler interleaves the rows' CREDUX / SHFL latencies.  exp(x - m) = ex2(x * log2e - m * log2e): one FFMA and
+        // one MUFU per logit (the kernel was issue-bound on libdevice's 9-instruction expf: ncu, profiles/r01_criterion_ncu.md).
+        if (kC > 0) {
 #pragma unroll
-        for (int r = 0; r < kFwdRows; ++r) {
-            const int q = base + r * kCritWarps + warp;
-            if (q >= Q) break;   // warp-uniform
-            float mx = -CUDART_INF_F, sum = 0.f;
-            int am = 0x7fffffff;
-            if (kC > 0) {
+            for (int r = 0; r < kFwdRows; ++r) {
+                const int q = base + r * kCritWarps + warp;
+                float mx = v[r][0];
 #pragma unroll
-                for (int c = 0; c < kCr; ++c) mx = fmaxf(mx, v[r][c]);
+                for (int c = 1; c < kCr; ++c) mx = fmaxf(mx, v[r][c]);
                 mx = redux_max_f32(mx);
+                const float nb = -mx * kLog2e;
+                int am = 0x7fffffff;
+                float sum = 0.f;
 #pragma unroll
                 for (int c = 0; c < kCr; ++c) {
-                    const int k = lane + 32 * c;
-                    if (k < K) {
-                        if (v[r][c] == mx) am = min(am, k);
-                        sum += expf(v[r][c] - mx);
-                    }
+                    am = v[r][c] == mx ? min(am, lane + 32 * c) : am;
+                    sum += ex2_approx(fmaf(v[r][c], kLog2e, nb));
                 }
-            } else {
+                am = __reduce_min_sync(FULL_MASK, am);
+                sum = warp_sum(sum);
+                if (lane == 0 && q < Q) { s_mx[q] = mx; s_sum[q] = sum; s_am[q] = am; }
+            }
+        } else {
+            for (int r = 0; r < kFwdRows; ++r) {
+                const int q = base + r * kCritWarps + warp;
+                if (q >= Q) break;   // warp-uniform
                 const float* row = lg + (int64_t)q * p.lg_sq;
+                float mx = -CUDART_INF_F, sum = 0.f;
+                int am = 0x7fffffff;
                 for (int k = lane; k < K; k += 32) mx = fmaxf(mx, row[k]);
                 mx = redux_max_f32(mx);
+                const float nb = -mx * kLog2e;
                 for (int k = lane; k < K; k += 32) {
                     const float x = row[k];
-                    if (x == mx) am = min(am, k);
-                    sum += expf(x - mx);
+                    am = x == mx ? min(am, k) : am;
+                    sum += ex2_approx(fmaf(x, kLog2e, nb));
                 }
+                am = __reduce_min_sync(FULL_MASK, am);
+                sum = warp_sum(sum);
+                if (lane == 0) { s_mx[q] = mx; s_sum[q] = sum; s_am[q] = am; }
             }
-            am = __reduce_min_sync(FULL_MASK, am);
-            sum = warp_sum(sum);
-            if (lane == 0) { s_lse[q] = mx + logf(sum); s_am[q] = am; }
         }
     }
     __syncthreads();
@@ -160,7 +183,7 @@ __global__ void __launch_bounds__(kCritThreads, 3) criterion_fwd_kernel(const Cr
     int32_t* tgt_out = p.tgt + (int64_t)blockIdx.x * Q;
     for (int q = tid; q < Q; q += kCritThreads) {
         const int t = s_tgt[q], am = s_am[q];
-        const float lse = s_lse[q];
+        const float lse = fmaf(lg2_approx(s_sum[q]), kLn2, s_mx[q]);
         const float w = p.class_weight[t];
         const float xt = lg[(int64_t)q * p.lg_sq + t];
         wnll += w * (lse - xt);
@@ -347,6 +370,10 @@ __global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritP
         const float* s_cc = reinterpret_cast<const float*>(s_dyn);
         const float* s_ls = s_cc + Q;
         const int* s_tt = s_dyn + 2 * Q;
+        // element 4e of the block is (row q, column k); consecutive float4 of a thread are 4 * 256 elements apart: one
+        // division per thread, then (q, k) advance incrementally
+        const int step_q = (4 * kCritThreads) / K, step_k = (4 * kCritThreads) - step_q * K;
+        int q = (4 * tid) / K, k = 4 * tid - q * K;
         for (int base = 0; base < n4; base += kBwdVec * kCritThreads) {
             if (base > 0) {
 #pragma unroll
@@ -358,16 +385,18 @@ __global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritP
 #pragma unroll
             for (int i = 0; i < kBwdVec; ++i) {
                 const int e = base + tid + i * kCritThreads;
-                if (e >= n4) break;
-                const int q = (4 * e) / K, k = 4 * e - q * K;   // K % 4 == 0: the four elements share a row
-                const float c = s_cc[q], ls = s_ls[q];
-                const int t = s_tt[q] - k;
-                float4 o;
-                o.x = c * (expf(x[i].x - ls) - (t == 0 ? 1.f : 0.f));
-                o.y = c * (expf(x[i].y - ls) - (t == 1 ? 1.f : 0.f));
-                o.z = c * (expf(x[i].z - ls) - (t == 2 ? 1.f : 0.f));
-                o.w = c * (expf(x[i].w - ls) - (t == 3 ? 1.f : 0.f));
-                reinterpret_cast<float4*>(dlg)[e] = o;
+                if (e < n4) {   // K % 4 == 0: the four elements share a row
+                    const float c = s_cc[q], nb = -s_ls[q] * kLog2e;
+                    const int t = s_tt[q] - k;
+                    float4 o;
+                    o.x = c * (ex2_approx(fmaf(x[i].x, kLog2e, nb)) - (t == 0 ? 1.f : 0.f));
+                    o.y = c * (ex2_approx(fmaf(x[i].y, kLog2e, nb)) - (t == 1 ? 1.f : 0.f));
+                    o.z = c * (ex2_approx(fmaf(x[i].z, kLog2e, nb)) - (t == 2 ? 1.f : 0.f));
+                    o.w = c * (ex2_approx(fmaf(x[i].w, kLog2e, nb)) - (t == 3 ? 1.f : 0.f));
+                    reinterpret_cast<float4*>(dlg)[e] = o;
+                }
+                q += step_q; k += step_k;
+                if (k >= K) { k -= K; ++q; }
             }
         }
     }
@@ -401,8 +430,8 @@ extern "C" int detr_criterion_fwd_f32(const float* logits, int64_t lg_sb, int64_
     if (check_common(p, "criterion_fwd")) return 1;
     DETR_CHECK_ARG(partials && lse && tgt && wsum && losses && status, "criterion_fwd: null output/workspace");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = 4 * (size_t)Q * sizeof(int);
-    DETR_CHECK_ARG(smem <= 48 * 1024, "criterion_fwd: Q=%d too large (<= 3072)", Q);
+    const size_t smem = 5 * (size_t)Q * sizeof(int);
+    DETR_CHECK_ARG(smem <= 48 * 1024, "criterion_fwd: Q=%d too large (<= 2457)", Q);
     const int chunks = (K + 31) / 32;
     if (chunks == 1) criterion_fwd_kernel<1><<<B * L, kCritThreads, smem, st>>>(p);
     else if (chunks == 2) criterion_fwd_kernel<2><<<B * L, kCritThreads, smem, st>>>(p);
