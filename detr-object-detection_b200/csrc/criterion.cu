@@ -1,12 +1,17 @@
-// Fused SetCriterion: forward (2 launches) and backward (1 launch) for ALL decoder layers at once.
+// Fused SetCriterion: forward (3 launches) and backward (1 launch) for ALL decoder layers at once.
 //
 // Replaces detr/loss.py:198-231: per layer { loss_labels (57-95), loss_cardinality (97-121), loss_boxes (123-164) },
 // i.e. ~60 ATen kernels + CPU-index -> CUDA-index copies per layer, by
-//   criterion_fwd_kernel       one CTA per (image, layer): one pass over the logits gives log-sum-exp, weighted NLL
-//                              numerator/denominator, arg-max (cardinality, class_error); one pass over the matched
-//                              pairs gives the L1 and GIoU sums.  Per-problem partial sums, no float atomics.
+//   criterion_expand_kernel    one small CTA per (image, layer): the assignment (idx_q, idx_gt) becomes two dense per-query
+//                              arrays -- target class (K-1 = "no object") and matched target box (NaN = unmatched).  This is
+//                              the only place where the dependent chain offsets -> indices -> labels/boxes is walked.
+//   criterion_fwd_kernel       one CTA per (image, layer), chain-free: every load (logits, classes, boxes) is issued up
+//                              front; one pass over the logits gives log-sum-exp, weighted NLL numerator/denominator and
+//                              arg-max (cardinality, class_error), one thread per query the L1 and GIoU terms.
+//                              Per-problem partial sums, no float atomics.
 //   criterion_finalize_kernel  fixed-order reduction over images -> the L x 5 loss table (deterministic).
-//   criterion_bwd_kernel       dense grad_logits (softmax - onehot, scaled) and grad_boxes (analytic L1 + GIoU).
+//   criterion_bwd_kernel       dense grad_logits (softmax - onehot, scaled) and grad_boxes (analytic L1 + GIoU) from the
+//                              same dense per-query arrays: no indices, no offsets, no dependent loads.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -26,7 +31,7 @@ struct CritParams {
     const float* class_weight; const float* num_boxes;
     int B, L, Q, K;
     float w_ce, w_l1, w_giou;
-    float* partials; float* lse; int32_t* tgt; float* wsum; float* losses;
+    float* partials; float* lse; int32_t* tgt; float* tbox; float* wsum; float* losses;
     int32_t* status;
     // backward only
     const float* grad_losses; float* grad_logits; float* grad_boxes;
@@ -60,26 +65,80 @@ __device__ __forceinline__ float redux_max_f32(float v) {
     return r;
 }
 
+// Pair losses of one query against its matched target box (XYXY): L1 against cxcywh(target) (detr/loss.py:149-156) and the
+// GIoU loss with eps (torchvision giou_loss.py:47-62, _utils.py:87-106).
+__device__ __forceinline__ void pair_losses(float4 s, float4 t, float& l1, float& gi) {
+    const float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
+    const float tcx = __fdiv_rn(__fadd_rn(__fmul_rn(t.x, 2.f), tw), 2.f);
+    const float tcy = __fdiv_rn(__fadd_rn(__fmul_rn(t.y, 2.f), th), 2.f);
+    l1 = fabsf(s.x - tcx) + fabsf(s.y - tcy) + fabsf(s.z - tw) + fabsf(s.w - th);
+    const Box4 a = cxcywh_to_xyxy(s);
+    const float eps = 1e-7f;
+    const float ix1 = fmaxf(a.x1, t.x), iy1 = fmaxf(a.y1, t.y), ix2 = fminf(a.x2, t.z), iy2 = fminf(a.y2, t.w);
+    const float inter = (iy2 > iy1 && ix2 > ix1) ? __fmul_rn(ix2 - ix1, iy2 - iy1) : 0.f;
+    const float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.x2 - a.x1, a.y2 - a.y1), __fmul_rn(t.z - t.x, t.w - t.y)), inter);
+    const float iou = __fdiv_rn(inter, uni + eps);
+    const float hull = __fmul_rn(fmaxf(a.x2, t.z) - fminf(a.x1, t.x), fmaxf(a.y2, t.w) - fminf(a.y1, t.y));
+    gi = 1.f - (iou - __fdiv_rn(hull - uni, hull + eps));
+}
+
+constexpr int kExpandThreads = 128;
+
+// (idx_q, idx_gt) of a problem -> dense per-query target class and matched target box (detr/loss.py:79-85, 144-147).
+__global__ void __launch_bounds__(kExpandThreads) criterion_expand_kernel(const CritParams p) {
+    extern __shared__ int s_g[];   // [Q] matched gt index (global row of the packed targets) or -1
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
+    const int Q = p.Q, K = p.K;
+    const int g0 = p.gt_off[b], M = p.gt_off[b + 1] - g0;
+    const int n = min(Q, M);
+    const int64_t moff = (int64_t)p.L * p.match_off[b] + (int64_t)l * n;
+    for (int q = tid; q < Q; q += kExpandThreads) s_g[q] = -1;
+    __syncthreads();
+    for (int k = tid; k < n; k += kExpandThreads) {
+        const int64_t q = p.idx_q[moff + k], g = p.idx_gt[moff + k];
+        if (q < 0 || q >= Q || g < 0 || g >= M) continue;  // poisoned by a failed assignment: status already set
+        s_g[q] = g0 + (int)g;
+    }
+    __syncthreads();
+    int32_t* tgt = p.tgt + (int64_t)blockIdx.x * Q;
+    float4* tbox = reinterpret_cast<float4*>(p.tbox) + (int64_t)blockIdx.x * Q;
+    for (int q = tid; q < Q; q += kExpandThreads) {
+        const int g = s_g[q];
+        int t = K - 1;
+        float4 tb = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+        if (g >= 0) {
+            int64_t lab = p.gt_labels[g];
+            tb = *reinterpret_cast<const float4*>(p.gt_boxes + (int64_t)g * 4);
+            if (lab < 0 || lab >= K) { atomicOr(p.status, DETR_ST_BAD_LABEL); lab = K - 1; }
+            t = (int)lab;
+            if (!(tb.x == tb.x)) tb.x = 0.f;   // NaN x1 is the "unmatched" flag; a NaN in the data has already raised
+                                               // DETR_ST_DEGENERATE_BOX in the matcher, which poisons the losses
+        }
+        tgt[q] = t;
+        tbox[q] = tb;
+    }
+}
+
 // One CTA per (image, layer).  kC = 32-wide column chunks of a logits row held in registers (K <= 32 * kC); kC == 0 is the
 // generic path for wider rows (one row per warp at a time, logits re-read from L1/L2).
 //
-// The problem is 36.8 KB of logits (Q=100, K=92) and finishes in a handful of dependent memory round trips, so the kernel
-// is written to put ALL of its logits loads in flight first (13 rows x kC registers per lane), resolve the matched pairs
-// (offsets -> indices -> labels / boxes: three dependent trips) underneath them, and only then reduce the rows.
+// A problem is 36.8 KB of logits (Q=100, K=92): all of its loads (13 rows x kC registers per lane, then class / boxes of
+// one query per thread) are in flight before the first use, and nothing in the kernel depends on a loaded index.
 template <int kC>
 __global__ void __launch_bounds__(kCritThreads, 3) criterion_fwd_kernel(const CritParams p) {
-    extern __shared__ int s_dyn[];  // [Q] target class | [Q] matched flag | [Q] row max | [Q] row arg-max | [Q] row sum of exp
+    extern __shared__ int s_dyn[];  // [Q] row max | [Q] row arg-max | [Q] row sum of exp
     __shared__ float red[kCritWarps][kPartials];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
     const int Q = p.Q, K = p.K;
-    int* s_tgt = s_dyn;
-    int* s_matched = s_dyn + Q;
-    float* s_mx = reinterpret_cast<float*>(s_dyn + 2 * Q);
-    int* s_am = s_dyn + 3 * Q;
-    float* s_sum = reinterpret_cast<float*>(s_dyn + 4 * Q);
+    float* s_mx = reinterpret_cast<float*>(s_dyn);
+    int* s_am = s_dyn + Q;
+    float* s_sum = reinterpret_cast<float*>(s_dyn + 2 * Q);
     const float* lg = p.logits + b * p.lg_sb + l * p.lg_sl;
     const float* bx = p.boxes + b * p.bx_sb + l * p.bx_sl;
+    const int32_t* tgt = p.tgt + (int64_t)blockIdx.x * Q;
+    const float4* tbox = reinterpret_cast<const float4*>(p.tbox) + (int64_t)blockIdx.x * Q;
     constexpr int kCr = kC > 0 ? kC : 1;
 
     float l1 = 0.f, gi = 0.f, npairs = 0.f;
@@ -98,36 +157,15 @@ __global__ void __launch_bounds__(kCritThreads, 3) criterion_fwd_kernel(const Cr
             }
         }
         if (base == 0) {
-            const int g0 = p.gt_off[b], M = p.gt_off[b + 1] - g0;
-            const int n = min(Q, M);
-            const int64_t moff = (int64_t)p.L * p.match_off[b] + (int64_t)l * n;
-            for (int q = tid; q < Q; q += kCritThreads) { s_tgt[q] = K - 1; s_matched[q] = 0; }
-            __syncthreads();
-            // scatter the matched labels (detr/loss.py:79-85) and accumulate the box losses of the matched pairs
-            for (int k = tid; k < n; k += kCritThreads) {
-                const int64_t q = p.idx_q[moff + k], g = p.idx_gt[moff + k];
-                if (q < 0 || q >= Q || g < 0 || g >= M) continue;  // poisoned by a failed assignment: status already set
-                int64_t lab = p.gt_labels[g0 + g];
-                const float4 s = *reinterpret_cast<const float4*>(bx + q * p.bx_sq);
-                const float4 t = *reinterpret_cast<const float4*>(p.gt_boxes + (int64_t)(g0 + g) * 4);
-                if (lab < 0 || lab >= K) { atomicOr(p.status, DETR_ST_BAD_LABEL); lab = K - 1; }
-                s_tgt[q] = (int)lab;
-                s_matched[q] = 1;
-                npairs += 1.f;
-                // L1 against cxcywh(target) (detr/loss.py:149-156)
-                const float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
-                const float tcx = __fdiv_rn(__fadd_rn(__fmul_rn(t.x, 2.f), tw), 2.f);
-                const float tcy = __fdiv_rn(__fadd_rn(__fmul_rn(t.y, 2.f), th), 2.f);
-                l1 += fabsf(s.x - tcx) + fabsf(s.y - tcy) + fabsf(s.z - tw) + fabsf(s.w - th);
-                // GIoU loss with eps (torchvision giou_loss.py:47-62, _utils.py:87-106)
-                const Box4 a = cxcywh_to_xyxy(s);
-                const float eps = 1e-7f;
-                const float ix1 = fmaxf(a.x1, t.x), iy1 = fmaxf(a.y1, t.y), ix2 = fminf(a.x2, t.z), iy2 = fminf(a.y2, t.w);
-                const float inter = (iy2 > iy1 && ix2 > ix1) ? __fmul_rn(ix2 - ix1, iy2 - iy1) : 0.f;
-                const float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.x2 - a.x1, a.y2 - a.y1), __fmul_rn(t.z - t.x, t.w - t.y)), inter);
-                const float iou = __fdiv_rn(inter, uni + eps);
-                const float hull = __fmul_rn(fmaxf(a.x2, t.z) - fminf(a.x1, t.x), fmaxf(a.y2, t.w) - fminf(a.y1, t.y));
-                gi += 1.f - (iou - __fdiv_rn(hull - uni, hull + eps));
+            // box losses of the matched queries, one query per thread (detr/loss.py:144-162)
+            for (int q = tid; q < Q; q += kCritThreads) {
+                const float4 t = tbox[q];
+                const float4 s = *reinterpret_cast<const float4*>(bx + (int64_t)q * p.bx_sq);
+                if (t.x == t.x) {
+                    float a, g;
+                    pair_losses(s, t, a, g);
+                    l1 += a; gi += g; npairs += 1.f;
+                }
             }
         }
         // row max, arg-max (lowest index wins ties: torch.argmax / topk on distinct values is unaffected) and sum of
@@ -180,18 +218,17 @@ __global__ void __launch_bounds__(kCritThreads, 3) criterion_fwd_kernel(const Cr
     // one thread per query row: weighted NLL of its target class, cardinality and class_error counts
     float wnll = 0.f, wsum = 0.f, nonempty = 0.f, correct = 0.f;
     float* lse_out = p.lse + (int64_t)blockIdx.x * Q;
-    int32_t* tgt_out = p.tgt + (int64_t)blockIdx.x * Q;
     for (int q = tid; q < Q; q += kCritThreads) {
-        const int t = s_tgt[q], am = s_am[q];
+        const int t = tgt[q], am = s_am[q];
         const float lse = fmaf(lg2_approx(s_sum[q]), kLn2, s_mx[q]);
         const float w = p.class_weight[t];
         const float xt = lg[(int64_t)q * p.lg_sq + t];
         wnll += w * (lse - xt);
         wsum += w;
         nonempty += (am != K - 1) ? 1.f : 0.f;
-        if (s_matched[q]) correct += (am == t) ? 1.f : 0.f;
+        const float tx = tbox[q].x;
+        if (tx == tx) correct += (am == t) ? 1.f : 0.f;   // matched queries only (detr/loss.py:93)
         lse_out[q] = lse;
-        tgt_out[q] = t;
     }
     const float vals[7] = {wnll, wsum, nonempty, correct, l1, gi, npairs};
 #pragma unroll
@@ -240,10 +277,52 @@ __device__ __forceinline__ float step_gt(float a, float b) { return a > b ? 1.f 
 
 constexpr int kBwdVec = 9;  // float4 per thread in flight on the dense path: 256 x 9 x 4 covers Q*K = 9 200 in one batch
 
+// Gradient of (s_l1 * L1 + s_gi * GIoU loss) of one matched pair w.r.t. the predicted cxcywh box.
+__device__ __forceinline__ float4 pair_grads(float4 s, float4 t, float s_l1, float s_gi) {
+    const float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
+    const float tcx = __fdiv_rn(__fadd_rn(__fmul_rn(t.x, 2.f), tw), 2.f);
+    const float tcy = __fdiv_rn(__fadd_rn(__fmul_rn(t.y, 2.f), th), 2.f);
+    auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+    float dcx = s_l1 * sgn(s.x - tcx), dcy = s_l1 * sgn(s.y - tcy), dw = s_l1 * sgn(s.z - tw), dh = s_l1 * sgn(s.w - th);
+
+    const Box4 a = cxcywh_to_xyxy(s);
+    const float eps = 1e-7f;
+    const float ix1 = fmaxf(a.x1, t.x), iy1 = fmaxf(a.y1, t.y), ix2 = fminf(a.x2, t.z), iy2 = fminf(a.y2, t.w);
+    const bool ok = (iy2 > iy1) && (ix2 > ix1);
+    const float iw = ix2 - ix1, ih = iy2 - iy1;
+    const float inter = ok ? iw * ih : 0.f;
+    const float aw = a.x2 - a.x1, ah = a.y2 - a.y1;
+    const float uni = aw * ah + (t.z - t.x) * (t.w - t.y) - inter;
+    const float hx1 = fminf(a.x1, t.x), hy1 = fminf(a.y1, t.y), hx2 = fmaxf(a.x2, t.z), hy2 = fmaxf(a.y2, t.w);
+    const float hw = hx2 - hx1, hh = hy2 - hy1;
+    const float hull = hw * hh;
+    // partial derivatives w.r.t. (x1, y1, x2, y2) of the predicted box; max/min split ties 0.5/0.5 like autograd
+    float dI[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ok) {
+        dI[0] = -ih * step_gt(a.x1, t.x); dI[1] = -iw * step_gt(a.y1, t.y);
+        dI[2] = ih * step_gt(t.z, a.x2);  dI[3] = iw * step_gt(t.w, a.y2);
+    }
+    const float dA[4] = {-ah, -aw, ah, aw};
+    const float dH[4] = {-hh * step_gt(t.x, a.x1), -hw * step_gt(t.y, a.y1), hh * step_gt(a.x2, t.z), hw * step_gt(a.y2, t.w)};
+    const float ue = uni + eps, he = hull + eps;
+    float dxy[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float dU = dA[c] - dI[c];
+        const float d_iou = dI[c] / ue - inter * dU / (ue * ue);
+        const float d_pen = (dH[c] - dU) / he - (hull - uni) * dH[c] / (he * he);
+        dxy[c] = s_gi * (-d_iou + d_pen);
+    }
+    // chain through x1 = cx - w/2, x2 = w + x1  =>  d/dcx = dx1 + dx2 ; d/dw = -dx1/2 + dx2/2
+    dcx += dxy[0] + dxy[2]; dcy += dxy[1] + dxy[3];
+    dw += 0.5f * (dxy[2] - dxy[0]); dh += 0.5f * (dxy[3] - dxy[1]);
+    return make_float4(dcx, dcy, dw, dh);
+}
+
 // kVec: the (Q, K) logits block of a problem is dense, 16-byte aligned and K % 4 == 0 -> walked as flat float4 with every
 // load of the block in flight before the first use; otherwise 4 rows per warp at a time.
 template <bool kVec>
-__global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritParams p) {
+__global__ void __launch_bounds__(kCritThreads, 3) criterion_bwd_kernel(const CritParams p) {
     extern __shared__ int s_dyn[];  // kVec: [Q] coefficient | [Q] row log-sum-exp | [Q] target class
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
@@ -260,26 +339,61 @@ __global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritP
             if (e < n4) x[i] = __ldg(reinterpret_cast<const float4*>(lg) + e);
         }
     }
-    const int g0 = p.gt_off[b], M = p.gt_off[b + 1] - g0;
-    const int n = min(Q, M);
-    const int64_t moff = (int64_t)p.L * p.match_off[b] + (int64_t)l * n;
     const float g_ce = p.grad_losses[l * 5 + 0], g_l1 = p.grad_losses[l * 5 + 2], g_gi = p.grad_losses[l * 5 + 3];
     const float nb = p.num_boxes ? *p.num_boxes : fmaxf((float)p.gt_off[p.B], 1.f);
-
-    // ---- d CE / d logits = g * w_ce * w[t]/W * (softmax - onehot) ----
-    const float ce_scale = g_ce * p.w_ce / p.wsum[l];
+    const float ce_scale = g_ce * p.w_ce / p.wsum[l];   // d CE / d logits = g * w_ce * w[t]/W * (softmax - onehot)
+    const float s_l1 = g_l1 * p.w_l1 / nb, s_gi = g_gi * p.w_giou / nb;
     const float* lse = p.lse + (int64_t)blockIdx.x * Q;
     const int32_t* tgt = p.tgt + (int64_t)blockIdx.x * Q;
+    const float4* tbox = reinterpret_cast<const float4*>(p.tbox) + (int64_t)blockIdx.x * Q;
     float4* dbx = reinterpret_cast<float4*>(p.grad_boxes + (int64_t)blockIdx.x * Q * 4);
+
+    // ---- per-query coefficients (dense path) and d boxes: zero for unmatched queries, analytic L1 + GIoU otherwise ----
+    for (int q = tid; q < Q; q += kCritThreads) {
+        const float4 t = tbox[q];
+        const float4 s = *reinterpret_cast<const float4*>(bx + (int64_t)q * p.bx_sq);
+        if (kVec) {
+            float* s_cc = reinterpret_cast<float*>(s_dyn);
+            const int tc = tgt[q];
+            s_dyn[2 * Q + q] = tc;
+            s_cc[Q + q] = lse[q];
+            s_cc[q] = ce_scale * p.class_weight[tc];
+        }
+        dbx[q] = (t.x == t.x) ? pair_grads(s, t, s_l1, s_gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (kVec) {
-        float* s_cc = reinterpret_cast<float*>(s_dyn);
-        float* s_ls = s_cc + Q;
-        int* s_tt = s_dyn + 2 * Q;
-        for (int q = tid; q < Q; q += kCritThreads) {
-            const int t = tgt[q];
-            s_tt[q] = t;
-            s_ls[q] = lse[q];
-            s_cc[q] = ce_scale * p.class_weight[t];
+        __syncthreads();
+        const float* s_cc = reinterpret_cast<const float*>(s_dyn);
+        const float* s_ls = s_cc + Q;
+        const int* s_tt = s_dyn + 2 * Q;
+        // element 4e of the block is (row q, column k); consecutive float4 of a thread are 4 * 256 elements apart: one
+        // division per thread, then (q, k) advance incrementally
+        const int step_q = (4 * kCritThreads) / K, step_k = (4 * kCritThreads) - step_q * K;
+        int q = (4 * tid) / K, k = 4 * tid - q * K;
+        for (int base = 0; base < n4; base += kBwdVec * kCritThreads) {
+            if (base > 0) {
+#pragma unroll
+                for (int i = 0; i < kBwdVec; ++i) {
+                    const int e = base + tid + i * kCritThreads;
+                    if (e < n4) x[i] = __ldg(reinterpret_cast<const float4*>(lg) + e);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kBwdVec; ++i) {
+                const int e = base + tid + i * kCritThreads;
+                if (e < n4) {   // K % 4 == 0: the four elements share a row
+                    const float c = s_cc[q], nbias = -s_ls[q] * kLog2e;
+                    const int t = s_tt[q] - k;
+                    float4 o;
+                    o.x = c * (ex2_approx(fmaf(x[i].x, kLog2e, nbias)) - (t == 0 ? 1.f : 0.f));
+                    o.y = c * (ex2_approx(fmaf(x[i].y, kLog2e, nbias)) - (t == 1 ? 1.f : 0.f));
+                    o.z = c * (ex2_approx(fmaf(x[i].z, kLog2e, nbias)) - (t == 2 ? 1.f : 0.f));
+                    o.w = c * (ex2_approx(fmaf(x[i].w, kLog2e, nbias)) - (t == 3 ? 1.f : 0.f));
+                    reinterpret_cast<float4*>(dlg)[e] = o;
+                }
+                q += step_q; k += step_k;
+                if (k >= K) { k -= K; ++q; }
+            }
         }
     } else {
         constexpr int kRows = 4, kMaxK = 4;
@@ -318,94 +432,11 @@ __global__ void __launch_bounds__(kCritThreads) criterion_bwd_kernel(const CritP
             }
         }
     }
-    // ---- d boxes: zero everywhere, analytic L1 + GIoU on matched queries ----
-    for (int q = tid; q < Q; q += kCritThreads) dbx[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const float s_l1 = g_l1 * p.w_l1 / nb, s_gi = g_gi * p.w_giou / nb;
-    for (int k = tid; k < n; k += kCritThreads) {
-        const int64_t q = p.idx_q[moff + k], g = p.idx_gt[moff + k];
-        if (q < 0 || q >= Q || g < 0 || g >= M) continue;
-        const float4 s = *reinterpret_cast<const float4*>(bx + q * p.bx_sq);
-        const float4 t = *reinterpret_cast<const float4*>(p.gt_boxes + (int64_t)(g0 + g) * 4);
-        const float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
-        const float tcx = __fdiv_rn(__fadd_rn(__fmul_rn(t.x, 2.f), tw), 2.f);
-        const float tcy = __fdiv_rn(__fadd_rn(__fmul_rn(t.y, 2.f), th), 2.f);
-        auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
-        float dcx = s_l1 * sgn(s.x - tcx), dcy = s_l1 * sgn(s.y - tcy), dw = s_l1 * sgn(s.z - tw), dh = s_l1 * sgn(s.w - th);
-
-        const Box4 a = cxcywh_to_xyxy(s);
-        const float eps = 1e-7f;
-        const float ix1 = fmaxf(a.x1, t.x), iy1 = fmaxf(a.y1, t.y), ix2 = fminf(a.x2, t.z), iy2 = fminf(a.y2, t.w);
-        const bool ok = (iy2 > iy1) && (ix2 > ix1);
-        const float iw = ix2 - ix1, ih = iy2 - iy1;
-        const float inter = ok ? iw * ih : 0.f;
-        const float aw = a.x2 - a.x1, ah = a.y2 - a.y1;
-        const float uni = aw * ah + (t.z - t.x) * (t.w - t.y) - inter;
-        const float hx1 = fminf(a.x1, t.x), hy1 = fminf(a.y1, t.y), hx2 = fmaxf(a.x2, t.z), hy2 = fmaxf(a.y2, t.w);
-        const float hw = hx2 - hx1, hh = hy2 - hy1;
-        const float hull = hw * hh;
-        // partial derivatives w.r.t. (x1, y1, x2, y2) of the predicted box; max/min split ties 0.5/0.5 like autograd
-        float dI[4] = {0.f, 0.f, 0.f, 0.f};
-        if (ok) {
-            dI[0] = -ih * step_gt(a.x1, t.x); dI[1] = -iw * step_gt(a.y1, t.y);
-            dI[2] = ih * step_gt(t.z, a.x2);  dI[3] = iw * step_gt(t.w, a.y2);
-        }
-        const float dA[4] = {-ah, -aw, ah, aw};
-        const float dH[4] = {-hh * step_gt(t.x, a.x1), -hw * step_gt(t.y, a.y1), hh * step_gt(a.x2, t.z), hw * step_gt(a.y2, t.w)};
-        const float ue = uni + eps, he = hull + eps;
-        float dxy[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float dU = dA[c] - dI[c];
-            const float d_iou = dI[c] / ue - inter * dU / (ue * ue);
-            const float d_pen = (dH[c] - dU) / he - (hull - uni) * dH[c] / (he * he);
-            dxy[c] = s_gi * (-d_iou + d_pen);
-        }
-        // chain through x1 = cx - w/2, x2 = w + x1  =>  d/dcx = dx1 + dx2 ; d/dw = -dx1/2 + dx2/2
-        dcx += dxy[0] + dxy[2]; dcy += dxy[1] + dxy[3];
-        dw += 0.5f * (dxy[2] - dxy[0]); dh += 0.5f * (dxy[3] - dxy[1]);
-        dbx[q] = make_float4(dcx, dcy, dw, dh);
-    }
-    if (kVec) {
-        const float* s_cc = reinterpret_cast<const float*>(s_dyn);
-        const float* s_ls = s_cc + Q;
-        const int* s_tt = s_dyn + 2 * Q;
-        // element 4e of the block is (row q, column k); consecutive float4 of a thread are 4 * 256 elements apart: one
-        // division per thread, then (q, k) advance incrementally
-        const int step_q = (4 * kCritThreads) / K, step_k = (4 * kCritThreads) - step_q * K;
-        int q = (4 * tid) / K, k = 4 * tid - q * K;
-        for (int base = 0; base < n4; base += kBwdVec * kCritThreads) {
-            if (base > 0) {
-#pragma unroll
-                for (int i = 0; i < kBwdVec; ++i) {
-                    const int e = base + tid + i * kCritThreads;
-                    if (e < n4) x[i] = __ldg(reinterpret_cast<const float4*>(lg) + e);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < kBwdVec; ++i) {
-                const int e = base + tid + i * kCritThreads;
-                if (e < n4) {   // K % 4 == 0: the four elements share a row
-                    const float c = s_cc[q], nb = -s_ls[q] * kLog2e;
-                    const int t = s_tt[q] - k;
-                    float4 o;
-                    o.x = c * (ex2_approx(fmaf(x[i].x, kLog2e, nb)) - (t == 0 ? 1.f : 0.f));
-                    o.y = c * (ex2_approx(fmaf(x[i].y, kLog2e, nb)) - (t == 1 ? 1.f : 0.f));
-                    o.z = c * (ex2_approx(fmaf(x[i].z, kLog2e, nb)) - (t == 2 ? 1.f : 0.f));
-                    o.w = c * (ex2_approx(fmaf(x[i].w, kLog2e, nb)) - (t == 3 ? 1.f : 0.f));
-                    reinterpret_cast<float4*>(dlg)[e] = o;
-                }
-                q += step_q; k += step_k;
-                if (k >= K) { k -= K; ++q; }
-            }
-        }
-    }
 }
 
 static int check_common(const CritParams& p, const char* who) {
     DETR_CHECK_ARG(p.B >= 1 && p.L >= 1 && p.Q >= 1 && p.K >= 1, "%s: bad sizes B=%d L=%d Q=%d K=%d", who, p.B, p.L, p.Q, p.K);
     DETR_CHECK_ARG(((uintptr_t)p.boxes % 16) == 0 && (p.bx_sb % 4) == 0 && (p.bx_sl % 4) == 0 && (p.bx_sq % 4) == 0, "%s: pred boxes must be 16-byte aligned rows", who);
-    DETR_CHECK_ARG(((uintptr_t)p.gt_boxes % 16) == 0, "%s: gt boxes must be 16-byte aligned", who);
     return 0;
 }
 
@@ -419,19 +450,23 @@ extern "C" int detr_criterion_fwd_f32(const float* logits, int64_t lg_sb, int64_
                                       const int32_t* match_off, const int64_t* idx_q, const int64_t* idx_gt,
                                       const float* class_weight, const float* num_boxes, int B, int L, int Q, int K,
                                       float w_ce, float w_l1, float w_giou, float* partials, float* lse, int32_t* tgt,
-                                      float* wsum, float* losses, int32_t* status, void* stream) {
+                                      float* tbox, float* wsum, float* losses, int32_t* status, void* stream) {
     CritParams p{};
     p.logits = logits; p.lg_sb = lg_sb; p.lg_sl = lg_sl; p.lg_sq = lg_sq;
     p.boxes = boxes; p.bx_sb = bx_sb; p.bx_sl = bx_sl; p.bx_sq = bx_sq;
     p.gt_labels = gt_labels; p.gt_boxes = gt_boxes; p.gt_off = gt_off; p.match_off = match_off;
     p.idx_q = idx_q; p.idx_gt = idx_gt; p.class_weight = class_weight; p.num_boxes = num_boxes;
     p.B = B; p.L = L; p.Q = Q; p.K = K; p.w_ce = w_ce; p.w_l1 = w_l1; p.w_giou = w_giou;
-    p.partials = partials; p.lse = lse; p.tgt = tgt; p.wsum = wsum; p.losses = losses; p.status = status;
+    p.partials = partials; p.lse = lse; p.tgt = tgt; p.tbox = tbox; p.wsum = wsum; p.losses = losses; p.status = status;
     if (check_common(p, "criterion_fwd")) return 1;
-    DETR_CHECK_ARG(partials && lse && tgt && wsum && losses && status, "criterion_fwd: null output/workspace");
+    DETR_CHECK_ARG(((uintptr_t)p.gt_boxes % 16) == 0, "criterion_fwd: gt boxes must be 16-byte aligned");
+    DETR_CHECK_ARG(partials && lse && tgt && tbox && wsum && losses && status, "criterion_fwd: null output/workspace");
+    DETR_CHECK_ARG(((uintptr_t)tbox % 16) == 0, "criterion_fwd: tbox must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = 5 * (size_t)Q * sizeof(int);
-    DETR_CHECK_ARG(smem <= 48 * 1024, "criterion_fwd: Q=%d too large (<= 2457)", Q);
+    const size_t smem = 3 * (size_t)Q * sizeof(int);
+    DETR_CHECK_ARG(smem <= 48 * 1024, "criterion_fwd: Q=%d too large (<= 4096)", Q);
+    criterion_expand_kernel<<<B * L, kExpandThreads, (size_t)Q * sizeof(int), st>>>(p);
+    DETR_CHECK_LAUNCH("criterion_expand");
     const int chunks = (K + 31) / 32;
     if (chunks == 1) criterion_fwd_kernel<1><<<B * L, kCritThreads, smem, st>>>(p);
     else if (chunks == 2) criterion_fwd_kernel<2><<<B * L, kCritThreads, smem, st>>>(p);
@@ -446,22 +481,21 @@ extern "C" int detr_criterion_fwd_f32(const float* logits, int64_t lg_sb, int64_
 
 extern "C" int detr_criterion_bwd_f32(const float* grad_losses, const float* logits, int64_t lg_sb, int64_t lg_sl,
                                       int64_t lg_sq, const float* boxes, int64_t bx_sb, int64_t bx_sl, int64_t bx_sq,
-                                      const float* gt_boxes, const int32_t* gt_off, const int32_t* match_off,
-                                      const int64_t* idx_q, const int64_t* idx_gt, const float* class_weight,
-                                      const float* num_boxes, const float* lse, const int32_t* tgt, const float* wsum,
+                                      const int32_t* gt_off, const float* class_weight, const float* num_boxes,
+                                      const float* lse, const int32_t* tgt, const float* tbox, const float* wsum,
                                       int B, int L, int Q, int K, float w_ce, float w_l1, float w_giou,
                                       float* grad_logits, float* grad_boxes, void* stream) {
     CritParams p{};
     p.logits = logits; p.lg_sb = lg_sb; p.lg_sl = lg_sl; p.lg_sq = lg_sq;
     p.boxes = boxes; p.bx_sb = bx_sb; p.bx_sl = bx_sl; p.bx_sq = bx_sq;
-    p.gt_boxes = gt_boxes; p.gt_off = gt_off; p.match_off = match_off;
-    p.idx_q = idx_q; p.idx_gt = idx_gt; p.class_weight = class_weight; p.num_boxes = num_boxes;
+    p.gt_off = gt_off; p.class_weight = class_weight; p.num_boxes = num_boxes;
     p.B = B; p.L = L; p.Q = Q; p.K = K; p.w_ce = w_ce; p.w_l1 = w_l1; p.w_giou = w_giou;
-    p.lse = const_cast<float*>(lse); p.tgt = const_cast<int32_t*>(tgt); p.wsum = const_cast<float*>(wsum);
+    p.lse = const_cast<float*>(lse); p.tgt = const_cast<int32_t*>(tgt); p.tbox = const_cast<float*>(tbox);
+    p.wsum = const_cast<float*>(wsum);
     p.grad_losses = grad_losses; p.grad_logits = grad_logits; p.grad_boxes = grad_boxes;
     if (check_common(p, "criterion_bwd")) return 1;
-    DETR_CHECK_ARG(grad_losses && grad_logits && grad_boxes && lse && tgt && wsum, "criterion_bwd: null pointer");
-    DETR_CHECK_ARG(((uintptr_t)grad_boxes % 16) == 0, "criterion_bwd: grad_boxes must be 16-byte aligned");
+    DETR_CHECK_ARG(grad_losses && grad_logits && grad_boxes && lse && tgt && tbox && wsum && gt_off, "criterion_bwd: null pointer");
+    DETR_CHECK_ARG(((uintptr_t)grad_boxes % 16) == 0 && ((uintptr_t)tbox % 16) == 0, "criterion_bwd: grad_boxes / tbox must be 16-byte aligned");
     const bool vec = (K % 4) == 0 && lg_sq == K && (lg_sb % 4) == 0 && (lg_sl % 4) == 0 && ((uintptr_t)logits % 16) == 0 &&
                      ((uintptr_t)grad_logits % 16) == 0 && 3 * (size_t)Q * sizeof(int) <= 48 * 1024;
     if (vec) criterion_bwd_kernel<true><<<B * L, kCritThreads, 3 * (size_t)Q * sizeof(int), (cudaStream_t)stream>>>(p);

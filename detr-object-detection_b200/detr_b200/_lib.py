@@ -32,8 +32,8 @@ SIGNATURES = {
     "detr_lsap_f32": [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P],
     "detr_lsap_f64": [P, P, P, P, c_int, c_int, c_int, P, P, P, P, P],
     "detr_criterion_fwd_f32": [P, *_STRIDES3, P, *_STRIDES3, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int,
-                               c_float, c_float, c_float, P, P, P, P, P, P, P],
-    "detr_criterion_bwd_f32": [P, P, *_STRIDES3, P, *_STRIDES3, P, P, P, P, P, P, P, P, P, P,
+                               c_float, c_float, c_float, P, P, P, P, P, P, P, P],
+    "detr_criterion_bwd_f32": [P, P, *_STRIDES3, P, *_STRIDES3, P, P, P, P, P, P, P,
                                c_int, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P],
     "detr_attention_fwd_workspace_floats": [c_int, c_int, c_int, c_int],
     "detr_attention_fwd_bf16": [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64,
@@ -93,7 +93,7 @@ class FoldTable(ctypes.Structure):
 
 # kernels launched per C-ABI call (bench.py's gpu_launches is counted from this table)
 KERNELS_PER_CALL = {"detr_cost_matrix_f32": 1, "detr_hungarian_match_f32": 1, "detr_lsap_f32": 1, "detr_lsap_f64": 1,
-                    "detr_criterion_fwd_f32": 2, "detr_criterion_bwd_f32": 1, "detr_attention_fwd_bf16": 2,
+                    "detr_criterion_fwd_f32": 3, "detr_criterion_bwd_f32": 1, "detr_attention_fwd_bf16": 2,
                     "detr_attention_bwd_bf16": 4, "detr_colsum_bf16": 1, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2,
                     "detr_epilogue_fwd": 1, "detr_epilogue_bwd": 1, "detr_scale_cast_multi": 1,
                     "detr_maxpool3x3s2_fwd_bf16": 1, "detr_maxpool3x3s2_bwd_bf16": 1,

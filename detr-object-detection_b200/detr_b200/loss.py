@@ -1,5 +1,5 @@
 """SetCriterion -- same constructor, forward signature, `empty_weight` buffer and 25 output keys as the reference
-(detr/loss.py:18-231), executed as: 1 matcher launch + 2 criterion launches for ALL decoder layers (forward) and
+(detr/loss.py:18-231), executed as: 1 matcher launch + 3 criterion launches for ALL decoder layers (forward) and
 1 launch (backward), with no host synchronisation and no CPU-index -> CUDA-index copies.
 """
 from __future__ import annotations
@@ -22,18 +22,19 @@ class _CriterionFn(torch.autograd.Function):
         B, L, Q, K = logits.shape
         dev = logits.device
         lg, bx = _rows(logits, K), _rows(boxes, 4)
-        ws = torch.empty(B * L * 8 + B * L * Q + L, dtype=torch.float32, device=dev)
-        partials, lse, wsum = ws[:B * L * 8], ws[B * L * 8:B * L * 8 + B * L * Q], ws[B * L * 8 + B * L * Q:]
-        tgt = torch.empty(B * L * Q, dtype=torch.int32, device=dev)
+        n = B * L * Q
+        ws = torch.empty(4 * n + n + B * L * 8 + L, dtype=torch.float32, device=dev)   # tbox first: 16-byte aligned
+        tbox, lse, partials, wsum = ws[:4 * n], ws[4 * n:5 * n], ws[5 * n:5 * n + B * L * 8], ws[5 * n + B * L * 8:]
+        tgt = torch.empty(n, dtype=torch.int32, device=dev)
         losses = torch.empty(L, 5, dtype=torch.float32, device=dev)
         _lib.call(
             "detr_criterion_fwd_f32",
             lg.data_ptr(), lg.stride(0), lg.stride(1), lg.stride(2), bx.data_ptr(), bx.stride(0), bx.stride(1), bx.stride(2),
             pt.labels.data_ptr(), pt.boxes.data_ptr(), pt.gt_off.data_ptr(), pt.match_off.data_ptr(),
             idx_q.data_ptr(), idx_gt.data_ptr(), class_weight.data_ptr(), _lib.ptr(num_boxes),
-            B, L, Q, K, w[0], w[1], w[2], partials.data_ptr(), lse.data_ptr(), tgt.data_ptr(), wsum.data_ptr(),
-            losses.data_ptr(), status.data_ptr(), _lib.stream_ptr())
-        ctx.save_for_backward(lg, bx, idx_q, idx_gt, class_weight, lse, tgt, wsum, pt.boxes, pt.gt_off, pt.match_off)
+            B, L, Q, K, w[0], w[1], w[2], partials.data_ptr(), lse.data_ptr(), tgt.data_ptr(), tbox.data_ptr(),
+            wsum.data_ptr(), losses.data_ptr(), status.data_ptr(), _lib.stream_ptr())
+        ctx.save_for_backward(lg, bx, class_weight, lse, tgt, tbox, wsum, pt.gt_off)
         ctx.num_boxes = num_boxes
         ctx.w = w
         ctx.shape = (B, L, Q, K)
@@ -41,7 +42,7 @@ class _CriterionFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_losses):
-        lg, bx, idx_q, idx_gt, class_weight, lse, tgt, wsum, gt_boxes, gt_off, match_off = ctx.saved_tensors
+        lg, bx, class_weight, lse, tgt, tbox, wsum, gt_off = ctx.saved_tensors
         B, L, Q, K = ctx.shape
         g = grad_losses.contiguous().float()
         d_logits = torch.empty(B, L, Q, K, dtype=torch.float32, device=lg.device)
@@ -50,9 +51,8 @@ class _CriterionFn(torch.autograd.Function):
         _lib.call(
             "detr_criterion_bwd_f32",
             g.data_ptr(), lg.data_ptr(), lg.stride(0), lg.stride(1), lg.stride(2),
-            bx.data_ptr(), bx.stride(0), bx.stride(1), bx.stride(2), gt_boxes.data_ptr(), gt_off.data_ptr(),
-            match_off.data_ptr(), idx_q.data_ptr(), idx_gt.data_ptr(), class_weight.data_ptr(), _lib.ptr(ctx.num_boxes),
-            lse.data_ptr(), tgt.data_ptr(), wsum.data_ptr(), B, L, Q, K, w[0], w[1], w[2],
+            bx.data_ptr(), bx.stride(0), bx.stride(1), bx.stride(2), gt_off.data_ptr(), class_weight.data_ptr(),
+            _lib.ptr(ctx.num_boxes), lse.data_ptr(), tgt.data_ptr(), tbox.data_ptr(), wsum.data_ptr(), B, L, Q, K, w[0], w[1], w[2],
             d_logits.data_ptr(), d_boxes.data_ptr(), _lib.stream_ptr())
         return d_logits, d_boxes, None, None, None, None, None, None, None
 

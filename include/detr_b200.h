@@ -83,7 +83,9 @@ int detr_lsap_f64(const double* cost, const int64_t* cost_off, const int32_t* nr
 /* Forward, all layers at once.  Outputs:
  *   losses float[L*5] = {loss_label_ce, cardinality_error, loss_l1_bbox, loss_giou, class_error} per layer
  *   (already multiplied by w_ce/w_l1/w_giou as detr/loss.py:91,152-162 does);
- * saved for backward: lse float[B*L*Q], tgt int32[B*L*Q], wsum float[L];
+ * saved for backward: lse float[B*L*Q], wsum float[L], and the assignment expanded to two dense per-query arrays --
+ * tgt int32[B*L*Q] (target class, K-1 = "no object") and tbox float[B*L*Q*4] (matched target box XYXY, NaN x1 =
+ * unmatched; 16-byte aligned) -- so that neither the loss kernel nor the backward walks indices or offsets;
  * partials float[B*L*8] is scratch.  class_weight float[K] is SetCriterion.empty_weight (detr/loss.py:53-55).
  * num_boxes: optional device scalar (the all-reduced normaliser); NULL -> max(sumM,1) local
  * as detr/loss.py:142 does. */
@@ -93,18 +95,18 @@ int detr_criterion_fwd_f32(const float* logits, int64_t lg_sb, int64_t lg_sl, in
                            const int32_t* match_off, const int64_t* idx_q, const int64_t* idx_gt,
                            const float* class_weight, const float* num_boxes,
                            int B, int L, int Q, int K, float w_ce, float w_l1, float w_giou,
-                           float* partials, float* lse, int32_t* tgt, float* wsum, float* losses,
+                           float* partials, float* lse, int32_t* tgt, float* tbox, float* wsum, float* losses,
                            int32_t* status, void* stream);
 
 /* Backward of the 3 differentiable losses per layer.  grad_losses float[L*5] (same layout as `losses`;
  * columns 1 and 4 ignored).  Writes dense grad_logits float[B*L*Q*K] and grad_boxes float[B*L*Q*4]
- * (both contiguous, (B,L,Q,.) order). */
+ * (both contiguous, (B,L,Q,.) order).  lse / tgt / tbox / wsum are the forward call's outputs; gt_off is read only
+ * for the local normaliser max(sum M, 1) when num_boxes is NULL. */
 int detr_criterion_bwd_f32(const float* grad_losses,
                            const float* logits, int64_t lg_sb, int64_t lg_sl, int64_t lg_sq,
                            const float* boxes, int64_t bx_sb, int64_t bx_sl, int64_t bx_sq,
-                           const float* gt_boxes, const int32_t* gt_off, const int32_t* match_off,
-                           const int64_t* idx_q, const int64_t* idx_gt, const float* class_weight,
-                           const float* num_boxes, const float* lse, const int32_t* tgt, const float* wsum,
+                           const int32_t* gt_off, const float* class_weight, const float* num_boxes,
+                           const float* lse, const int32_t* tgt, const float* tbox, const float* wsum,
                            int B, int L, int Q, int K, float w_ce, float w_l1, float w_giou,
                            float* grad_logits, float* grad_boxes, void* stream);
 
