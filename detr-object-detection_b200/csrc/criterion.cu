@@ -15,6 +15,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace detr {
 
@@ -247,6 +248,140 @@ __global__ void __launch_bounds__(kCritThreads, 3) criterion_fwd_kernel(const Cr
     }
 }
 
+// =========================================================================================================
+// Dense path: the (Q, K) logits block of a problem is contiguous and 16-byte aligned.  It is staged in shared memory by
+// bulk asynchronous copies (cp.async.bulk, the 1-D TMA path) issued by one thread and tracked by an mbarrier, so the
+// bytes in flight cost no registers: 5 problems (5 x 37 KB) are resident per SM instead of 3 with register staging, and
+// the small per-query loads and the box math run underneath the copy.
+// =========================================================================================================
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+// whole block in <= 4 copies (each a multiple of 16 bytes) so that several requests are in flight per CTA
+__device__ __forceinline__ void stage_block(float* s_dst, const float* g_src, uint32_t bytes, uint64_t* bar) {
+    tc::mbar_expect_tx(bar, bytes);
+    const uint32_t chunk = ((bytes / 4 + 15u) / 16u) * 16u;
+    for (uint32_t off = 0; off < bytes; off += chunk)
+        bulk_load_1d(reinterpret_cast<char*>(s_dst) + off, reinterpret_cast<const char*>(g_src) + off, min(chunk, bytes - off), bar);
+}
+
+constexpr int kRowThreads = 128;   // one query row per thread: Q = 100 fills 4 warps, one per scheduler
+constexpr int kRowWarps = kRowThreads / 32;
+
+// One CTA per (image, layer), one THREAD per query row.  The warp-per-row kernels above spend ~140 instructions per row on
+// predicated loads and three warp reductions (ncu: 23 M warp instructions at config 3 = issue-bound at ~20 us); here a row
+// is walked by one thread as K/4 LDS.128 (a row is K/4 float4 long: conflict-free when K/4 is odd, e.g. K = 92), no
+// reduction at all, ~6x fewer instructions.  The assignment is expanded by the same CTA while the copy is in flight
+// (offsets -> indices -> labels / boxes is a chain of 4 dependent loads, about as long as the copy itself), so the forward
+// call is 2 launches instead of 3.
+__global__ void __launch_bounds__(kRowThreads) criterion_fwd_dense_kernel(const CritParams p) {
+    extern __shared__ __align__(16) int s_dyn[];  // [Q*K] logits | [Q] matched gt row of the packed targets or -1
+    __shared__ float red[kRowWarps][kPartials];
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
+    const int Q = p.Q, K = p.K;
+    float* s_lg = reinterpret_cast<float*>(s_dyn);
+    int* s_g = s_dyn + Q * K;
+    const float* lg = p.logits + b * p.lg_sb + l * p.lg_sl;
+    const float* bx = p.boxes + b * p.bx_sb + l * p.bx_sl;
+    int32_t* tgt = p.tgt + (int64_t)blockIdx.x * Q;
+    float4* tbox = reinterpret_cast<float4*>(p.tbox) + (int64_t)blockIdx.x * Q;
+    float* lse_out = p.lse + (int64_t)blockIdx.x * Q;
+
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+    for (int q = tid; q < Q; q += kRowThreads) s_g[q] = -1;
+    __syncthreads();
+    if (tid == 0) stage_block(s_lg, lg, (uint32_t)(Q * K) * 4u, &bar);
+
+    // under the copy: (idx_q, idx_gt) -> matched gt row per query (detr/loss.py:79-85, 144-147)
+    const int g0 = p.gt_off[b], M = p.gt_off[b + 1] - g0;
+    const int n = min(Q, M);
+    const int64_t moff = (int64_t)p.L * p.match_off[b] + (int64_t)l * n;
+    for (int k = tid; k < n; k += kRowThreads) {
+        const int64_t q = p.idx_q[moff + k], g = p.idx_gt[moff + k];
+        if (q < 0 || q >= Q || g < 0 || g >= M) continue;  // poisoned by a failed assignment: status already set
+        s_g[q] = g0 + (int)g;
+    }
+    __syncthreads();
+
+    float wnll = 0.f, wsum = 0.f, nonempty = 0.f, correct = 0.f, l1 = 0.f, gi = 0.f, npairs = 0.f;
+    bool landed = false;
+    const int K4 = K >> 2;
+    for (int q = tid; q < Q; q += kRowThreads) {
+        // still under the copy: target class / box of this query, class weight, box losses (detr/loss.py:144-162)
+        const int g = s_g[q];
+        const float4 s = *reinterpret_cast<const float4*>(bx + (int64_t)q * p.bx_sq);
+        int t = K - 1;
+        float4 tb = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+        if (g >= 0) {
+            int64_t lab = p.gt_labels[g];
+            tb = *reinterpret_cast<const float4*>(p.gt_boxes + (int64_t)g * 4);
+            if (lab < 0 || lab >= K) { atomicOr(p.status, DETR_ST_BAD_LABEL); lab = K - 1; }
+            t = (int)lab;
+            if (!(tb.x == tb.x)) tb.x = 0.f;   // NaN x1 is the "unmatched" flag; a NaN in the data has already raised
+                                               // DETR_ST_DEGENERATE_BOX in the matcher, which poisons the losses
+        }
+        const float w = p.class_weight[t];
+        tgt[q] = t;
+        tbox[q] = tb;
+        if (g >= 0) {
+            float a, gl;
+            pair_losses(s, tb, a, gl);
+            l1 += a; gi += gl; npairs += 1.f;
+        }
+        if (!landed) { tc::mbar_wait(&bar, 0); landed = true; }
+
+        // row max; then arg-max (lowest index wins ties: walked from the last column down) and sum of
+        // exp(x - max) = ex2(x * log2e - max * log2e)
+        const float4* row = reinterpret_cast<const float4*>(s_lg + q * K);
+        float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
+#pragma unroll 4
+        for (int j = 0; j < K4; ++j) {
+            const float4 x = row[j];
+            m0 = fmaxf(m0, x.x); m1 = fmaxf(m1, x.y); m2 = fmaxf(m2, x.z); m3 = fmaxf(m3, x.w);
+        }
+        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        const float nb = -mx * kLog2e;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int am = 0;
+#pragma unroll 4
+        for (int j = K4 - 1; j >= 0; --j) {
+            const float4 x = row[j];
+            am = x.w == mx ? 4 * j + 3 : am;
+            am = x.z == mx ? 4 * j + 2 : am;
+            am = x.y == mx ? 4 * j + 1 : am;
+            am = x.x == mx ? 4 * j : am;
+            s0 += ex2_approx(fmaf(x.x, kLog2e, nb)); s1 += ex2_approx(fmaf(x.y, kLog2e, nb));
+            s2 += ex2_approx(fmaf(x.z, kLog2e, nb)); s3 += ex2_approx(fmaf(x.w, kLog2e, nb));
+        }
+        const float lse = fmaf(lg2_approx((s0 + s1) + (s2 + s3)), kLn2, mx);
+        wnll += w * (lse - s_lg[q * K + t]);
+        wsum += w;
+        nonempty += (am != K - 1) ? 1.f : 0.f;
+        if (g >= 0) correct += (am == t) ? 1.f : 0.f;   // matched queries only (detr/loss.py:93)
+        lse_out[q] = lse;
+    }
+    if (!landed) tc::mbar_wait(&bar, 0);   // the copy must have landed before the CTA may retire
+
+    const float vals[7] = {wnll, wsum, nonempty, correct, l1, gi, npairs};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const float v = warp_sum(vals[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < kPartials) {
+        float v = 0.f;
+        if (tid < 7) {
+#pragma unroll
+            for (int w = 0; w < kRowWarps; ++w) v += red[w][tid];   // fixed order: deterministic
+        }
+        p.partials[(int64_t)blockIdx.x * kPartials + tid] = v;
+    }
+}
+
 // one warp per layer; images are folded in a fixed order -> bitwise reproducible losses
 __global__ void criterion_finalize_kernel(const CritParams p) {
     const int l = blockIdx.x, lane = threadIdx.x;
@@ -434,6 +569,65 @@ __global__ void __launch_bounds__(kCritThreads, 3) criterion_bwd_kernel(const Cr
     }
 }
 
+__global__ void __launch_bounds__(kCritThreads) criterion_bwd_dense_kernel(const CritParams p) {
+    extern __shared__ __align__(16) int s_dyn[];  // [Q*K] logits | [Q] coefficient | [Q] -lse*log2e | [Q] target class
+    __shared__ uint64_t bar;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
+    const int Q = p.Q, K = p.K;
+    float* s_lg = reinterpret_cast<float*>(s_dyn);
+    float* s_cc = s_lg + Q * K;
+    float* s_nb = s_cc + Q;
+    int* s_tt = s_dyn + Q * K + 2 * Q;
+    const float* lg = p.logits + b * p.lg_sb + l * p.lg_sl;
+    const float* bx = p.boxes + b * p.bx_sb + l * p.bx_sl;
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
+    __syncthreads();
+    if (tid == 0) stage_block(s_lg, lg, (uint32_t)(Q * K) * 4u, &bar);
+
+    const float g_ce = p.grad_losses[l * 5 + 0], g_l1 = p.grad_losses[l * 5 + 2], g_gi = p.grad_losses[l * 5 + 3];
+    const float nb = p.num_boxes ? *p.num_boxes : fmaxf((float)p.gt_off[p.B], 1.f);
+    const float ce_scale = g_ce * p.w_ce / p.wsum[l];   // d CE / d logits = g * w_ce * w[t]/W * (softmax - onehot)
+    const float s_l1 = g_l1 * p.w_l1 / nb, s_gi = g_gi * p.w_giou / nb;
+    const float* lse = p.lse + (int64_t)blockIdx.x * Q;
+    const int32_t* tgt = p.tgt + (int64_t)blockIdx.x * Q;
+    const float4* tbox = reinterpret_cast<const float4*>(p.tbox) + (int64_t)blockIdx.x * Q;
+    float4* dbx = reinterpret_cast<float4*>(p.grad_boxes + (int64_t)blockIdx.x * Q * 4);
+    // under the copy: per-query coefficients, and d boxes (zero for unmatched queries, analytic L1 + GIoU otherwise)
+    for (int q = tid; q < Q; q += kCritThreads) {
+        const float4 t = tbox[q];
+        const float4 s = *reinterpret_cast<const float4*>(bx + (int64_t)q * p.bx_sq);
+        const int tc_ = tgt[q];
+        s_tt[q] = tc_;
+        s_nb[q] = -lse[q] * kLog2e;
+        s_cc[q] = ce_scale * p.class_weight[tc_];
+        dbx[q] = (t.x == t.x) ? pair_grads(s, t, s_l1, s_gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    tc::mbar_wait(&bar, 0);
+    // element 4e of the block is (row q, column k), K % 4 == 0: the four elements of a float4 share a row; consecutive
+    // float4 of a thread are 4 * 256 elements apart: one division per thread, then (q, k) advance incrementally
+    const int n4 = (Q * K) >> 2;
+    const int step_q = (4 * kCritThreads) / K, step_k = (4 * kCritThreads) - step_q * K;
+    int q = (4 * tid) / K, k = 4 * tid - q * K;
+    const float4* s_x = reinterpret_cast<const float4*>(s_lg);
+    float4* dlg = reinterpret_cast<float4*>(p.grad_logits + (int64_t)blockIdx.x * Q * K);
+#pragma unroll 4
+    for (int e = tid; e < n4; e += kCritThreads) {
+        const float4 x = s_x[e];
+        const float c = s_cc[q], nbias = s_nb[q];
+        const int t = s_tt[q] - k;
+        float4 o;
+        o.x = c * (ex2_approx(fmaf(x.x, kLog2e, nbias)) - (t == 0 ? 1.f : 0.f));
+        o.y = c * (ex2_approx(fmaf(x.y, kLog2e, nbias)) - (t == 1 ? 1.f : 0.f));
+        o.z = c * (ex2_approx(fmaf(x.z, kLog2e, nbias)) - (t == 2 ? 1.f : 0.f));
+        o.w = c * (ex2_approx(fmaf(x.w, kLog2e, nbias)) - (t == 3 ? 1.f : 0.f));
+        dlg[e] = o;
+        q += step_q; k += step_k;
+        if (k >= K) { k -= K; ++q; }
+    }
+}
+
 static int check_common(const CritParams& p, const char* who) {
     DETR_CHECK_ARG(p.B >= 1 && p.L >= 1 && p.Q >= 1 && p.K >= 1, "%s: bad sizes B=%d L=%d Q=%d K=%d", who, p.B, p.L, p.Q, p.K);
     DETR_CHECK_ARG(((uintptr_t)p.boxes % 16) == 0 && (p.bx_sb % 4) == 0 && (p.bx_sl % 4) == 0 && (p.bx_sq % 4) == 0, "%s: pred boxes must be 16-byte aligned rows", who);
@@ -465,14 +659,27 @@ extern "C" int detr_criterion_fwd_f32(const float* logits, int64_t lg_sb, int64_
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = 3 * (size_t)Q * sizeof(int);
     DETR_CHECK_ARG(smem <= 48 * 1024, "criterion_fwd: Q=%d too large (<= 4096)", Q);
-    criterion_expand_kernel<<<B * L, kExpandThreads, (size_t)Q * sizeof(int), st>>>(p);
-    DETR_CHECK_LAUNCH("criterion_expand");
+    // dense logits blocks with K % 4 == 0: bulk-copy staged, one thread per query row, assignment expanded in the same CTA
+    const size_t dense_smem = ((size_t)Q * K + (size_t)Q) * sizeof(int);
+    const bool dense = (K % 4) == 0 && lg_sq == K && (lg_sb % 4) == 0 && (lg_sl % 4) == 0 && ((uintptr_t)logits % 16) == 0 &&
+                       dense_smem <= 200 * 1024;
     const int chunks = (K + 31) / 32;
-    if (chunks == 1) criterion_fwd_kernel<1><<<B * L, kCritThreads, smem, st>>>(p);
-    else if (chunks == 2) criterion_fwd_kernel<2><<<B * L, kCritThreads, smem, st>>>(p);
-    else if (chunks == 3) criterion_fwd_kernel<3><<<B * L, kCritThreads, smem, st>>>(p);
-    else if (chunks == 4) criterion_fwd_kernel<4><<<B * L, kCritThreads, smem, st>>>(p);
-    else criterion_fwd_kernel<0><<<B * L, kCritThreads, smem, st>>>(p);
+    if (dense) {
+        if (dense_smem > 48 * 1024 &&
+            cudaFuncSetAttribute(criterion_fwd_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem) != cudaSuccess) {
+            set_error("criterion_fwd: cannot reserve %zu B of shared memory", dense_smem);
+            return 2;
+        }
+        criterion_fwd_dense_kernel<<<B * L, kRowThreads, dense_smem, st>>>(p);
+    } else {
+        criterion_expand_kernel<<<B * L, kExpandThreads, (size_t)Q * sizeof(int), st>>>(p);
+        DETR_CHECK_LAUNCH("criterion_expand");
+        if (chunks == 1) criterion_fwd_kernel<1><<<B * L, kCritThreads, smem, st>>>(p);
+        else if (chunks == 2) criterion_fwd_kernel<2><<<B * L, kCritThreads, smem, st>>>(p);
+        else if (chunks == 3) criterion_fwd_kernel<3><<<B * L, kCritThreads, smem, st>>>(p);
+        else if (chunks == 4) criterion_fwd_kernel<4><<<B * L, kCritThreads, smem, st>>>(p);
+        else criterion_fwd_kernel<0><<<B * L, kCritThreads, smem, st>>>(p);
+    }
     DETR_CHECK_LAUNCH("criterion_fwd");
     criterion_finalize_kernel<<<L, 32, 0, st>>>(p);
     DETR_CHECK_LAUNCH("criterion_finalize");
@@ -498,7 +705,16 @@ extern "C" int detr_criterion_bwd_f32(const float* grad_losses, const float* log
     DETR_CHECK_ARG(((uintptr_t)grad_boxes % 16) == 0 && ((uintptr_t)tbox % 16) == 0, "criterion_bwd: grad_boxes / tbox must be 16-byte aligned");
     const bool vec = (K % 4) == 0 && lg_sq == K && (lg_sb % 4) == 0 && (lg_sl % 4) == 0 && ((uintptr_t)logits % 16) == 0 &&
                      ((uintptr_t)grad_logits % 16) == 0 && 3 * (size_t)Q * sizeof(int) <= 48 * 1024;
-    if (vec) criterion_bwd_kernel<true><<<B * L, kCritThreads, 3 * (size_t)Q * sizeof(int), (cudaStream_t)stream>>>(p);
+    const size_t dense_smem = ((size_t)Q * K + 3 * (size_t)Q) * sizeof(int);
+    if (vec && dense_smem <= 200 * 1024) {
+        if (dense_smem > 48 * 1024 &&
+            cudaFuncSetAttribute(criterion_bwd_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem) != cudaSuccess) {
+            set_error("criterion_bwd: cannot reserve %zu B of shared memory", dense_smem);
+            return 2;
+        }
+        criterion_bwd_dense_kernel<<<B * L, kCritThreads, dense_smem, (cudaStream_t)stream>>>(p);
+    }
+    else if (vec) criterion_bwd_kernel<true><<<B * L, kCritThreads, 3 * (size_t)Q * sizeof(int), (cudaStream_t)stream>>>(p);
     else criterion_bwd_kernel<false><<<B * L, kCritThreads, 0, (cudaStream_t)stream>>>(p);
     DETR_CHECK_LAUNCH("criterion_bwd");
     return 0;
