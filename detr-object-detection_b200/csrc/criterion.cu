@@ -382,18 +382,31 @@ __global__ void __launch_bounds__(kRowThreads) criterion_fwd_dense_kernel(const 
     }
 }
 
-// one warp per layer; images are folded in a fixed order -> bitwise reproducible losses
-__global__ void criterion_finalize_kernel(const CritParams p) {
-    const int l = blockIdx.x, lane = threadIdx.x;
+// one CTA per layer; images are folded in a fixed order (thread -> warp -> CTA) -> bitwise reproducible losses
+constexpr int kFinThreads = 256;
+__global__ void __launch_bounds__(kFinThreads) criterion_finalize_kernel(const CritParams p) {
+    __shared__ float red[kFinThreads / 32][8];
+    const int l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int b = lane; b < p.B; b += 32) {
+    for (int b = tid; b < p.B; b += kFinThreads) {   // one image per thread: all loads of the launch are in flight at once
         const float* s = p.partials + ((int64_t)b * p.L + l) * kPartials;
         const float m = (float)(p.gt_off[b + 1] - p.gt_off[b]);
         acc[0] += s[0]; acc[1] += s[1]; acc[2] += fabsf(s[2] - m); acc[3] += s[3]; acc[4] += s[4]; acc[5] += s[5]; acc[6] += s[6];
     }
 #pragma unroll
-    for (int k = 0; k < 7; ++k) acc[k] = warp_sum(acc[k]);
-    if (lane == 0) {
+    for (int k = 0; k < 7; ++k) {
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kFinThreads / 32; ++w) v += red[w][k];
+            acc[k] = v;
+        }
         const float nb = p.num_boxes ? *p.num_boxes : fmaxf((float)p.gt_off[p.B], 1.f);  // detr/loss.py:142
         float* o = p.losses + l * 5;
         o[0] = p.w_ce * (acc[0] / acc[1]);                 // weighted mean CE (detr/loss.py:90-91)
@@ -569,16 +582,60 @@ __global__ void __launch_bounds__(kCritThreads, 3) criterion_bwd_kernel(const Cr
     }
 }
 
-__global__ void __launch_bounds__(kCritThreads) criterion_bwd_dense_kernel(const CritParams p) {
-    extern __shared__ __align__(16) int s_dyn[];  // [Q*K] logits | [Q] coefficient | [Q] -lse*log2e | [Q] target class
+// pair_grads with the 16 IEEE divisions folded into two reciprocals (the divisions were a third of the backward kernel's
+// instructions: ncu, profiles/r01_criterion_ncu_v2.md); same derivative, differences at the 1e-7 relative level.
+__device__ __forceinline__ float4 pair_grads_fast(float4 s, float4 t, float s_l1, float s_gi) {
+    const float tw = __fsub_rn(t.z, t.x), th = __fsub_rn(t.w, t.y);
+    const float tcx = __fmul_rn(__fadd_rn(__fmul_rn(t.x, 2.f), tw), 0.5f);
+    const float tcy = __fmul_rn(__fadd_rn(__fmul_rn(t.y, 2.f), th), 0.5f);
+    auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
+    float dcx = s_l1 * sgn(s.x - tcx), dcy = s_l1 * sgn(s.y - tcy), dw = s_l1 * sgn(s.z - tw), dh = s_l1 * sgn(s.w - th);
+    Box4 a;
+    a.x1 = __fsub_rn(s.x, __fmul_rn(s.z, 0.5f)); a.y1 = __fsub_rn(s.y, __fmul_rn(s.w, 0.5f));
+    a.x2 = __fadd_rn(s.z, a.x1); a.y2 = __fadd_rn(s.w, a.y1);
+    const float eps = 1e-7f;
+    const float ix1 = fmaxf(a.x1, t.x), iy1 = fmaxf(a.y1, t.y), ix2 = fminf(a.x2, t.z), iy2 = fminf(a.y2, t.w);
+    const bool ok = (iy2 > iy1) && (ix2 > ix1);
+    const float iw = ix2 - ix1, ih = iy2 - iy1;
+    const float inter = ok ? iw * ih : 0.f;
+    const float aw = a.x2 - a.x1, ah = a.y2 - a.y1;
+    const float uni = aw * ah + (t.z - t.x) * (t.w - t.y) - inter;
+    const float hx1 = fminf(a.x1, t.x), hy1 = fminf(a.y1, t.y), hx2 = fmaxf(a.x2, t.z), hy2 = fmaxf(a.y2, t.w);
+    const float hw = hx2 - hx1, hh = hy2 - hy1;
+    const float hull = hw * hh;
+    float dI[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ok) {
+        dI[0] = -ih * step_gt(a.x1, t.x); dI[1] = -iw * step_gt(a.y1, t.y);
+        dI[2] = ih * step_gt(t.z, a.x2);  dI[3] = iw * step_gt(t.w, a.y2);
+    }
+    const float dA[4] = {-ah, -aw, ah, aw};
+    const float dH[4] = {-hh * step_gt(t.x, a.x1), -hw * step_gt(t.y, a.y1), hh * step_gt(a.x2, t.z), hw * step_gt(a.y2, t.w)};
+    const float ru = __frcp_rn(uni + eps), rh = __frcp_rn(hull + eps);
+    const float k_iou = inter * ru * ru, k_pen = (hull - uni) * rh * rh;
+    float dxy[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float dU = dA[c] - dI[c];
+        const float d_iou = dI[c] * ru - k_iou * dU;
+        const float d_pen = (dH[c] - dU) * rh - k_pen * dH[c];
+        dxy[c] = s_gi * (d_pen - d_iou);
+    }
+    dcx += dxy[0] + dxy[2]; dcy += dxy[1] + dxy[3];
+    dw += 0.5f * (dxy[2] - dxy[0]); dh += 0.5f * (dxy[3] - dxy[1]);
+    return make_float4(dcx, dcy, dw, dh);
+}
+
+// One CTA per (image, layer), one thread per query row (as the dense forward kernel): the block is staged by bulk copies,
+// every row is turned into its gradient IN PLACE (c * (softmax - onehot): coefficient, log-sum-exp and target class live in
+// the owning thread's registers) and the block leaves by bulk stores -- no per-thread global stores, no per-row shared
+// arrays, 36.8 KB of shared memory per problem (6 problems resident per SM).
+__global__ void __launch_bounds__(kRowThreads) criterion_bwd_dense_kernel(const CritParams p) {
+    extern __shared__ __align__(16) int s_dyn[];  // [Q*K] logits -> grad_logits
     __shared__ uint64_t bar;
     const int tid = threadIdx.x;
     const int b = blockIdx.x / p.L, l = blockIdx.x % p.L;
     const int Q = p.Q, K = p.K;
     float* s_lg = reinterpret_cast<float*>(s_dyn);
-    float* s_cc = s_lg + Q * K;
-    float* s_nb = s_cc + Q;
-    int* s_tt = s_dyn + Q * K + 2 * Q;
     const float* lg = p.logits + b * p.lg_sb + l * p.lg_sl;
     const float* bx = p.boxes + b * p.bx_sb + l * p.bx_sl;
     if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
@@ -593,38 +650,40 @@ __global__ void __launch_bounds__(kCritThreads) criterion_bwd_dense_kernel(const
     const int32_t* tgt = p.tgt + (int64_t)blockIdx.x * Q;
     const float4* tbox = reinterpret_cast<const float4*>(p.tbox) + (int64_t)blockIdx.x * Q;
     float4* dbx = reinterpret_cast<float4*>(p.grad_boxes + (int64_t)blockIdx.x * Q * 4);
-    // under the copy: per-query coefficients, and d boxes (zero for unmatched queries, analytic L1 + GIoU otherwise)
-    for (int q = tid; q < Q; q += kCritThreads) {
+    bool landed = false;
+    const int K4 = K >> 2;
+    for (int q = tid; q < Q; q += kRowThreads) {
+        // under the copy: coefficients of this row and d boxes (zero for unmatched queries, analytic L1 + GIoU otherwise)
         const float4 t = tbox[q];
         const float4 s = *reinterpret_cast<const float4*>(bx + (int64_t)q * p.bx_sq);
         const int tc_ = tgt[q];
-        s_tt[q] = tc_;
-        s_nb[q] = -lse[q] * kLog2e;
-        s_cc[q] = ce_scale * p.class_weight[tc_];
-        dbx[q] = (t.x == t.x) ? pair_grads(s, t, s_l1, s_gi) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-    tc::mbar_wait(&bar, 0);
-    // element 4e of the block is (row q, column k), K % 4 == 0: the four elements of a float4 share a row; consecutive
-    // float4 of a thread are 4 * 256 elements apart: one division per thread, then (q, k) advance incrementally
-    const int n4 = (Q * K) >> 2;
-    const int step_q = (4 * kCritThreads) / K, step_k = (4 * kCritThreads) - step_q * K;
-    int q = (4 * tid) / K, k = 4 * tid - q * K;
-    const float4* s_x = reinterpret_cast<const float4*>(s_lg);
-    float4* dlg = reinterpret_cast<float4*>(p.grad_logits + (int64_t)blockIdx.x * Q * K);
+        const float nbias = -lse[q] * kLog2e;
+        const float c = ce_scale * p.class_weight[tc_];
+        dbx[q] = (t.x == t.x) ? pair_grads_fast(s, t, s_l1, s_gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!landed) { tc::mbar_wait(&bar, 0); landed = true; }
+        float4* row = reinterpret_cast<float4*>(s_lg + q * K);
+        const float o_t = c * (ex2_approx(fmaf(s_lg[q * K + tc_], kLog2e, nbias)) - 1.f);
 #pragma unroll 4
-    for (int e = tid; e < n4; e += kCritThreads) {
-        const float4 x = s_x[e];
-        const float c = s_cc[q], nbias = s_nb[q];
-        const int t = s_tt[q] - k;
-        float4 o;
-        o.x = c * (ex2_approx(fmaf(x.x, kLog2e, nbias)) - (t == 0 ? 1.f : 0.f));
-        o.y = c * (ex2_approx(fmaf(x.y, kLog2e, nbias)) - (t == 1 ? 1.f : 0.f));
-        o.z = c * (ex2_approx(fmaf(x.z, kLog2e, nbias)) - (t == 2 ? 1.f : 0.f));
-        o.w = c * (ex2_approx(fmaf(x.w, kLog2e, nbias)) - (t == 3 ? 1.f : 0.f));
-        dlg[e] = o;
-        q += step_q; k += step_k;
-        if (k >= K) { k -= K; ++q; }
+        for (int j = 0; j < K4; ++j) {
+            float4 x = row[j];
+            x.x = c * ex2_approx(fmaf(x.x, kLog2e, nbias)); x.y = c * ex2_approx(fmaf(x.y, kLog2e, nbias));
+            x.z = c * ex2_approx(fmaf(x.z, kLog2e, nbias)); x.w = c * ex2_approx(fmaf(x.w, kLog2e, nbias));
+            row[j] = x;
+        }
+        s_lg[q * K + tc_] = o_t;
+    }
+    if (!landed) tc::mbar_wait(&bar, 0);
+    tc::fence_proxy_async_smem();   // the rows were written through the generic proxy; the bulk store reads through the async one
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(Q * K) * 4u;
+        const uint32_t chunk = ((bytes / 4 + 15u) / 16u) * 16u;
+        char* dst = reinterpret_cast<char*>(p.grad_logits + (int64_t)blockIdx.x * Q * K);
+        for (uint32_t off = 0; off < bytes; off += chunk)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(dst + off), "r"(tc::smem_u32(reinterpret_cast<char*>(s_lg) + off)), "r"(min(chunk, bytes - off)) : "memory");
+        tc::tma_store_commit();
+        tc::tma_store_wait_read0();   // shared memory must stay valid until the copy engine has read it
     }
 }
 
@@ -681,7 +740,7 @@ extern "C" int detr_criterion_fwd_f32(const float* logits, int64_t lg_sb, int64_
         else criterion_fwd_kernel<0><<<B * L, kCritThreads, smem, st>>>(p);
     }
     DETR_CHECK_LAUNCH("criterion_fwd");
-    criterion_finalize_kernel<<<L, 32, 0, st>>>(p);
+    criterion_finalize_kernel<<<L, kFinThreads, 0, st>>>(p);
     DETR_CHECK_LAUNCH("criterion_finalize");
     return 0;
 }
@@ -705,14 +764,14 @@ extern "C" int detr_criterion_bwd_f32(const float* grad_losses, const float* log
     DETR_CHECK_ARG(((uintptr_t)grad_boxes % 16) == 0 && ((uintptr_t)tbox % 16) == 0, "criterion_bwd: grad_boxes / tbox must be 16-byte aligned");
     const bool vec = (K % 4) == 0 && lg_sq == K && (lg_sb % 4) == 0 && (lg_sl % 4) == 0 && ((uintptr_t)logits % 16) == 0 &&
                      ((uintptr_t)grad_logits % 16) == 0 && 3 * (size_t)Q * sizeof(int) <= 48 * 1024;
-    const size_t dense_smem = ((size_t)Q * K + 3 * (size_t)Q) * sizeof(int);
+    const size_t dense_smem = (size_t)Q * K * sizeof(int);
     if (vec && dense_smem <= 200 * 1024) {
         if (dense_smem > 48 * 1024 &&
             cudaFuncSetAttribute(criterion_bwd_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem) != cudaSuccess) {
             set_error("criterion_bwd: cannot reserve %zu B of shared memory", dense_smem);
             return 2;
         }
-        criterion_bwd_dense_kernel<<<B * L, kCritThreads, dense_smem, (cudaStream_t)stream>>>(p);
+        criterion_bwd_dense_kernel<<<B * L, kRowThreads, dense_smem, (cudaStream_t)stream>>>(p);
     }
     else if (vec) criterion_bwd_kernel<true><<<B * L, kCritThreads, 3 * (size_t)Q * sizeof(int), (cudaStream_t)stream>>>(p);
     else criterion_bwd_kernel<false><<<B * L, kCritThreads, 0, (cudaStream_t)stream>>>(p);

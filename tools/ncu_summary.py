@@ -26,9 +26,10 @@ if len(sys.argv) > 3:
     li = sys.argv[3]
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", li, "--launch-count", "1"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
-    h = rows[0] if "Source" in rows[0] else rows[1]
+    hi = 0 if "Source" in rows[0] else 1
+    h = rows[hi]
     iS, iN, iP = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
-    data = [(r[iS].strip(), int(r[iN]), int(r[iP])) for r in rows[2:] if len(r) > iN]
+    data = [(r[iS].strip(), int(r[iN]), int(r[iP])) for r in rows[hi + 1:] if len(r) > iN and r[iN].isdigit()]
     tot, ts = sum(d[1] for d in data), sum(d[2] for d in data)
     print(f"\n## source page launch {li}: {tot} warp-instructions, {ts} samples, {len(data)} SASS lines")
     op, ops = collections.Counter(), collections.Counter()
