@@ -14,7 +14,7 @@
 //   so "S_{j+2} is ready" also means "P V of pair j is complete": the P buffer and the O_tile columns of pair j are free /
 //   readable, and S_j had been copied to registers before p_full(j) was signalled.  The output accumulates in registers
 //   two pairs late:  acc = (acc + O_tile(j-2) * alpha(j-1)) * alpha(j).
-// TMEM: S x2 [0,256) | O_tile x2 [256,320).  Shared memory: Q 8 KB | K/V ring 4 x 16 KB | P x2 64 KB | row-max exchange.
+// TMEM: S x2 [0,256) | O_tile x2 [256,320).  Shared memory: Q x2 16 KB | K/V ring 4 x 16 KB | P x2 64 KB | row-max exchange | deferred-finish stash 24 KB.
 //
 // Masking follows the reference: key_padding_mask / attention_mask entries get a huge FINITE negative score
 // (detr/model.py:326-334 uses finfo.min, so a fully masked row is uniform, not NaN); keys beyond S (tile
@@ -40,6 +40,31 @@ constexpr uint32_t kTmemCols = 512;
 // multiply-add s*scale - m*scale cancels to exactly 0 when a whole row is masked (-> uniform probabilities).
 constexpr float kMaskedScore = -8.507059173023462e37f;
 
+// EXPERIMENT, off by default: the 8-key groups selected by kPolyGroups (bit g = group g of a thread's 32 keys) take their
+// exponentials on the FMA pipe instead of the exp unit (MUFU, 4 lanes per scheduler):
+// 2^x = 2^n * p(f), n = round(x), f = x - n in [-0.5, 0.5], p = degree-3 minimax polynomial (relative error 7.5e-5, far
+// below the bf16 rounding of P), n added into the exponent field, packed fp32x2 arithmetic throughout.
+// Measured on B200 (config 2 encoder shape / DC5): groups 0xA (half of the keys) 50.2 -> 52.2 us / 126 -> 138 us: the
+// softmax warps are bound by issue slots (4 warps per scheduler, 54 % issue-active, XU 35 %: profiles/r01_attention_ncu_full_v4.md),
+// so trading 1 MUFU for ~5 FMA-pipe instructions loses.  Kept for head dims / shapes where the balance differs.
+#ifndef DETR_FWD_POLY_GROUPS
+#define DETR_FWD_POLY_GROUPS 0x0
+#endif
+constexpr uint32_t kPolyGroups = DETR_FWD_POLY_GROUPS;
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+    const float kMagic = 12582912.f;   // 1.5 * 2^23: x + kMagic holds round(x) in its low mantissa bits
+    x.x = fmaxf(x.x, -125.f); x.y = fmaxf(x.y, -125.f);   // masked / out-of-range keys: 2^-125 instead of 0
+    const float2 t = __fadd2_rn(x, make_float2(kMagic, kMagic));
+    const float2 n = __fadd2_rn(t, make_float2(-kMagic, -kMagic));
+    const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+    float2 r = __ffma2_rn(f, make_float2(0.05517143756151199f, 0.05517143756151199f), make_float2(0.24261081218719482f, 0.24261081218719482f));
+    r = __ffma2_rn(r, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+    r = __ffma2_rn(r, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+    r.x = __int_as_float(__float_as_int(r.x) + (__float_as_int(t.x) << 23));
+    r.y = __int_as_float(__float_as_int(r.y) + (__float_as_int(t.y) << 23));
+    return r;
+}
+
 struct AttnFwdParams {
     __nv_bfloat16* O; int64_t o_sb, o_sl;  // (B, L, nh*32): element strides of batch and row
     float* lse;                            // (B, nh, L)
@@ -57,12 +82,13 @@ struct AttnFwdParams {
 constexpr int kPartRow = 36;   // 32 output columns, row max, row sum, padding to a 16-byte multiple
 
 struct FwdSmem {
-    static constexpr uint32_t q = 0;
-    static constexpr uint32_t kv = q + kTileBytes;                       // kStages x (K tile, V tile)
-    static constexpr uint32_t p = 73728;                                 // 2 x (128 x 128 bf16, two 64-key blocks, SWIZZLE_128B)
+    static constexpr uint32_t q = 0;                                     // 2 x Q tile: the next item's Q arrives while the current one is in use
+    static constexpr uint32_t kv = q + 2 * kTileBytes;                   // kStages x (K tile, V tile)
+    static constexpr uint32_t p = 81920;                                 // 2 x (128 x 128 bf16, two 64-key blocks, SWIZZLE_128B)
     static constexpr uint32_t xch = p + 2 * kBM * kBN * 2;               // float[2 parity + 1 (row sums)][4 key quarters][128 rows]
     static constexpr uint32_t bars = xch + 3 * 4 * kBM * 4;
-    static constexpr uint32_t total = bars + 256 + 1024;                 // + alignment slack
+    static constexpr uint32_t stash = bars + 256;                        // float4[512 threads][3]: accumulator, alpha, row max of a segment whose finish is deferred
+    static constexpr uint32_t total = stash + kSoftmaxThreads * 48 + 1024;   // + alignment slack
 };
 static_assert(FwdSmem::kv + kStages * 2 * kTileBytes <= FwdSmem::p && FwdSmem::p % 1024 == 0, "smem layout");
 
@@ -101,9 +127,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const int NT = sc.NT;
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::bars);
-    uint64_t* q_full = bars + 0;
-    uint64_t* q_empty = bars + 1;
-    uint64_t* kv_full = bars + 2;               // [kStages]
+    uint64_t* q_full = bars + 0;                // [2]
+    uint64_t* q_empty = bars + 2;               // [2]
+    uint64_t* kv_full = bars + 4;               // [kStages]
     uint64_t* kv_empty = kv_full + kStages;     // [kStages]
     uint64_t* s_full = kv_empty + kStages;      // [2]
     uint64_t* p_full = s_full + 2;              // [2]
@@ -111,7 +137,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
 
     if (tid == 0) {
-        mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(o_done, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(q_full + s, 1); mbar_init(q_empty + s, 1); }
+        mbar_init(o_done, 1);
         for (int s = 0; s < kStages; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(p_full + s, kSoftmaxThreads); }
         fence_barrier_init();
@@ -131,12 +158,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             int seg = -1, b = 0, h = 0, qt = 0;
             FwdCursor cur(sc);
             for (int j = 0; j < NT; ++j, cur.next(sc)) {
-                if (j == 0 || cur.t == 0) {   // new segment: its Q tile, once the previous segment's last score MMAs have read the old one
-                    ++seg;
-                    sc.split(cur.item, b, h, qt);
-                    if (seg >= 1) mbar_wait_sleep(q_empty, (seg - 1) & 1);
-                    mbar_expect_tx(q_full, kTileBytes);
-                    tma_load_3d(smem + FwdSmem::q, &tm_q, q_full, h * kD, qt * kBM, b);
+                if (j == 0 || cur.t == 0) {   // new segment: its Q tile goes to buffer seg & 1, free once the last score MMAs of segment seg-2 have
+                    ++seg;                    // read it -- long ago: with a single buffer the producer stalled here until the END of the previous
+                    sc.split(cur.item, b, h, qt);   // segment and the K/V ring drained behind it (~5 000 cycles per item boundary)
+                    if (seg >= 2) mbar_wait_sleep(q_empty + (seg & 1), ((seg >> 1) - 1) & 1);
+                    mbar_expect_tx(q_full + (seg & 1), kTileBytes);
+                    tma_load_3d(smem + FwdSmem::q + (seg & 1) * kTileBytes, &tm_q, q_full + (seg & 1), h * kD, qt * kBM, b);
                 }
                 const int st = j % kStages;
                 if (j >= kStages) mbar_wait_sleep(kv_empty + st, ((j / kStages) - 1) & 1);
@@ -152,7 +179,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             // descriptor words (tc.cuh): high word per layout, low word = (address >> 4) + constant
             constexpr uint32_t hi64 = desc_hi(512, SWZ_64B);      // Q/K/V tiles: 64-byte rows, 8-row groups 512 B apart
             constexpr uint32_t hi128 = desc_hi(1024, SWZ_128B);   // P tile: 128-byte rows, 8-row groups 1024 B apart
-            const uint32_t q_lo = smem_u32(smem + FwdSmem::q) >> 4;
+            const uint32_t q_lo0 = smem_u32(smem + FwdSmem::q) >> 4;
             // `seg_of_scores`: segment of the last score MMA issued; scores of a new segment wait for its Q tile
             int seg_scores = -1;
             FwdCursor sc_cur(sc);   // cursor of the NEXT pair whose scores will be issued
@@ -160,7 +187,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             auto scores = [&]() {
                 const int j = js;
                 const bool first = j == 0 || sc_cur.t == 0, last = j == NT - 1 || sc_cur.t == sc.T - 1;
-                if (first) { ++seg_scores; mbar_wait_sleep(q_full, seg_scores & 1); }
+                if (first) { ++seg_scores; mbar_wait_sleep(q_full + (seg_scores & 1), (seg_scores >> 1) & 1); }
+                const uint32_t q_lo = q_lo0 + (uint32_t)(seg_scores & 1) * (kTileBytes >> 4);
                 mbar_wait_sleep(kv_full + (j % kStages), (j / kStages) & 1);
                 tc_fence_after();
                 const uint32_t k_lo = smem_u32(smem + FwdSmem::kv + (j % kStages) * 2 * kTileBytes) >> 4;
@@ -168,7 +196,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 for (int ks = 0; ks < kD / 16; ++ks)  // K-major, 64-byte rows, SWIZZLE_64B: 32 B per 16-channel step
                     umma_bf16_lh(tmem_s + (j & 1) * kBN, q_lo + desc_lo(ks * 32, 16), hi64, k_lo + desc_lo(ks * 32, 16), hi64, idesc_s, ks > 0);
                 umma_commit(s_full + (j & 1));
-                if (last) umma_commit(q_empty);   // no later MMA of this segment reads the Q tile
+                if (last) umma_commit(q_empty + (seg_scores & 1));   // no later MMA of this segment reads the Q tile
                 ++js; sc_cur.next(sc);
             };
             if (NT > 0) scores();
@@ -217,21 +245,46 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         uint8_t pad_next = 0;
         FwdCursor cur(sc);
 
-        // finish a segment: the last two O tiles, total row sum, then either the normalised output + LSE or the partial slot
+        // normalised output + LSE of a whole item, or the (unnormalised O, row max, row sum) partial slot of a split one
+        auto store_out = [&](const float (&o)[8], float l_tot, float m, int b_, int h_, int q_, int item, bool whole, int slot) {
+            if (q_ >= p.L) return;
+            if (whole) {
+                const float inv = 1.f / l_tot;
+                uint4 w;
+                w.x = pack_bf16x2(o[0] * inv, o[1] * inv); w.y = pack_bf16x2(o[2] * inv, o[3] * inv);
+                w.z = pack_bf16x2(o[4] * inv, o[5] * inv); w.w = pack_bf16x2(o[6] * inv, o[7] * inv);
+                *reinterpret_cast<uint4*>(p.O + b_ * p.o_sb + (int64_t)q_ * p.o_sl + h_ * kD + kq * 8) = w;
+                // natural-log LSE of the scaled scores: m/sqrt(d) + ln(l).  A row whose keys are all masked is flagged
+                // with +inf: the backward kernel then skips it.
+                if (kq == 0)
+                    p.lse[((int64_t)b_ * p.nh + h_) * p.L + q_] =
+                        m == kMaskedScore ? CUDART_INF_F : (m * sc_l2 + log2f(l_tot)) * 0.6931471805599453f;
+            } else {
+                float* dst = p.part + (((int64_t)item * 2 + slot) * kBM + row) * kPartRow;
+                *reinterpret_cast<float4*>(dst + kq * 8) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(dst + kq * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                if (kq == 0) { dst[32] = m; dst[33] = l_tot; }
+            }
+        };
+        // total row sum = sum over the 4 key quarters (same running max, same alpha history), from the third exchange buffer
+        auto row_sum_total = [&]() {
+            const float* xr = xch + 2 * 512 + row;
+            float l_tot = (xr[0] + xr[128]) + (xr[256] + xr[384]);
+            if (drop) l_tot *= 1.f / p.drop_scale;              // the exponentials were pre-scaled by 1/(1-p)
+            return l_tot;
+        };
+        // finish a segment NOW: wait for its last P V, read the two outstanding O tiles, exchange the row sums, store.  Used
+        // where the finish cannot be deferred (see `pend` below): it costs ~5 000 cycles during which these warps start nothing.
         auto finish = [&](int j_last, int item, bool whole, int slot, int n_tiles) {
             mbar_wait(o_done, seg & 1);
             tc_fence_after();
             uint32_t o0[8], o1[8];
             if (n_tiles >= 2) tmem_ld8(tmem_o + ((j_last - 1) & 1) * kD + lane_addr + kq * 8, o0);
             tmem_ld8(tmem_o + (j_last & 1) * kD + lane_addr + kq * 8, o1);
-            // total row sum = sum over the 4 key quarters (same running max, same alpha history)
             // (third exchange buffer: a fast warp may already be writing the next pair's row max into either parity buffer)
-            float* xm = xch + 2 * 512 + kq * 128 + row;
-            *xm = l_run;
+            xch[2 * 512 + kq * 128 + row] = l_run;
             named_bar_sync(1 + lq, 128);
-            const float* xr = xch + 2 * 512 + row;
-            float l_tot = (xr[0] + xr[128]) + (xr[256] + xr[384]);
-            if (drop) l_tot *= 1.f / p.drop_scale;              // the exponentials were pre-scaled by 1/(1-p)
+            const float l_tot = row_sum_total();
             tmem_ld_wait();
             tc_fence_before();
             float o[8];
@@ -241,26 +294,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 if (n_tiles >= 2) v += __uint_as_float(o0[e]) * alpha_prev;   // O_tile(last-1) is relative to the max before the last pair
                 o[e] = v + __uint_as_float(o1[e]);
             }
-            if (q < p.L) {
-                if (whole) {
-                    const float inv = 1.f / l_tot;
-                    uint4 w;
-                    w.x = pack_bf16x2(o[0] * inv, o[1] * inv); w.y = pack_bf16x2(o[2] * inv, o[3] * inv);
-                    w.z = pack_bf16x2(o[4] * inv, o[5] * inv); w.w = pack_bf16x2(o[6] * inv, o[7] * inv);
-                    *reinterpret_cast<uint4*>(p.O + b * p.o_sb + (int64_t)q * p.o_sl + h * kD + kq * 8) = w;
-                    // natural-log LSE of the scaled scores: m/sqrt(d) + ln(l).  A row whose keys are all masked is flagged
-                    // with +inf: the backward kernel then skips it.
-                    if (kq == 0)
-                        p.lse[((int64_t)b * p.nh + h) * p.L + q] =
-                            m_run == kMaskedScore ? CUDART_INF_F : (m_run * sc_l2 + log2f(l_tot)) * 0.6931471805599453f;
-                } else {
-                    float* dst = p.part + (((int64_t)item * 2 + slot) * kBM + row) * kPartRow;
-                    *reinterpret_cast<float4*>(dst + kq * 8) = make_float4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<float4*>(dst + kq * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                    if (kq == 0) { dst[32] = m_run; dst[33] = l_tot; }
-                }
-            }
+            store_out(o, l_tot, m_run, b, h, q, item, whole, slot);
         };
+        // DEFERRED finish.  A segment that ends at pair j with at least three more pairs of the NEXT item behind it in this CTA
+        // does not wait: its accumulator, last alpha and row max go to the stash, its row sum to the third exchange buffer, and
+        // the two outstanding O tiles are picked up by the loads the next two pairs issue anyway (s_full(j+1) implies
+        // P V(j-1) complete, s_full(j+2) implies P V(j) complete; the new item has no O tile of its own to read there).
+        // pend: 0 = nothing, 2 = O_tile(last-1) comes with the next pair, 1 = O_tile(last) comes with the next pair.
+        // pend_info = item << 3 | whole << 2 | slot << 1 | (n_tiles >= 2).
+        int pend = 0, pend_info = 0;
+        float4* stash = reinterpret_cast<float4*>(smem + FwdSmem::stash) + tid * 3;
 
         uint32_t s[32];
         for (int j = 0; j < NT; ++j, cur.next(sc)) {
@@ -298,18 +341,25 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             tmem_ld32(tmem_s + (j & 1) * kBN + lane_addr + kq * 32, s);
             uint32_t o_old[8];
             const bool have_old = j - 2 >= jt;                     // O_tile(j-2) belongs to this segment
-            if (have_old) tmem_ld8(tmem_o + (j & 1) * kD + lane_addr + kq * 8, o_old);
+            if (have_old || pend != 0) tmem_ld8(tmem_o + (j & 1) * kD + lane_addr + kq * 8, o_old);
             tmem_ld_wait();
             tc_fence_before();
             FWD_STAMP(2, j);
 
             if (any) {
+                // bit i of `fin`: finite mask (key padding / attention mask), of `oob`: beyond S.  Two bit tests + selects per
+                // score (the per-element short-circuit form cost ~1 400 cycles on the last key tile of every item: timeline)
+                uint32_t fin = pad;
+                if (arow != nullptr) {
+#pragma unroll 4
+                    for (int i = 0; i < 32; ++i)
+                        if (i < n_valid && arow[i] != 0) fin |= 1u << i;
+                }
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const bool am = arow != nullptr && (key0 + i) < p.S && arow[i] != 0;
                     float v = __uint_as_float(s[i]);
-                    v = (((pad >> i) & 1u) || am) ? kMaskedScore : v;
-                    v = ((oob >> i) & 1u) ? -CUDART_INF_F : v;
+                    v = (fin & (1u << i)) ? kMaskedScore : v;
+                    v = (oob & (1u << i)) ? -CUDART_INF_F : v;
                     s[i] = __float_as_uint(v);
                 }
             }
@@ -340,7 +390,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 for (int jj = 0; jj < 4; ++jj) {
                     const int i = g * 8 + 2 * jj;
                     const float2 e = __ffma2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), sc2, bias2);
-                    const float2 x = make_float2(ex2(e.x), ex2(e.y));
+                    const float2 x = ((kPolyGroups >> g) & 1) ? exp2_poly2(e) : make_float2(ex2(e.x), ex2(e.y));
                     rs = __fadd2_rn(rs, x);
                     w[jj] = pack_bf16x2(x.x, x.y);
                 }
@@ -355,6 +405,28 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             fence_proxy_async_smem();
             mbar_arrive(p_full + (j & 1));
             FWD_STAMP(5, j);
+            if (pend != 0) {   // the O tile just read belongs to the previous item (have_old is false in an item's first two pairs)
+                float4 a0 = stash[0], a1 = stash[1];
+                const float4 a2 = stash[2];   // (last alpha, row max, -, -)
+                if (pend == 2) {
+                    if (pend_info & 1) {
+                        a0.x = fmaf(__uint_as_float(o_old[0]), a2.x, a0.x); a0.y = fmaf(__uint_as_float(o_old[1]), a2.x, a0.y);
+                        a0.z = fmaf(__uint_as_float(o_old[2]), a2.x, a0.z); a0.w = fmaf(__uint_as_float(o_old[3]), a2.x, a0.w);
+                        a1.x = fmaf(__uint_as_float(o_old[4]), a2.x, a1.x); a1.y = fmaf(__uint_as_float(o_old[5]), a2.x, a1.y);
+                        a1.z = fmaf(__uint_as_float(o_old[6]), a2.x, a1.z); a1.w = fmaf(__uint_as_float(o_old[7]), a2.x, a1.w);
+                        stash[0] = a0; stash[1] = a1;
+                    }
+                    pend = 1;
+                } else {
+                    const float o[8] = {a0.x + __uint_as_float(o_old[0]), a0.y + __uint_as_float(o_old[1]), a0.z + __uint_as_float(o_old[2]),
+                                        a0.w + __uint_as_float(o_old[3]), a1.x + __uint_as_float(o_old[4]), a1.y + __uint_as_float(o_old[5]),
+                                        a1.z + __uint_as_float(o_old[6]), a1.w + __uint_as_float(o_old[7])};
+                    int pb, ph, pqt;
+                    sc.split(pend_info >> 3, pb, ph, pqt);
+                    store_out(o, row_sum_total(), a2.y, pb, ph, pqt * kBM + row, pend_info >> 3, (pend_info >> 2) & 1, (pend_info >> 1) & 1);
+                    pend = 0;
+                }
+            }
             // output accumulation, two pairs late: acc = (acc + O_tile(j-2) * alpha(j-1)) * alpha(j)
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -367,7 +439,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             alpha_prev = alpha;
             if (j == NT - 1 || t == sc.T - 1) {
                 const int n_tiles = j - jt + 1;
-                finish(j, cur.item, seg_t0 == 0 && t == sc.T - 1, seg_t0 == 0 ? 0 : 1, n_tiles);
+                const bool whole = seg_t0 == 0 && t == sc.T - 1;
+                const int slot = seg_t0 == 0 ? 0 : 1;
+#ifndef DETR_FWD_NO_DEFER
+                // pairs j+1, j+2 exist in this CTA and belong to the next item, and that item cannot end before pair j+3: its own
+                // finish (which reuses the third exchange buffer) is separated from the deferred read by a named barrier
+                if (sc.T >= 3 && j + 3 <= NT - 1) {
+                    stash[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    stash[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                    stash[2] = make_float4(alpha_prev, m_run, 0.f, 0.f);
+                    xch[2 * 512 + kq * 128 + row] = l_run;   // read two pairs (two named barriers) later
+                    pend = 2;
+                    pend_info = (cur.item << 3) | (whole ? 4 : 0) | (slot << 1) | (n_tiles >= 2 ? 1 : 0);
+                } else
+#endif
+                    finish(j, cur.item, whole, slot, n_tiles);
             }
         }
         tc_fence_before();

@@ -48,6 +48,9 @@ def _check(q, k, v, nh, kpm=None, am=None):
 @pytest.mark.parametrize("B,L,S,nh", [(2, 128, 128, 2), (1, 256, 384, 8), (2, 100, 100, 8), (2, 100, 850, 8), (2, 850, 850, 8), (1, 37, 5, 1),
                                       # more (batch, head, query tile) items than SMs: persistent CTAs split items between them
                                       (3, 850, 850, 8), (24, 100, 300, 8), (5, 600, 130, 8),
+                                      # several items per persistent CTA: the finish of an item is deferred into the first
+                                      # two pairs of the next one (BASELINE config 2 encoder shape; 5-pair items)
+                                      (8, 850, 850, 8), (16, 256, 640, 8),
                                       # BASELINE config 4: DC5 encoder self-attention (stride 16, 50 x 67 = 3 350 tokens)
                                       (1, 3350, 3350, 8)])
 def test_attention_forward_shapes(cuda, B, L, S, nh):

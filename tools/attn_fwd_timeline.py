@@ -22,10 +22,10 @@ t0 = int(d[d > 0].min())
 n = int((d[0, :, 0] > 0).sum())
 print("softmax warp: [top, s_full seen, TMEM loaded, row max exchanged, P stored, arrived]")
 for w in (0, 5, 10, 15):
-    for j in range(min(n, 16)):
+    for j in range(min(n, 24)):
         r = [int(x) - t0 for x in d[w, j, :6]]
         print(f"warp {w:2d} pair {j:2d}: {r}  wait_s={r[1]-r[0]} ld={r[2]-r[1]} max+xch={r[3]-r[2]} math={r[4]-r[3]} fence={r[5]-r[4]}" + (f" period={int(d[w,j,0]-d[w,j-1,0])}" if j else ""))
 print("MMA warp: [before p_full wait, after, PV + next scores issued]")
-for j in range(min(n, 16)):
+for j in range(min(n, 24)):
     r = [int(x) - t0 for x in d[17, j, :3]]
     print(f"pair {j:2d}: {r} waited={r[1]-r[0]} issue={r[2]-r[1]}")
