@@ -77,13 +77,24 @@ struct LsapScratch {
     int* row_of_col; // [nc]
     int* col_of_row; // [nr]
     int* todo;       // [nc] unvisited columns, SciPy's `remaining`
+    int spare;       // index (relative to pred) of a spare word: target of predecessor stores that must not land
 };
 
-// One warp solves one problem.  W(i,j) = W[i*si + j*sj].  Returns 0 or a DETR_ST_* bit.
-template <int SLOTS, typename T>
-__device__ int lsap_solve_warp(const T* __restrict__ W, int64_t si, int64_t sj, int nr, int nc, LsapScratch s, int lane) {
+// One warp solves one problem.  W(i,j) = W[i*si + j*sj]; UNIT: sj == 1 (the shared-memory work matrix).  Returns 0 or a
+// DETR_ST_* bit.
+//
+// The scan of one row is a chain of ~140 dependent-ish instructions issued by a single warp (~3 cycles each), so the
+// instruction count IS the run time (ncu: 203 instructions and ~600 cycles per scan before this layout).  Hence:
+//  * the lane-local arg-min over the SLOTS columns runs on doubles (DSETP), only the winner is mapped to its sortable bits;
+//  * the tie-break key is one IMAD per column: key = kb0 + ksg * pos, with (kb0, ksg) fixed while a row is being inserted;
+//  * loads use a clamped column index fixed per problem instead of a per-scan select;
+//  * the set of removed columns is read off `pos` after the scan loop instead of being tracked inside it.
+template <int SLOTS, typename T, bool UNIT>
+__device__ int lsap_solve_warp(const T* __restrict__ W, int64_t si64, int64_t sj64, int nr, int nc, LsapScratch s, int lane) {
+    const int si = (int)si64, sj = UNIT ? 1 : (int)sj64;   // nr, nc <= 1024: every element offset fits 32 bits
     double dist[SLOTS], v[SLOTS];
-    int rowof[SLOTS], pos[SLOTS];
+    int rowof[SLOTS], pos[SLOTS], ksg[SLOTS];
+    unsigned kb0[SLOTS];
 #pragma unroll
     for (int k = 0; k < SLOTS; ++k) { v[k] = 0.0; rowof[k] = -1; dist[k] = 0.0; pos[k] = -1; }
     for (int i = lane; i < nr; i += 32) { s.u[i] = 0.0; s.col_of_row[i] = -1; }
@@ -98,6 +109,12 @@ __device__ int lsap_solve_warp(const T* __restrict__ W, int64_t si, int64_t sj, 
             const int j = lane + 32 * k;
             dist[k] = CUDART_INF;
             pos[k] = (j < nc) ? (nc - 1 - j) : -1;  // todo[t] = nc-1-t  (reverse fill)
+            // smaller key wins among equal distances: unassigned columns first, LAST in array order;
+            // otherwise assigned columns, FIRST in array order.  key = flag | order | column | row_of_col
+            //   unassigned: ((1023 - pos) << 20) | (j << 10)              = kb0 - (pos << 20)
+            //   assigned:   (1 << 30) | (pos << 20) | (j << 10) | rowof   = kb0 + (pos << 20)
+            kb0[k] = rowof[k] < 0 ? ((1023u << 20) | ((unsigned)j << 10)) : ((1u << 30) | ((unsigned)j << 10) | (unsigned)rowof[k]);
+            ksg[k] = rowof[k] < 0 ? -(1 << 20) : (1 << 20);
         }
         for (int t = lane; t < nc; t += 32) s.todo[t] = nc - 1 - t;
         __syncwarp();
@@ -106,45 +123,45 @@ __device__ int lsap_solve_warp(const T* __restrict__ W, int64_t si, int64_t sj, 
         double reach = 0.0;
         int i = cur;
         int sink = -1;
-        unsigned removed = 0;
 
         while (true) {
             const double ui = s.u[i];
-            const T* Wi = W + (int64_t)i * si;
-            // Branch-free over the SLOTS columns a lane owns: all loads first, then the float64 chains interleaved.  (One
-            // divergent block per slot serialised four load -> convert -> 3 x DADD -> compare chains: ~450 of the ~800 cycles
-            // an iteration cost, measured on 100 x 100 problems.)
+            const T* Wi = W + i * si;
+            // all loads first, then the float64 chains of the SLOTS columns interleaved (branch-free)
             T wv[SLOTS];
 #pragma unroll
-            for (int k = 0; k < SLOTS; ++k) {
-                const int j = lane + 32 * k;
-                wv[k] = Wi[(int64_t)(pos[k] >= 0 ? j : 0) * sj];
-            }
-            unsigned long long sbk[SLOTS];
-            unsigned keyk[SLOTS];
+            for (int k = 0; k < SLOTS; ++k) wv[k] = Wi[min(lane + 32 * k, nc - 1) * sj];
+            // Every chain is evaluated unconditionally and kept out of any branch (the empty asm pins r[k] here): when the
+            // compiler guards a chain by "column still active" the SLOTS chains end up in SLOTS divergent regions, one after
+            // the other (measured: 1.06 -> 1.27 ms at config 3).  Improvements are applied by selects; the predecessor store
+            // of a column that does not improve goes to a spare word.
+            double r[SLOTS];
 #pragma unroll
             for (int k = 0; k < SLOTS; ++k) {
-                const int j = lane + 32 * k;
-                const bool act = pos[k] >= 0;
                 // ((reach + c) - u_i) - v_j : SciPy's evaluation order, float64
-                const double r = __dsub_rn(__dsub_rn(__dadd_rn(reach, (double)wv[k]), ui), v[k]);
-                if (act && r < dist[k]) { dist[k] = r; s.pred[j] = i; }
-                // smaller key wins among equal distances: unassigned columns first, LAST in array order;
-                // otherwise assigned columns, FIRST in array order.  key = flag | order | column | row_of_col
-                const unsigned key = rowof[k] < 0
-                    ? (((1023u - (unsigned)pos[k]) << 20) | ((unsigned)j << 10))
-                    : ((1u << 30) | ((unsigned)pos[k] << 20) | ((unsigned)j << 10) | (unsigned)rowof[k]);
-                sbk[k] = act ? to_sortable(dist[k]) : ~0ull;
-                keyk[k] = act ? key : ~0u;
+                r[k] = __dsub_rn(__dsub_rn(__dadd_rn(reach, (double)wv[k]), ui), v[k]);
+                asm volatile("" : "+d"(r[k]));
             }
-            unsigned long long best = ~0ull;
-            unsigned best_key = ~0u;
+            double cd[SLOTS];
+            unsigned ck[SLOTS];
 #pragma unroll
             for (int k = 0; k < SLOTS; ++k) {
-                const bool better = sbk[k] < best || (sbk[k] == best && keyk[k] < best_key);
-                best = better ? sbk[k] : best;
-                best_key = better ? keyk[k] : best_key;
+                const bool act = pos[k] >= 0;
+                const bool imp = act & (r[k] < dist[k]);
+                dist[k] = imp ? r[k] : dist[k];
+                s.pred[imp ? lane + 32 * k : s.spare] = i;
+                cd[k] = act ? dist[k] : CUDART_INF;
+                ck[k] = act ? kb0[k] + (unsigned)(ksg[k] * pos[k]) : ~0u;
             }
+            double bd = cd[0];
+            unsigned best_key = ck[0];
+#pragma unroll
+            for (int k = 1; k < SLOTS; ++k) {   // -0.0 == +0.0 here, as in SciPy's comparisons; folded by to_sortable below
+                const bool better = cd[k] < bd || (cd[k] == bd && ck[k] < best_key);
+                bd = better ? cd[k] : bd;
+                best_key = better ? ck[k] : best_key;
+            }
+            const unsigned long long best = to_sortable(bd);
             const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
             const unsigned mhi = __reduce_min_sync(FULL_MASK, hi);
             const unsigned mlo = __reduce_min_sync(FULL_MASK, hi == mhi ? lo : 0xffffffffu);
@@ -166,18 +183,19 @@ __device__ int lsap_solve_warp(const T* __restrict__ W, int64_t si, int64_t sj, 
 #pragma unroll
             for (int k = 0; k < SLOTS; ++k) {
                 const int j = lane + 32 * k;
-                if (j == jstar) { pos[k] = -1; removed |= 1u << k; }
-                else if (j == jlast) pos[k] = tstar;
+                pos[k] = j == jlast ? tstar : pos[k];
+                pos[k] = j == jstar ? -1 : pos[k];   // (jstar == jlast when the last entry is the one removed)
             }
             if (!assigned) { sink = jstar; break; }
             i = (int)(mkey & 1023u);
         }
 
-        // dual update (rows reached are exactly row_of_col of the removed, non-sink columns, plus `cur`)
+        // dual update (rows reached are exactly row_of_col of the removed, non-sink columns, plus `cur`); a column j < nc
+        // without a position has been removed during this scan
 #pragma unroll
         for (int k = 0; k < SLOTS; ++k) {
-            if ((removed >> k) & 1u) {
-                const int j = lane + 32 * k;
+            const int j = lane + 32 * k;
+            if (j < nc && pos[k] < 0) {
                 const double delta = __dsub_rn(reach, dist[k]);
                 if (j != sink) s.u[rowof[k]] = __dadd_rn(s.u[rowof[k]], delta);
                 v[k] = __dsub_rn(v[k], delta);
@@ -236,7 +254,7 @@ __device__ __forceinline__ LsapScratch carve(char* smem, const SmemPlan& pl, int
     s.row_of_col = ip + cols_max;
     s.todo = ip + 2 * cols_max;
     s.col_of_row = ip + 3 * cols_max;
-    (void)rows_max;
+    s.spare = 3 * cols_max + rows_max;   // first of the 4 spare ints of plan_smem's n_ints
     return s;
 }
 
@@ -366,7 +384,7 @@ __global__ void __launch_bounds__(kMatchThreads) hungarian_match_kernel(const Ma
     if (warp != 0) return;
     if (!W_SMEM) __threadfence_block();
     LsapScratch s = carve(smem, pl, rows_max, cols_max);
-    const int rc = lsap_solve_warp<SLOTS, float>(W, si, sj, nr, nc, s, lane);
+    const int rc = lsap_solve_warp<SLOTS, float, W_SMEM>(W, si, sj, nr, nc, s, lane);
     if (rc) {
         if (lane == 0) atomicOr(p.status, rc);
         for (int k = lane; k < n; k += 32) { oq[k] = -1; og[k] = -1; }
@@ -420,7 +438,7 @@ __global__ void __launch_bounds__(kMatchThreads) lsap_kernel(const LsapParams p)
     const T* W = W_SMEM ? Wsm : C;
     const int64_t si = W_SMEM ? nc : (flip ? 1 : C0);
     const int64_t sj = W_SMEM ? 1 : (flip ? C0 : 1);
-    const int rc = lsap_solve_warp<SLOTS, T>(W, si, sj, nr, nc, s, lane);
+    const int rc = lsap_solve_warp<SLOTS, T, W_SMEM>(W, si, sj, nr, nc, s, lane);
     if (rc) {
         if (lane == 0) atomicOr(p.status, rc);
         for (int k = lane; k < n; k += 32) { ro[k] = -1; co[k] = -1; }
