@@ -153,19 +153,32 @@ __device__ int lsap_solve_warp(const T* __restrict__ W, int64_t si64, int64_t sj
                 cd[k] = act ? dist[k] : CUDART_INF;
                 ck[k] = act ? kb0[k] + (unsigned)(ksg[k] * pos[k]) : ~0u;
             }
-            double bd = cd[0];
-            unsigned best_key = ck[0];
+            // lane-local arg-min as a balanced tree ((distance, key) is a total order, so the grouping is free): two levels
+            // of dependent compares for 4 columns instead of three.  -0.0 == +0.0 here, as in SciPy's comparisons.
 #pragma unroll
-            for (int k = 1; k < SLOTS; ++k) {   // -0.0 == +0.0 here, as in SciPy's comparisons; folded by to_sortable below
-                const bool better = cd[k] < bd || (cd[k] == bd && ck[k] < best_key);
-                bd = better ? cd[k] : bd;
-                best_key = better ? ck[k] : best_key;
+            for (int w = 1; w < SLOTS; w *= 2) {
+#pragma unroll
+                for (int k = 0; k + w < SLOTS; k += 2 * w) {
+                    const bool better = cd[k + w] < cd[k] || (cd[k + w] == cd[k] && ck[k + w] < ck[k]);
+                    cd[k] = better ? cd[k + w] : cd[k];
+                    ck[k] = better ? ck[k + w] : ck[k];
+                }
             }
-            const unsigned long long best = to_sortable(bd);
+            const unsigned long long best = to_sortable(cd[0]);
             const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
             const unsigned mhi = __reduce_min_sync(FULL_MASK, hi);
-            const unsigned mlo = __reduce_min_sync(FULL_MASK, hi == mhi ? lo : 0xffffffffu);
-            const unsigned mkey = __reduce_min_sync(FULL_MASK, (hi == mhi && lo == mlo) ? best_key : 0xffffffffu);
+            // Almost always a single lane holds the minimal high word: its (low word, key) then come by two independent
+            // shuffles instead of two more dependent reductions.
+            const unsigned cand = __ballot_sync(FULL_MASK, hi == mhi);
+            unsigned mlo, mkey;
+            if ((cand & (cand - 1u)) == 0u) {   // warp-uniform
+                const int src = __ffs((int)cand) - 1;
+                mlo = __shfl_sync(FULL_MASK, lo, src);
+                mkey = __shfl_sync(FULL_MASK, ck[0], src);
+            } else {
+                mlo = __reduce_min_sync(FULL_MASK, hi == mhi ? lo : 0xffffffffu);
+                mkey = __reduce_min_sync(FULL_MASK, (hi == mhi && lo == mlo) ? ck[0] : 0xffffffffu);
+            }
             const unsigned long long mbest = ((unsigned long long)mhi << 32) | mlo;
             if (mbest >= INF_S) return DETR_ST_INFEASIBLE;
             reach = from_sortable(mbest);
@@ -318,16 +331,46 @@ __global__ void __launch_bounds__(kMatchThreads) hungarian_match_kernel(const Ma
         o[9] = __int_as_float((int)min(max(lab, (int64_t)0), (int64_t)K - 1));
         if (!(g.z >= g.x) || !(g.w >= g.y)) local_flags |= DETR_ST_DEGENERATE_BOX;
     }
-    // ---- warp-level softmax statistics, one query row per warp (coalesced) ----
-    for (int q = warp; q < Q; q += kMatchThreads / 32) {
-        const float* row = lg + (int64_t)q * p.lg_sq;
-        float mx = -CUDART_INF_F;
-        for (int k = lane; k < K; k += 32) mx = fmaxf(mx, row[k]);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int k = lane; k < K; k += 32) sum += expf(row[k] - mx);
-        sum = warp_sum(sum);
-        if (lane == 0) { pq[q * 11 + 9] = mx; pq[q * 11 + 10] = sum; }
+    // ---- warp-level softmax statistics, one query row per warp (coalesced); the loads of 4 rows are in flight together
+    //      (one row at a time was a chain of L2 round trips: ~25 per warp and problem) ----
+    constexpr int kStatRows = 4, kStatChunks = 4;   // register path: K <= 128
+    if (K <= 32 * kStatChunks) {
+        for (int q0 = warp; q0 < Q; q0 += (kMatchThreads / 32) * kStatRows) {
+            float x[kStatRows][kStatChunks];
+#pragma unroll
+            for (int r = 0; r < kStatRows; ++r) {
+                const int q = min(q0 + r * (kMatchThreads / 32), Q - 1);
+                const float* row = lg + (int64_t)q * p.lg_sq;
+#pragma unroll
+                for (int c = 0; c < kStatChunks; ++c) {
+                    const int k = lane + 32 * c;
+                    x[r][c] = k < K ? row[k] : -CUDART_INF_F;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kStatRows; ++r) {
+                const int q = q0 + r * (kMatchThreads / 32);
+                float mx = fmaxf(fmaxf(x[r][0], x[r][1]), fmaxf(x[r][2], x[r][3]));
+                mx = warp_max(mx);
+                float sum = 0.f;
+#pragma unroll
+                for (int c = 0; c < kStatChunks; ++c)
+                    if (lane + 32 * c < K) sum += expf(x[r][c] - mx);   // same terms, same per-lane order as the generic loop
+                sum = warp_sum(sum);
+                if (lane == 0 && q < Q) { pq[q * 11 + 9] = mx; pq[q * 11 + 10] = sum; }
+            }
+        }
+    } else {
+        for (int q = warp; q < Q; q += kMatchThreads / 32) {
+            const float* row = lg + (int64_t)q * p.lg_sq;
+            float mx = -CUDART_INF_F;
+            for (int k = lane; k < K; k += 32) mx = fmaxf(mx, row[k]);
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int k = lane; k < K; k += 32) sum += expf(row[k] - mx);
+            sum = warp_sum(sum);
+            if (lane == 0) { pq[q * 11 + 9] = mx; pq[q * 11 + 10] = sum; }
+        }
     }
     __syncthreads();
 
