@@ -1,17 +1,19 @@
-// Fused SetCriterion: forward (3 launches) and backward (1 launch) for ALL decoder layers at once.
+// Fused SetCriterion: forward (2 launches; 3 on the fallback path) and backward (1 launch) for ALL decoder layers at once.
 //
 // Replaces detr/loss.py:198-231: per layer { loss_labels (57-95), loss_cardinality (97-121), loss_boxes (123-164) },
 // i.e. ~60 ATen kernels + CPU-index -> CUDA-index copies per layer, by
-//   criterion_expand_kernel    one small CTA per (image, layer): the assignment (idx_q, idx_gt) becomes two dense per-query
-//                              arrays -- target class (K-1 = "no object") and matched target box (NaN = unmatched).  This is
-//                              the only place where the dependent chain offsets -> indices -> labels/boxes is walked.
-//   criterion_fwd_kernel       one CTA per (image, layer), chain-free: every load (logits, classes, boxes) is issued up
-//                              front; one pass over the logits gives log-sum-exp, weighted NLL numerator/denominator and
-//                              arg-max (cardinality, class_error), one thread per query the L1 and GIoU terms.
-//                              Per-problem partial sums, no float atomics.
+//   criterion_fwd_dense_kernel one CTA per (image, layer), dense logits blocks with K % 4 == 0 (the DETR case): the 36.8 KB
+//                              block is staged by cp.async.bulk + mbarrier; under the copy the assignment (idx_q, idx_gt) is
+//                              expanded to dense per-query arrays -- target class (K-1 = "no object") and matched target box
+//                              (NaN = unmatched) -- and the L1 / GIoU terms are computed; then ONE THREAD PER QUERY ROW walks
+//                              its row (LDS.128, conflict-free): log-sum-exp, weighted NLL numerator/denominator, arg-max
+//                              (cardinality, class_error).  Per-problem partial sums, no float atomics.
+//   criterion_expand_kernel +  fallback for strided rows or K % 4 != 0: assignment expanded by a small kernel, then one warp
+//   criterion_fwd_kernel<C>    per row with the logits of 13 rows in registers (C = 32-wide column chunks).
 //   criterion_finalize_kernel  fixed-order reduction over images -> the L x 5 loss table (deterministic).
-//   criterion_bwd_kernel       dense grad_logits (softmax - onehot, scaled) and grad_boxes (analytic L1 + GIoU) from the
-//                              same dense per-query arrays: no indices, no offsets, no dependent loads.
+//   criterion_bwd_dense_kernel same staging; each thread turns its row into c * (softmax - onehot) IN PLACE and the block
+//                              leaves by cp.async.bulk stores; grad_boxes analytic (L1 + GIoU) from the dense per-query
+//                              arrays: no indices, no offsets, no dependent loads.  Fallback: criterion_bwd_kernel<vec>.
 #include <math_constants.h>
 
 #include "common.cuh"

@@ -1,6 +1,6 @@
 """SetCriterion -- same constructor, forward signature, `empty_weight` buffer and 25 output keys as the reference
-(detr/loss.py:18-231), executed as: 1 matcher launch + 3 criterion launches for ALL decoder layers (forward) and
-1 launch (backward), with no host synchronisation and no CPU-index -> CUDA-index copies.
+(detr/loss.py:18-231), executed as: 1 matcher launch + 2 criterion launches for ALL decoder layers (forward; 3 for strided
+or K % 4 != 0 logits) and 1 launch (backward), with no host synchronisation and no CPU-index -> CUDA-index copies.
 """
 from __future__ import annotations
 
