@@ -57,25 +57,61 @@ def attention_forward(q, k, v, key_padding_mask=None, attention_mask=None, dropo
 
 
 def attention_backward(d_out, q, k, v, out, lse, key_padding_mask=None, attention_mask=None, dropout_p: float = 0.0,
-                       seed: int = 0, seed_tensor: Optional[torch.Tensor] = None):
-    """Raw backward launches -> (dq, dk, dv) bf16 with the shapes of q, k, v."""
+                       seed: int = 0, seed_tensor: Optional[torch.Tensor] = None, outs: Optional[tuple] = None):
+    """Raw backward launches -> (dq, dk, dv) bf16 with the shapes of q, k, v.  `outs`: caller-provided (dq, dk, dv) bf16
+    buffers (channel stride 1, 16-byte aligned, row / batch strides multiples of 8 -- e.g. the two halves of one (B, L, 2C)
+    gradient of a fused q/k projection)."""
     B, L, C = q.shape
     S = k.shape[1]
     nh = C // HEAD_DIM
     q, k, v, out, d_out = _tma_ok(q), _tma_ok(k), _tma_ok(v), _tma_ok(out), _tma_ok(d_out)
     kpm = _mask_bytes(key_padding_mask, (B, S), "key_padding_mask")
     am = _mask_bytes(attention_mask, (L, S), "attention_mask")
-    dq = torch.empty(B, L, C, dtype=torch.bfloat16, device=q.device)
-    dkv = torch.empty(2, B, S, C, dtype=torch.bfloat16, device=q.device)
+    if outs is None:
+        dq = torch.empty(B, L, C, dtype=torch.bfloat16, device=q.device)
+        dkv = torch.empty(2, B, S, C, dtype=torch.bfloat16, device=q.device)
+        dk, dv = dkv[0], dkv[1]
+    else:
+        dq, dk, dv = outs
+        for t, n in ((dq, L), (dk, S), (dv, S)):
+            if (t.dtype != torch.bfloat16 or tuple(t.shape) != (B, n, C) or t.stride(2) != 1 or t.data_ptr() % 16
+                    or t.stride(0) % 8 or t.stride(1) % 8):
+                raise ValueError("attention_backward: `outs` must be bf16 (B, rows, C) buffers with channel stride 1, 16-byte aligned")
     delta = torch.empty(B, nh, L, dtype=torch.float32, device=q.device)
     dq_part = torch.empty(_lib.load().detr_attention_bwd_workspace_floats(B, nh, L, S), dtype=torch.float32, device=q.device)
     st = lambda t: (t.data_ptr(), t.stride(0), t.stride(1))
     _lib.call(
         "detr_attention_bwd_bf16",
-        *st(q), *st(k), *st(v), *st(out), *st(d_out), lse.data_ptr(), delta.data_ptr(), dq_part.data_ptr(), *st(dq), *st(dkv[0]), *st(dkv[1]),
+        *st(q), *st(k), *st(v), *st(out), *st(d_out), lse.data_ptr(), delta.data_ptr(), dq_part.data_ptr(), *st(dq), *st(dk), *st(dv),
         _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0, _lib.ptr(am), B, nh, L, S, float(dropout_p),
         int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_tensor), _lib.stream_ptr(), tag=(B, nh, L, S))
-    return dq, dkv[0], dkv[1]
+    return dq, dk, dv
+
+
+class _FlashAttentionQK(torch.autograd.Function):
+    """Self-attention on the output of ONE fused q/k projection: qk (B, L, 2C), q = qk[..., :C], k = qk[..., C:].  The kernels
+    take the two halves as strided views in both directions: backward writes dq and dk straight into the halves of one
+    (B, L, 2C) buffer.  (With q and k as autograd slices every layer paid two zero-fills, two slice copies and one add of
+    (B, L, 2C) in backward.)"""
+
+    @staticmethod
+    def forward(ctx, qk, v, key_padding_mask, attention_mask, dropout_p, seed, seed_tensor):
+        C = qk.shape[-1] // 2
+        out, lse = attention_forward(qk[..., :C], qk[..., C:], v, key_padding_mask, attention_mask, dropout_p, seed, seed_tensor)
+        ctx.save_for_backward(qk, v, out, lse, key_padding_mask, attention_mask, seed_tensor)
+        ctx.dropout_p, ctx.seed = dropout_p, seed
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qk, v, out, lse, kpm, am, seed_tensor = ctx.saved_tensors
+        B, L, C2 = qk.shape
+        C = C2 // 2
+        dqk = torch.empty(B, L, C2, dtype=torch.bfloat16, device=qk.device)
+        dv = torch.empty(B, v.shape[1], C, dtype=torch.bfloat16, device=qk.device)
+        attention_backward(d_out, qk[..., :C], qk[..., C:], v, out, lse, kpm, am, ctx.dropout_p, ctx.seed, seed_tensor,
+                           outs=(dqk[..., :C], dqk[..., C:], dv))
+        return dqk.to(qk.dtype), dv.to(v.dtype), None, None, None, None, None
 
 
 class _FlashAttention(torch.autograd.Function):
@@ -106,6 +142,18 @@ def flash_attention(q, k, v, key_padding_mask: Optional[torch.Tensor] = None,
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     st = _STEP_TENSOR if (dropout_p > 0.0 and _STEP_TENSOR is not None and _STEP_TENSOR.device == q.device) else None
     return _FlashAttention.apply(q, k, v, key_padding_mask, attention_mask, float(dropout_p), int(seed or 0), st)
+
+
+def flash_attention_qk(qk, v, key_padding_mask: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
+                       dropout_p: float = 0.0, seed: Optional[int] = None) -> torch.Tensor:
+    """`flash_attention(qk[..., :C], qk[..., C:], v, ...)` for the (B, L, 2C) output of a fused q/k projection, as one autograd
+    node (see _FlashAttentionQK)."""
+    if qk.dim() != 3 or qk.shape[-1] % 2 or v.shape[-1] * 2 != qk.shape[-1]:
+        raise ValueError("flash_attention_qk: qk must be (B, L, 2C) and v (B, S, C)")
+    if dropout_p > 0.0 and seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    st = _STEP_TENSOR if (dropout_p > 0.0 and _STEP_TENSOR is not None and _STEP_TENSOR.device == qk.device) else None
+    return _FlashAttentionQK.apply(qk, v, key_padding_mask, attention_mask, float(dropout_p), int(seed or 0), st)
 
 
 _STEP_TENSOR: Optional[torch.Tensor] = None

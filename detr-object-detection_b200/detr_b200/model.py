@@ -22,7 +22,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .attention import HEAD_DIM, flash_attention
+from .attention import HEAD_DIM, flash_attention, flash_attention_qk
 from .rowops import (ShadowedLinears, fused_epilogues_enabled, layer_norm_add, linear, linear_dropout_add, linear_gelu_dropout,
                      stacked_linear)
 
@@ -103,19 +103,24 @@ class ScaledDotProductAttention(nn.Module):
         (key_proj(key), value_proj(value)) computed by the caller (the decoder projects the encoder memory for all its
         layers in one GEMM), `key` / `value` are then ignored."""
         C = self.hidden_size
+        qk = None
         if projected_kv is not None:
             q = self._lin(query, "query")
             k, v = projected_kv
         elif key is query:
             # self-attention: one GEMM for both projections; q/k are strided views the TMA descriptors take as they are
             qk = self._lin(query, "qk")
-            q, k = qk[..., :C], qk[..., C:]
         else:
             q, k = self._lin(query, "query"), self._lin(key, "key")
         if projected_kv is None:
             v = self._lin(value, "value")
         p_drop = self.dropout_attn.p if self.training else 0.0
-        y = flash_attention(q, k, v, key_padding_mask, attention_mask, p_drop)
+        if qk is not None and qk.stride(2) == 1 and qk.stride(1) % 8 == 0 and qk.stride(0) % 8 == 0 and qk.data_ptr() % 16 == 0:
+            y = flash_attention_qk(qk, v, key_padding_mask, attention_mask, p_drop)
+        else:
+            if qk is not None:
+                q, k = qk[..., :C], qk[..., C:]
+            y = flash_attention(q, k, v, key_padding_mask, attention_mask, p_drop)
         if residual is not None and fused_epilogues_enabled(y):
             w16, b16 = self._shadows.get((self._skey, "output")) if self._shadows is not None else (None, None)
             return linear_dropout_add(y, residual, self.output_proj, self.dropout.p if self.training else 0.0, w16, b16)
