@@ -213,6 +213,7 @@ struct LnParams {
     int rows, C; float eps;
     // backward
     const void* dy; const void* dy2; void* dx;
+    const void* dres;   // optional gradient of the residual branch that bypasses the LayerNorm (x's dtype, contiguous rows): dx += dres
     float* partial; float* dgamma; float* dbeta; unsigned* counters;
 };
 
@@ -280,6 +281,11 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnParams p) {
         c1 = warp_sum(c1) / (float)C;
         c2 = warp_sum(c2) / (float)C;
         _Pragma("unroll") for (int i = 0; i < K; ++i) d[i] = rs * (d[i] - c2 - x[i] * c1);
+        if (p.dres) {   // x also feeds the block's residual add: its gradient arrives here instead of in a separate add kernel
+            float e[KA];
+            load_row<TX>(reinterpret_cast<const TX*>(p.dres) + (int64_t)r * C, lane, K, e);
+            _Pragma("unroll") for (int i = 0; i < K; ++i) d[i] += e[i];
+        }
         store_row<TX>(reinterpret_cast<TX*>(p.dx) + (int64_t)r * C, lane, K, d);
     }
     // ---- dgamma / dbeta: warps -> CTA partial; fold_partials_kernel adds the CTA partials ----
@@ -334,14 +340,15 @@ extern "C" int detr_layernorm_fwd(const void* x, int x_dtype, int64_t x_ld, cons
     return 0;
 }
 
-extern "C" int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, const void* x, int x_dtype, int64_t x_ld,
+extern "C" int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, const void* dres, const void* x, int x_dtype, int64_t x_ld,
                                   const float* gamma, const float* mean, const float* rstd, void* dx, float* partial,
                                   float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* stream) {
     DETR_CHECK_ARG(rows >= 1 && C >= 32 && C % 32 == 0 && C <= 32 * kLnMaxPerLane, "layernorm_bwd: bad C=%d", C);
     DETR_CHECK_ARG(dy != nullptr || dy2 != nullptr, "layernorm_bwd: no incoming gradient");
     LnParams p{};
     p.x = x; p.x_ld = x_ld; p.gamma = gamma; p.mean = const_cast<float*>(mean); p.rstd = const_cast<float*>(rstd); p.rows = rows; p.C = C;
-    p.dy = dy; p.dy2 = dy2; p.dx = dx; p.partial = partial; p.dgamma = dgamma; p.dbeta = dbeta; p.counters = counters;
+    DETR_CHECK_ARG(((uintptr_t)dres % 16) == 0, "layernorm_bwd: dres must be 16-byte aligned");
+    p.dy = dy; p.dy2 = dy2; p.dres = dres; p.dx = dx; p.partial = partial; p.dgamma = dgamma; p.dbeta = dbeta; p.counters = counters;
     const int grid = ln_grid(rows);
     const size_t smem = (size_t)(kLnThreads / 32) * 2 * C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;

@@ -45,7 +45,7 @@ SIGNATURES = {
     "detr_colsum_bf16": [P, c_int64, c_int, c_int, P, P, P, P],
     "detr_layernorm_grid": [c_int],
     "detr_layernorm_fwd": [P, c_int, c_int64, P, P, P, c_int, c_int64, c_int64, c_int, P, P, c_int, P, P, c_int, c_int, c_float, P],
-    "detr_layernorm_bwd": [P, P, c_int, P, c_int, c_int64, P, P, P, P, P, P, P, P, c_int, c_int, P],
+    "detr_layernorm_bwd": [P, P, c_int, P, P, c_int, c_int64, P, P, P, P, P, P, P, P, c_int, c_int, P],
     "detr_epilogue_fwd": [c_int, P, c_int, P, P, c_int, c_int, c_float, ctypes.c_uint64, P, P],
     "detr_epilogue_chunks": [c_int, c_int],
     "detr_scale_cast_multi": [P, c_int, c_int, P],

@@ -178,9 +178,12 @@ class EncoderLayer(nn.Module):
         self.norm2 = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
 
     def forward(self, x: torch.Tensor, position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
-        x_attn, query = layer_norm_add(x, self.norm1, position_embedding)      # LN and "+ pos" in one kernel
+        # LN and "+ pos" in one kernel; the third output is x itself: used as the residual input, its gradient is added inside
+        # the LayerNorm backward kernel (no autograd accumulation kernel per residual branch)
+        x_attn, query, x = layer_norm_add(x, self.norm1, position_embedding, pass_x=True)
         x = self.self_attention(query, query, value=x_attn, key_padding_mask=key_padding_mask, residual=x)
-        x = self.ffn(layer_norm_add(x, self.norm2)[0], residual=x)
+        h, _, x = layer_norm_add(x, self.norm2, pass_x=True)
+        x = self.ffn(h, residual=x)
         return x
 
 
@@ -217,13 +220,14 @@ class DecoderLayer(nn.Module):
     def forward(self, x: torch.Tensor, encoded_image_tokens: torch.Tensor, object_query_embedding: torch.Tensor,
                 position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor,
                 cross_key: Optional[torch.Tensor] = None, cross_kv: Optional[tuple] = None):
-        x_attn, query = layer_norm_add(x, self.norm1, object_query_embedding)
+        x_attn, query, x = layer_norm_add(x, self.norm1, object_query_embedding, pass_x=True)
         x = self.self_attention(query, query, value=x_attn, residual=x)
-        _, query = layer_norm_add(x, self.norm2, object_query_embedding, want_y=False)
+        _, query, x = layer_norm_add(x, self.norm2, object_query_embedding, want_y=False, pass_x=True)
         key = cross_key if (cross_key is not None or cross_kv is not None) else encoded_image_tokens + position_embedding
         x = self.cross_attention(query, key, value=encoded_image_tokens, key_padding_mask=key_padding_mask, residual=x,
                                  projected_kv=cross_kv)
-        x = self.ffn(layer_norm_add(x, self.norm3)[0], residual=x)
+        h, _, x = layer_norm_add(x, self.norm3, pass_x=True)
+        x = self.ffn(h, residual=x)
         return x
 
 

@@ -234,10 +234,12 @@ class ShadowedLinears:
 class _LayerNormAdd(torch.autograd.Function):
     """(y, y2) = (LN(x), LN(x) + addend) in one kernel; y / y2 in `out_dtype`.  `addend` is fp32 (B, R, C) (any batch /
     row strides, e.g. an expanded (R, C) embedding) or None; `want_y=False` skips writing y (decoder cross-attention
-    only needs the query = LN(x) + query_embed)."""
+    only needs the query = LN(x) + query_embed).  `pass_x=True` adds a third output: x itself, to be used as the residual
+    input of the block's tail (x + f(LN(x))); the gradient that comes back through it is added to dx inside the LayerNorm
+    backward kernel instead of by a separate autograd accumulation kernel."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, addend, eps, out_dtype, want_y):
+    def forward(ctx, x, gamma, beta, addend, eps, out_dtype, want_y, pass_x=False):
         shape = x.shape
         C = shape[-1]
         x2 = x.reshape(-1, C)
@@ -264,15 +266,17 @@ class _LayerNormAdd(torch.autograd.Function):
         ctx.addend_dtype = addend.dtype if addend is not None else None
         ctx.x_dtype = x.dtype
         ctx.mark_non_differentiable()
-        return y, y2
+        return (y, y2, x) if pass_x else (y, y2)
 
     @staticmethod
-    def backward(ctx, dy, dy2):
+    def backward(ctx, dy, dy2, dres=None):
         x2, g32, stats = ctx.saved_tensors
         rows, C = x2.shape
         gs = [t for t in (dy, dy2) if t is not None]
         if not gs:
-            return None, None, None, None, None, None, None
+            return dres, None, None, None, None, None, None, None
+        if dres is not None:
+            dres = dres.to(x2.dtype).reshape(rows, C).contiguous()
         gdt = torch.float32 if any(t.dtype == torch.float32 for t in gs) else torch.bfloat16
         prep = lambda t: None if t is None else t.to(gdt).reshape(rows, C).contiguous()
         dyc, dy2c = prep(dy), prep(dy2)
@@ -280,18 +284,19 @@ class _LayerNormAdd(torch.autograd.Function):
         grid = _lib.load().detr_layernorm_grid(rows)
         partial = torch.empty(grid * 2 * C, dtype=torch.float32, device=x2.device)
         dgb = torch.empty(2, C, dtype=torch.float32, device=x2.device)
-        _lib.call("detr_layernorm_bwd", _lib.ptr(dyc), _lib.ptr(dy2c), _DT[gdt], x2.data_ptr(), _DT[x2.dtype], x2.stride(0),
+        _lib.call("detr_layernorm_bwd", _lib.ptr(dyc), _lib.ptr(dy2c), _DT[gdt], _lib.ptr(dres), x2.data_ptr(), _DT[x2.dtype], x2.stride(0),
                   g32.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), dx.data_ptr(), partial.data_ptr(),
                   dgb[0].data_ptr(), dgb[1].data_ptr(), _lib.zero_counters(x2.device).data_ptr(), rows, C, _lib.stream_ptr())
         d_add = dy2.to(ctx.addend_dtype) if (ctx.has_addend and dy2 is not None and ctx.needs_input_grad[3]) else None
-        return dx.view(ctx.shape), dgb[0], dgb[1], d_add, None, None, None
+        return dx.view(ctx.shape), dgb[0], dgb[1], d_add, None, None, None, None
 
 
-def layer_norm_add(x, norm: torch.nn.LayerNorm, addend=None, want_y: bool = True):
-    """-> (LN(x), LN(x) + addend).  bf16 outputs under bf16 autocast (what the following GEMMs consume), else x.dtype."""
+def layer_norm_add(x, norm: torch.nn.LayerNorm, addend=None, want_y: bool = True, pass_x: bool = False):
+    """-> (LN(x), LN(x) + addend[, x]).  bf16 outputs under bf16 autocast (what the following GEMMs consume), else x.dtype.
+    With `pass_x` the third output is x, to be used as the block's residual input (see _LayerNormAdd)."""
     out_dtype = torch.bfloat16 if (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16) else x.dtype
     if x.dtype not in _DT or out_dtype not in _DT:
         raise TypeError(f"layer_norm_add supports float32 / bfloat16, got {x.dtype}")
     _lib.require_cuda(x, "layer_norm_add")
     with torch.autocast("cuda", enabled=False):
-        return _LayerNormAdd.apply(x, norm.weight, norm.bias, addend, norm.eps, out_dtype, want_y)
+        return _LayerNormAdd.apply(x, norm.weight, norm.bias, addend, norm.eps, out_dtype, want_y, pass_x)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DETR_B200_ABI_VERSION 3
+#define DETR_B200_ABI_VERSION 4
 
 /* status bits (device-side, sticky) -- mirror the reference's failure modes */
 #define DETR_ST_DEGENERATE_BOX 1 /* AssertionError at detr/utils.py:87-88 */
@@ -158,9 +158,11 @@ int detr_layernorm_grid(int rows);
 int detr_layernorm_fwd(const void* x, int x_dtype, int64_t x_ld, const float* gamma, const float* beta,
                        const void* addend, int add_dtype, int64_t add_sb, int64_t add_sr, int rows_per_batch,
                        void* y, void* y2, int out_dtype, float* mean, float* rstd, int rows, int C, float eps, void* stream);
-/* Backward: dy / dy2 are the gradients of y / y2 (dtype g_dtype, contiguous rows, either may be NULL); dx has x's
- * dtype, contiguous; dgamma/dbeta float[C]; partial float[detr_layernorm_grid(rows)*2*C] scratch; counters as colsum. */
-int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, const void* x, int x_dtype, int64_t x_ld,
+/* Backward: dy / dy2 are the gradients of y / y2 (dtype g_dtype, contiguous rows, either may be NULL); dres (x's dtype,
+ * contiguous rows, may be NULL) is the gradient that reaches x through the block's residual add (x + f(LN(x)),
+ * detr/model.py:223-224,176-182) and is added to dx in the same pass; dx has x's dtype, contiguous; dgamma/dbeta float[C];
+ * partial float[detr_layernorm_grid(rows)*2*C] scratch; counters as colsum. */
+int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, const void* dres, const void* x, int x_dtype, int64_t x_ld,
                        const float* gamma, const float* mean, const float* rstd, void* dx, float* partial,
                        float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* stream);
 
