@@ -172,3 +172,28 @@ def test_attention_backward_dropout_consistency(cuda):
     assert torch.allclose(colsum_fwd, colsum_bwd, rtol=2e-2, atol=1e-3), (colsum_fwd, colsum_bwd)
     kept = (out.float()[0] > 0).float().mean().item()
     assert abs(kept - 0.75) < 0.03
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L,nh,masked", [(2, 100, 8, False), (3, 850, 8, True)])
+def test_fused_qk_node_matches_separate_projections(cuda, B, L, nh, masked):
+    """flash_attention_qk (one autograd node on the (B, L, 2C) output of a fused q/k projection, dq / dk written into the halves
+    of one gradient buffer) == flash_attention on the two slices: bitwise in forward, and in the gradients."""
+    from detr_b200.attention import flash_attention, flash_attention_qk
+    g = torch.Generator(device="cpu").manual_seed(7 * L)
+    C = nh * 32
+    qk = torch.randn(B, L, 2 * C, generator=g).to(cuda, torch.bfloat16)
+    v = torch.randn(B, L, C, generator=g).to(cuda, torch.bfloat16)
+    do = torch.randn(B, L, C, generator=g).to(cuda, torch.bfloat16)
+    kpm = None
+    if masked:
+        kpm = torch.zeros(B, L, dtype=torch.bool, device=cuda)
+        kpm[0, L - 37:] = True
+    a_qk, a_v = qk.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    ya = flash_attention_qk(a_qk, a_v, kpm, None, 0.1, seed=11)
+    ya.backward(do)
+    b_qk, b_v = qk.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    yb = flash_attention(b_qk[..., :C], b_qk[..., C:], b_v, kpm, None, 0.1, seed=11)
+    yb.backward(do)
+    assert torch.equal(ya, yb)
+    assert torch.equal(a_qk.grad, b_qk.grad) and torch.equal(a_v.grad, b_v.grad)

@@ -343,3 +343,36 @@ def test_stem_space_to_depth_matches_direct_conv(cuda):
     (y1, g1), (y0, g0) = res
     assert (y1 - y0).abs().max().item() <= 3e-2 * y0.abs().max().item()
     assert ((g1 - g0).norm() / g0.norm()).item() <= 5e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16])
+def test_fused_layernorm_passes_residual_gradient(cuda, xdt):
+    """pass_x: x comes back as a third output (the block's residual input) and the gradient that returns through it is
+    added to dx inside the LayerNorm backward kernel: x + f(LN(x)) against torch autograd in fp32."""
+    from detr_b200.rowops import layer_norm_add
+    torch.manual_seed(3)
+    B, R, C = 2, 131, 256
+    x = torch.randn(B, R, C, device=cuda).mul(1.5).to(xdt)
+    ln = torch.nn.LayerNorm(C).to(cuda)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5); ln.bias.normal_(0, 0.2)
+    w1, w2 = torch.randn(B, R, C, device=cuda), torch.randn(B, R, C, device=cuda)
+    xa = x.clone().requires_grad_(True)
+    y, y2, xres = layer_norm_add(xa, ln, None, pass_x=True)
+    assert y2 is None and xres.shape == xa.shape and xres.dtype == xa.dtype
+    out = xres.float() * w2 + y.float() * w1          # residual branch + f(LN(x))
+    out.sum().backward()
+    got = (xa.grad.float().clone(), ln.weight.grad.clone(), ln.bias.grad.clone())
+    ln.zero_grad()
+    xr = x.float().clone().requires_grad_(True)
+    (xr * w2 + torch.nn.functional.layer_norm(xr, (C,), ln.weight, ln.bias, ln.eps) * w1).sum().backward()
+    ref = (xr.grad, ln.weight.grad, ln.bias.grad)
+    for name, a, b in zip(("dx", "dgamma", "dbeta"), got, ref):
+        tol = (3e-2 if xdt == torch.bfloat16 else 2e-5) * max(1.0, b.abs().max().item())
+        assert (a - b).abs().max().item() <= tol, (name, (a - b).abs().max().item(), tol)
+    # only the residual branch is used: the gradient passes straight through
+    xb = x.clone().requires_grad_(True)
+    _, _, xres = layer_norm_add(xb, ln, None, pass_x=True)
+    (xres.float() * w2).sum().backward()
+    assert (xb.grad.float() - w2).abs().max().item() <= (2e-2 if xdt == torch.bfloat16 else 0.0) * w2.abs().max().item()
