@@ -162,6 +162,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128, tmem_acc = tmem_base + 256 /* 2 x (dK 32 | dV 32) */,
                    tmem_dq = tmem_base + 384 /* 3 x 32 */;
+    pdl_wait();      // launched programmatically behind the delta kernel: barrier init / TMEM allocation above overlap its tail
+    pdl_trigger();   // the reduction launches may be scheduled as SMs free up (they wait for this grid before reading the partials)
 
     if (warp >= kComputeWarps) {
         reg_dealloc<64>();   // the CTA register pool is what its own warps release: 128 x (96-64) == 512 x (104-96)
@@ -505,6 +507,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 __global__ void attention_delta_kernel(const __nv_bfloat16* __restrict__ dO, int64_t do_sb, int64_t do_sl,
                                        const __nv_bfloat16* __restrict__ O, int64_t o_sb, int64_t o_sl,
                                        float* __restrict__ delta, int B, int nh, int L) {
+    pdl_trigger();   // the main kernel's prologue may start while this grid drains; it waits before reading delta
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)B * L * nh) return;
     const int h = (int)(idx % nh);
@@ -531,6 +534,7 @@ __global__ void attention_delta_kernel(const __nv_bfloat16* __restrict__ dO, int
 // dQ[b,q,c] = scale * sum_kt part[kt][b][q][c]   (fixed summation order; 8 channels per thread)
 __global__ void attention_dq_reduce_kernel(const float* __restrict__ part, int KT, int64_t part_stride /* B*L*C */,
                                            __nv_bfloat16* __restrict__ dq, int64_t dq_sb, int64_t dq_sl, int B, int L, int C, float scale) {
+    pdl_wait();
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*L*C/8
     const int c8 = C >> 3;
     if (idx >= (int64_t)B * L * c8) return;
@@ -558,6 +562,7 @@ __global__ void attention_dq_reduce_kernel(const float* __restrict__ part, int K
 __global__ void __launch_bounds__(256) attention_dkv_reduce_kernel(const float* __restrict__ kv_part, __nv_bfloat16* __restrict__ dk,
                                                                    int64_t dk_sb, int64_t dk_sl, __nv_bfloat16* __restrict__ dv,
                                                                    int64_t dv_sb, int64_t dv_sl, int B, int nh, int L, int S, int G, float scale) {
+    pdl_wait();
     const int T = (L + kT - 1) / kT, KT = (S + kT - 1) / kT;
     const long long total = (long long)KT * nh * B * T;
     const long long n = total * (blockIdx.x + 1) / G;
@@ -662,15 +667,15 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     }
     const int64_t items = (int64_t)KT * nh * B;
     const int G = (int)(items < num_sms ? items : num_sms);   // G <= items: a CTA's pair range is never shorter than one item
-    attention_bwd_kernel<<<G, kThreads, Smem::total, st>>>(tq, tk, tv, tdo, tdqp, p);
+    launch_pdl(attention_bwd_kernel, dim3(G), dim3(kThreads), Smem::total, st, tq, tk, tv, tdo, tdqp, p);
     DETR_CHECK_LAUNCH("attention_bwd");
     if (items > G) {   // only then can a boundary between two CTAs fall inside an item
-        attention_dkv_reduce_kernel<<<G - 1, 256, 0, st>>>(p.kv_part, p.dk, dk_sb, dk_sl, p.dv, dv_sb, dv_sl, B, nh, L, S, G, p.scale);
+        launch_pdl(attention_dkv_reduce_kernel, dim3(G - 1), dim3(256), 0, st, p.kv_part, p.dk, dk_sb, dk_sl, p.dv, dv_sb, dv_sl, B, nh, L, S, G, p.scale);
         DETR_CHECK_LAUNCH("attention_dkv_reduce");
     }
     const int64_t n8 = (int64_t)B * L * (C / 8);
-    attention_dq_reduce_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
-        dq_partial, KT, (int64_t)B * L * C, reinterpret_cast<__nv_bfloat16*>(dq), dq_sb, dq_sl, B, L, C, p.scale);
+    launch_pdl(attention_dq_reduce_kernel, dim3((unsigned)((n8 + 255) / 256)), dim3(256), 0, st,
+               dq_partial, KT, (int64_t)B * L * C, reinterpret_cast<__nv_bfloat16*>(dq), dq_sb, dq_sl, B, L, C, p.scale);
     DETR_CHECK_LAUNCH("attention_dq_reduce");
     return 0;
 }

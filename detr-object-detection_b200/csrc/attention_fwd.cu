@@ -149,6 +149,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 256;
+    pdl_trigger();   // the combine launch may be scheduled as SMs free up (it waits for this grid before reading the partial slots)
 
     if (warp >= kSoftmaxWarps) {
         reg_dealloc<64>();
@@ -466,6 +467,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 //   m = max(m0, m1), l = l0 2^{(m0-m) s} + l1 2^{(m1-m) s}, O = (O0 2^{(m0-m) s} + O1 2^{(m1-m) s}) / l
 // CTA c handles the boundary between persistent CTAs c and c+1 (nothing to do when it falls on an item edge).
 __global__ void __launch_bounds__(512) attention_fwd_combine_kernel(const AttnFwdParams p, int G) {
+    pdl_wait();
     const int T = (p.S + kBN - 1) / kBN, QT = (p.L + kBM - 1) / kBM;
     const long long total = (long long)QT * p.nh * p.B * T;
     const long long n = total * (blockIdx.x + 1) / G;
@@ -602,7 +604,7 @@ extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     attention_fwd_kernel<<<G, kFwdThreads, FwdSmem::total, st>>>(tq, tk, tv, p);
     DETR_CHECK_LAUNCH("attention_fwd");
     if (items > G) {   // only then can a boundary between two CTAs fall inside an item
-        attention_fwd_combine_kernel<<<G - 1, 512, 0, st>>>(p, G);
+        launch_pdl(attention_fwd_combine_kernel, dim3(G - 1), dim3(512), 0, st, p, G);
         DETR_CHECK_LAUNCH("attention_fwd_combine");
     }
     return 0;

@@ -1,5 +1,6 @@
 // Library-level C ABI: version, per-thread error text, device check.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -12,6 +13,11 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("DETR_B200_NO_PDL"); return !(e && e[0] && e[0] != '0'); }();
+    return on;
 }
 }  // namespace detr
 

@@ -44,4 +44,26 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// A kernel launched through launch_pdl may be scheduled while its predecessor in the stream is still running (its CTAs
+// become resident as SMs free up, so launch latency and prologue overlap the predecessor's tail); it must execute
+// pdl_wait() before it touches anything the predecessor wrote -- the wait returns once the predecessor grid has completed
+// and its writes are visible.  pdl_trigger() in the predecessor allows the scheduling early; both are no-ops for kernels
+// launched the ordinary way.  DETR_B200_NO_PDL=1 turns launch_pdl into an ordinary launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 }  // namespace detr

@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(kRowThreads) criterion_fwd_dense_kernel(const 
     float4* tbox = reinterpret_cast<float4*>(p.tbox) + (int64_t)blockIdx.x * Q;
     float* lse_out = p.lse + (int64_t)blockIdx.x * Q;
 
+    pdl_trigger();   // the finalize launch may be scheduled early; it waits for this grid before reading the partial sums
     if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
     for (int q = tid; q < Q; q += kRowThreads) s_g[q] = -1;
     __syncthreads();
@@ -389,6 +390,7 @@ constexpr int kFinThreads = 256;
 __global__ void __launch_bounds__(kFinThreads) criterion_finalize_kernel(const CritParams p) {
     __shared__ float red[kFinThreads / 32][8];
     const int l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_wait();
     float acc[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int b = tid; b < p.B; b += kFinThreads) {   // one image per thread: all loads of the launch are in flight at once
         const float* s = p.partials + ((int64_t)b * p.L + l) * kPartials;
@@ -742,7 +744,7 @@ extern "C" int detr_criterion_fwd_f32(const float* logits, int64_t lg_sb, int64_
         else criterion_fwd_kernel<0><<<B * L, kCritThreads, smem, st>>>(p);
     }
     DETR_CHECK_LAUNCH("criterion_fwd");
-    criterion_finalize_kernel<<<L, kFinThreads, 0, st>>>(p);
+    launch_pdl(criterion_finalize_kernel, dim3(L), dim3(kFinThreads), 0, st, p);
     DETR_CHECK_LAUNCH("criterion_finalize");
     return 0;
 }
