@@ -91,7 +91,8 @@ class FoldTable(ctypes.Structure):
                 ("src_stride", (c_int * 3) * FOLD_MAX_TENSORS), ("dst_stride", (c_int * 3) * FOLD_MAX_TENSORS), ("n", c_int)]
 
 
-# kernels launched per C-ABI call (bench.py's gpu_launches is counted from this table)
+# kernels launched per C-ABI call (bench.py's gpu_launches is counted from this table; callers whose launch count depends on
+# the shape pass the exact number through call(..., launches=))
 KERNELS_PER_CALL = {"detr_cost_matrix_f32": 1, "detr_hungarian_match_f32": 1, "detr_lsap_f32": 1, "detr_lsap_f64": 1,
                     "detr_criterion_fwd_f32": 3, "detr_criterion_bwd_f32": 1, "detr_attention_fwd_bf16": 2,
                     "detr_attention_bwd_bf16": 4, "detr_colsum_bf16": 1, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2,
@@ -135,11 +136,22 @@ class profile:
         return {k: sorted(v)[len(v) // 2] for k, v in per.items()}
 
 
-def call(name: str, *args, tag=None) -> None:
+_NUM_SMS = {}
+
+
+def num_sms() -> int:
+    """SM count of the current device (the persistent kernels launch min(#SMs, #items) CTAs)."""
+    dev = torch.cuda.current_device()
+    if dev not in _NUM_SMS:
+        _NUM_SMS[dev] = torch.cuda.get_device_properties(dev).multi_processor_count
+    return _NUM_SMS[dev]
+
+
+def call(name: str, *args, tag=None, launches=None) -> None:
     """Invoke a launcher of the C ABI, count its kernels, raise on a non-zero return code."""
     global launch_count
     fn = getattr(load(), name)
-    launch_count += KERNELS_PER_CALL[name]
+    launch_count += KERNELS_PER_CALL[name] if launches is None else launches
     if _profile is None:
         rc = fn(*args)
     else:

@@ -52,7 +52,7 @@ def attention_forward(q, k, v, key_padding_mask=None, attention_mask=None, dropo
         q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0), v.stride(1),
         out.data_ptr(), out.stride(0), out.stride(1), lse.data_ptr(), ws.data_ptr(), _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0,
         _lib.ptr(am), B, nh, L, S, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_tensor), _lib.stream_ptr(),
-        tag=(B, nh, L, S))
+        tag=(B, nh, L, S), launches=2 if -(-L // 128) * nh * B > _lib.num_sms() else 1)   # + combine when items are split between CTAs
     return out, lse
 
 
@@ -84,7 +84,8 @@ def attention_backward(d_out, q, k, v, out, lse, key_padding_mask=None, attentio
         "detr_attention_bwd_bf16",
         *st(q), *st(k), *st(v), *st(out), *st(d_out), lse.data_ptr(), delta.data_ptr(), dq_part.data_ptr(), *st(dq), *st(dk), *st(dv),
         _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0, _lib.ptr(am), B, nh, L, S, float(dropout_p),
-        int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_tensor), _lib.stream_ptr(), tag=(B, nh, L, S))
+        int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_tensor), _lib.stream_ptr(), tag=(B, nh, L, S),
+        launches=4 if -(-S // 128) * nh * B > _lib.num_sms() else 3)   # delta, main, dQ reduction (+ dK/dV reduction when items are split)
     return dq, dk, dv
 
 

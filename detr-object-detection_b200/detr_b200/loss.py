@@ -36,7 +36,10 @@ class _CriterionFn(torch.autograd.Function):
             pt.labels.data_ptr(), pt.boxes.data_ptr(), pt.gt_off.data_ptr(), pt.match_off.data_ptr(),
             idx_q.data_ptr(), idx_gt.data_ptr(), class_weight.data_ptr(), _lib.ptr(num_boxes),
             B, L, Q, K, w[0], w[1], w[2], partials.data_ptr(), lse.data_ptr(), tgt.data_ptr(), tbox.data_ptr(),
-            wsum.data_ptr(), losses.data_ptr(), status.data_ptr(), _lib.stream_ptr())
+            wsum.data_ptr(), losses.data_ptr(), status.data_ptr(), _lib.stream_ptr(),
+            # dense logits rows with K % 4 == 0: fused expand + forward, finalize; otherwise expand, forward, finalize
+            launches=2 if (K % 4 == 0 and lg.stride(2) == K and lg.stride(0) % 4 == 0 and lg.stride(1) % 4 == 0
+                           and lg.data_ptr() % 16 == 0 and (Q * K + Q) * 4 <= 200 * 1024) else 3)
         ctx.save_for_backward(lg, bx, class_weight, lse, tgt, tbox, wsum, pt.gt_off)
         ctx.num_boxes = num_boxes
         ctx.w = w
