@@ -13,7 +13,7 @@ namespace detr {
 constexpr int kOptThreads = 256;
 
 __global__ void __launch_bounds__(kOptThreads) sumsq_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partial,
-                                                            float* __restrict__ out, unsigned* __restrict__ counter) {
+                                                            float* __restrict__ out, unsigned* __restrict__ counter, float* __restrict__ step) {
     __shared__ float red[kOptThreads / 32];
     __shared__ bool is_last;
     float acc = 0.f;
@@ -45,6 +45,9 @@ __global__ void __launch_bounds__(kOptThreads) sumsq_kernel(const float* __restr
             for (int w = 0; w < kOptThreads / 32; ++w) t += red[w];
             *out = t;
             *counter = 0;
+            // the optimizer's step counter advances only when the update will be applied (adamw_clip_kernel skips a step whose
+            // gradient norm is not finite: a faulted batch must not poison the weights and the moments)
+            if (step != nullptr && isfinite(t)) *step += 1.f;
         }
     }
 }
@@ -53,6 +56,7 @@ __global__ void __launch_bounds__(kOptThreads) adamw_clip_kernel(float* __restri
                                                                  float* __restrict__ v, int64_t n, const float* __restrict__ lr_ptr, float beta1, float beta2,
                                                                  float eps, float weight_decay, const float* __restrict__ step,
                                                                  const float* __restrict__ sumsq, float max_norm, float grad_div) {
+    if (sumsq != nullptr && !isfinite(*sumsq)) return;   // NaN / inf gradients (e.g. a faulted batch whose losses were poisoned): skip the update
     const float t = *step, lr = *lr_ptr;   // both in device memory: a captured CUDA graph follows the LR schedule and the step count
     const float bc1 = 1.f - powf(beta1, t), bc2_sqrt = sqrtf(1.f - powf(beta2, t));
     float coef = grad_div;                                      // 1 / world size folded in (data-parallel mean)
@@ -95,9 +99,9 @@ extern "C" int detr_sumsq_grid(long long n) {
     return (int)(g < 1 ? 1 : g);
 }
 
-extern "C" int detr_sumsq_f32(const float* g, long long n, float* partial, float* out, uint32_t* counter, void* stream) {
+extern "C" int detr_sumsq_f32(const float* g, long long n, float* partial, float* out, uint32_t* counter, float* step, void* stream) {
     DETR_CHECK_ARG(g != nullptr && n >= 1 && ((uintptr_t)g % 16) == 0 && partial && out && counter, "sumsq: bad arguments");
-    sumsq_kernel<<<detr_sumsq_grid(n), kOptThreads, 0, (cudaStream_t)stream>>>(g, n, partial, out, counter);
+    sumsq_kernel<<<detr_sumsq_grid(n), kOptThreads, 0, (cudaStream_t)stream>>>(g, n, partial, out, counter, step);
     DETR_CHECK_LAUNCH("sumsq");
     return 0;
 }

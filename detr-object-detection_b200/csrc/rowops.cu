@@ -382,6 +382,7 @@ extern "C" int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, 
 // chunk (row * N/8 + column/8): nothing is stored for backward, p is quantised to k/128.
 // =========================================================================================================
 #include "tc.cuh"
+#include "rowmath.cuh"
 
 namespace detr {
 
@@ -396,20 +397,6 @@ struct EwParams {
     uint32_t thr4; float scale;    // dropout: thresh * 0x01010101 (0 = off), 1 / keep
     uint64_t seed; const uint64_t* seed_ptr;
 };
-
-__device__ __forceinline__ float gelu_tanh_fwd(float a, float& t_out) {
-    const float u = 0.7978845608028654f * (a + 0.044715f * a * a * a);
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-    t_out = t;
-    return 0.5f * a * (1.f + t);
-}
-__device__ __forceinline__ float gelu_tanh_grad(float a) {
-    float t;
-    gelu_tanh_fwd(a, t);
-    const float du = 0.7978845608028654f * (1.f + 3.f * 0.044715f * a * a);
-    return 0.5f * (1.f + t) + 0.5f * a * (1.f - t * t) * du;
-}
 
 template <typename T> __device__ __forceinline__ void ld8(const T* p, float* v);
 template <> __device__ __forceinline__ void ld8<float>(const float* p, float* v) {
@@ -435,25 +422,13 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
     *reinterpret_cast<uint4*>(p) = u;
 }
 
-// keep[e] for the 8 elements of chunk `idx8`
-__device__ __forceinline__ void ew_keep8(uint32_t key, uint32_t idx8, uint32_t thr4, bool* keep) {
-    uint32_t st = tc::dropout_group_state(key, idx8);
-    const uint32_t t0 = tc::dropout_quad(st, thr4), t1 = tc::dropout_quad(st, thr4);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { keep[e] = (t0 >> (8 * e + 7)) & 1u; keep[4 + e] = (t1 >> (8 * e + 7)) & 1u; }
-}
-__device__ __forceinline__ uint32_t ew_key(const EwParams& p) {
-    const uint64_t s = p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull);
-    return tc::mix32((uint32_t)s ^ tc::mix32((uint32_t)(s >> 32) + 0x9E3779B9u));
-}
-
 constexpr int kEwThreads = 256;
 
 template <int MODE, typename TX>
 __global__ void __launch_bounds__(kEwThreads) epilogue_fwd_kernel(const EwParams p) {
     const int64_t n8 = (int64_t)p.M * (p.N >> 3);
     const bool drop = p.thr4 != 0;
-    const uint32_t key = drop ? ew_key(p) : 0u;
+    const uint32_t key = drop ? ew_key(p.seed, p.seed_ptr) : 0u;
     for (int64_t i = (int64_t)blockIdx.x * kEwThreads + threadIdx.x; i < n8; i += (int64_t)gridDim.x * kEwThreads) {
         float y[8], o[8];
         ld8<__nv_bfloat16>(p.y + i * 8, y);
@@ -486,7 +461,7 @@ __global__ void __launch_bounds__(kCsThreads) epilogue_bwd_kernel(const EwParams
     const int c0 = blockIdx.x * kColsPerCta + lane * 8;
     const int r0 = blockIdx.y * p.rows_per_cta, r1 = min(p.M, r0 + p.rows_per_cta);
     const bool drop = p.thr4 != 0;
-    const uint32_t key = drop ? ew_key(p) : 0u;
+    const uint32_t key = drop ? ew_key(p.seed, p.seed_ptr) : 0u;
     const int n8 = p.N >> 3;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (c0 < p.N) {

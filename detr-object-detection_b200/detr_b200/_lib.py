@@ -51,7 +51,7 @@ SIGNATURES = {
     "detr_scale_cast_multi": [P, c_int, c_int, P],
     "detr_positional_encoding_f32": [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P],
     "detr_sumsq_grid": [ctypes.c_longlong],
-    "detr_sumsq_f32": [P, ctypes.c_longlong, P, P, P, P],
+    "detr_sumsq_f32": [P, ctypes.c_longlong, P, P, P, P, P],
     "detr_adamw_clip_f32": [P, P, P, P, ctypes.c_longlong, P, c_float, c_float, c_float, c_float, P, P, c_float, c_float, P],
     "detr_add_relu_mask_bf16": [P, P, P, P, ctypes.c_longlong, P],
     "detr_stem_s2d_bf16": [P, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_int, c_int, P, c_int, P],
@@ -59,8 +59,14 @@ SIGNATURES = {
     "detr_maxpool3x3s2_fwd_bf16": [P, P, P, c_int, c_int, c_int, c_int, P],
     "detr_maxpool3x3s2_bwd_bf16": [P, P, P, c_int, c_int, c_int, c_int, P],
     "detr_epilogue_bwd": [c_int, P, c_int, P, P, P, P, P, c_int, c_int, c_float, ctypes.c_uint64, P, P],
+    "detr_gemm_bf16": [P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int64, P, c_int64, P, c_int64,
+                       c_float, ctypes.c_uint64, P, P],
+    "detr_gemm_ln_bf16": [P, c_int, c_int64, P, P, c_float, P, c_int64, c_int64, c_int, c_int, P, c_int64, c_int, c_int, c_int, P, P, c_int64,
+                          P, c_int64, P, P, P, P, c_float, ctypes.c_uint64, P, P],
+    "detr_gemm_wgrad_workspace_floats": [c_int, c_int, c_int],
+    "detr_gemm_wgrad_bf16": [P, c_int64, P, c_int64, P, c_int64, c_int, c_int, c_int, c_int, P, P, P, P],
 }
-_RESTYPE = {"detr_matcher_smem_bytes": c_int64, "detr_attention_bwd_workspace_floats": c_int64,
+_RESTYPE = {"detr_gemm_wgrad_workspace_floats": c_int64, "detr_matcher_smem_bytes": c_int64, "detr_attention_bwd_workspace_floats": c_int64,
             "detr_attention_fwd_workspace_floats": c_int64}
 
 
@@ -98,6 +104,7 @@ KERNELS_PER_CALL = {"detr_cost_matrix_f32": 1, "detr_hungarian_match_f32": 1, "d
                     "detr_attention_bwd_bf16": 4, "detr_colsum_bf16": 1, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2,
                     "detr_epilogue_fwd": 1, "detr_epilogue_bwd": 1, "detr_scale_cast_multi": 1,
                     "detr_maxpool3x3s2_fwd_bf16": 1, "detr_maxpool3x3s2_bwd_bf16": 1,
+                    "detr_gemm_bf16": 1, "detr_gemm_ln_bf16": 1, "detr_gemm_wgrad_bf16": 2,
                     "detr_positional_encoding_f32": 1, "detr_sumsq_f32": 1, "detr_adamw_clip_f32": 1, "detr_add_relu_mask_bf16": 1, "detr_stem_s2d_bf16": 1}
 launch_count = 0          # kernels of libdetr_b200.so launched by this process
 _profile = None           # when a list: (name, tag, start_event, end_event) per call

@@ -499,7 +499,9 @@ def make_optimizer(model: nn.Module, lr: float = 3e-4, lr_backbone_scale: float 
     inner = model.module if hasattr(model, "module") else model
     bb = [p for n, p in inner.named_parameters() if n.startswith("backbone.") and p.requires_grad]
     rest = [p for n, p in inner.named_parameters() if not n.startswith("backbone.") and p.requires_grad]
-    groups = [{"params": rest, "lr": lr}, {"params": bb, "lr": lr * lr_backbone_scale}]
+    # group order as the reference (detr/train.py:172-181: backbone first), so optimizer state_dicts and
+    # `backbone_lr, transformer_lr = scheduler.get_last_lr()` line up
+    groups = [{"params": bb, "lr": lr * lr_backbone_scale}, {"params": rest, "lr": lr}]
     return torch.optim.AdamW(groups, lr=lr, weight_decay=weight_decay, fused=fused, capturable=capturable)
 
 
@@ -607,10 +609,11 @@ class FlatAdamW:
     def step(self, max_norm: float, grad_div: float = 1.0) -> None:
         """One update from the gradients in `flat_g` (scaled by grad_div, e.g. 1 / world size, then clipped to max_norm)."""
         from . import _lib
-        self.step_t.add_(1.0)
         st = _lib.stream_ptr()
+        # the sumsq launch also advances the step counter -- unless the gradient norm is not finite, in which case the AdamW
+        # launches below leave parameters and moments untouched (a faulted batch is skipped, not applied)
         _lib.call("detr_sumsq_f32", self.flat_g.data_ptr(), self.total, self.partial.data_ptr(), self.sumsq.data_ptr(),
-                  self.counter.data_ptr(), st)
+                  self.counter.data_ptr(), self.step_t.data_ptr(), st)
         for gi, (g, (start, n)) in enumerate(zip(self.opt.param_groups, self.ranges)):
             if n == 0:
                 continue
@@ -635,7 +638,8 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model: nn.Module, criterion: nn.Module, optimizer, example: Dict, gt_cap: int = 100,
-                 autocast_dtype=torch.bfloat16, max_grad_norm: float = 1.0, warmup: int = 3, flat_optimizer: bool = True):
+                 autocast_dtype=torch.bfloat16, max_grad_norm: float = 1.0, warmup: int = 3, flat_optimizer: bool = True,
+                 restore_state: bool = True, check_faults: bool = True):
         from . import attention
         from .targets import StaticTargets
         import torch.distributed as dist
@@ -660,7 +664,11 @@ class GraphedTrainStep:
             self.params = self.fopt.params
             self.flat, self.flat_views = self.fopt.flat_g, self.fopt.grad_views
         self.load(example)
-        # warm-up on a side stream (allocator, cuDNN autotune, lazy attribute setup), then capture
+        # The warm-up iterations below are REAL optimizer steps (they have to be: allocator, cuDNN autotune, lazy attributes):
+        # snapshot parameters, buffers and optimizer state first and put them back after the capture, so that training starts
+        # from exactly the state the caller handed in (loss-curve parity with detr/train.py from init or from a checkpoint).
+        snap = self._snapshot_state() if restore_state else None
+        # warm-up on a side stream, then capture
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -680,6 +688,43 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
             self._update()
         self.own_launches_per_step = _lib.launch_count - l0   # kernels of libdetr_b200.so inside one replay of both graphs
+        if snap is not None:
+            self._restore_state(snap)
+        # device fault word of the matcher / criterion, read back asynchronously after every step and checked one step late
+        self.check_faults = check_faults
+        self._fault_host = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._fault_event = [None, None]
+        self._fault_i = 0
+        self.skipped_steps = 0
+
+    def _snapshot_state(self):
+        with torch.no_grad():
+            snap = {"params": self.fopt.flat_p.clone() if self.fopt is not None else [q.detach().clone() for q in self.params],
+                    "buffers": [(b, b.detach().clone()) for b in self.model.buffers()],
+                    "opt": {id(v): v.detach().clone() for st in self.opt.state.values() for v in st.values() if torch.is_tensor(v)}}
+            if self.fopt is not None:
+                snap["flat"] = (self.fopt.flat_m.clone(), self.fopt.flat_v.clone(), self.fopt.step_t.clone())
+        return snap
+
+    def _restore_state(self, snap) -> None:
+        """In place (the captured graphs hold the addresses): parameters, buffers, moments, step counts, dropout step."""
+        with torch.no_grad():
+            if self.fopt is not None:
+                self.fopt.flat_p.copy_(snap["params"])
+                m, v, t = snap["flat"]
+                self.fopt.flat_m.copy_(m); self.fopt.flat_v.copy_(v); self.fopt.step_t.copy_(t)
+            else:
+                for q, q0 in zip(self.params, snap["params"]):
+                    q.copy_(q0)
+            for b, b0 in snap["buffers"]:
+                b.copy_(b0)
+            for st in self.opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.copy_(snap["opt"][id(v)]) if id(v) in snap["opt"] else v.zero_()   # state created by the warm-up: back to zero
+            self.step_counter.zero_()
+            self.loss.zero_()
+        torch.cuda.synchronize()
 
     # -- pieces -------------------------------------------------------------------------------------------
     def _forward_backward(self):
@@ -781,9 +826,44 @@ class GraphedTrainStep:
             self.targets.num_boxes.copy_((t / self.world).clamp_(min=1.0))
         return (batch["image"].numel() * batch["image"].element_size() + 8 * self.heights.numel() + self.targets.bytes_per_update())
 
+    def _status_tensor(self):
+        m = getattr(self.criterion, "matcher", None)
+        return m.status_tensor(self.dev) if hasattr(m, "status_tensor") else None
+
+    def poll_faults(self, wait: bool = False) -> None:
+        """Raise the reference's exception (detr/utils.py:87-88 AssertionError, SciPy's ValueError) for a data fault recorded
+        by an EARLIER step whose status read-back has completed (`wait=True`: block for the latest one).  The faulty step's
+        update was skipped on the device (non-finite gradient norm) and the status word has been cleared, so training can
+        continue past the exception if the caller chooses to."""
+        from .matcher import raise_for_status
+        for i in (0, 1):
+            ev = self._fault_event[i]
+            if ev is not None and (wait or ev.query()):
+                ev.synchronize()
+                self._fault_event[i] = None
+                bits = int(self._fault_host[i][0])
+                if bits:
+                    self.skipped_steps += 1
+                    raise_for_status(bits)
+
     def step(self) -> torch.Tensor:
-        """One optimizer step on whatever `load()` put in the static buffers. Returns the (device) loss scalar."""
+        """One optimizer step on whatever `load()` put in the static buffers. Returns the (device) loss scalar.
+        A data fault (degenerate box, NaN cost, bad label) poisons that step's losses with NaN; the optimizer kernels then
+        skip the update, the status word is read back asynchronously, cleared, and the fault is raised by the NEXT
+        `step()` / `poll_faults()` call -- no host synchronisation on the hot path, no sticky poisoning of later steps."""
+        if self.check_faults:
+            self.poll_faults()
         self.graph_a.replay()
+        st = self._status_tensor() if self.check_faults else None
+        if st is not None:
+            i = self._fault_i
+            if self._fault_event[i] is not None:          # slot still in flight (two steps ago): it has long completed
+                self.poll_faults(wait=True)
+            self._fault_host[i].copy_(st, non_blocking=True)
+            st.zero_()
+            self._fault_event[i] = torch.cuda.Event()
+            self._fault_event[i].record(torch.cuda.current_stream())
+            self._fault_i = 1 - i
         self._allreduce()
         if self.fopt is not None:
             self.fopt.sync_lr()

@@ -55,19 +55,47 @@ def pack_targets(gt_labels: Sequence[torch.Tensor], gt_boxes: Sequence[torch.Ten
     return PackedTargets(labels, boxes, offs[0], offs[1], counts, n_match, num_queries)
 
 
+class _PinnedRing:
+    """`depth` pinned host staging tensors used round robin for async H2D copies.  A slot is rewritten only after the
+    copy that last read it has executed (an event recorded behind that copy is synchronised first), so the host may
+    run any number of steps ahead of the device without tearing a batch that is still waiting in the stream."""
+
+    def __init__(self, shape, dtype, device: torch.device, depth: int = 3, fill=0):
+        self.cuda = device.type == "cuda"
+        self.slots = [torch.full(shape, fill, dtype=dtype) for _ in range(depth)]
+        if self.cuda:
+            self.slots = [t.pin_memory() for t in self.slots]
+        self.events = [None] * depth
+        self.i = -1
+
+    def next(self) -> torch.Tensor:
+        self.i = (self.i + 1) % len(self.slots)
+        if self.events[self.i] is not None:
+            self.events[self.i].synchronize()
+        return self.slots[self.i]
+
+    def submit(self, dst: torch.Tensor) -> None:
+        """Copy the slot handed out by the last `next()` into `dst` on the current stream."""
+        dst.copy_(self.slots[self.i], non_blocking=True)
+        if self.cuda:
+            if self.events[self.i] is None:
+                self.events[self.i] = torch.cuda.Event()
+            self.events[self.i].record(torch.cuda.current_stream())
+
+
 class StaticTargets:
     """Packed targets in FIXED device buffers (capacity `cap` boxes per image) so that a CUDA graph captured once can
     be replayed on new ground truth: `update()` repacks on the host into pinned staging and issues async H2D copies;
-    the kernels read the actual per-image counts from the device offsets."""
+    the kernels read the actual per-image counts from the device offsets.  The staging is a ring guarded by events
+    (`_PinnedRing`): `update()` / `set_num_boxes()` never overwrite host memory an enqueued copy has yet to read."""
 
-    def __init__(self, batch: int, num_queries: int, cap: int, device: torch.device):
+    def __init__(self, batch: int, num_queries: int, cap: int, device: torch.device, depth: int = 3):
         self.batch, self.num_queries, self.cap, self.device = batch, num_queries, cap, device
         n = batch * cap
-        self._h_labels = torch.zeros(n, dtype=torch.int64).pin_memory() if device.type == "cuda" else torch.zeros(n, dtype=torch.int64)
-        self._h_boxes = torch.zeros(n, 4).pin_memory() if device.type == "cuda" else torch.zeros(n, 4)
-        self._h_offs = torch.zeros(2, batch + 1, dtype=torch.int32)
-        self._h_offs = self._h_offs.pin_memory() if device.type == "cuda" else self._h_offs
-        self._h_nb = torch.ones(1).pin_memory() if device.type == "cuda" else torch.ones(1)
+        self._r_labels = _PinnedRing((n,), torch.int64, device, depth)
+        self._r_boxes = _PinnedRing((n, 4), torch.float32, device, depth)
+        self._r_offs = _PinnedRing((2, batch + 1), torch.int32, device, depth)
+        self._r_nb = _PinnedRing((1,), torch.float32, device, depth, fill=1)
         self.labels = torch.zeros(n, dtype=torch.int64, device=device)
         self.boxes = torch.zeros(n, 4, device=device)
         self.offs = torch.zeros(2, batch + 1, dtype=torch.int32, device=device)
@@ -79,27 +107,29 @@ class StaticTargets:
         counts = [int(l.shape[0]) for l in gt_labels]
         if len(counts) != self.batch or max(counts, default=0) > self.cap:
             raise ValueError(f"StaticTargets(batch={self.batch}, cap={self.cap}) cannot hold counts {counts}")
+        h_labels, h_boxes, h_offs = self._r_labels.next(), self._r_boxes.next(), self._r_offs.next()
         o = 0
         for l, b in zip(gt_labels, gt_boxes):
             m = l.shape[0]
-            self._h_labels[o:o + m] = l.reshape(-1)
-            self._h_boxes[o:o + m] = b.reshape(-1, 4)
+            h_labels[o:o + m] = l.reshape(-1)
+            h_boxes[o:o + m] = b.reshape(-1, 4)
             o += m
         c = torch.tensor(counts, dtype=torch.int32)
-        self._h_offs[0, 1:] = c.cumsum(0)
-        self._h_offs[1, 1:] = c.clamp(max=self.num_queries).cumsum(0)
-        self.labels.copy_(self._h_labels, non_blocking=True)
-        self.boxes.copy_(self._h_boxes, non_blocking=True)
-        self.offs.copy_(self._h_offs, non_blocking=True)
+        h_offs[0, 1:] = c.cumsum(0)
+        h_offs[1, 1:] = c.clamp(max=self.num_queries).cumsum(0)
+        self._r_labels.submit(self.labels)
+        self._r_boxes.submit(self.boxes)
+        self._r_offs.submit(self.offs)
         self.actual_counts = counts
         return o
 
     def set_num_boxes(self, value: float) -> None:
-        self._h_nb[0] = max(float(value), 1.0)
-        self.num_boxes.copy_(self._h_nb, non_blocking=True)
+        h = self._r_nb.next()
+        h[0] = max(float(value), 1.0)
+        self._r_nb.submit(self.num_boxes)
 
     def bytes_per_update(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self._h_labels, self._h_boxes, self._h_offs, self._h_nb))
+        return sum(r.slots[0].numel() * r.slots[0].element_size() for r in (self._r_labels, self._r_boxes, self._r_offs, self._r_nb))
 
     @property
     def packed(self) -> PackedTargets:

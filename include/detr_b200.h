@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DETR_B200_ABI_VERSION 4
+#define DETR_B200_ABI_VERSION 5
 
 /* status bits (device-side, sticky) -- mirror the reference's failure modes */
 #define DETR_ST_DEGENERATE_BOX 1 /* AssertionError at detr/utils.py:87-88 */
@@ -180,6 +180,37 @@ int detr_epilogue_chunks(int M, int N);
 int detr_epilogue_bwd(int mode, const void* g, int g_dtype, const void* y, void* dy, float* partial, float* db,
                       uint32_t* counters, int M, int N, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
 
+/* ---- tcgen05 GEMMs of the transformer's nn.Linear layers (detr/model.py:312-314,354 attention projections;
+ *      :405-411 FFN) with the surrounding row work fused in (csrc/gemm.cu) -------------------------------------- */
+/* C[M][N] = epilogue(A[M][K] . B^T): a, b bf16 row-major with row strides lda / ldb (elements); b_kn = 0: b is [N][K]
+ * (an nn.Linear weight), b_kn = 1: b is [K][N] (C = A . B, the input-gradient form dX = dY . W).  N % 32 == 0, K % 64 == 0.
+ * epilogue 0: out = acc + bias                                   (bias fp32 [N] or NULL; out_dtype 0 fp32 / 1 bf16)
+ *          1: aux = bf16(acc + bias); out = dropout(gelu_tanh(aux))          (detr/model.py:405-408; out bf16)
+ *          2: out = res + dropout(acc + bias)                    (detr/model.py:223-224,354-355,410; res has out's dtype)
+ *          3: out = acc * dropout_mask/(1-p) * gelu_tanh'(aux)   (backward of 1; no bias)
+ * dropout as detr_epilogue_*: counter-based, regenerated by the backward launches from (seed + *seed_ptr). */
+int detr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int b_kn, int M, int N, int K, int epilogue,
+                   const float* bias, void* out, int out_dtype, int64_t ldo, void* aux, int64_t ld_aux, const void* res,
+                   int64_t ld_res, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
+/* out[M][N] (bf16) = epilogue((LayerNorm(x) [+ addend]) . w[N][256]^T): the pre-LN LayerNorm and the "+ positional /
+ * query embedding" of detr/model.py:221-224,173-182 run as the PROLOGUE of the projections that consume them.  x fp32 /
+ * bf16 (x_dtype 0 / 1) [M][256] row stride ldx; output columns < n_pos_end (a multiple of 128) are computed from
+ * LN(x) + addend, the others from LN(x) (q|k|v in one launch: n_pos_end = 512).  addend fp32, row of flattened row m at
+ * (m / rows_per_batch) * add_sb + (m % rows_per_batch) * add_sr.  epilogue 0 or 1 as above.  Optional outputs for the
+ * backward pass: a_plain / a_pos bf16 [M][256] (the two normalised operands), mean / rstd float[M]. */
+int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
+                      const float* addend, int64_t add_sb, int64_t add_sr, int rows_per_batch, int n_pos_end,
+                      const void* w, int64_t ldw, int M, int N, int epilogue, const float* bias, void* out, int64_t ldo,
+                      void* aux, int64_t ld_aux, void* a_plain, void* a_pos, float* mean, float* rstd, float dropout_p,
+                      uint64_t seed, const uint64_t* seed_ptr, void* stream);
+/* Weight and bias gradients of nn.Linear: dw[N][K] (fp32, contiguous) = dy[M][N]^T . x[M][K], db[N] (optional) = column
+ * sums of dy; dy, x bf16 row-major.  Rows n >= n_switch (a multiple of 128) of dw are computed from x1 instead of x0
+ * (fused q|k|v projection: q/k rows from LN(x)+pos, v rows from LN(x)); x1 may be NULL.  Split over M with fp32
+ * partials folded in a fixed order (deterministic); workspace: detr_gemm_wgrad_workspace_floats(M, N, K) floats. */
+int64_t detr_gemm_wgrad_workspace_floats(int M, int N, int K);
+int detr_gemm_wgrad_bf16(const void* dy, int64_t ld_dy, const void* x0, int64_t ld_x0, const void* x1, int64_t ld_x1, int n_switch,
+                         int M, int N, int K, float* dw, float* db, float* workspace, void* stream);
+
 /* ---- caller-side glue: frozen-BatchNorm fold of the backbone weights (detr/model.py:427-438) ----------------- */
 /* dst[o][i][hw] = (out dtype)(src[o][i][hw] * scale[o]) for up to 64 (O, I, H*W) tensors in ONE launch; element strides
  * are given per tensor for (o, i, hw) on both sides (hw must be flattenable: stride_h == W * stride_w).  Used forward
@@ -225,9 +256,12 @@ int detr_positional_encoding_f32(const int32_t* heights, const int32_t* widths, 
  * buffers.  detr_sumsq_f32: out[0] = sum g^2 (partial float[detr_sumsq_grid(n)] scratch, counter: one zeroed uint32,
  * left zero).  detr_adamw_clip_f32 updates p, m, v in place with g scaled by grad_div * min(1, max_norm /
  * (grad_div * sqrt(*sumsq) + 1e-6)) (sumsq NULL or max_norm <= 0: no clipping); `step` (1-based step count, for the bias
- * correction) and `lr` are DEVICE floats, so a captured CUDA graph follows the step count and the LR schedule. */
+ * correction) and `lr` are DEVICE floats, so a captured CUDA graph follows the step count and the LR schedule.
+ * Fault gating: detr_sumsq_f32 adds 1 to *step (optional) only when the sum is finite, and detr_adamw_clip_f32 leaves p, m, v
+ * untouched when *sumsq is NaN / inf -- a batch whose losses were poisoned by the device status word (degenerate box, NaN
+ * cost) is skipped instead of destroying the weights; the reference raises at that point (detr/utils.py:87-88). */
 int detr_sumsq_grid(long long n);
-int detr_sumsq_f32(const float* g, long long n, float* partial, float* out, uint32_t* counter, void* stream);
+int detr_sumsq_f32(const float* g, long long n, float* partial, float* out, uint32_t* counter, float* step, void* stream);
 int detr_adamw_clip_f32(float* p, const float* g, float* m, float* v, long long n, const float* lr, float beta1, float beta2, float eps,
                         float weight_decay, const float* step, const float* sumsq, float max_norm, float grad_div, void* stream);
 
