@@ -504,8 +504,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 }
 
 // D[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (one thread per (b,q,h), 64-byte vector loads)
+// O_lo (optional, O's strides): the rounding residual of O written by the forward kernel; delta is then computed from O + O_lo
 __global__ void attention_delta_kernel(const __nv_bfloat16* __restrict__ dO, int64_t do_sb, int64_t do_sl,
-                                       const __nv_bfloat16* __restrict__ O, int64_t o_sb, int64_t o_sl,
+                                       const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ O_lo, int64_t o_sb, int64_t o_sl,
                                        float* __restrict__ delta, int B, int nh, int L) {
     pdl_trigger();   // the main kernel's prologue may start while this grid drains; it waits before reading delta
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -515,19 +516,25 @@ __global__ void attention_delta_kernel(const __nv_bfloat16* __restrict__ dO, int
     const int q = (int)(bq % L), b = (int)(bq / L);
     const uint4* a = reinterpret_cast<const uint4*>(dO + b * do_sb + (int64_t)q * do_sl + h * 32);
     const uint4* c = reinterpret_cast<const uint4*>(O + b * o_sb + (int64_t)q * o_sl + h * 32);
-    float acc = 0.f;
+    const uint4* cl = O_lo ? reinterpret_cast<const uint4*>(O_lo + b * o_sb + (int64_t)q * o_sl + h * 32) : nullptr;
+    float acc = 0.f, acc_lo = 0.f;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const uint4 x = a[g], y = c[g];
+        const uint4 z = cl ? cl[g] : make_uint4(0, 0, 0, 0);
         const __nv_bfloat162* xv = reinterpret_cast<const __nv_bfloat162*>(&x);
         const __nv_bfloat162* yv = reinterpret_cast<const __nv_bfloat162*>(&y);
+        const __nv_bfloat162* zv = reinterpret_cast<const __nv_bfloat162*>(&z);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float2 fx = __bfloat1622float2(xv[e]), fy = __bfloat1622float2(yv[e]);
+            const float2 fx = __bfloat1622float2(xv[e]), fy = __bfloat1622float2(yv[e]), fz = __bfloat1622float2(zv[e]);
             acc = fmaf(fx.x, fy.x, acc);
             acc = fmaf(fx.y, fy.y, acc);
+            acc_lo = fmaf(fx.x, fz.x, acc_lo);
+            acc_lo = fmaf(fx.y, fz.y, acc_lo);
         }
     }
+    acc += acc_lo;
     delta[((int64_t)b * nh + h) * L + q] = acc;
 }
 
@@ -608,7 +615,7 @@ extern "C" int64_t detr_attention_bwd_workspace_floats(int B, int nh, int L, int
 }
 
 extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
-                                       const void* v, int64_t v_sb, int64_t v_sl, const void* o, int64_t o_sb, int64_t o_sl,
+                                       const void* v, int64_t v_sb, int64_t v_sl, const void* o, int64_t o_sb, int64_t o_sl, const void* o_lo,
                                        const void* d_o, int64_t do_sb, int64_t do_sl, const float* lse, float* delta,
                                        float* dq_partial, void* dq, int64_t dq_sb, int64_t dq_sl, void* dk, int64_t dk_sb, int64_t dk_sl,
                                        void* dv, int64_t dv_sb, int64_t dv_sl, const uint8_t* key_padding_mask, int64_t kpm_sb,
@@ -633,7 +640,8 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
 
     const int64_t n = (int64_t)B * L * nh;
     attention_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(d_o), do_sb, do_sl, reinterpret_cast<const __nv_bfloat16*>(o), o_sb, o_sl, delta, B, nh, L);
+        reinterpret_cast<const __nv_bfloat16*>(d_o), do_sb, do_sl, reinterpret_cast<const __nv_bfloat16*>(o),
+        reinterpret_cast<const __nv_bfloat16*>(o_lo), o_sb, o_sl, delta, B, nh, L);
     DETR_CHECK_LAUNCH("attention_delta");
 
     Params p;

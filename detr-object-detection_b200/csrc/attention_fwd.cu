@@ -67,6 +67,9 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 
 struct AttnFwdParams {
     __nv_bfloat16* O; int64_t o_sb, o_sl;  // (B, L, nh*32): element strides of batch and row
+    __nv_bfloat16* O_lo;                   // optional, same strides: bf16(O_fp32 - bf16(O_fp32)), the rounding residual of O.  The backward
+                                           // pass computes delta = rowsum(dO * (O + O_lo)): with the rounded O alone the error of delta is common to all
+                                           // keys of a row and does not average out in dQ / dK when the attention is nearly uniform
     float* lse;                            // (B, nh, L)
     float* part;                           // [items][2 slots][128 rows][36]: unnormalised O (32), row max, row sum of split items
     const uint8_t* kpm; int64_t kpm_sb;    // key padding mask (B, S) bytes, may be null
@@ -115,6 +118,16 @@ struct FwdCursor {
 #define FWD_STAMP(ev, j) do { if (p.dbg != nullptr && lane == 0 && blockIdx.x == 0 && (j) < 32) \
     p.dbg[(warp * 32 + (j)) * 8 + (ev)] = clock64(); } while (0)
 #endif
+
+// bf16 of (o[e] * inv - what the packed bf16 words w hold): the part of the output lost to rounding
+__device__ __forceinline__ uint4 residual_bf16x8(const float (&o)[8], float inv, const uint4& w) {
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        r[j] = pack_bf16x2(o[2 * j] * inv - __uint_as_float(ww[j] << 16), o[2 * j + 1] * inv - __uint_as_float(ww[j] & 0xffff0000u));
+    return make_uint4(r[0], r[1], r[2], r[3]);
+}
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -254,7 +267,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 uint4 w;
                 w.x = pack_bf16x2(o[0] * inv, o[1] * inv); w.y = pack_bf16x2(o[2] * inv, o[3] * inv);
                 w.z = pack_bf16x2(o[4] * inv, o[5] * inv); w.w = pack_bf16x2(o[6] * inv, o[7] * inv);
-                *reinterpret_cast<uint4*>(p.O + b_ * p.o_sb + (int64_t)q_ * p.o_sl + h_ * kD + kq * 8) = w;
+                const int64_t off = b_ * p.o_sb + (int64_t)q_ * p.o_sl + h_ * kD + kq * 8;
+                *reinterpret_cast<uint4*>(p.O + off) = w;
+                if (p.O_lo != nullptr) *reinterpret_cast<uint4*>(p.O_lo + off) = residual_bf16x8(o, inv, w);
                 // natural-log LSE of the scaled scores: m/sqrt(d) + ln(l).  A row whose keys are all masked is flagged
                 // with +inf: the backward kernel then skips it.
                 if (kq == 0)
@@ -490,7 +505,13 @@ __global__ void __launch_bounds__(512) attention_fwd_combine_kernel(const AttnFw
     w.y = pack_bf16x2((x0.z * a0 + y0.z * a1) * inv, (x0.w * a0 + y0.w * a1) * inv);
     w.z = pack_bf16x2((x1.x * a0 + y1.x * a1) * inv, (x1.y * a0 + y1.y * a1) * inv);
     w.w = pack_bf16x2((x1.z * a0 + y1.z * a1) * inv, (x1.w * a0 + y1.w * a1) * inv);
-    *reinterpret_cast<uint4*>(p.O + b * p.o_sb + (int64_t)q * p.o_sl + h * kD + g * 8) = w;
+    const int64_t off = b * p.o_sb + (int64_t)q * p.o_sl + h * kD + g * 8;
+    *reinterpret_cast<uint4*>(p.O + off) = w;
+    if (p.O_lo != nullptr) {
+        const float o[8] = {x0.x * a0 + y0.x * a1, x0.y * a0 + y0.y * a1, x0.z * a0 + y0.z * a1, x0.w * a0 + y0.w * a1,
+                            x1.x * a0 + y1.x * a1, x1.y * a0 + y1.y * a1, x1.z * a0 + y1.z * a1, x1.w * a0 + y1.w * a1};
+        *reinterpret_cast<uint4*>(p.O_lo + off) = residual_bf16x8(o, inv, w);
+    }
     if (g == 0)
         p.lse[((int64_t)b * p.nh + h) * p.L + q] = m == kMaskedScore ? CUDART_INF_F : (m * p.scale_log2 + log2f(l)) * 0.6931471805599453f;
 }
@@ -563,7 +584,7 @@ extern "C" int64_t detr_attention_fwd_workspace_floats(int B, int nh, int L, int
 }
 
 extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
-                                       const void* v, int64_t v_sb, int64_t v_sl, void* o, int64_t o_sb, int64_t o_sl,
+                                       const void* v, int64_t v_sb, int64_t v_sl, void* o, int64_t o_sb, int64_t o_sl, void* o_lo,
                                        float* lse, float* workspace, const uint8_t* key_padding_mask, int64_t kpm_sb,
                                        const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
                                        uint64_t seed, const uint64_t* seed_ptr, void* stream) {
@@ -577,7 +598,9 @@ extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     if (int rc = make_head_tile_map(&tk, k, C, S, B, k_sl, k_sb, kBN, "attention_fwd(K)")) return rc;
     if (int rc = make_head_tile_map(&tv, v, C, S, B, v_sl, v_sb, kBN, "attention_fwd(V)")) return rc;
     AttnFwdParams p;
-    p.O = reinterpret_cast<__nv_bfloat16*>(o); p.o_sb = o_sb; p.o_sl = o_sl; p.lse = lse; p.part = workspace;
+    DETR_CHECK_ARG(((uintptr_t)o_lo % 16) == 0, "attention_fwd: O_lo must be 16-byte aligned");
+    p.O = reinterpret_cast<__nv_bfloat16*>(o); p.o_sb = o_sb; p.o_sl = o_sl; p.O_lo = reinterpret_cast<__nv_bfloat16*>(o_lo);
+    p.lse = lse; p.part = workspace;
     p.kpm = key_padding_mask; p.kpm_sb = kpm_sb; p.amask = attention_mask;
     p.B = B; p.nh = nh; p.L = L; p.S = S;
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)kD);

@@ -60,16 +60,38 @@ struct EpiParams {
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
 
-// dropout of 32 consecutive columns starting at n0 of row m (chunk index as in epilogue_bwd_kernel: m * N/8 + n/8)
-__device__ __forceinline__ void drop32(const EpiParams& e, uint32_t key, int m, int n0, float* x) {
-    const uint32_t base = (uint32_t)m * (uint32_t)(e.N >> 3) + (uint32_t)(n0 >> 3);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        bool keep[8];
-        ew_keep8(key, base + j, e.thr4, keep);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[8 * j + i] = keep[i] ? x[8 * j + i] * e.scale : 0.f;
-    }
+// ---- epilogue math: packed fp32x2 (two columns per FMA-pipe instruction), one MUFU tanh per element -----------------------
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+// hs * (1 + tanh(u(a))) * a with hs = 0.5 [* dropout scale]: gelu_tanh(a) (detr/model.py:406), u = a * (c1 + c2 a^2)
+__device__ __forceinline__ float2 gelu2(float2 a, float hs) {
+    const float2 a2 = __fmul2_rn(a, a);
+    const float2 u = __fmul2_rn(__ffma2_rn(a2, f2(0.0356774081f), f2(0.7978845608f)), a);
+    const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+    const float2 ha = __fmul2_rn(a, f2(hs));
+    return __ffma2_rn(ha, t, ha);
+}
+// hs * d/dy [y (1 + tanh(u(y)))] = hs * (1 + t + y u'(y) (1 - t^2))
+__device__ __forceinline__ float2 gelu_grad2(float2 y, float hs) {
+    const float2 y2 = __fmul2_rn(y, y);
+    const float2 u = __fmul2_rn(__ffma2_rn(y2, f2(0.0356774081f), f2(0.7978845608f)), y);
+    const float2 t = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+    const float2 r = __fmul2_rn(__ffma2_rn(y2, f2(0.1070322243f), f2(0.7978845608f)), y);   // y * u'(y)
+    const float2 rt = __fmul2_rn(r, t);
+    const float2 q = __ffma2_rn(make_float2(-rt.x, -rt.y), t, r);                            // r (1 - t^2)
+    return __ffma2_rn(__fadd2_rn(t, q), f2(hs), f2(hs));
+}
+// keep masks of the 8 elements of chunk idx8 (same generator and indexing as ew_keep8 / epilogue_bwd_kernel): byte e of t0 / t1
+// has bit 7 set iff element e / 4 + e is kept
+__device__ __forceinline__ void drop_quads(uint32_t key, uint32_t idx8, uint32_t thr4, uint32_t& t0, uint32_t& t1) {
+    uint32_t st = dropout_group_state(key, idx8);
+    t0 = dropout_quad(st, thr4);
+    t1 = dropout_quad(st, thr4);
+}
+__device__ __forceinline__ void mask_packed8(uint32_t (&w)[4], uint32_t t0, uint32_t t1) {
+    w[0] &= dropout_mask_bf16x2<0>(t0); w[1] &= dropout_mask_bf16x2<1>(t0);
+    w[2] &= dropout_mask_bf16x2<0>(t1); w[3] &= dropout_mask_bf16x2<1>(t1);
 }
 
 // 16-byte chunk c (0..7) of row r (0..31) of a SWIZZLE_128B staging box
@@ -92,6 +114,7 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& e, uint32_t key, in
                                             const uint32_t (&v)[32]) {
     constexpr bool kOutF32 = sizeof(TO) == 4;
     const bool drop = e.thr4 != 0;
+    const uint32_t idx8 = (uint32_t)m * (uint32_t)(e.N >> 3) + (uint32_t)(n0 >> 3);   // dropout chunk index of the first 8 columns
     float x[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
@@ -99,34 +122,62 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& e, uint32_t key, in
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0) + j);
-            x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
+            const float2 lo = __fadd2_rn(make_float2(x[4 * j], x[4 * j + 1]), make_float2(b.x, b.y));
+            const float2 hi = __fadd2_rn(make_float2(x[4 * j + 2], x[4 * j + 3]), make_float2(b.z, b.w));
+            x[4 * j] = lo.x; x[4 * j + 1] = lo.y; x[4 * j + 2] = hi.x; x[4 * j + 3] = hi.y;
         }
     }
     if (EPI == EPI_GELU) {
         // the pre-activation is kept in bf16 for the backward pass (box 0); the activation is computed from the rounded value
-        // so that forward and backward see the same function (box 1)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) *box_chunk(stg, r, half * 4 + j) = pack8(x + 8 * j);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { float t; x[i] = gelu_tanh_fwd(bf16_round(x[i]), t); }
-        if (drop) drop32(e, key, m, n0, x);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) *box_chunk(stg + kBoxBytes, r, half * 4 + j) = pack8(x + 8 * j);
-        return;
-    }
-    if (EPI == EPI_GELU_BWD) {   // pre-activation tile in box 1 (bf16); result (bf16) to box 0
-        if (drop) drop32(e, key, m, n0, x);
+        // so that forward and backward see the same function (box 1).  The dropout scale rides in the GELU's factor 0.5.
+        const float hs = drop ? 0.5f * e.scale : 0.5f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float y[8];
-            unpack8(*box_chunk(stg + kBoxBytes, r, half * 4 + j), y);
+            const uint4 wy = pack8(x + 8 * j);
+            *box_chunk(stg, r, half * 4 + j) = wy;
+            const uint32_t wy4[4] = {wy.x, wy.y, wy.z, wy.w};
+            uint32_t wo[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[8 * j + i] *= gelu_tanh_grad(y[i]);
-            *box_chunk(stg, r, half * 4 + j) = pack8(x + 8 * j);
+            for (int p = 0; p < 4; ++p) { const float2 o = gelu2(bf16x2_to_f2(wy4[p]), hs); wo[p] = pack_bf16x2(o.x, o.y); }
+            if (drop) { uint32_t t0, t1; drop_quads(key, idx8 + j, e.thr4, t0, t1); mask_packed8(wo, t0, t1); }
+            *box_chunk(stg + kBoxBytes, r, half * 4 + j) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
         }
         return;
     }
-    if (EPI == EPI_RES && drop) drop32(e, key, m, n0, x);
+    if (EPI == EPI_GELU_BWD) {   // pre-activation tile in box 1 (bf16); result (bf16) to box 0
+        const float hs = drop ? 0.5f * e.scale : 0.5f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 wy = *box_chunk(stg + kBoxBytes, r, half * 4 + j);
+            const uint32_t wy4[4] = {wy.x, wy.y, wy.z, wy.w};
+            uint32_t wo[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float2 g = gelu_grad2(bf16x2_to_f2(wy4[p]), hs);
+                const float2 d = __fmul2_rn(make_float2(x[8 * j + 2 * p], x[8 * j + 2 * p + 1]), g);
+                wo[p] = pack_bf16x2(d.x, d.y);
+            }
+            if (drop) { uint32_t t0, t1; drop_quads(key, idx8 + j, e.thr4, t0, t1); mask_packed8(wo, t0, t1); }
+            *box_chunk(stg, r, half * 4 + j) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+        }
+        return;
+    }
+    if (EPI == EPI_RES && drop) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t t0, t1;
+            drop_quads(key, idx8 + j, e.thr4, t0, t1);
+            float* y = x + 8 * j;
+            y[0] = __uint_as_float(__float_as_uint(y[0] * e.scale) & dropout_mask_f32<0>(t0));
+            y[1] = __uint_as_float(__float_as_uint(y[1] * e.scale) & dropout_mask_f32<1>(t0));
+            y[2] = __uint_as_float(__float_as_uint(y[2] * e.scale) & dropout_mask_f32<2>(t0));
+            y[3] = __uint_as_float(__float_as_uint(y[3] * e.scale) & dropout_mask_f32<3>(t0));
+            y[4] = __uint_as_float(__float_as_uint(y[4] * e.scale) & dropout_mask_f32<0>(t1));
+            y[5] = __uint_as_float(__float_as_uint(y[5] * e.scale) & dropout_mask_f32<1>(t1));
+            y[6] = __uint_as_float(__float_as_uint(y[6] * e.scale) & dropout_mask_f32<2>(t1));
+            y[7] = __uint_as_float(__float_as_uint(y[7] * e.scale) & dropout_mask_f32<3>(t1));
+        }
+    }
     if (kOutF32) {
         uint8_t* box = stg + half * kBoxBytes;
 #pragma unroll
@@ -175,21 +226,29 @@ __device__ __forceinline__ void epi_tile(const EpiParams& e, const CUtensorMap* 
             tma_load_2d(stg + kBoxBytes, tm_aux, ldbar, nc, mr);
         }
     }
+    // this tile's 64 bias values (two 128-byte lines) are pulled into L1 while the MMAs run: the loads in epi_chunk32 then hit
+    if (EPI != EPI_GELU_BWD && active && e.bias != nullptr && lane < 2)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(e.bias + nc + lane * 32));
     mbar_wait_sleep(acc_full, acc_parity);
     tc_fence_after();
     const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 64);
-    uint32_t v0[32], v1[32];
-    tmem_ld32(taddr, v0);
-    tmem_ld32(taddr + 32, v1);
-    tmem_ld_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(acc_empty);        // the accumulator buffer is free as soon as its values are in registers
-    if (!active) return;
-    if (kLoad) { mbar_wait_sleep(ldbar, n_ld & 1); ++n_ld; }
     const int m = mr + lane;
-    epi_chunk32<EPI, TO>(e, key, m, nc, lane, 0, stg, v0);
-    epi_chunk32<EPI, TO>(e, key, m, nc + 32, lane, 1, stg, v1);
+    // the two 32-column halves run through ONE copy of the epilogue code (rolled loop: the instruction footprint of these
+    // short-lived kernels matters more than the second TMEM load being issued a little later)
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(taddr + 32 * half, v);
+        tmem_ld_wait();
+        if (half == 1) {   // both halves are in registers: the accumulator buffer is free
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+        if (half == 0 && active && kLoad) { mbar_wait_sleep(ldbar, n_ld & 1); ++n_ld; }
+        if (active) epi_chunk32<EPI, TO>(e, key, m, nc + 32 * half, lane, half, stg, v);
+    }
+    if (!active) return;
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -343,7 +402,14 @@ struct LnGemmParams {
     __nv_bfloat16* a_plain; __nv_bfloat16* a_pos;   // optional [M][256] copies of the two A variants (the weight gradients need them)
     float* mean; float* rstd;                       // optional [M]
     int m_tiles, n_tiles, groups;                   // CTA = (row block, column group): groups column groups per row block
+    long long* dbg;                                 // optional clock64 timeline of CTA 0 (DETR_GEMM_TIMELINE builds), NULL in production
 };
+
+#ifndef DETR_GEMM_TIMELINE
+#define LN_STAMP(slot) do {} while (0)
+#else
+#define LN_STAMP(slot) do { if (p.dbg != nullptr && lane == 0 && blockIdx.x == 0) p.dbg[warp * 16 + (slot)] = clock64(); } while (0)
+#endif
 
 template <typename TX> struct RawRow;
 template <> struct RawRow<float> { float4 a, b; };
@@ -352,88 +418,115 @@ __device__ __forceinline__ void raw_load(RawRow<float>& r, const float* p) { r.a
 __device__ __forceinline__ void raw_load(RawRow<__nv_bfloat16>& r, const __nv_bfloat16* p) { r.a = *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void raw_zero(RawRow<float>& r) { r.a = make_float4(0, 0, 0, 0); r.b = r.a; }
 __device__ __forceinline__ void raw_zero(RawRow<__nv_bfloat16>& r) { r.a = make_uint4(0, 0, 0, 0); }
-__device__ __forceinline__ void raw_unpack(const RawRow<float>& r, float* v) {
-    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+// 8 values as four packed pairs
+__device__ __forceinline__ void raw_unpack(const RawRow<float>& r, float2 (&v)[4]) {
+    v[0] = make_float2(r.a.x, r.a.y); v[1] = make_float2(r.a.z, r.a.w); v[2] = make_float2(r.b.x, r.b.y); v[3] = make_float2(r.b.z, r.b.w);
 }
-__device__ __forceinline__ void raw_unpack(const RawRow<__nv_bfloat16>& r, float* v) { unpack8(r.a, v); }
+__device__ __forceinline__ void raw_unpack(const RawRow<__nv_bfloat16>& r, float2 (&v)[4]) {
+    v[0] = bf16x2_to_f2(r.a.x); v[1] = bf16x2_to_f2(r.a.y); v[2] = bf16x2_to_f2(r.a.z); v[3] = bf16x2_to_f2(r.a.w);
+}
+__device__ __forceinline__ uint4 pack4(const float2 (&y)[4]) {
+    return make_uint4(pack_bf16x2(y[0].x, y[0].y), pack_bf16x2(y[1].x, y[1].y), pack_bf16x2(y[2].x, y[2].y), pack_bf16x2(y[3].x, y[3].y));
+}
 
-// Normalise the 128-row block `mt` into the resident A tiles.  8 warps; warp w takes rows w, w+8, ..: sixteen rows whose x
-// loads are ALL issued up front (bf16: 4 registers per row; fp32: two rounds of 8 rows), the addend rows are fetched four at a
-// time one group ahead of their use.  lane = 8 consecutive channels = one 16-byte chunk: k-block lane >> 3, chunk lane & 7 of
-// the 128-byte swizzle row.
+// Normalise the 128-row block `mt` into the resident A tiles.  8 warps; warp w takes rows w, w+8, .. (sixteen rows) in four
+// rounds of 4 rows -- a ROLLED loop: the fully unrolled version was ~3 000 straight-line instructions that every launch
+// executed exactly once, i.e. at instruction-fetch speed (measured: 18 000 cycles per row block whatever the arithmetic).
+// A round: the raw rows of the NEXT round (x and addend) are requested first, then the statistics of the round's 4 rows are
+// reduced together (their butterfly steps interleave), then normalise, add the addend, pack, store to shared memory.
+// Branch-free: rows beyond M re-read row M-1 (finite values that no store keeps: the global copies of the operands leave by TMA
+// stores of the finished tiles, which clip at M).  Two-pass variance, packed fp32x2 arithmetic.
+// lane = 8 consecutive channels = one 16-byte chunk: k-block lane >> 3, chunk lane & 7 of the 128-byte swizzle row.
 template <typename TX>
 __device__ __forceinline__ void ln_prologue(const LnGemmParams& p, uint8_t* a_plain_s, uint8_t* a_pos_s, int mt, int warp, int lane,
                                             bool has_plain, bool has_pos, bool side) {
     constexpr int kRows = kGM / kEpiWarps;                  // 16 rows per warp
-    constexpr int kRound = sizeof(TX) == 2 ? kRows : 8;     // rows of x in flight
-    float g[8], b[8];
+    constexpr int kRound = 4;
+    float2 g[4], b[4];
     raw_unpack(*reinterpret_cast<const RawRow<float>*>(p.gamma + lane * 8), g);
     raw_unpack(*reinterpret_cast<const RawRow<float>*>(p.beta + lane * 8), b);
     const uint32_t kb_off = (uint32_t)(lane >> 3) * kOpBytes;
     const int c = lane & 7;
-    auto add_ptr = [&](int m) {
-        const int bb = m / p.rows_per_batch, rr = m - bb * p.rows_per_batch;
-        return p.addend + bb * p.add_sb + rr * p.add_sr + lane * 8;
-    };
-    for (int r0 = 0; r0 < kRows; r0 += kRound) {
-        RawRow<TX> xr[kRound];
+    const int m_last = p.e.M - 1, rpb = p.rows_per_batch;
+    // addend row of flattened row m: m * add_sr when the addend is one dense (M, C) block (add_sb == rpb * add_sr), else the
+    // broadcast form (add_sb == 0: every batch adds the same rpb rows, e.g. the decoder's query embedding): (m mod rpb) * add_sr,
+    // kept incrementally -- rows advance by kEpiWarps <= rpb (the launcher guarantees one of the two forms)
+    const bool a_bcast = p.add_sb == 0 && rpb < p.e.M;
+    int a_r = has_pos && a_bcast ? (mt * kGM + warp) % rpb : 0;
+    RawRow<TX> xn[kRound];
+    RawRow<float> an[kRound];
+    auto request = [&](int r0) {   // raw loads of the round that starts at local row r0
 #pragma unroll
         for (int u = 0; u < kRound; ++u) {
-            const int m = mt * kGM + warp + (r0 + u) * kEpiWarps;
-            if (m < p.e.M) raw_load(xr[u], reinterpret_cast<const TX*>(p.x) + (int64_t)m * p.x_ld + lane * 8);
-            else raw_zero(xr[u]);
-        }
-        RawRow<float> ar[2][4];
-        if (has_pos) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int m = mt * kGM + warp + (r0 + u) * kEpiWarps;
-                if (m < p.e.M) raw_load(ar[0][u], add_ptr(m)); else raw_zero(ar[0][u]);
+            const int m = min(mt * kGM + warp + (r0 + u) * kEpiWarps, m_last);
+            raw_load(xn[u], reinterpret_cast<const TX*>(p.x) + (int64_t)m * p.x_ld + lane * 8);
+            if (has_pos) {
+                raw_load(an[u], p.addend + (int64_t)(a_bcast ? a_r : m) * p.add_sr + lane * 8);
+                a_r += kEpiWarps;
+                a_r -= a_r >= rpb ? rpb : 0;
             }
         }
+    };
+    request(0);
+#pragma unroll 1
+    for (int r0 = 0; r0 < kRows; r0 += kRound) {
+        RawRow<TX> xr[kRound];
+        RawRow<float> ar[kRound];
 #pragma unroll
-        for (int gq = 0; gq < kRound / 4; ++gq) {
-            if (has_pos && gq + 1 < kRound / 4) {
+        for (int u = 0; u < kRound; ++u) { xr[u] = xn[u]; ar[u] = an[u]; }
+        if (r0 + kRound < kRows) request(r0 + kRound);
+        float mu[kRound], rs[kRound];
+        // ---- pass 1: means ----
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int m = mt * kGM + warp + (r0 + (gq + 1) * 4 + u) * kEpiWarps;
-                    if (m < p.e.M) raw_load(ar[(gq + 1) & 1][u], add_ptr(m)); else raw_zero(ar[(gq + 1) & 1][u]);
-                }
+        for (int u = 0; u < kRound; ++u) {
+            float2 v[4];
+            raw_unpack(xr[u], v);
+            const float2 t = __fadd2_rn(__fadd2_rn(v[0], v[1]), __fadd2_rn(v[2], v[3]));
+            mu[u] = t.x + t.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < kRound; ++u) mu[u] += __shfl_xor_sync(FULL_MASK, mu[u], o);
+        }
+        // ---- pass 2: variances ----
+#pragma unroll
+        for (int u = 0; u < kRound; ++u) {
+            mu[u] *= (1.f / kLnC);
+            float2 v[4];
+            raw_unpack(xr[u], v);
+            const float2 nmu = f2(-mu[u]);
+            float2 d = __fadd2_rn(v[0], nmu);
+            float2 q = __fmul2_rn(d, d);
+#pragma unroll
+            for (int i = 1; i < 4; ++i) { d = __fadd2_rn(v[i], nmu); q = __ffma2_rn(d, d, q); }
+            rs[u] = q.x + q.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < kRound; ++u) rs[u] += __shfl_xor_sync(FULL_MASK, rs[u], o);
+        }
+        // ---- normalise, add, pack, store ----
+#pragma unroll
+        for (int u = 0; u < kRound; ++u) {
+            const int r = warp + (r0 + u) * kEpiWarps, m = mt * kGM + r;
+            const float rstd = rsqrtf(rs[u] * (1.f / kLnC) + p.eps);
+            float2 v[4], y[4];
+            raw_unpack(xr[u], v);
+            const float2 nmu = f2(-mu[u]), rs2 = f2(rstd);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[i] = __ffma2_rn(__fmul2_rn(__fadd2_rn(v[i], nmu), rs2), g[i], b[i]);
+            const uint32_t off = kb_off + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+            if (has_plain) *reinterpret_cast<uint4*>(a_plain_s + off) = pack4(y);
+            if (has_pos) {
+                float2 a[4];
+                raw_unpack(ar[u], a);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) y[i] = __fadd2_rn(y[i], a[i]);
+                *reinterpret_cast<uint4*>(a_pos_s + off) = pack4(y);
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int r = warp + (r0 + gq * 4 + u) * kEpiWarps, m = mt * kGM + r;
-                const bool ok = m < p.e.M;
-                float v[8];
-                raw_unpack(xr[gq * 4 + u], v);
-                float s = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s += v[i];
-                const float mu = warp_sum(s) * (1.f / kLnC);
-                float q = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { const float d = v[i] - mu; q += d * d; }
-                const float rs = rsqrtf(warp_sum(q) * (1.f / kLnC) + p.eps);
-                float y[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = ok ? (v[i] - mu) * rs * g[i] + b[i] : 0.f;
-                const uint32_t off = kb_off + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-                if (has_plain) {
-                    const uint4 w = pack8(y);
-                    *reinterpret_cast<uint4*>(a_plain_s + off) = w;
-                    if (side && ok && p.a_plain) *reinterpret_cast<uint4*>(p.a_plain + (int64_t)m * kLnC + lane * 8) = w;
-                }
-                if (has_pos) {
-                    float a[8];
-                    raw_unpack(ar[gq & 1][u], a);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = ok ? y[i] + a[i] : 0.f;
-                    const uint4 w = pack8(y);
-                    *reinterpret_cast<uint4*>(a_pos_s + off) = w;
-                    if (side && ok && p.a_pos) *reinterpret_cast<uint4*>(p.a_pos + (int64_t)m * kLnC + lane * 8) = w;
-                }
-                if (side && ok && lane == 0 && p.mean) { p.mean[m] = mu; p.rstd[m] = rs; }
-            }
+            if (side && lane == 0 && m <= m_last) { p.mean[m] = mu[u]; p.rstd[m] = rstd; }
         }
     }
 }
@@ -443,7 +536,7 @@ __device__ __forceinline__ void ln_prologue(const LnGemmParams& p, uint8_t* a_pl
 template <int EPI, typename TX>
 __global__ void __launch_bounds__(kLnThreads, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_aux,
-               const LnGemmParams p) {
+               const __grid_constant__ CUtensorMap tm_aplain, const __grid_constant__ CUtensorMap tm_apos, const LnGemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = align1024(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -473,10 +566,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    LN_STAMP(0);
     const int mt = blockIdx.x / p.groups, gi = blockIdx.x - mt * p.groups;
     const int nt0 = p.n_tiles * gi / p.groups, nt1 = p.n_tiles * (gi + 1) / p.groups;
     pdl_wait();
     pdl_trigger();
+    LN_STAMP(1);
 
     if (warp == kEpiWarps) {
         if (lane == 0) {
@@ -491,6 +586,18 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
                     tma_load_2d(ring + s * kOpBytes, &tm_w, full + s, kb * kGK, nt * kGN);
                 }
             }
+            if (gi == 0 && (p.a_plain != nullptr || p.a_pos != nullptr)) {
+                // the operand copies the weight-gradient GEMMs need: the finished A tiles leave by TMA stores (4 boxes of 64
+                // channels x 128 rows per variant, rows >= M clipped) -- no per-thread global store in the prologue
+                mbar_wait_sleep(a_full, 0);
+#pragma unroll
+                for (int kb = 0; kb < kLnKb; ++kb) {
+                    if (has_plain && p.a_plain != nullptr) tma_store_2d(&tm_aplain, a_plain_s + kb * kOpBytes, kb * kGK, mt * kGM);
+                    if (has_pos && p.a_pos != nullptr) tma_store_2d(&tm_apos, a_pos_s + kb * kOpBytes, kb * kGK, mt * kGM);
+                }
+                tma_store_commit();
+                tma_store_wait_all0();
+            }
         }
     } else if (warp == kEpiWarps + 1) {
         if (elect_one()) {
@@ -498,6 +605,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
             constexpr uint32_t idesc = make_idesc_bf16(kGM, kGN, false, false);
             constexpr uint32_t hi = desc_hi(1024, SWZ_128B);
             mbar_wait_sleep(a_full, 0);
+            LN_STAMP(2);
             int it = 0, li = 0;
             for (int nt = nt0; nt < nt1; ++nt, ++li) {
                 const int buf = li % kAccBufs;
@@ -516,12 +624,15 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
                     umma_commit(empty + s);
                 }
                 umma_commit(acc_full + buf);
+                if (li < 6) LN_STAMP(3 + li);
             }
         }
     } else {
         // ================= worker warps: LayerNorm prologue, then the epilogues =================
         const uint32_t key = p.e.thr4 ? ew_key(p.e.seed, p.e.seed_ptr) : 0u;
-        ln_prologue<TX>(p, a_plain_s, a_pos_s, mt, warp, lane, has_plain, has_pos, gi == 0);
+        const bool side = gi == 0 && p.mean != nullptr;
+        ln_prologue<TX>(p, a_plain_s, a_pos_s, mt, warp, lane, has_plain, has_pos, side);
+        LN_STAMP(2);
         fence_proxy_async_smem();
         mbar_arrive(a_full);
         uint8_t* stg = stg_all + warp * LnCfg<EPI>::stg_warp;
@@ -530,11 +641,15 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
             const int buf = li % kAccBufs;
             epi_tile<EPI, __nv_bfloat16>(p.e, &tm_out, &tm_aux, &tm_out, key, tmem + buf * kGN, stg, ldbar + warp, n_ld, warp, lane, mt * kGM,
                                          nt * kGN, acc_full + buf, (li / kAccBufs) & 1, acc_empty + buf);
+            if (li < 6) LN_STAMP(3 + li);
         }
+        LN_STAMP(9);
         if (lane == 0) tma_store_wait_all0();
+        LN_STAMP(10);
     }
     tc_fence_before();
     __syncthreads();
+    LN_STAMP(11);
     if (warp == kEpiWarps + 1) tmem_dealloc(tmem, kAccCols);
 }
 
@@ -774,6 +889,10 @@ static int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
 
 using namespace detr;
 
+static long long* g_gemm_dbg = nullptr;
+/* debugging aid (not part of the drop-in surface): device buffer of 10*16 int64 that receives clock64 stamps of CTA 0 */
+extern "C" void detr_gemm_set_debug(long long* buf) { g_gemm_dbg = buf; }
+
 /* dtype codes: 0 = float32, 1 = bfloat16.  epilogue: 0 bias, 1 bias + GELU(tanh) + dropout (aux receives the bf16
  * pre-activation), 2 bias + dropout + residual (out and res share out_dtype), 3 GELU backward (aux = pre-activation,
  * no bias, bf16 out).  b_kn = 0: b is [N][K] (nn.Linear weight, C = A B^T); 1: b is [K][N] (C = A B). */
@@ -825,13 +944,20 @@ extern "C" int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const 
     DETR_CHECK_ARG(((uintptr_t)gamma % 16) == 0 && ((uintptr_t)beta % 16) == 0, "gemm_ln: gamma / beta must be 16-byte aligned");
     DETR_CHECK_ARG(n_pos_end >= 0 && n_pos_end <= N && n_pos_end % kGN == 0, "gemm_ln: n_pos_end must be a multiple of %d", kGN);
     DETR_CHECK_ARG(n_pos_end == 0 || (addend && ((uintptr_t)addend % 16) == 0 && add_sb % 4 == 0 && add_sr % 4 == 0), "gemm_ln: addend required (16-byte aligned rows)");
+    {
+        const int rpb_ = rows_per_batch > 0 ? rows_per_batch : M;
+        DETR_CHECK_ARG(n_pos_end == 0 || rpb_ >= M || add_sb == (int64_t)rpb_ * add_sr || (add_sb == 0 && rpb_ >= 8),
+                       "gemm_ln: the addend must be one dense (M, 256) block or a broadcast (add_sb == 0) of >= 8 rows");
+    }
     DETR_CHECK_ARG(out != nullptr && (epilogue != EPI_GELU || aux != nullptr), "gemm_ln: out / aux required");
     DETR_CHECK_ARG(((uintptr_t)a_plain % 16) == 0 && ((uintptr_t)a_pos % 16) == 0, "gemm_ln: operand copies must be 16-byte aligned");
     DETR_CHECK_ARG(!bias || ((uintptr_t)bias % 16) == 0, "gemm_ln: bias must be 16-byte aligned");
-    CUtensorMap tw, to, tx;
+    CUtensorMap tw, to, tx, tap, tao;
     if (int rc = make_map_2d(&tw, w, N, kLnC, ldw, kGN, false, "gemm_ln(W)")) return rc;
     if (int rc = make_map_2d(&to, out, M, N, ldo, 32, false, "gemm_ln(out)")) return rc;
-    tx = to;
+    tx = to; tap = to; tao = to;
+    if (a_plain) { if (int rc = make_map_2d(&tap, a_plain, M, kLnC, kLnC, kGM, false, "gemm_ln(a_plain)")) return rc; }
+    if (a_pos) { if (int rc = make_map_2d(&tao, a_pos, M, kLnC, kLnC, kGM, false, "gemm_ln(a_pos)")) return rc; }
     if (epilogue == EPI_GELU) { if (int rc = make_map_2d(&tx, aux, M, N, ld_aux, 32, false, "gemm_ln(aux)")) return rc; }
     LnGemmParams p{};
     if (int rc = fill_epi(p.e, M, N, bias, dropout_p, seed, seed_ptr, "gemm_ln")) return rc;
@@ -839,6 +965,7 @@ extern "C" int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const 
     p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : M; p.n_pos_end = n_pos_end;
     p.a_plain = reinterpret_cast<__nv_bfloat16*>(a_plain); p.a_pos = reinterpret_cast<__nv_bfloat16*>(a_pos); p.mean = mean; p.rstd = rstd;
     p.m_tiles = (M + kGM - 1) / kGM; p.n_tiles = (N + kGN - 1) / kGN;
+    p.dbg = g_gemm_dbg;
     // column groups per row block: as many as fit in one wave (each group repeats the prologue of its row block)
     int groups = device_sms() / p.m_tiles;
     if (groups > p.n_tiles) groups = p.n_tiles;
@@ -850,7 +977,7 @@ extern "C" int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const 
     do {                                                                         \
         auto kern = gemm_ln_kernel<E, TX>;                                       \
         if (int rc = opt_in_smem(kern, kLnSmem, "gemm_ln")) return rc;           \
-        launch_pdl(kern, grid, dim3(kLnThreads), kLnSmem, st, tw, to, tx, p);    \
+        launch_pdl(kern, grid, dim3(kLnThreads), kLnSmem, st, tw, to, tx, tap, tao, p); \
     } while (0)
     if (epilogue == EPI_BIAS) { if (x_dtype == 0) LN_GO(EPI_BIAS, float); else LN_GO(EPI_BIAS, __nv_bfloat16); }
     else                      { if (x_dtype == 0) LN_GO(EPI_GELU, float); else LN_GO(EPI_GELU, __nv_bfloat16); }

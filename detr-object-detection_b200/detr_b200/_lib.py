@@ -36,10 +36,10 @@ SIGNATURES = {
     "detr_criterion_bwd_f32": [P, P, *_STRIDES3, P, *_STRIDES3, P, P, P, P, P, P, P,
                                c_int, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P],
     "detr_attention_fwd_workspace_floats": [c_int, c_int, c_int, c_int],
-    "detr_attention_fwd_bf16": [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64,
+    "detr_attention_fwd_bf16": [P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64, P, c_int64, c_int64, P,
                                 P, P, P, c_int64, P, c_int, c_int, c_int, c_int, c_float, ctypes.c_uint64, P, P],
     "detr_attention_bwd_workspace_floats": [c_int, c_int, c_int, c_int],
-    "detr_attention_bwd_bf16": [P, c_int64, c_int64] * 5 + [P, P, P] + [P, c_int64, c_int64] * 3 +
+    "detr_attention_bwd_bf16": [P, c_int64, c_int64] * 4 + [P] + [P, c_int64, c_int64] + [P, P, P] + [P, c_int64, c_int64] * 3 +
                                [P, c_int64, P, c_int, c_int, c_int, c_int, c_float, ctypes.c_uint64, P, P],
     "detr_colsum_chunks": [c_int, c_int],
     "detr_colsum_bf16": [P, c_int64, c_int, c_int, P, P, P, P],

@@ -33,8 +33,9 @@ def _mask_bytes(m: Optional[torch.Tensor], shape, name: str) -> Optional[torch.T
 
 
 def attention_forward(q, k, v, key_padding_mask=None, attention_mask=None, dropout_p: float = 0.0, seed: int = 0,
-                      seed_tensor: Optional[torch.Tensor] = None):
-    """Raw forward launch -> (out bf16 (B,L,C), lse fp32 (B,nh,L))."""
+                      seed_tensor: Optional[torch.Tensor] = None, residual: bool = False):
+    """Raw forward launch -> (out bf16 (B,L,C), lse fp32 (B,nh,L)).  With `residual` the output is (2, B, L, C): out[0] is
+    the attention output, out[1] its bf16 rounding residual (what `attention_backward(out_lo=)` uses for an exact delta)."""
     _lib.require_cuda(q, "attention")
     B, L, C = q.shape
     S = k.shape[1]
@@ -44,20 +45,23 @@ def attention_forward(q, k, v, key_padding_mask=None, attention_mask=None, dropo
     q, k, v = _tma_ok(q), _tma_ok(k), _tma_ok(v)
     kpm = _mask_bytes(key_padding_mask, (B, S), "key_padding_mask")
     am = _mask_bytes(attention_mask, (L, S), "attention_mask")
-    out = torch.empty(B, L, C, dtype=torch.bfloat16, device=q.device)
+    out2 = torch.empty(2 if residual else 1, B, L, C, dtype=torch.bfloat16, device=q.device)
+    out = out2[0]
     lse = torch.empty(B, nh, L, dtype=torch.float32, device=q.device)
     ws = torch.empty(_lib.load().detr_attention_fwd_workspace_floats(B, nh, L, S), dtype=torch.float32, device=q.device)
     _lib.call(
         "detr_attention_fwd_bf16",
         q.data_ptr(), q.stride(0), q.stride(1), k.data_ptr(), k.stride(0), k.stride(1), v.data_ptr(), v.stride(0), v.stride(1),
-        out.data_ptr(), out.stride(0), out.stride(1), lse.data_ptr(), ws.data_ptr(), _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0,
+        out.data_ptr(), out.stride(0), out.stride(1), out2[1].data_ptr() if residual else None, lse.data_ptr(), ws.data_ptr(),
+        _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0,
         _lib.ptr(am), B, nh, L, S, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_tensor), _lib.stream_ptr(),
         tag=(B, nh, L, S), launches=2 if -(-L // 128) * nh * B > _lib.num_sms() else 1)   # + combine when items are split between CTAs
-    return out, lse
+    return (out2 if residual else out), lse
 
 
 def attention_backward(d_out, q, k, v, out, lse, key_padding_mask=None, attention_mask=None, dropout_p: float = 0.0,
-                       seed: int = 0, seed_tensor: Optional[torch.Tensor] = None, outs: Optional[tuple] = None):
+                       seed: int = 0, seed_tensor: Optional[torch.Tensor] = None, outs: Optional[tuple] = None,
+                       out_lo: Optional[torch.Tensor] = None):
     """Raw backward launches -> (dq, dk, dv) bf16 with the shapes of q, k, v.  `outs`: caller-provided (dq, dk, dv) bf16
     buffers (channel stride 1, 16-byte aligned, row / batch strides multiples of 8 -- e.g. the two halves of one (B, L, 2C)
     gradient of a fused q/k projection)."""
@@ -65,6 +69,8 @@ def attention_backward(d_out, q, k, v, out, lse, key_padding_mask=None, attentio
     S = k.shape[1]
     nh = C // HEAD_DIM
     q, k, v, out, d_out = _tma_ok(q), _tma_ok(k), _tma_ok(v), _tma_ok(out), _tma_ok(d_out)
+    if out_lo is not None and (out_lo.dtype != torch.bfloat16 or out_lo.shape != out.shape or out_lo.stride() != out.stride() or out_lo.data_ptr() % 16):
+        raise ValueError("attention_backward: out_lo must be a bf16 tensor with out's shape and strides")
     kpm = _mask_bytes(key_padding_mask, (B, S), "key_padding_mask")
     am = _mask_bytes(attention_mask, (L, S), "attention_mask")
     if outs is None:
@@ -82,7 +88,7 @@ def attention_backward(d_out, q, k, v, out, lse, key_padding_mask=None, attentio
     st = lambda t: (t.data_ptr(), t.stride(0), t.stride(1))
     _lib.call(
         "detr_attention_bwd_bf16",
-        *st(q), *st(k), *st(v), *st(out), *st(d_out), lse.data_ptr(), delta.data_ptr(), dq_part.data_ptr(), *st(dq), *st(dk), *st(dv),
+        *st(q), *st(k), *st(v), *st(out), _lib.ptr(out_lo), *st(d_out), lse.data_ptr(), delta.data_ptr(), dq_part.data_ptr(), *st(dq), *st(dk), *st(dv),
         _lib.ptr(kpm), kpm.stride(0) if kpm is not None else 0, _lib.ptr(am), B, nh, L, S, float(dropout_p),
         int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_tensor), _lib.stream_ptr(), tag=(B, nh, L, S),
         launches=4 if -(-S // 128) * nh * B > _lib.num_sms() else 3)   # delta, main, dQ reduction (+ dK/dV reduction when items are split)
@@ -98,36 +104,36 @@ class _FlashAttentionQK(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qk, v, key_padding_mask, attention_mask, dropout_p, seed, seed_tensor):
         C = qk.shape[-1] // 2
-        out, lse = attention_forward(qk[..., :C], qk[..., C:], v, key_padding_mask, attention_mask, dropout_p, seed, seed_tensor)
-        ctx.save_for_backward(qk, v, out, lse, key_padding_mask, attention_mask, seed_tensor)
+        out2, lse = attention_forward(qk[..., :C], qk[..., C:], v, key_padding_mask, attention_mask, dropout_p, seed, seed_tensor, residual=True)
+        ctx.save_for_backward(qk, v, out2, lse, key_padding_mask, attention_mask, seed_tensor)
         ctx.dropout_p, ctx.seed = dropout_p, seed
-        return out
+        return out2[0]
 
     @staticmethod
     def backward(ctx, d_out):
-        qk, v, out, lse, kpm, am, seed_tensor = ctx.saved_tensors
+        qk, v, out2, lse, kpm, am, seed_tensor = ctx.saved_tensors
         B, L, C2 = qk.shape
         C = C2 // 2
         dqk = torch.empty(B, L, C2, dtype=torch.bfloat16, device=qk.device)
         dv = torch.empty(B, v.shape[1], C, dtype=torch.bfloat16, device=qk.device)
-        attention_backward(d_out, qk[..., :C], qk[..., C:], v, out, lse, kpm, am, ctx.dropout_p, ctx.seed, seed_tensor,
-                           outs=(dqk[..., :C], dqk[..., C:], dv))
+        attention_backward(d_out, qk[..., :C], qk[..., C:], v, out2[0], lse, kpm, am, ctx.dropout_p, ctx.seed, seed_tensor,
+                           outs=(dqk[..., :C], dqk[..., C:], dv), out_lo=out2[1])
         return dqk.to(qk.dtype), dv.to(v.dtype), None, None, None, None, None
 
 
 class _FlashAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, key_padding_mask, attention_mask, dropout_p, seed, seed_tensor):
-        out, lse = attention_forward(q, k, v, key_padding_mask, attention_mask, dropout_p, seed, seed_tensor)
-        ctx.save_for_backward(q, k, v, out, lse, key_padding_mask, attention_mask, seed_tensor)
+        out2, lse = attention_forward(q, k, v, key_padding_mask, attention_mask, dropout_p, seed, seed_tensor, residual=True)
+        ctx.save_for_backward(q, k, v, out2, lse, key_padding_mask, attention_mask, seed_tensor)
         ctx.dropout_p, ctx.seed = dropout_p, seed
         ctx.in_dtypes = (q.dtype, k.dtype, v.dtype)
-        return out
+        return out2[0]
 
     @staticmethod
     def backward(ctx, d_out):
-        q, k, v, out, lse, kpm, am, seed_tensor = ctx.saved_tensors
-        dq, dk, dv = attention_backward(d_out, q, k, v, out, lse, kpm, am, ctx.dropout_p, ctx.seed, seed_tensor)
+        q, k, v, out2, lse, kpm, am, seed_tensor = ctx.saved_tensors
+        dq, dk, dv = attention_backward(d_out, q, k, v, out2[0], lse, kpm, am, ctx.dropout_p, ctx.seed, seed_tensor, out_lo=out2[1])
         tq, tk, tv = ctx.in_dtypes
         return dq.to(tq), dk.to(tk), dv.to(tv), None, None, None, None, None
 
@@ -155,6 +161,42 @@ def flash_attention_qk(qk, v, key_padding_mask: Optional[torch.Tensor] = None, a
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     st = _STEP_TENSOR if (dropout_p > 0.0 and _STEP_TENSOR is not None and _STEP_TENSOR.device == qk.device) else None
     return _FlashAttentionQK.apply(qk, v, key_padding_mask, attention_mask, float(dropout_p), int(seed or 0), st)
+
+
+class _FlashAttentionQKV(torch.autograd.Function):
+    """Self-attention on the output of ONE fused q|k|v projection: qkv (B, L, 3C).  The kernels take the three column blocks as
+    strided views in both directions: backward writes dq, dk, dv straight into one (B, L, 3C) gradient buffer, which is what
+    the projection's input-gradient / weight-gradient GEMMs consume."""
+
+    @staticmethod
+    def forward(ctx, qkv, key_padding_mask, attention_mask, dropout_p, seed, seed_tensor):
+        C = qkv.shape[-1] // 3
+        out2, lse = attention_forward(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], key_padding_mask, attention_mask, dropout_p, seed,
+                                      seed_tensor, residual=True)
+        ctx.save_for_backward(qkv, out2, lse, key_padding_mask, attention_mask, seed_tensor)
+        ctx.dropout_p, ctx.seed = dropout_p, seed
+        return out2[0]
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, out2, lse, kpm, am, seed_tensor = ctx.saved_tensors
+        B, L, C3 = qkv.shape
+        C = C3 // 3
+        dqkv = torch.empty(B, L, C3, dtype=torch.bfloat16, device=qkv.device)
+        attention_backward(d_out, qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], out2[0], lse, kpm, am, ctx.dropout_p, ctx.seed, seed_tensor,
+                           outs=(dqkv[..., :C], dqkv[..., C:2 * C], dqkv[..., 2 * C:]), out_lo=out2[1])
+        return dqkv, None, None, None, None, None
+
+
+def flash_attention_qkv(qkv, key_padding_mask: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
+                        dropout_p: float = 0.0, seed: Optional[int] = None) -> torch.Tensor:
+    """Self-attention core on the (B, L, 3C) bf16 output of a fused q|k|v projection, one autograd node."""
+    if qkv.dim() != 3 or qkv.shape[-1] % 3 or qkv.dtype != torch.bfloat16:
+        raise ValueError("flash_attention_qkv: qkv must be a bf16 (B, L, 3C) tensor")
+    if dropout_p > 0.0 and seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    st = _STEP_TENSOR if (dropout_p > 0.0 and _STEP_TENSOR is not None and _STEP_TENSOR.device == qkv.device) else None
+    return _FlashAttentionQKV.apply(qkv, key_padding_mask, attention_mask, float(dropout_p), int(seed or 0), st)
 
 
 _STEP_TENSOR: Optional[torch.Tensor] = None

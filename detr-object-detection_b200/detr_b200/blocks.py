@@ -90,9 +90,13 @@ class _LnProj(torch.autograd.Function):
         add_t, sb, sr = None, 0, 0
         if n_pos_end > 0:
             add_t = addend if addend.dtype == torch.float32 else addend.float()
-            if add_t.dim() != 3 or add_t.shape[1:] != (L, C) or add_t.stride(2) != 1 or add_t.stride(1) % 4 or add_t.stride(0) % 4 or add_t.data_ptr() % 16:
+            sb = add_t.stride(0) if (add_t.dim() == 3 and add_t.shape[0] > 1) else 0
+            ok = (add_t.dim() == 3 and add_t.shape[1:] == (L, C) and add_t.stride(2) == 1 and add_t.stride(1) % 4 == 0 and add_t.data_ptr() % 16 == 0
+                  and (B == 1 or sb == L * add_t.stride(1) or (sb == 0 and L >= 8)))     # dense block or batch broadcast
+            if not ok:
                 add_t = add_t.expand(B, L, C).contiguous()
-            sb, sr = (add_t.stride(0) if add_t.shape[0] > 1 else 0), add_t.stride(1)
+                sb = add_t.stride(0)
+            sr = add_t.stride(1)
         g32, be32 = gamma.float(), beta.float()
         out, a_plain, a_pos, stats = G.gemm_ln(x2, g32, be32, eps, w16, addend=add_t, rows_per_batch=L, add_sb=sb, add_sr=sr,
                                                n_pos_end=n_pos_end, bias=b32)

@@ -40,7 +40,7 @@ class _CriterionFn(torch.autograd.Function):
             # dense logits rows with K % 4 == 0: fused expand + forward, finalize; otherwise expand, forward, finalize
             launches=2 if (K % 4 == 0 and lg.stride(2) == K and lg.stride(0) % 4 == 0 and lg.stride(1) % 4 == 0
                            and lg.data_ptr() % 16 == 0 and (Q * K + Q) * 4 <= 200 * 1024) else 3)
-        ctx.save_for_backward(lg, bx, class_weight, lse, tgt, tbox, wsum, pt.gt_off)
+        ctx.save_for_backward(lg, bx, class_weight, lse, tgt, tbox, wsum, pt.gt_off, losses)
         ctx.num_boxes = num_boxes
         ctx.w = w
         ctx.shape = (B, L, Q, K)
@@ -51,11 +51,14 @@ class _CriterionFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_diff, _grad_metrics=None):
-        lg, bx, class_weight, lse, tgt, tbox, wsum, gt_off = ctx.saved_tensors
+        lg, bx, class_weight, lse, tgt, tbox, wsum, gt_off, losses = ctx.saved_tensors
         B, L, Q, K = ctx.shape
-        g = torch.zeros(L, 5, dtype=torch.float32, device=lg.device)   # the kernel's table layout: columns 0, 2, 3 carry gradients
-        g[:, 0] = grad_diff[:, 0]
-        g[:, 2:4] = grad_diff[:, 1:3]
+        # the kernel's table layout: columns 0, 2, 3 carry gradients.  `losses * 0` is 0 for a clean step and NaN for one whose
+        # losses were poisoned by the device fault word: the gradients of a faulted batch are then NaN as well, which is what makes
+        # the optimizer kernels skip the update (detr_adamw_clip_f32) instead of applying an assignment made on bad data
+        g = losses * 0.0
+        g[:, 0] += grad_diff[:, 0]
+        g[:, 2:4] += grad_diff[:, 1:3]
         d_logits = torch.empty(B, L, Q, K, dtype=torch.float32, device=lg.device)
         d_boxes = torch.empty(B, L, Q, 4, dtype=torch.float32, device=lg.device)
         w = ctx.w

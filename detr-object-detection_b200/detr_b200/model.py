@@ -15,6 +15,7 @@ There is no CPU path: inputs must be CUDA tensors.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -22,7 +23,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .attention import HEAD_DIM, flash_attention, flash_attention_qk
+from . import blocks
+from .attention import HEAD_DIM, flash_attention, flash_attention_qk, flash_attention_qkv
 from .rowops import (ShadowedLinears, fused_epilogues_enabled, layer_norm_add, linear, linear_dropout_add, linear_gelu_dropout,
                      stacked_linear)
 
@@ -83,6 +85,8 @@ class ScaledDotProductAttention(nn.Module):
         object.__setattr__(self, "_shadows", sh)
         object.__setattr__(self, "_skey", prefix)
         sh.register((prefix, "qk"), (self.query_proj.weight, self.key_proj.weight), (self.query_proj.bias, self.key_proj.bias))
+        sh.register((prefix, "qkv"), (self.query_proj.weight, self.key_proj.weight, self.value_proj.weight),
+                    (self.query_proj.bias, self.key_proj.bias, self.value_proj.bias))
         for name in ("query", "key", "value", "output"):
             lin = getattr(self, name + "_proj")
             sh.register((prefix, name), (lin.weight,), (lin.bias,))
@@ -130,8 +134,39 @@ class ScaledDotProductAttention(nn.Module):
         return y if residual is None else residual + y
 
 
+    # -- fused pre-LN blocks (bf16 autocast, hidden size 256): every GEMM is a tcgen05 kernel of csrc/gemm.cu ---------------
+    def _shadow(self, name):
+        return self._shadows.get_w_b32((self._skey, name)) if self._shadows is not None else (None, None)
+
+    def self_block(self, x, norm: nn.LayerNorm, addend, key_padding_mask=None, attention_mask=None):
+        """x + dropout(output_proj(attention(q = k = LN(x) + addend, v = LN(x))))  (detr/model.py:221-223, 173-175):
+        LayerNorm, the "+ embedding" and the q|k|v projections are ONE launch, the output projection with bias, dropout and
+        the residual add another."""
+        C = self.hidden_size
+        qkv, x = blocks.ln_proj(x, norm, (self.query_proj, self.key_proj, self.value_proj), addend, 2 * C, *self._shadow("qkv"))
+        y = flash_attention_qkv(qkv, key_padding_mask, attention_mask, self.dropout_attn.p if self.training else 0.0)
+        return blocks.proj_res(y, x, self.output_proj, self.dropout.p if self.training else 0.0, self._shadow("output")[0])
+
+    def cross_block(self, x, norm: nn.LayerNorm, addend, projected_kv, key_padding_mask=None):
+        """x + dropout(output_proj(attention(q = LN(x) + addend, k, v)))  with k, v projected by the caller
+        (detr/model.py:177-180)."""
+        C = self.hidden_size
+        q, x = blocks.ln_proj(x, norm, (self.query_proj,), addend, C, *self._shadow("query"))
+        k, v = projected_kv
+        y = flash_attention(q, k, v, key_padding_mask, None, self.dropout_attn.p if self.training else 0.0)
+        return blocks.proj_res(y, x, self.output_proj, self.dropout.p if self.training else 0.0, self._shadow("output")[0])
+
+
+_FUSED_BLOCKS = os.environ.get("DETR_B200_FUSED_BLOCKS", "1") != "0"   # development switch: 0 = round-1 path (cuBLASLt GEMMs + row kernels)
+
+
+def _fused_blocks_enabled(x: torch.Tensor, hidden: int) -> bool:
+    """The fused tcgen05 path: CUDA tensors under bf16 autocast with the hidden size the LayerNorm-prologue kernel is built for."""
+    return _FUSED_BLOCKS and fused_epilogues_enabled(x) and hidden == blocks.C_MODEL
+
+
 class FFN(nn.Module):
-    """detr/model.py:395-424 (Linear -> GELU(tanh) -> Dropout -> Linear -> Dropout); cuBLASLt GEMMs."""
+    """detr/model.py:395-424 (Linear -> GELU(tanh) -> Dropout -> Linear -> Dropout)."""
 
     def __init__(self, config):
         super().__init__()
@@ -152,6 +187,15 @@ class FFN(nn.Module):
         object.__setattr__(self, "_skey", prefix)
         sh.register((prefix, 0), (self.layers[0].weight,), (self.layers[0].bias,))
         sh.register((prefix, 3), (self.layers[3].weight,), (self.layers[3].bias,))
+
+    def block(self, x, norm: nn.LayerNorm):
+        """x + FFN(LN(x)) (detr/model.py:224,182) in two launches: LayerNorm-prologue GEMM with the GELU + dropout epilogue,
+        GEMM with the bias + dropout + residual epilogue."""
+        fc1, _, drop1, fc2, drop2 = self.layers
+        sh = self._shadows
+        w1 = sh.get_w_b32((self._skey, 0))[0] if sh is not None else None
+        w2 = sh.get_w_b32((self._skey, 3))[0] if sh is not None else None
+        return blocks.ln_ffn(x, norm, fc1, fc2, drop1.p if self.training else 0.0, drop2.p if self.training else 0.0, w1, w2)
 
     def forward(self, x, residual: Optional[torch.Tensor] = None):
         """The reference's forward (detr/model.py:413-424); with `residual` (this package's layers) the result is
@@ -178,6 +222,9 @@ class EncoderLayer(nn.Module):
         self.norm2 = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
 
     def forward(self, x: torch.Tensor, position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
+        if _fused_blocks_enabled(x, self.self_attention.hidden_size):
+            x = self.self_attention.self_block(x, self.norm1, position_embedding, key_padding_mask)
+            return self.ffn.block(x, self.norm2)
         # LN and "+ pos" in one kernel; the third output is x itself: used as the residual input, its gradient is added inside
         # the LayerNorm backward kernel (no autograd accumulation kernel per residual branch)
         x_attn, query, x = layer_norm_add(x, self.norm1, position_embedding, pass_x=True)
@@ -200,6 +247,7 @@ class Encoder(nn.Module):
 
     def forward(self, x: torch.Tensor, position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
         _refresh_shadows(self, x)
+        position_embedding = _dense_fp32(position_embedding)   # once per forward, not once per layer (detr/model.py:79 hands a permuted view)
         for layer in self.layers:
             x = layer(x, position_embedding, key_padding_mask)
         return layer_norm_add(x, self.norm)[0]
@@ -220,6 +268,10 @@ class DecoderLayer(nn.Module):
     def forward(self, x: torch.Tensor, encoded_image_tokens: torch.Tensor, object_query_embedding: torch.Tensor,
                 position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor,
                 cross_key: Optional[torch.Tensor] = None, cross_kv: Optional[tuple] = None):
+        if cross_kv is not None and _fused_blocks_enabled(encoded_image_tokens, self.self_attention.hidden_size):
+            x = self.self_attention.self_block(x, self.norm1, object_query_embedding)
+            x = self.cross_attention.cross_block(x, self.norm2, object_query_embedding, cross_kv, key_padding_mask)
+            return self.ffn.block(x, self.norm3)
         x_attn, query, x = layer_norm_add(x, self.norm1, object_query_embedding, pass_x=True)
         x = self.self_attention(query, query, value=x_attn, residual=x)
         _, query, x = layer_norm_add(x, self.norm2, object_query_embedding, want_y=False, pass_x=True)
@@ -247,11 +299,17 @@ class Decoder(nn.Module):
                 object_query_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor):
         _refresh_shadows(self, encoded_image_tokens)
         x = torch.zeros_like(object_query_embedding)
+        position_embedding = _dense_fp32(position_embedding)
         cross_key = encoded_image_tokens + position_embedding   # layer-invariant: computed once, not 6 times
         # ... and so are the cross-attention key / value projections' INPUTS: all layers' projections run as two wide GEMMs
         # (n_layers*C outputs each) whose column slices feed the per-layer attention kernels as strided views
         kvs = [None] * len(self.layers)
-        if fused_epilogues_enabled(encoded_image_tokens):
+        if _fused_blocks_enabled(encoded_image_tokens, self.config.hidden_size):
+            sh, C = self._shadows, self.config.hidden_size
+            ks = blocks.proj(cross_key, [l.cross_attention.key_proj for l in self.layers], *sh.get_w_b32(("", "cross_keys")))
+            vs = blocks.proj(encoded_image_tokens, [l.cross_attention.value_proj for l in self.layers], *sh.get_w_b32(("", "cross_values")))
+            kvs = [(ks[..., i * C:(i + 1) * C], vs[..., i * C:(i + 1) * C]) for i in range(len(self.layers))]
+        elif fused_epilogues_enabled(encoded_image_tokens):
             sh = self._shadows
             ks = stacked_linear(cross_key, [l.cross_attention.key_proj for l in self.layers], *sh.get(("", "cross_keys")))
             vs = stacked_linear(encoded_image_tokens, [l.cross_attention.value_proj for l in self.layers], *sh.get(("", "cross_values")))
@@ -266,6 +324,14 @@ class Decoder(nn.Module):
         B, L, Q, C = stacked.shape
         with torch.autocast("cuda", enabled=False):   # the prediction heads get the reference's fp32 LayerNorm output
             return layer_norm_add(stacked.view(B, L * Q, C), self.norm)[0].view(B, L, Q, C)
+
+
+def _dense_fp32(t: torch.Tensor) -> torch.Tensor:
+    """(B, S, C) embedding with unit channel stride and 16-byte aligned rows (what the kernels read); a no-op for the harness's
+    own tensors, one copy for the permuted view the reference's DETR.forward passes (detr/model.py:78-80)."""
+    if t.dtype == torch.float32 and t.dim() == 3 and t.stride(2) == 1 and t.stride(1) % 4 == 0 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    return t.float().contiguous()
 
 
 def _attach_shadows(root: nn.Module) -> None:

@@ -199,6 +199,7 @@ class ShadowedLinears:
     def __init__(self):
         self.groups = []      # (key, [weights], [biases])
         self.shadow = {}      # key -> (w16, b16)
+        self.shadow32 = {}    # key -> stacked fp32 bias
         self._src, self._dst = [], []
         self._device = None
 
@@ -211,23 +212,35 @@ class ShadowedLinears:
             out = sum(w.shape[0] for w in ws)
             w16 = torch.empty(out, ws[0].shape[1], dtype=torch.bfloat16, device=device)
             b16 = torch.empty(out, dtype=torch.bfloat16, device=device) if bs else None
+            b32 = torch.empty(out, dtype=torch.float32, device=device) if bs else None   # stacked fp32 bias for the GEMM epilogues
             o = 0
             for i, w in enumerate(ws):
                 self._src.append(w); self._dst.append(w16[o:o + w.shape[0]])
                 if bs:
                     self._src.append(bs[i]); self._dst.append(b16[o:o + w.shape[0]])
+                    self._src.append(bs[i]); self._dst.append(b32[o:o + w.shape[0]])
                 o += w.shape[0]
             self.shadow[key] = (w16, b16)
+            self.shadow32[key] = b32
         self._device = device
 
     @torch.no_grad()
     def refresh(self, device):
         if self._device != device:
             self._build(device)
-        torch._foreach_copy_(self._dst, [p.detach() for p in self._src])
+        # one multi-tensor launch per destination dtype (a list that mixes dtypes makes _foreach_copy_ fall back to one copy
+        # kernel per tensor: ~400 launches per step)
+        for dt in (torch.bfloat16, torch.float32):
+            dst = [d for d in self._dst if d.dtype == dt]
+            if dst:
+                torch._foreach_copy_(dst, [p.detach() for p, d in zip(self._src, self._dst) if d.dtype == dt])
 
     def get(self, key):
         return self.shadow.get(key, (None, None))
+
+    def get_w_b32(self, key):
+        """(bf16 stacked weight, fp32 stacked bias) of a group, (None, None) before the first refresh."""
+        return self.shadow.get(key, (None, None))[0], self.shadow32.get(key)
 # ------------------------------------------------------------------------------------------------ fused LayerNorm
 
 

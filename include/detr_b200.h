@@ -123,19 +123,23 @@ int detr_criterion_bwd_f32(const float* grad_losses,
  * that the persistent kernel splits between two CTAs (merged by a second small launch). */
 int64_t detr_attention_fwd_workspace_floats(int B, int nh, int L, int S);
 int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
-                            const void* v, int64_t v_sb, int64_t v_sl, void* o, int64_t o_sb, int64_t o_sl,
+                            const void* v, int64_t v_sb, int64_t v_sl, void* o, int64_t o_sb, int64_t o_sl, void* o_lo,
                             float* lse, float* workspace, const uint8_t* key_padding_mask, int64_t kpm_sb,
                             const uint8_t* attention_mask, int B, int nh, int L, int S, float dropout_p,
                             uint64_t seed, const uint64_t* seed_ptr, void* stream);
 
-/* Backward of the call above: dq (B,L,C), dk/dv (B,S,C) bf16 from d_o (B,L,C) bf16, the forward's inputs, output
+/* `o_lo` (optional, forward output / backward input, bf16 with o's strides): the part of the fp32 output lost when o is
+ * rounded to bf16.  The backward's delta = rowsum(dO * (o + o_lo)) is then exact to ~2^-17: an error of delta is common to all
+ * keys of a row, so with nearly uniform attention (dS = P (dP - delta) is a difference of almost equal numbers) it does not
+ * average out in dQ / dK the way the reference's per-element bf16 rounding does.
+ * Backward of the call above: dq (B,L,C), dk/dv (B,S,C) bf16 from d_o (B,L,C) bf16, the forward's inputs, output
  * `o` and `lse`.  Scratch: delta float[B*nh*L] (rowsum(dO o O)) and dq_partial
  * float[detr_attention_bwd_workspace_floats(B,nh,L,S)] (one fp32 dQ partial per 128-key tile).  Same masks /
  * dropout_p / seed as forward.  Three launches: delta, the fused dK+dV+dQ-partial kernel (CTA per key tile, every
  * score tile recomputed once), the fixed-order dQ reduction; deterministic, no atomics. */
 int64_t detr_attention_bwd_workspace_floats(int B, int nh, int L, int S);
 int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl, const void* k, int64_t k_sb, int64_t k_sl,
-                            const void* v, int64_t v_sb, int64_t v_sl, const void* o, int64_t o_sb, int64_t o_sl,
+                            const void* v, int64_t v_sb, int64_t v_sl, const void* o, int64_t o_sb, int64_t o_sl, const void* o_lo,
                             const void* d_o, int64_t do_sb, int64_t do_sl, const float* lse, float* delta,
                             float* dq_partial, void* dq, int64_t dq_sb, int64_t dq_sl, void* dk, int64_t dk_sb, int64_t dk_sl,
                             void* dv, int64_t dv_sb, int64_t dv_sl, const uint8_t* key_padding_mask, int64_t kpm_sb,
@@ -196,7 +200,8 @@ int detr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int b
  * query embedding" of detr/model.py:221-224,173-182 run as the PROLOGUE of the projections that consume them.  x fp32 /
  * bf16 (x_dtype 0 / 1) [M][256] row stride ldx; output columns < n_pos_end (a multiple of 128) are computed from
  * LN(x) + addend, the others from LN(x) (q|k|v in one launch: n_pos_end = 512).  addend fp32, row of flattened row m at
- * (m / rows_per_batch) * add_sb + (m % rows_per_batch) * add_sr.  epilogue 0 or 1 as above.  Optional outputs for the
+ * (m / rows_per_batch) * add_sb + (m % rows_per_batch) * add_sr, in one of two forms: a dense (M, 256) block
+ * (add_sb == rows_per_batch * add_sr) or a broadcast of rows_per_batch >= 8 rows over the batch (add_sb == 0).  epilogue 0 or 1 as above.  Optional outputs for the
  * backward pass: a_plain / a_pos bf16 [M][256] (the two normalised operands), mean / rstd float[M]. */
 int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, float eps,
                       const float* addend, int64_t add_sb, int64_t add_sr, int rows_per_batch, int n_pos_end,

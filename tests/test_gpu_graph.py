@@ -31,9 +31,11 @@ def test_graphed_step_matches_eager(cuda):
     o2 = make_optimizer(m2, lr=1e-4, capturable=True)
     snapshot = copy.deepcopy(m2.state_dict())
     g = GraphedTrainStep(m2, c2, o2, batches[0], gt_cap=8, warmup=2)
-    # warm-up inside the constructor already stepped the weights: rewind model and optimizer state, then replay
-    m2.load_state_dict(snapshot)
-    g.reset_optimizer_state()
+    # the constructor's warm-up iterations are real optimizer steps, but it puts parameters, buffers, moments and step
+    # counts back afterwards: training starts from exactly the state that was handed in
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, snapshot[k]), k
+    assert float(g.fopt.step_t) == 0.0 and float(g.fopt.flat_m.abs().max()) == 0.0 and float(g.fopt.flat_v.abs().max()) == 0.0
     graphed = []
     for b in batches:
         g.load(b)
@@ -54,7 +56,7 @@ def test_graph_replays_draw_fresh_dropout_masks(cuda):
     g = GraphedTrainStep(m, c, opt, b, gt_cap=8, warmup=2)
     losses = [float(g.step()) for _ in range(4)]
     assert len(set(round(l, 6) for l in losses)) > 1, losses
-    assert int(g.step_counter.item()) >= 6
+    assert int(g.step_counter.item()) == 4        # one per replay; the warm-up's increments were rolled back
 
 
 def test_prefetch_commit_equals_load(cuda):
@@ -112,3 +114,52 @@ def test_flat_adamw_matches_torch(cuda):
     for q1, q2 in zip(p1, f.params):
         assert q1.shape == q2.shape and q1.stride() == q2.stride()
         assert torch.allclose(q1, q2, rtol=1e-4, atol=1e-6), (q1 - q2).abs().max()
+
+
+def test_load_without_sync_keeps_batches_apart(cuda):
+    """load() rewrites pinned staging on the host and enqueues async copies; with the host running steps ahead
+    of the device the next load() must not overwrite staging an enqueued copy has yet to read.  Queue several DISTINCT batches
+    back to back with no synchronisation in between (a slow kernel holds the stream back) and compare every step's loss with
+    the fully synchronised run."""
+    from detr_b200.harness import GraphedTrainStep, make_optimizer, synthetic_batch
+    m, c = _make(cuda, train=False)
+    opt = make_optimizer(m, lr=0.0, weight_decay=0.0, capturable=True)      # frozen weights: a batch's loss identifies it
+    batches = [synthetic_batch(2, 160, 200, 11, 6, seed=s, pin=True) for s in range(20, 28)]
+    g = GraphedTrainStep(m, c, opt, batches[0], gt_cap=8, warmup=2)
+    ref = []
+    for b in batches:
+        g.load(b)
+        ref.append(float(g.step()))
+        torch.cuda.synchronize()
+    assert len(set(round(r, 5) for r in ref)) > 1
+    got = []
+    torch.cuda._sleep(int(2e8))                 # ~0.1 s of device work queued first: every load() below runs ahead of the GPU
+    for b in batches:
+        g.load(b)
+        got.append(g.step().clone())
+    torch.cuda.synchronize()
+    assert [float(x) for x in got] == ref
+
+
+def test_faulty_batch_is_skipped_and_reported(cuda):
+    """a data fault (here a degenerate ground-truth box) poisons that step's losses; the optimizer kernels must
+    skip the update (weights, moments and step count untouched), the status word must not stay set, the fault is raised by the
+    next step()/poll_faults(), and the following clean batch trains normally."""
+    from detr_b200.harness import GraphedTrainStep, make_optimizer, synthetic_batch
+    m, c = _make(cuda, train=False)
+    opt = make_optimizer(m, lr=1e-4, capturable=True)
+    good = synthetic_batch(2, 160, 200, 11, 6, seed=31)
+    bad = synthetic_batch(2, 160, 200, 11, 6, seed=32)
+    bad["boxes_normalized"][0][0] = torch.tensor([0.6, 0.6, 0.2, 0.2])      # x2 < x1: detr/utils.py:87-88 would assert
+    g = GraphedTrainStep(m, c, opt, good, gt_cap=8, warmup=2)
+    g.load(good); l0 = float(g.step())
+    assert l0 == l0 and float(g.fopt.step_t) == 1.0
+    before = g.fopt.flat_p.clone()
+    g.load(bad); l1 = float(g.step())
+    assert l1 != l1                                                            # NaN: poisoned
+    assert torch.equal(g.fopt.flat_p, before) and float(g.fopt.step_t) == 1.0  # update skipped
+    with pytest.raises(AssertionError):
+        g.poll_faults(wait=True)
+    g.load(good); l2 = float(g.step())
+    assert l2 == l2 and float(g.fopt.step_t) == 2.0 and not torch.equal(g.fopt.flat_p, before)
+    g.poll_faults(wait=True)                                                   # nothing pending
