@@ -39,6 +39,17 @@ NUM_CLASSES = 91
 H, W = 800, 1066
 SP = (H // 32) * ((W + 31) // 32)  # 850 tokens
 WORKLOAD = "DETR-R50 full training step bf16, 8 img/GPU synthetic 800x1066 (padded 800x1088, 850 tokens), 100 queries, 91 classes"
+# BASELINE.json configs that are bench lines: 2 (the headline metric, what the driver runs), 5 (R101, 300 queries, 4 img/GPU) and
+# 4 (DC5: the 6+6 layer transformer on synthetic stride-16 tokens, 3 350 per image -- the reference's Backbone hard-codes stride 32,
+# detr/model.py:431-435, so DC5 exists only as the transformer workload of SURVEY.md 8d)
+CONFIGS = {
+    2: {"backbone": "resnet50", "queries": 100, "per_gpu_batch": 8, "metric": METRIC, "workload": WORKLOAD},
+    5: {"backbone": "resnet101", "queries": 300, "per_gpu_batch": 4, "metric": "detr_r101_q300_train_images_per_sec",
+        "workload": "DETR-R101 full training step bf16, 300 object queries, 4 img/GPU synthetic 800x1066 (BASELINE config 5)"},
+    4: {"backbone": None, "queries": 100, "per_gpu_batch": 8, "metric": "detr_dc5_transformer_fwd_bwd_images_per_sec",
+        "workload": "DETR-R50-DC5 transformer (6 encoder + 6 decoder layers, 100 queries) forward + backward on synthetic stride-16 "
+                    "tokens: 50 x 67 = 3 350 per image, 8 img/GPU, bf16 autocast, train mode (BASELINE config 4)"},
+}
 
 
 def peaks():
@@ -145,7 +156,12 @@ def run_b200(args):
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(1234 + rank)
 
-    cfg = DETRConfig(num_classes=NUM_CLASSES)
+    C = CONFIGS[args.config]
+    if args.config == 4:
+        return run_dc5(args, dev, world, rank, C)
+    global PER_GPU_BATCH
+    PER_GPU_BATCH = C["per_gpu_batch"]
+    cfg = DETRConfig(num_classes=NUM_CLASSES, backbone=C["backbone"], num_object_queries=C["queries"])
     torch.manual_seed(1234)   # identical replicas on every rank (data differs per rank)
     model = DetrHarness(cfg).to(dev).to(memory_format=torch.channels_last).train()
     crit = SetCriterion(NUM_CLASSES, HungarianMatcher(cost_class=1.0, cost_bbox=5.0, cost_giou=2.0), 1.0, 5.0, 2.0, 0.1).to(dev).train()
@@ -174,11 +190,13 @@ def run_b200(args):
     else:
         # default: the same step captured in CUDA graphs (harness.GraphedTrainStep) -- replay is GPU-bound
         opt = make_optimizer(model, capturable=True)
-        graphed = GraphedTrainStep(model, crit, opt, host)
+        graphed = GraphedTrainStep(model, crit, opt, host, accumulate=args.accum)
         h2d = graphed.load(host)
         torch.cuda.synchronize()
 
         def step_resident():
+            for _ in range(args.accum - 1):       # non-boundary micro-steps: forward/backward only (no collective, no update)
+                graphed.step()
             return graphed.step()
 
         graphed.prefetch(host)
@@ -187,10 +205,13 @@ def run_b200(args):
             # double-buffered input pipeline, as a data loader feeds a training loop: this step consumes the batch whose H2D
             # copy (pinned host memory -> staging buffer, copy stream) was started during the previous step, and starts the
             # copy for the next one -- one full-batch H2D copy and one loss read-back inside every timed step
-            graphed.commit()                                # wait for the staged images, D2D into the graph's input, GT upload
-            graphed.prefetch(host)                          # H2D of the next step's images, overlapping this step's compute
-            return float(graphed.step().item())             # D2H read of the step's loss
-        own_launches = graphed.own_launches_per_step
+            for _ in range(args.accum):
+                graphed.commit()                            # wait for the staged images, D2D into the graph's input, GT upload
+                graphed.prefetch(host)                      # H2D of the next micro-batch's images, overlapping this one's compute
+                loss = graphed.step()
+            return float(loss.item())                       # D2H read of the step's loss
+        own_launches = graphed.own_launches_per_step * args.accum
+        h2d *= args.accum
 
     def barrier():
         if world > 1:
@@ -242,15 +263,21 @@ def run_b200(args):
         prof_step = lambda: train_step(model, crit, eager_opt, resident)
         # (at N > 1 these three untimed steps skip the gradient all-reduce: the replicas diverge AFTER every timed region
         #  has ended, which is harmless; every rank runs them so that the num_boxes all-reduce stays collective)
+    prof_step()                                  # (the eager step's own warm-up: allocator, autograd graph)
+    torch.cuda.synchronize()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with _lib.profile() as prof:
+        pe0.record()
         for _ in range(3):
             prof_step()
+        pe1.record()
     torch.cuda.synchronize()
     rows = prof.summary()
+    eager_step_ms = pe0.elapsed_time(pe1) / 3
     step_ms = ms / args.steps
 
     if rank == 0:
-        imgs = PER_GPU_BATCH * world
+        imgs = PER_GPU_BATCH * world * args.accum
         pk = peaks()
         own = {f"{n}{list(t) if t else ''}": {"calls_per_step": c / 3, "ms_per_step": round(t_ms / 3, 4)} for (n, t), (c, t_ms) in sorted(rows.items(), key=lambda kv: -kv[1][1])}
         # dominant own launch: encoder self-attention backward (dK/dV + dQ + delta), shape (B=8, nh=8, L=S=850)
@@ -265,10 +292,10 @@ def run_b200(args):
             roof = {"kernel": "attention_bwd (delta + fused dK/dV/dQ-partial + dQ reduction), encoder self-attention B=8 nh=8 L=S=850", "bound": "tensor",
                     "achieved": round(ach, 2), "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops_sustained"], 4),
                     "peak_source": pk["src"] + " sustained (kernel timed inside a long step)",
-                    # dram__bytes_read.sum + dram__bytes_write.sum of the call's three kernels, one `ncu --set full` capture
-                    # (profiles/r01_attention_ncu_full_v4.md; ncu flushes L2 between kernels, so the 48.8 MB the dQ reduction
-                    # re-reads from L2 in a real step counts as DRAM traffic here)
-                    "traffic": 82.0e6, "traffic_algorithmic": 14.1e6,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of the call's kernels from the committed `ncu --set full` capture
+                    # (written by tools/ncu_traffic.py; ncu flushes L2 between kernels, so what the dQ reduction re-reads from L2 in a
+                    # real step counts as DRAM traffic there); null when no capture of this build is committed
+                    "traffic": ncu_traffic("attention_bwd_encoder"), "traffic_algorithmic": 14.1e6,
                     "ms_per_launch": round(tot / calls, 4), "flops_per_launch": flops,
                     "note": "head_dim 32: one MUFU exp per 128 tensor FLOPs caps the tensor pipe at ~25% (SURVEY.md 7.1); the persistent "
                             "kernel is bound by per-warp latency chains and issue slots, not by a pipe (profiles/r01_attention_ncu_full_v4.md)"}
@@ -279,10 +306,11 @@ def run_b200(args):
                                    "frac": round(f2 / (t2 / c2 * 1e-3) / 1e12 / pk["tflops_sustained"], 4)}
         own_ms = sum(t for _, t in rows.values()) / 3
         out = {
-            "metric": METRIC, "value": round(imgs * args.steps / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": C["metric"], "value": round(imgs * args.steps / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "impl": "b200",
-            "config": {"workload": WORKLOAD, "global_batch": imgs, "per_gpu_batch": PER_GPU_BATCH, "parallelism": f"dp{world}",
+            "config": {"workload": C["workload"], "baseline_config": args.config, "global_batch": imgs, "per_gpu_batch": PER_GPU_BATCH,
+                       "gradient_accumulation": args.accum, "parallelism": f"dp{world}",
                        "mode": "train (dropout on)", "optimizer": "AdamW fused, clip 1.0",
                        "execution": "eager + DDP" if args.eager else "CUDA graphs (fwd+bwd | NCCL all-reduce of flat grads | clip+AdamW)",
                        "l2": "no explicit flush: every step streams >1 GB of ResNet activations through the 126 MB L2",
@@ -291,15 +319,183 @@ def run_b200(args):
             "e2e": {"value": round(imgs * args.steps / (ms_e2e * 1e-3), 3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-            "own_kernels": {"ms_per_step": round(own_ms, 3), "share_of_step": round(own_ms / step_ms, 4), "by_call": own},
+            # event-timed launches of libdetr_b200.so in the EAGER replay of the step, as a share of that same eager step (host-launch
+            # bound, ~3x the graph replay); the share of the graph-replayed step is the ncu launch-list share in profiles/
+            "own_kernels": {"ms_per_step": round(own_ms, 3), "eager_step_ms": round(eager_step_ms, 3),
+                            "share_of_eager_step": round(own_ms / eager_step_ms, 4), "ncu_share_of_step": ncu_traffic("own_share_of_step"),
+                            "by_call": own},
         }
-        if world == 1:
-            out["matcher"] = matcher_metric(dev)
+        if world == 1 and args.config == 2:
+            m = matcher_metric(dev)
+            out["roofline_matcher"] = m.pop("roofline_matcher")
+            out["roofline_criterion"] = m.pop("roofline_criterion")
+            out["matcher"] = m
             out["cpu_baseline"] = cpu_baseline(sample_steps=8)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_dc5(args, dev, world, rank, C):
+    """BASELINE config 4: the 6 + 6 layer transformer on stride-16 tokens (50 x 67 = 3 350 per image), forward + backward captured
+    in one CUDA graph.  No backbone (the reference's is stride 32 only), no optimizer: this is the attention-dominated workload."""
+    import torch.distributed as dist
+    from detr_b200 import _lib, attention
+    from detr_b200.harness import positional_encoding_tokens
+    from detr_b200.model import DETRConfig, Decoder, Encoder
+    eh, ew = (int(v) for v in args.grid.split("x"))       # default 50 x 67 (stride 16); 25x34 = the stride-32 map of config 2
+    B, Q = C["per_gpu_batch"], C["queries"]
+    S = eh * ew
+    torch.manual_seed(1234)
+    cfg = DETRConfig(num_classes=NUM_CLASSES, num_object_queries=Q)
+    enc, dec = Encoder(cfg).to(dev).train(), Decoder(cfg).to(dev).train()
+    qe = torch.nn.Parameter(0.02 * torch.randn(Q, 256, device=dev))
+    params = list(enc.parameters()) + list(dec.parameters()) + [qe]
+    heights = torch.full((B,), 800, dtype=torch.int32, device=dev)
+    widths = torch.full((B,), 1066, dtype=torch.int32, device=dev)
+    pos, mask = positional_encoding_tokens(eh, ew, heights, widths, 16 if eh >= 50 else 32, 128, 10000)
+    host_x = torch.randn(B, S, 256).bfloat16().pin_memory()        # what input_proj hands the encoder under autocast
+    x = torch.empty(B, S, 256, dtype=torch.bfloat16, device=dev)
+    x.copy_(host_x)
+    w = torch.randn(B, 6, Q, 256, device=dev)
+    loss_buf = torch.zeros((), device=dev)
+    step_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    attention.set_dropout_step_tensor(step_counter)
+
+    def fwd_bwd():
+        for q in params:
+            q.grad = None
+        step_counter.add_(1)
+        xin = x.detach().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            mem = enc(xin, position_embedding=pos, key_padding_mask=mask)
+            out = dec(mem, position_embedding=pos, object_query_embedding=qe[None].expand(B, -1, -1), key_padding_mask=mask)
+        loss = (out.float() * w).mean()
+        loss.backward()
+        loss_buf.copy_(loss.detach())
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fwd_bwd()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fwd_bwd()
+    own_launches = _lib.launch_count - l0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_e2e():
+        x.copy_(host_x, non_blocking=True)
+        graph.replay()
+        return float(loss_buf.item())
+
+    for _ in range(max(args.warmup, 3)):
+        graph.replay()
+    if args.ncu_step:   # profiling aid (never a bench number): one replay between cudaProfilerStart/Stop
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        graph.replay()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    if args.graph_profile:
+        # profiling aid: a second capture with timable event-record nodes around every C-ABI call: per-call time INSIDE the replay
+        with _lib.profile(external=True) as gp:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                fwd_bwd()
+        for _ in range(3):
+            g2.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g2.replay(); e1.record()
+        torch.cuda.synchronize()
+        agg = {}
+        for name, tag, a, b in gp.records:
+            k = f"{name}{list(tag) if tag else ''}"
+            n, t = agg.get(k, (0, 0.0))
+            agg[k] = (n + 1, t + a.elapsed_time(b))
+        tot = sum(t for _, t in agg.values())
+        print(f"graph replay {e0.elapsed_time(e1):.3f} ms; C-ABI calls inside it: {tot:.3f} ms in {sum(n for n, _ in agg.values())} calls")
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {t * 1e3:8.1f} us {n:4d} calls {t * 1e3 / n:7.1f} us/call  {k}")
+        return
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    ms = timed(graph.replay, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+    with _lib.profile() as prof:
+        for _ in range(3):
+            fwd_bwd()
+    torch.cuda.synchronize()
+    rows = prof.summary()
+    if rank == 0:
+        pk = peaks()
+        imgs = B * world
+        roof = None
+        kb, kf = ("detr_attention_bwd_bf16", (B, 8, S, S)), ("detr_attention_fwd_bf16", (B, 8, S, S))
+        if kb in rows:
+            calls, tot = rows[kb]
+            flops = 2.5 * 4.0 * S * S * 256 * B
+            ach = flops / (tot / calls * 1e-3) / 1e12
+            roof = {"kernel": f"attention_bwd, DC5 encoder self-attention B={B} nh=8 L=S={S}", "bound": "tensor", "achieved": round(ach, 2),
+                    "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tflops_sustained"], 4),
+                    "peak_source": pk["src"] + " sustained", "ms_per_launch": round(tot / calls, 4), "flops_per_launch": flops,
+                    "traffic": ncu_traffic("attention_bwd_dc5")}
+            if kf in rows:
+                c2, t2 = rows[kf]
+                f2 = 4.0 * S * S * 256 * B
+                roof["forward"] = {"ms_per_launch": round(t2 / c2, 4), "achieved": round(f2 / (t2 / c2 * 1e-3) / 1e12, 2),
+                                   "frac": round(f2 / (t2 / c2 * 1e-3) / 1e12 / pk["tflops_sustained"], 4)}
+        own = {f"{n}{list(t) if t else ''}": {"calls_per_step": c / 3, "ms_per_step": round(t_ms / 3, 4)}
+               for (n, t), (c, t_ms) in sorted(rows.items(), key=lambda kv: -kv[1][1])}
+        print(json.dumps({
+            "metric": C["metric"], "value": round(imgs * args.steps / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "b200",
+            "config": {"workload": C["workload"], "baseline_config": 4, "global_batch": imgs, "per_gpu_batch": B, "parallelism": f"replicas x{world}",
+                       "tokens_per_image": S, "execution": "one CUDA graph (forward + backward)",
+                       "l2": "no explicit flush: one step streams ~2 GB of activations through the 126 MB L2"},
+            "e2e": {"value": round(imgs * args.steps / (ms_e2e * 1e-3), 3), "unit": UNIT, "h2d_bytes_per_step": host_x.numel() * 2,
+                    "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": own_launches * args.steps, "clocks": clocks, "roofline": roof, "own_kernels": {"by_call": own},
+        }), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ncu_traffic(key):
+    """Numbers read from the committed ncu captures (profiles/r02_ncu_numbers.json, written by tools/ncu_traffic.py): never a
+    literal in this file.  None when the key is absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_numbers.json"))).get(key)
+    except Exception:
+        return None
 
 
 def matcher_metric(dev):
@@ -342,6 +538,29 @@ def matcher_metric(dev):
         out = crit({"pred_logits": lg, "pred_boxes": bx}, tg)
         sum(v for k, v in out.items() if k.startswith("loss")).backward()
     ms_full = med(full)
+    # per-kernel CUDA-event timings of the criterion launches in the same loop (the C-ABI calls are bracketed on their stream)
+    from detr_b200 import _lib
+    for _ in range(2):
+        full()
+    with _lib.profile() as prof:
+        for _ in range(10):
+            full()
+    torch.cuda.synchronize()
+    kms = {n: v for (n, _), v in prof.median().items()}
+    pk = peaks()
+    by_m = sum(38400 + 40 * c for c in counts) * L                    # logits + boxes + GT in, indices out; costs stay in smem
+    by_f = sum(36800 + 40 * c for c in counts) * L                    # criterion forward: logits + matched boxes / labels
+    by_b = sum(2 * 36800 + 1600 + 40 * c for c in counts) * L         # backward: logits re-read, d_logits + d_boxes written
+    def roof(name, byt, ms_k, note):
+        ach = byt / (ms_k * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach / pk["hbm"], 4),
+                "peak_source": pk["src"] + " burst (kernel timed alone)", "ms_per_launch": round(ms_k, 4), "bytes_per_launch": byt,
+                "traffic": ncu_traffic(name.split()[0]), "note": note}
+    roof_m = roof("hungarian_match_kernel (cost matrix + assignment, 1 536 problems)", by_m, ms_match,
+                  "latency-bound by construction: serial augmenting paths (~500 dependent row scans per problem); reported against HBM for transparency")
+    roof_c = {"forward": roof("criterion_fwd (dense kernel + finalize)", by_f, kms.get("detr_criterion_fwd_f32", float("nan")),
+                              "two launches; ~17 us latency floor (offset -> index -> label/box -> class weight load chain per CTA)"),
+              "backward": roof("criterion_bwd_dense_kernel", by_b, kms.get("detr_criterion_bwd_f32", float("nan")), "one launch, bulk-copy staged")}
     # the reference's path for the same problems on the host cores (all 256 images x 6 layers, a few seconds): per-image
     # Python loop, torch fp32 cost matrix, SciPy-equivalent LSAP (oracle/lsap.c), as detr/matcher.py:40-99 + detr/loss.py:213-217
     from oracle import detr_oracle as O
@@ -354,7 +573,8 @@ def matcher_metric(dev):
     for l in range(L):
         O.hungarian_match(c_lg[:, l], c_bx[:, l], c_lab, c_gt, 1.0, 5.0, 2.0)
     cpu_s = time.perf_counter() - t0
-    return {"metric": "matcher_images_per_sec", "value": round(B / ms_match * 1e3, 1), "unit": "images/s", "ms": round(ms_match, 4),
+    return {"roofline_matcher": roof_m, "roofline_criterion": roof_c,
+            "metric": "matcher_images_per_sec", "value": round(B / ms_match * 1e3, 1), "unit": "images/s", "ms": round(ms_match, 4),
             "problems": B * L, "sum_gt": sum(counts),
             "workload": "HungarianMatcher only: batch 256 x 6 layers, 100 queries x 1-100 GT boxes, 92 logits, fp32 (BASELINE config 3)",
             "matcher_plus_criterion_fwd_bwd": {"value": round(B / ms_full * 1e3, 1), "unit": "images/s", "ms": round(ms_full, 4)},
@@ -395,27 +615,55 @@ def build_cpu_reference():
     return model, OracleCriterion()
 
 
+def build_real_reference():
+    """The UNMODIFIED reference classes from the git-ignored baseline/_ref/ (tools/vendor_reference.py copies /root/reference/detr
+    there; it travels to the GPU box with the snapshot): detr.model.DETR + detr.matcher.HungarianMatcher + detr.loss.SetCriterion.
+    None when the copy is absent."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import refshim
+        if refshim.import_reference() is None:
+            return None
+        import detr.loss as rloss
+        import detr.matcher as rmatcher
+        import detr.model as rmodel
+    except Exception as ex:          # noqa: BLE001 -- any import problem means "fall back to the port", never a crash of the bench
+        print(f"bench.py: reference import failed ({ex}); falling back to the oracle port", file=sys.stderr)
+        return None
+    torch.manual_seed(0)
+    model = rmodel.DETR(rmodel.DETRConfig(num_classes=NUM_CLASSES)).train()
+    crit = rloss.SetCriterion(NUM_CLASSES, rmatcher.HungarianMatcher(cost_class=1.0, cost_bbox=5.0, cost_giou=2.0),
+                              weight_label_ce=1.0, weight_bbox_l1=5.0, weight_bbox_giou=2.0, eos_coef=0.1).train()
+    return model, crit
+
+
 def cpu_step_fn(batch_size: int):
+    """-> (step function, cores, kind): one fp32 training step (detr/train.py:258-267 body) of the reference on the host cores:
+    the real classes when baseline/_ref is present (kind "reference"), else the oracle port (kind "port")."""
     from detr_b200.harness import make_optimizer, synthetic_batch, train_step
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model, crit = build_cpu_reference()
+    real = build_real_reference()
+    kind = "reference" if real is not None else "port"
+    model, crit = real if real is not None else build_cpu_reference()
     opt = make_optimizer(model, fused=False)
     batch = synthetic_batch(batch_size, H, W, NUM_CLASSES, 20, seed=7)
-    return (lambda: float(train_step(model, crit, opt, batch, autocast_dtype=None))), cores
+    return (lambda: float(train_step(model, crit, opt, batch, autocast_dtype=None))), cores, kind
 
 
 def cpu_baseline(sample_steps: int = 1, batch_size: int = 2):
     """Bounded CPU sample of the same workload: full fp32 training steps of batch 2 (BASELINE config 1 shape)."""
-    step, cores = cpu_step_fn(batch_size)
+    step, cores, kind = cpu_step_fn(batch_size)
     step()  # warm-up (allocator, oneDNN primitive caches)
     t0 = time.perf_counter()
     for _ in range(sample_steps):
         step()
     dt = (time.perf_counter() - t0) / sample_steps
-    return {"value": round(batch_size / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{sample_steps} fp32 training step(s) of batch {batch_size} at 800x1066 through the oracle port "
-                      f"(oracle/detr_oracle.py + torchvision ResNet-50 on CPU), {dt:.2f} s/step; SciPy-equivalent LSAP is single-threaded"}
+    what = ("the reference's own classes (baseline/_ref: detr.model.DETR, HungarianMatcher with SciPy, SetCriterion)" if kind == "reference"
+            else "the oracle port (oracle/detr_oracle.py + torchvision ResNet-50)")
+    return {"value": round(batch_size / dt, 4), "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{sample_steps} fp32 training step(s) of batch {batch_size} at 800x1066 through {what} on the host cores, "
+                      f"{dt:.2f} s/step; the LSAP is single-threaded"}
 
 
 def run_reference(args):
@@ -423,7 +671,7 @@ def run_reference(args):
     if rank != 0:
         return
     batch_size = 2
-    step, cores = cpu_step_fn(batch_size)
+    step, cores, kind = cpu_step_fn(batch_size)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -437,7 +685,7 @@ def run_reference(args):
         "ms_per_step": round(dt / args.steps * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "reference",
         "config": {"workload": WORKLOAD, "sample": sample, "parallelism": "cpu"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -450,6 +698,10 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--eager", action="store_true", help="do not capture the step in CUDA graphs (DDP eager path)")
     ap.add_argument("--ncu-step", action="store_true", help="warm up, then run exactly one step between cudaProfilerStart/Stop")
+    ap.add_argument("--config", type=int, choices=[2, 4, 5], default=2, help="BASELINE.json config: 2 (default, the headline metric), 4 (DC5 transformer), 5 (R101, 300 queries)")
+    ap.add_argument("--graph-profile", action="store_true", help="--config 4: per-call timings inside a CUDA-graph replay (event-record nodes)")
+    ap.add_argument("--grid", default="50x67", help="--config 4 only: feature-map size H'xW' (50x67 = DC5 stride 16; 25x34 = the stride-32 map)")
+    ap.add_argument("--accum", type=int, default=1, help="gradient-accumulation micro-batches per optimizer step (detr/train.py:116; fixed global batch 64 = 8 img x N GPUs x accum)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -26,6 +26,8 @@
 // cross-warp synchronisation.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <set>
 #include <utility>
@@ -207,12 +209,12 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& e, uint32_t key, in
 template <int EPI, typename TO>
 __device__ __forceinline__ void epi_tile(const EpiParams& e, const CUtensorMap* tm_out, const CUtensorMap* tm_aux, const CUtensorMap* tm_res,
                                          uint32_t key, uint32_t tmem_acc, uint8_t* stg, uint64_t* ldbar, int& n_ld, int warp, int lane,
-                                         int m0, int n0, uint64_t* acc_full, uint32_t acc_parity, uint64_t* acc_empty) {
+                                         int m0, int n0, uint64_t* acc_full, uint32_t acc_parity, uint64_t* acc_empty, int rows_valid = kGM) {
     constexpr bool kOutF32 = sizeof(TO) == 4;
     constexpr bool kLoad = EPI == EPI_RES || EPI == EPI_GELU_BWD;
     const int q = warp & 3, h = warp >> 2;
     const int mr = m0 + q * 32, nc = n0 + h * 64;
-    const bool active = nc < e.N;                 // warp-uniform
+    const bool active = nc < e.N && q * 32 < rows_valid && mr < e.M;   // warp-uniform; rows beyond rows_valid belong to other CTAs
     // the previous tile's TMA stores have finished READING the patch before anything is written into it
     if (lane == 0) tma_store_wait_read0();
     __syncwarp();
@@ -305,7 +307,6 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const uint32_t tmem = *tmem_slot;
     const int tiles = p.m_tiles * p.n_tiles;
     pdl_wait();      // everything below reads what the previous kernel of the stream wrote
-    pdl_trigger();
 
     if (warp == kEpiWarps) {
         if (lane == 0) {
@@ -367,8 +368,9 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             epi_tile<EPI, TO>(p.e, &tm_out, &tm_aux, &tm_res, key, tmem + buf * kGN, stg, ldbar + warp, n_ld, warp, lane, mt * kGM, nt * kGN,
                               acc_full + buf, (li / kAccBufs) & 1, acc_empty + buf);
         }
-        if (lane == 0) tma_store_wait_all0();
+        if (lane == 0) tma_store_wait_read0();   // shared memory must outlive the reads; the writes complete with the grid
     }
+    pdl_trigger();   // a dependent launch may start its prologue while this CTA tears down (it waits for the whole grid before reading)
     tc_fence_before();
     __syncthreads();
     if (warp == kEpiWarps + 1) tmem_dealloc(tmem, kAccCols);
@@ -402,6 +404,8 @@ struct LnGemmParams {
     __nv_bfloat16* a_plain; __nv_bfloat16* a_pos;   // optional [M][256] copies of the two A variants (the weight gradients need them)
     float* mean; float* rstd;                       // optional [M]
     int m_tiles, n_tiles, groups;                   // CTA = (row block, column group): groups column groups per row block
+    int rows_per_cta;                               // 128, 64 or 32 real rows per row block (the MMA tile always has 128: with few rows the
+                                                    // prologue -- a latency chain per round of 32 rows -- is spread over more CTAs instead)
     long long* dbg;                                 // optional clock64 timeline of CTA 0 (DETR_GEMM_TIMELINE builds), NULL in production
 };
 
@@ -440,7 +444,7 @@ __device__ __forceinline__ uint4 pack4(const float2 (&y)[4]) {
 template <typename TX>
 __device__ __forceinline__ void ln_prologue(const LnGemmParams& p, uint8_t* a_plain_s, uint8_t* a_pos_s, int mt, int warp, int lane,
                                             bool has_plain, bool has_pos, bool side) {
-    constexpr int kRows = kGM / kEpiWarps;                  // 16 rows per warp
+    const int kRows = p.rows_per_cta / kEpiWarps;           // 16 / 8 / 4 rows per warp
     constexpr int kRound = 4;
     float2 g[4], b[4];
     raw_unpack(*reinterpret_cast<const RawRow<float>*>(p.gamma + lane * 8), g);
@@ -452,13 +456,14 @@ __device__ __forceinline__ void ln_prologue(const LnGemmParams& p, uint8_t* a_pl
     // broadcast form (add_sb == 0: every batch adds the same rpb rows, e.g. the decoder's query embedding): (m mod rpb) * add_sr,
     // kept incrementally -- rows advance by kEpiWarps <= rpb (the launcher guarantees one of the two forms)
     const bool a_bcast = p.add_sb == 0 && rpb < p.e.M;
-    int a_r = has_pos && a_bcast ? (mt * kGM + warp) % rpb : 0;
+    const int m_base = mt * p.rows_per_cta;
+    int a_r = has_pos && a_bcast ? (m_base + warp) % rpb : 0;
     RawRow<TX> xn[kRound];
     RawRow<float> an[kRound];
     auto request = [&](int r0) {   // raw loads of the round that starts at local row r0
 #pragma unroll
         for (int u = 0; u < kRound; ++u) {
-            const int m = min(mt * kGM + warp + (r0 + u) * kEpiWarps, m_last);
+            const int m = min(m_base + warp + (r0 + u) * kEpiWarps, m_last);
             raw_load(xn[u], reinterpret_cast<const TX*>(p.x) + (int64_t)m * p.x_ld + lane * 8);
             if (has_pos) {
                 raw_load(an[u], p.addend + (int64_t)(a_bcast ? a_r : m) * p.add_sr + lane * 8);
@@ -510,7 +515,7 @@ __device__ __forceinline__ void ln_prologue(const LnGemmParams& p, uint8_t* a_pl
         // ---- normalise, add, pack, store ----
 #pragma unroll
         for (int u = 0; u < kRound; ++u) {
-            const int r = warp + (r0 + u) * kEpiWarps, m = mt * kGM + r;
+            const int r = warp + (r0 + u) * kEpiWarps, m = m_base + r;
             const float rstd = rsqrtf(rs[u] * (1.f / kLnC) + p.eps);
             float2 v[4], y[4];
             raw_unpack(xr[u], v);
@@ -570,7 +575,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const int mt = blockIdx.x / p.groups, gi = blockIdx.x - mt * p.groups;
     const int nt0 = p.n_tiles * gi / p.groups, nt1 = p.n_tiles * (gi + 1) / p.groups;
     pdl_wait();
-    pdl_trigger();
     LN_STAMP(1);
 
     if (warp == kEpiWarps) {
@@ -592,11 +596,11 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
                 mbar_wait_sleep(a_full, 0);
 #pragma unroll
                 for (int kb = 0; kb < kLnKb; ++kb) {
-                    if (has_plain && p.a_plain != nullptr) tma_store_2d(&tm_aplain, a_plain_s + kb * kOpBytes, kb * kGK, mt * kGM);
-                    if (has_pos && p.a_pos != nullptr) tma_store_2d(&tm_apos, a_pos_s + kb * kOpBytes, kb * kGK, mt * kGM);
+                    if (has_plain && p.a_plain != nullptr) tma_store_2d(&tm_aplain, a_plain_s + kb * kOpBytes, kb * kGK, mt * p.rows_per_cta);
+                    if (has_pos && p.a_pos != nullptr) tma_store_2d(&tm_apos, a_pos_s + kb * kOpBytes, kb * kGK, mt * p.rows_per_cta);
                 }
                 tma_store_commit();
-                tma_store_wait_all0();
+                tma_store_wait_read0();
             }
         }
     } else if (warp == kEpiWarps + 1) {
@@ -639,14 +643,15 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         int li = 0, n_ld = 0;
         for (int nt = nt0; nt < nt1; ++nt, ++li) {
             const int buf = li % kAccBufs;
-            epi_tile<EPI, __nv_bfloat16>(p.e, &tm_out, &tm_aux, &tm_out, key, tmem + buf * kGN, stg, ldbar + warp, n_ld, warp, lane, mt * kGM,
-                                         nt * kGN, acc_full + buf, (li / kAccBufs) & 1, acc_empty + buf);
+            epi_tile<EPI, __nv_bfloat16>(p.e, &tm_out, &tm_aux, &tm_out, key, tmem + buf * kGN, stg, ldbar + warp, n_ld, warp, lane,
+                                         mt * p.rows_per_cta, nt * kGN, acc_full + buf, (li / kAccBufs) & 1, acc_empty + buf, p.rows_per_cta);
             if (li < 6) LN_STAMP(3 + li);
         }
         LN_STAMP(9);
-        if (lane == 0) tma_store_wait_all0();
+        if (lane == 0) tma_store_wait_read0();
         LN_STAMP(10);
     }
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     LN_STAMP(11);
@@ -694,7 +699,6 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     pdl_wait();
-    pdl_trigger();
 
     if (warp == kEpiWarps) {
         if (lane == 0) {
@@ -776,10 +780,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_consta
                 tma_store_2d(&tm_out, stg, k0, split * p.N + n0);
                 tma_store_2d(&tm_out, stg + kBoxBytes, k0 + 32, split * p.N + n0);
                 tma_store_commit();
-                tma_store_wait_all0();
+                tma_store_wait_read0();
             }
         }
     }
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     if (warp == kEpiWarps + 1) tmem_dealloc(tmem, kGN);
@@ -841,6 +846,14 @@ static int make_map_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t
     return 0;
 }
 
+// Programmatic dependent launch of the GEMM kernels: OFF by default.  Measured on the captured training step (B200): with the
+// attribute the step is 0.14-0.18 ms SLOWER (12.76 vs 12.58 ms) whether the kernels trigger early or late -- every CTA of these
+// kernels needs the whole SM (225 KB of shared memory, TMEM), so a dependent grid can only sit and wait.  DETR_B200_GEMM_PDL=1 turns it on.
+static bool gemm_pdl() {
+    static const bool on = []() { const char* e = getenv("DETR_B200_GEMM_PDL"); return e && e[0] && e[0] != '0'; }();
+    return on;
+}
+
 static int device_sms() {
     static int sms[64] = {0};
     int dev = 0;
@@ -880,7 +893,7 @@ static int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
     auto kern = gemm_stream_kernel<EPI, TO, kBMn>;
     if (int rc = opt_in_smem(kern, kStSmem, "gemm")) return rc;
     const int tiles = p.m_tiles * p.n_tiles, sms = device_sms();
-    launch_pdl(kern, dim3(tiles < sms ? tiles : sms), dim3(kStThreads), kStSmem, st, ta, tb, to, tx, tr, p);
+    launch_pdl_if(gemm_pdl(), kern, dim3(tiles < sms ? tiles : sms), dim3(kStThreads), kStSmem, st, ta, tb, to, tx, tr, p);
     DETR_CHECK_LAUNCH("gemm");
     return 0;
 }
@@ -956,15 +969,19 @@ extern "C" int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const 
     if (int rc = make_map_2d(&tw, w, N, kLnC, ldw, kGN, false, "gemm_ln(W)")) return rc;
     if (int rc = make_map_2d(&to, out, M, N, ldo, 32, false, "gemm_ln(out)")) return rc;
     tx = to; tap = to; tao = to;
-    if (a_plain) { if (int rc = make_map_2d(&tap, a_plain, M, kLnC, kLnC, kGM, false, "gemm_ln(a_plain)")) return rc; }
-    if (a_pos) { if (int rc = make_map_2d(&tao, a_pos, M, kLnC, kLnC, kGM, false, "gemm_ln(a_pos)")) return rc; }
+    // real rows per row block: 128 unless that leaves most of the machine idle (fewer than a quarter wave of row blocks: the
+    // decoder's 800 / 2 400 rows) -- then 32, so that the prologue's latency chain (one round per 32 rows) is one round long
+    const int rpc = (M + 127) / 128 >= device_sms() / 4 ? 128 : 32;
+    if (a_plain) { if (int rc = make_map_2d(&tap, a_plain, M, kLnC, kLnC, rpc, false, "gemm_ln(a_plain)")) return rc; }
+    if (a_pos) { if (int rc = make_map_2d(&tao, a_pos, M, kLnC, kLnC, rpc, false, "gemm_ln(a_pos)")) return rc; }
     if (epilogue == EPI_GELU) { if (int rc = make_map_2d(&tx, aux, M, N, ld_aux, 32, false, "gemm_ln(aux)")) return rc; }
     LnGemmParams p{};
     if (int rc = fill_epi(p.e, M, N, bias, dropout_p, seed, seed_ptr, "gemm_ln")) return rc;
     p.x = x; p.x_ld = ldx; p.gamma = gamma; p.beta = beta; p.eps = eps; p.addend = n_pos_end > 0 ? addend : nullptr; p.add_sb = add_sb; p.add_sr = add_sr;
     p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : M; p.n_pos_end = n_pos_end;
     p.a_plain = reinterpret_cast<__nv_bfloat16*>(a_plain); p.a_pos = reinterpret_cast<__nv_bfloat16*>(a_pos); p.mean = mean; p.rstd = rstd;
-    p.m_tiles = (M + kGM - 1) / kGM; p.n_tiles = (N + kGN - 1) / kGN;
+    p.rows_per_cta = rpc;
+    p.m_tiles = (M + rpc - 1) / rpc; p.n_tiles = (N + kGN - 1) / kGN;
     p.dbg = g_gemm_dbg;
     // column groups per row block: as many as fit in one wave (each group repeats the prologue of its row block)
     int groups = device_sms() / p.m_tiles;
@@ -977,7 +994,7 @@ extern "C" int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const 
     do {                                                                         \
         auto kern = gemm_ln_kernel<E, TX>;                                       \
         if (int rc = opt_in_smem(kern, kLnSmem, "gemm_ln")) return rc;           \
-        launch_pdl(kern, grid, dim3(kLnThreads), kLnSmem, st, tw, to, tx, tap, tao, p); \
+        launch_pdl_if(gemm_pdl(), kern, grid, dim3(kLnThreads), kLnSmem, st, tw, to, tx, tap, tao, p); \
     } while (0)
     if (epilogue == EPI_BIAS) { if (x_dtype == 0) LN_GO(EPI_BIAS, float); else LN_GO(EPI_BIAS, __nv_bfloat16); }
     else                      { if (x_dtype == 0) LN_GO(EPI_GELU, float); else LN_GO(EPI_GELU, __nv_bfloat16); }
@@ -986,10 +1003,13 @@ extern "C" int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const 
     return 0;
 }
 
+// Split of the M (contraction) dimension: enough CTAs to fill the machine, but every CTA keeps at least 8 blocks of 64 rows --
+// below that the partial slabs and their reduction launch cost more than the MMAs they save (M = 800: no split at all)
 static int wgrad_splits(int M, int N, int K) {
     const int tiles = ((N + kGN - 1) / kGN) * ((K + kGN - 1) / kGN), m_blocks = (M + kGK - 1) / kGK;
     int s = (device_sms() + tiles - 1) / tiles;
-    if (s > m_blocks) s = m_blocks;
+    const int cap = m_blocks / 8;
+    if (s > cap) s = cap;
     if (s > 64) s = 64;
     return s < 1 ? 1 : s;
 }
@@ -1023,11 +1043,11 @@ extern "C" int detr_gemm_wgrad_bf16(const void* dy, int64_t ld_dy, const void* x
     p.dbout = db ? (splits > 1 ? workspace + (int64_t)splits * N * K : db) : nullptr;
     if (int rc = opt_in_smem(gemm_wgrad_kernel, kWgSmem, "gemm_wgrad")) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    launch_pdl(gemm_wgrad_kernel, dim3(p.n_tiles * p.k_tiles * splits), dim3(kWgThreads), kWgSmem, st, tdy, tx0, tx1, to, p);
+    launch_pdl_if(gemm_pdl(), gemm_wgrad_kernel, dim3(p.n_tiles * p.k_tiles * splits), dim3(kWgThreads), kWgSmem, st, tdy, tx0, tx1, to, p);
     DETR_CHECK_LAUNCH("gemm_wgrad");
     if (splits > 1) {
         const int64_t n4 = (int64_t)N * K / 4, total = n4 + (db ? N : 0);
-        launch_pdl(wgrad_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float*)workspace, splits, n4, dw,
+        launch_pdl_if(gemm_pdl(), wgrad_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float*)workspace, splits, n4, dw,
                    (const float*)(db ? workspace + (int64_t)splits * N * K : nullptr), N, db);
         DETR_CHECK_LAUNCH("gemm_wgrad_reduce");
     }

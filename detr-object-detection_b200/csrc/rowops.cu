@@ -7,6 +7,8 @@
 //                 partials go through fold_partials_kernel instead.)
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include "tc.cuh"
+#include "rowmath.cuh"
 
 namespace detr {
 
@@ -17,7 +19,8 @@ constexpr int kCsThreads = 256;    // 8 warps: each warp takes every 8th row of 
 // CTA = 32 columns; warp w adds partials w, w+8, ... (independent coalesced loads), then the 8 warps are combined.
 constexpr int kFoldThreads = 1024;
 __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(const float* __restrict__ partial, int n_partials, int N,
-                                                                     float* __restrict__ out0, float* __restrict__ out1, int split) {
+                                                                     float* __restrict__ out0, float* __restrict__ out1, int split,
+                                                                     float* __restrict__ out2 = nullptr) {
     __shared__ float red[kFoldThreads / 32][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
@@ -39,7 +42,7 @@ __global__ void __launch_bounds__(kFoldThreads) fold_partials_kernel(const float
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kFoldThreads / 32; ++w) s += red[w][lane];
-        if (c < split) out0[c] = s; else out1[c - split] = s;
+        if (c < split) out0[c] = s; else if (c < 2 * split || out2 == nullptr) out1[c - split] = s; else out2[c - 2 * split] = s;
     }
 }
 
@@ -215,6 +218,10 @@ struct LnParams {
     const void* dy; const void* dy2; void* dx;
     const void* dres;   // optional gradient of the residual branch that bypasses the LayerNorm (x's dtype, contiguous rows): dx += dres
     float* partial; float* dgamma; float* dbeta; unsigned* counters;
+    // optional third product of the backward pass: dx is also the gradient that reaches the PREVIOUS block's tail
+    // (x = res + dropout(z), detr/model.py:223-224); its masked bf16 form dz = mask(dx) / (1 - p) and the bias gradient
+    // column sums of dz are produced here, so that the tail's backward needs no pass of its own
+    void* dz; float* dbias; uint32_t thr4; float scale; uint64_t seed; const uint64_t* seed_ptr; int has_dz;
 };
 
 // KT > 0: compile-time columns per lane (rows stay in registers); KT == 0: run-time (local-memory arrays)
@@ -255,9 +262,11 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = KT ? KT : p.C / 32, C = p.C;
     constexpr int KA = KT ? KT : kLnMaxPerLane;
-    float g[KA], dg[KA], db[KA];
+    float g[KA], dg[KA], db[KA], dzs[KA];
     load_row<float>(p.gamma, lane, K, g);
-    _Pragma("unroll") for (int i = 0; i < K; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+    _Pragma("unroll") for (int i = 0; i < K; ++i) { dg[i] = 0.f; db[i] = 0.f; dzs[i] = 0.f; }
+    const bool has_dz = KT == 8 && p.has_dz;   // (the 8-columns-per-lane layout is exactly one dropout chunk per lane)
+    const uint32_t zkey = (has_dz && p.thr4) ? ew_key(p.seed, p.seed_ptr) : 0u;
     for (int r = blockIdx.x * (kLnThreads / 32) + warp; r < p.rows; r += gridDim.x * (kLnThreads / 32)) {
         float x[KA], d[KA];
         load_row<TX>(reinterpret_cast<const TX*>(p.x) + (int64_t)r * p.x_ld, lane, K, x);
@@ -287,15 +296,35 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnParams p) {
             _Pragma("unroll") for (int i = 0; i < K; ++i) d[i] += e[i];
         }
         store_row<TX>(reinterpret_cast<TX*>(p.dx) + (int64_t)r * C, lane, K, d);
+        if (has_dz) {
+            // the same mask as the tail's forward epilogue: chunk index r * C/8 + lane, 8 columns per chunk
+            if (p.thr4) {
+                bool keep[8];
+                ew_keep8(zkey, (uint32_t)r * (uint32_t)(C >> 3) + (uint32_t)lane, p.thr4, keep);
+                _Pragma("unroll") for (int i = 0; i < 8; ++i) d[i] = keep[i] ? d[i] * p.scale : 0.f;
+            }
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            _Pragma("unroll") for (int e = 0; e < 4; ++e) {
+                h[e] = __floats2bfloat162_rn(d[2 * e], d[2 * e + 1]);
+                const float2 f = __bfloat1622float2(h[e]);      // the bias gradient sums what the GEMMs will see
+                dzs[2 * e] += f.x; dzs[2 * e + 1] += f.y;
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dz) + (int64_t)r * C + lane * 8) = u;
+        }
     }
-    // ---- dgamma / dbeta: warps -> CTA partial; fold_partials_kernel adds the CTA partials ----
-    _Pragma("unroll") for (int i = 0; i < K; ++i) { sm[(warp * 2 + 0) * C + lane * K + i] = dg[i]; sm[(warp * 2 + 1) * C + lane * K + i] = db[i]; }
+    // ---- dgamma / dbeta (/ dbias): warps -> CTA partial; fold_partials_kernel adds the CTA partials ----
+    const int NP = has_dz ? 3 : 2;
+    _Pragma("unroll") for (int i = 0; i < K; ++i) {
+        sm[(warp * 3 + 0) * C + lane * K + i] = dg[i]; sm[(warp * 3 + 1) * C + lane * K + i] = db[i];
+        if (has_dz) sm[(warp * 3 + 2) * C + lane * K + i] = dzs[i];
+    }
     __syncthreads();
-    for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) {
+    for (int c = threadIdx.x; c < NP * C; c += kLnThreads) {
         const int which = c / C, col = c - which * C;
         float s = 0.f;
-        for (int w = 0; w < kLnThreads / 32; ++w) s += sm[(w * 2 + which) * C + col];
-        p.partial[(int64_t)blockIdx.x * 2 * C + c] = s;
+        for (int w = 0; w < kLnThreads / 32; ++w) s += sm[(w * 3 + which) * C + col];
+        p.partial[(int64_t)blockIdx.x * NP * C + c] = s;
     }
 }
 
@@ -340,17 +369,45 @@ extern "C" int detr_layernorm_fwd(const void* x, int x_dtype, int64_t x_ld, cons
     return 0;
 }
 
+static int layernorm_bwd_impl(const void* dy, const void* dy2, int g_dtype, const void* dres, const void* x, int x_dtype, int64_t x_ld,
+                              const float* gamma, const float* mean, const float* rstd, void* dx, float* partial,
+                              float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* stream,
+                              void* dz, float* dbias, float dropout_p, uint64_t seed, const uint64_t* seed_ptr);
+
 extern "C" int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, const void* dres, const void* x, int x_dtype, int64_t x_ld,
                                   const float* gamma, const float* mean, const float* rstd, void* dx, float* partial,
                                   float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* stream) {
+    return layernorm_bwd_impl(dy, dy2, g_dtype, dres, x, x_dtype, x_ld, gamma, mean, rstd, dx, partial, dgamma, dbeta, counters, rows, C, stream,
+                              nullptr, nullptr, 0.f, 0, nullptr);
+}
+
+extern "C" int detr_layernorm_bwd_tail(const void* dy, const void* dy2, int g_dtype, const void* dres, const void* x, int x_dtype, int64_t x_ld,
+                                       const float* gamma, const float* mean, const float* rstd, void* dx, float* partial,
+                                       float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* dz, float* dbias,
+                                       float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream) {
+    DETR_CHECK_ARG(C == 256 && dz != nullptr && dbias != nullptr && ((uintptr_t)dz % 16) == 0, "layernorm_bwd_tail: C must be 256, dz / dbias required");
+    DETR_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "layernorm_bwd_tail: dropout_p must be in [0,1)");
+    return layernorm_bwd_impl(dy, dy2, g_dtype, dres, x, x_dtype, x_ld, gamma, mean, rstd, dx, partial, dgamma, dbeta, counters, rows, C, stream,
+                              dz, dbias, dropout_p, seed, seed_ptr);
+}
+
+static int layernorm_bwd_impl(const void* dy, const void* dy2, int g_dtype, const void* dres, const void* x, int x_dtype, int64_t x_ld,
+                              const float* gamma, const float* mean, const float* rstd, void* dx, float* partial,
+                              float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* stream,
+                              void* dz, float* dbias, float dropout_p, uint64_t seed, const uint64_t* seed_ptr) {
     DETR_CHECK_ARG(rows >= 1 && C >= 32 && C % 32 == 0 && C <= 32 * kLnMaxPerLane, "layernorm_bwd: bad C=%d", C);
     DETR_CHECK_ARG(dy != nullptr || dy2 != nullptr, "layernorm_bwd: no incoming gradient");
     LnParams p{};
     p.x = x; p.x_ld = x_ld; p.gamma = gamma; p.mean = const_cast<float*>(mean); p.rstd = const_cast<float*>(rstd); p.rows = rows; p.C = C;
     DETR_CHECK_ARG(((uintptr_t)dres % 16) == 0, "layernorm_bwd: dres must be 16-byte aligned");
     p.dy = dy; p.dy2 = dy2; p.dres = dres; p.dx = dx; p.partial = partial; p.dgamma = dgamma; p.dbeta = dbeta; p.counters = counters;
+    p.dz = dz; p.dbias = dbias; p.has_dz = dz != nullptr; p.seed = seed; p.seed_ptr = seed_ptr;
+    {
+        const uint32_t th = (uint32_t)lrintf(dropout_p * 128.f);
+        p.thr4 = th * 0x01010101u; p.scale = 128.f / (128.f - (float)th);
+    }
     const int grid = ln_grid(rows);
-    const size_t smem = (size_t)(kLnThreads / 32) * 2 * C * sizeof(float);
+    const size_t smem = (size_t)(kLnThreads / 32) * 3 * C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
 #define LN_BWD(TX, TG)                                                               \
     do {                                                                             \
@@ -364,7 +421,8 @@ extern "C" int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, 
 #undef LN_BWD
     DETR_CHECK_LAUNCH("layernorm_bwd");
     (void)counters;
-    fold_partials_kernel<<<(2 * C + 31) / 32, kFoldThreads, 0, st>>>(partial, grid, 2 * C, dgamma, dbeta, C);
+    const int NP = p.has_dz ? 3 : 2;
+    fold_partials_kernel<<<(NP * C + 31) / 32, kFoldThreads, 0, st>>>(partial, grid, NP * C, dgamma, dbeta, C, dbias);
     DETR_CHECK_LAUNCH("layernorm_bwd_fold");
     return 0;
 }

@@ -46,6 +46,7 @@ SIGNATURES = {
     "detr_layernorm_grid": [c_int],
     "detr_layernorm_fwd": [P, c_int, c_int64, P, P, P, c_int, c_int64, c_int64, c_int, P, P, c_int, P, P, c_int, c_int, c_float, P],
     "detr_layernorm_bwd": [P, P, c_int, P, P, c_int, c_int64, P, P, P, P, P, P, P, P, c_int, c_int, P],
+    "detr_layernorm_bwd_tail": [P, P, c_int, P, P, c_int, c_int64, P, P, P, P, P, P, P, P, c_int, c_int, P, P, c_float, ctypes.c_uint64, P, P],
     "detr_epilogue_fwd": [c_int, P, c_int, P, P, c_int, c_int, c_float, ctypes.c_uint64, P, P],
     "detr_epilogue_chunks": [c_int, c_int],
     "detr_scale_cast_multi": [P, c_int, c_int, P],
@@ -101,13 +102,14 @@ class FoldTable(ctypes.Structure):
 # the shape pass the exact number through call(..., launches=))
 KERNELS_PER_CALL = {"detr_cost_matrix_f32": 1, "detr_hungarian_match_f32": 1, "detr_lsap_f32": 1, "detr_lsap_f64": 1,
                     "detr_criterion_fwd_f32": 3, "detr_criterion_bwd_f32": 1, "detr_attention_fwd_bf16": 2,
-                    "detr_attention_bwd_bf16": 4, "detr_colsum_bf16": 1, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2,
+                    "detr_attention_bwd_bf16": 4, "detr_colsum_bf16": 1, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2, "detr_layernorm_bwd_tail": 2,
                     "detr_epilogue_fwd": 1, "detr_epilogue_bwd": 1, "detr_scale_cast_multi": 1,
                     "detr_maxpool3x3s2_fwd_bf16": 1, "detr_maxpool3x3s2_bwd_bf16": 1,
                     "detr_gemm_bf16": 1, "detr_gemm_ln_bf16": 1, "detr_gemm_wgrad_bf16": 2,
                     "detr_positional_encoding_f32": 1, "detr_sumsq_f32": 1, "detr_adamw_clip_f32": 1, "detr_add_relu_mask_bf16": 1, "detr_stem_s2d_bf16": 1}
 launch_count = 0          # kernels of libdetr_b200.so launched by this process
 _profile = None           # when a list: (name, tag, start_event, end_event) per call
+_profile_external = False
 
 
 class profile:
@@ -117,10 +119,16 @@ class profile:
         torch.cuda.synchronize(); rows = prof.summary()   # {(name, tag): (calls, total_ms)}
     """
 
+    def __init__(self, external: bool = False):
+        # external=True: the events become timable event-record NODES when the calls are made under CUDA-graph capture -- per-call
+        # durations INSIDE a graph replay (read them after a replay + synchronize)
+        self.external = external
+
     def __enter__(self):
-        global _profile
+        global _profile, _profile_external
         self.records = []
         _profile = self.records
+        _profile_external = self.external
         return self
 
     def __exit__(self, *exc):
@@ -162,7 +170,8 @@ def call(name: str, *args, tag=None, launches=None) -> None:
     if _profile is None:
         rc = fn(*args)
     else:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kw = {"external": True} if _profile_external else {}
+        a, b = torch.cuda.Event(enable_timing=True, **kw), torch.cuda.Event(enable_timing=True, **kw)
         a.record()
         rc = fn(*args)
         b.record()

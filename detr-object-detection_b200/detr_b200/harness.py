@@ -639,7 +639,8 @@ class GraphedTrainStep:
 
     def __init__(self, model: nn.Module, criterion: nn.Module, optimizer, example: Dict, gt_cap: int = 100,
                  autocast_dtype=torch.bfloat16, max_grad_norm: float = 1.0, warmup: int = 3, flat_optimizer: bool = True,
-                 restore_state: bool = True, check_faults: bool = True):
+                 restore_state: bool = True, check_faults: bool = True, accumulate: int = 1, overlap_allreduce: bool = True,
+                 bucket_mb: float = 32.0):
         from . import attention
         from .targets import StaticTargets
         import torch.distributed as dist
@@ -647,6 +648,11 @@ class GraphedTrainStep:
         self.dev = next(model.parameters()).device
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.autocast_dtype, self.max_grad_norm = autocast_dtype, max_grad_norm
+        # gradient accumulation (detr/train.py:116,258 `accelerator.accumulate`): `accumulate` micro-batches per optimizer step; the
+        # forward/backward graph then ADDS into the flat gradient buffer, the all-reduce and the update run once per step
+        # (DDP's no_sync on the non-boundary micro-steps), and the 1 / accumulate of `accelerator.backward` rides in grad_div
+        self.accumulate = max(int(accumulate), 1)
+        self._micro = 0
         B = example["image"].shape[0]
         self.images = torch.empty_like(example["image"], device=self.dev, memory_format=torch.channels_last)
         self.heights = torch.empty(B, dtype=torch.int32, device=self.dev)
@@ -663,6 +669,17 @@ class GraphedTrainStep:
             self.fopt = FlatAdamW(optimizer, self.dev)
             self.params = self.fopt.params
             self.flat, self.flat_views = self.fopt.flat_g, self.fopt.grad_views
+        if self.accumulate > 1 and self.fopt is None:
+            raise ValueError("gradient accumulation in GraphedTrainStep needs the flat optimizer (torch.optim.AdamW groups)")
+        # Bucketed gradient all-reduce INSIDE the forward/backward graph, overlapped with the rest of backward (what DDP does for
+        # the reference, detr/train.py:218,263): the flat gradient buffer is cut into contiguous buckets; when the last gradient
+        # of a bucket has been produced (post-accumulate hooks: the transformer's bucket is complete ~5 ms before the ResNet
+        # stem's), the bucket is copied into the flat buffer and its NCCL all-reduce starts on the communication stream while
+        # autograd keeps going.  Captured in graph A as a fork / join; the single un-overlapped all-reduce between the two graphs
+        # (r1: +0.5 ms per step at 8 GPUs) is only the fallback (gradient accumulation, non-flat optimizer).
+        self._buckets = None
+        if overlap_allreduce and self.world > 1 and self.fopt is not None and self.accumulate == 1:
+            self._make_buckets(bucket_mb)
         self.load(example)
         # The warm-up iterations below are REAL optimizer steps (they have to be: allocator, cuDNN autotune, lazy attributes):
         # snapshot parameters, buffers and optimizer state first and put them back after the capture, so that training starts
@@ -727,9 +744,44 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
 
     # -- pieces -------------------------------------------------------------------------------------------
+    def _make_buckets(self, bucket_mb: float) -> None:
+        """Contiguous ranges of the flat gradient buffer of ~bucket_mb each, in flat (= parameter-group) order."""
+        lim = int(bucket_mb * (1 << 20) / 4)
+        self._buckets, cur = [], None
+        offs = {}
+        for v in self.flat_views:
+            offs[id(v)] = v.storage_offset()
+        for q, v in zip(self.params, self.flat_views):
+            o = v.storage_offset()
+            if cur is None or (o + q.numel() - cur["start"]) > lim:
+                cur = {"start": o, "end": o, "params": [], "views": [], "pending": 0}
+                self._buckets.append(cur)
+            cur["params"].append(q); cur["views"].append(v); cur["end"] = max(cur["end"], o + q.numel())
+        # a bucket's range must not overlap the next one's start (parameter groups are padded to 16 bytes: ranges are disjoint)
+        self._works = []
+        for b in self._buckets:
+            for q in b["params"]:
+                q.register_post_accumulate_grad_hook(lambda p_, b=b: self._grad_ready(b))
+
+    def _grad_ready(self, b) -> None:
+        if not self._hooks_live:
+            return
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            import torch.distributed as dist
+            torch._foreach_copy_(b["views"], [q.grad for q in b["params"]])
+            self._works.append(dist.all_reduce(self.flat[b["start"]:b["end"]], async_op=True))
+
+    _hooks_live = False
+
     def _forward_backward(self):
         for q in self.params:          # fresh gradient tensors (no accumulation kernels); Python-only, nothing is launched
             q.grad = None
+        if self._buckets is not None:
+            for b in self._buckets:
+                b["pending"] = len(b["params"])
+            self._works = []
+            self._hooks_live = True
         self.step_counter.add_(1)
         with torch.autocast(device_type="cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
             out = self.model(self.images, self.heights, self.widths)
@@ -738,6 +790,17 @@ class GraphedTrainStep:
         loss = sum(v for k, v in losses.items() if k.startswith("loss"))
         loss.backward()
         self.loss.copy_(loss.detach())
+        if self._buckets is not None:
+            self._hooks_live = False
+            missing = [b for b in self._buckets if b["pending"] != 0]
+            if missing:       # parameters that received no gradient in this graph (unused): reduce their buckets now, zeros included
+                import torch.distributed as dist
+                for b in missing:
+                    torch._foreach_copy_(b["views"], [q.grad if q.grad is not None else torch.zeros_like(q) for q in b["params"]])
+                    self._works.append(dist.all_reduce(self.flat[b["start"]:b["end"]], async_op=True))
+            for w in self._works:   # join: the optimizer graph starts after the last bucket
+                w.wait()
+            return
         if self.world > 1 or self.fopt is not None:
             # one multi-tensor copy into the flat gradient / all-reduce buffer (torch.cat over ~330 gradients costs 0.8 ms, measured)
             if self.flat is None:
@@ -747,20 +810,24 @@ class GraphedTrainStep:
                     # the view must look like the parameter (channels_last conv weights included) for the fused optimizer
                     self.flat_views.append(torch.as_strided(self.flat, q.shape, q.stride(), o))
                     o += q.numel()
-            torch._foreach_copy_(self.flat_views, [q.grad if q.grad is not None else torch.zeros_like(q) for q in self.params])
+            grads = [q.grad if q.grad is not None else torch.zeros_like(q) for q in self.params]
+            if self.accumulate > 1:
+                torch._foreach_add_(self.flat_views, grads)      # the buffer is zeroed at the start of every optimizer step
+            else:
+                torch._foreach_copy_(self.flat_views, grads)
 
     def _allreduce(self):
-        if self.world > 1:
+        if self.world > 1 and self._buckets is None:
             import torch.distributed as dist
             dist.all_reduce(self.flat)
 
     def _update(self):
         if self.fopt is not None:
-            self.fopt.step(self.max_grad_norm, 1.0 / self.world)   # the data-parallel mean rides in the clip coefficient
+            self.fopt.step(self.max_grad_norm, 1.0 / (self.world * self.accumulate))   # the data-parallel / accumulation mean rides in the clip coefficient
             return
         if self.world > 1:
             # the reduced gradients are consumed in place: .grad becomes a view of the flat buffer, averaged by ONE kernel
-            self.flat.div_(float(self.world))
+            self.flat.div_(float(self.world * self.accumulate))
             for q, v in zip(self.params, self.flat_views):
                 q.grad = v
         torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm)
@@ -853,7 +920,16 @@ class GraphedTrainStep:
         `step()` / `poll_faults()` call -- no host synchronisation on the hot path, no sticky poisoning of later steps."""
         if self.check_faults:
             self.poll_faults()
-        self.graph_a.replay()
+        if self.accumulate > 1:
+            if self._micro == 0:
+                self.flat.zero_()
+            self.graph_a.replay()
+            self._micro += 1
+            if self._micro < self.accumulate:
+                return self.loss            # non-boundary micro-step: no collective, no update
+            self._micro = 0
+        else:
+            self.graph_a.replay()
         st = self._status_tensor() if self.check_faults else None
         if st is not None:
             i = self._fault_i

@@ -308,7 +308,7 @@ class Decoder(nn.Module):
             sh, C = self._shadows, self.config.hidden_size
             ks = blocks.proj(cross_key, [l.cross_attention.key_proj for l in self.layers], *sh.get_w_b32(("", "cross_keys")))
             vs = blocks.proj(encoded_image_tokens, [l.cross_attention.value_proj for l in self.layers], *sh.get_w_b32(("", "cross_values")))
-            kvs = [(ks[..., i * C:(i + 1) * C], vs[..., i * C:(i + 1) * C]) for i in range(len(self.layers))]
+            kvs = list(zip(ks, vs))
         elif fused_epilogues_enabled(encoded_image_tokens):
             sh = self._shadows
             ks = stacked_linear(cross_key, [l.cross_attention.key_proj for l in self.layers], *sh.get(("", "cross_keys")))

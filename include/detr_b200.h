@@ -170,6 +170,16 @@ int detr_layernorm_bwd(const void* dy, const void* dy2, int g_dtype, const void*
                        const float* gamma, const float* mean, const float* rstd, void* dx, float* partial,
                        float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* stream);
 
+/* The same backward pass with a third product: dx is also the gradient that reaches the PREVIOUS block's tail
+ * (x = res + dropout(z), detr/model.py:223-224,354-355,410), so its masked bf16 form dz = mask(dx)/(1-p) (the operand of that
+ * tail's input- and weight-gradient GEMMs) and dbias[n] = sum_m dz[m][n] are written here instead of by a separate
+ * detr_epilogue_bwd(mode 0) launch.  C = 256; partial float[detr_layernorm_grid(rows)*3*C]; (dropout_p, seed, seed_ptr) are the
+ * TAIL's forward values. */
+int detr_layernorm_bwd_tail(const void* dy, const void* dy2, int g_dtype, const void* dres, const void* x, int x_dtype, int64_t x_ld,
+                            const float* gamma, const float* mean, const float* rstd, void* dx, float* partial,
+                            float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* dz, float* dbias,
+                            float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
+
 /* Block epilogues of the pre-LN layers, one pass each (detr/model.py:223-224, 176-182, FFN 405-411).
  * mode 0: out(x's dtype) = x + dropout(y)  -- residual add after the attention output / second FFN projection;
  * mode 1: out(bf16) = dropout(gelu_tanh(y)) -- between the FFN projections (x unused).

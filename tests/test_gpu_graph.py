@@ -163,3 +163,24 @@ def test_faulty_batch_is_skipped_and_reported(cuda):
     g.load(good); l2 = float(g.step())
     assert l2 == l2 and float(g.fopt.step_t) == 2.0 and not torch.equal(g.fopt.flat_p, before)
     g.poll_faults(wait=True)                                                   # nothing pending
+
+
+def test_gradient_accumulation_matches_single_step(cuda):
+    """detr/train.py:116,258: `accumulate` micro-batches per optimizer step.  The same micro-batch twice with accumulate = 2 gives
+    the gradient of that batch again (sum of two equal gradients times grad_div = 1/2): same update as accumulate = 1, no update on
+    the non-boundary micro-step."""
+    from detr_b200.harness import GraphedTrainStep, make_optimizer, synthetic_batch
+    b = synthetic_batch(2, 160, 200, 11, 6, seed=41)
+    m1, c1 = _make(cuda, train=False)
+    m2, c2 = copy.deepcopy(m1), copy.deepcopy(c1)
+    g1 = GraphedTrainStep(m1, c1, make_optimizer(m1, lr=1e-4, capturable=True), b, gt_cap=8, warmup=2)
+    g2 = GraphedTrainStep(m2, c2, make_optimizer(m2, lr=1e-4, capturable=True), b, gt_cap=8, warmup=2, accumulate=2)
+    p0 = g2.fopt.flat_p.clone()
+    g1.load(b); g1.step()
+    g2.load(b); g2.step()
+    assert torch.equal(g2.fopt.flat_p, p0) and float(g2.fopt.step_t) == 0.0          # micro-step 1 of 2: nothing applied yet
+    g2.load(b); g2.step()
+    assert float(g2.fopt.step_t) == 1.0
+    torch.cuda.synchronize()
+    d = (g1.fopt.flat_p - g2.fopt.flat_p).abs()
+    assert d.max().item() <= 2.5e-4 and (d > 1e-5).float().mean().item() <= 0.01, (d.max().item(), (d > 1e-5).float().mean().item())
