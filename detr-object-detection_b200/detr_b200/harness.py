@@ -639,7 +639,7 @@ class GraphedTrainStep:
 
     def __init__(self, model: nn.Module, criterion: nn.Module, optimizer, example: Dict, gt_cap: int = 100,
                  autocast_dtype=torch.bfloat16, max_grad_norm: float = 1.0, warmup: int = 3, flat_optimizer: bool = True,
-                 restore_state: bool = True, check_faults: bool = True, accumulate: int = 1, overlap_allreduce: bool = True,
+                 restore_state: bool = True, check_faults: bool = True, accumulate: int = 1, overlap_allreduce: bool = False,
                  bucket_mb: float = 32.0):
         from . import attention
         from .targets import StaticTargets
@@ -675,8 +675,10 @@ class GraphedTrainStep:
         # the reference, detr/train.py:218,263): the flat gradient buffer is cut into contiguous buckets; when the last gradient
         # of a bucket has been produced (post-accumulate hooks: the transformer's bucket is complete ~5 ms before the ResNet
         # stem's), the bucket is copied into the flat buffer and its NCCL all-reduce starts on the communication stream while
-        # autograd keeps going.  Captured in graph A as a fork / join; the single un-overlapped all-reduce between the two graphs
-        # (r1: +0.5 ms per step at 8 GPUs) is only the fallback (gradient accumulation, non-flat optimizer).
+        # autograd keeps going.  Captured in graph A as a fork / join.  OPT-IN: measured on 2 B200s it does not pay (12.83 ms vs
+        # 12.74 ms for the single all-reduce between the two graphs -- the NCCL kernels take SMs from the backward kernels they
+        # overlap with, and the whole 166 MB all-reduce is only ~0.3 ms over NVLink 5), and NCCL's asynchronous error handling has to
+        # be switched off for the capture (TORCH_NCCL_ASYNC_ERROR_HANDLING=0).
         self._buckets = None
         if overlap_allreduce and self.world > 1 and self.fopt is not None and self.accumulate == 1:
             self._make_buckets(bucket_mb)
