@@ -59,9 +59,9 @@ struct Params {
     const uint8_t* amask;
     int B, nh, L, S;
     float scale_log2, scale;   // log2(e)/sqrt(d), 1/sqrt(d)
-    uint32_t drop_thresh;      // 0 = no dropout; a key is dropped if its 7 random bits < thresh
+    uint32_t drop_thresh;      // 0 = no dropout; a key is dropped if its 15 random bits < thresh
     float drop_log2_scale;     // log2(128 / (128 - thresh)): folded into the exponent, P comes out pre-scaled by 1/(1-p)
-    float drop_keep;           // (128 - thresh) / 128
+    float drop_keep;           // (32768 - thresh) / 32768
     uint64_t seed; const uint64_t* seed_ptr;
     long long* dbg;            // optional timeline of CTA 0 (clock64 stamps; tools/attn_timeline.py), NULL in production
 };
@@ -301,7 +301,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
         const bool drop = p.drop_thresh != 0;
         const uint64_t seed = drop ? p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull) : 0ull;
-        const uint32_t thr4 = p.drop_thresh * 0x01010101u;
+        const uint32_t thr2 = p.drop_thresh * 0x00010001u;
         // byte offset of this thread's row inside a [query][64-key block] SWIZZLE_128B tile; its 4 chunks are (kq&1)*4 + g
         const uint32_t row_off = (uint32_t)((kq >> 1) * 16384 + (row >> 3) * 1024 + (row & 7) * 128);
         const uint32_t chunk0 = (uint32_t)((kq & 1) * 4);
@@ -439,8 +439,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nl2 = make_float2(nl, nl), ndl2 = make_float2(-dlt, -dlt);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {               // 8 keys = one 16-byte chunk of the dS / P~ rows
-                    uint32_t t0 = 0, t1 = 0;
-                    if (DROP) { t0 = dropout_quad(rng, thr4); t1 = dropout_quad(rng, thr4); }
                     uint32_t pk[4], dk[4];
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
@@ -459,7 +457,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                         if (DROP) {
                             const float2 bb = __fmul2_rn(x, ndl2);
                             const uint32_t bk = pack_bf16x2(bb.x, bb.y);
-                            const uint32_t m = (jj & 1) ? dropout_mask_bf16x2<1>(jj < 2 ? t0 : t1) : dropout_mask_bf16x2<0>(jj < 2 ? t0 : t1);
+                            const uint32_t m = dropout_mask_bf16x2(dropout_pair(rng, thr2));
                             dk[jj] = (dk[jj] & m) | (bk & ~m);
                             pk[jj] &= m;
                         }
@@ -653,8 +651,8 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.B = B; p.nh = nh; p.L = L; p.S = S;
     p.scale = 1.f / sqrtf((float)kD);
     p.scale_log2 = 1.4426950408889634f * p.scale;
-    p.drop_thresh = (uint32_t)lrintf(dropout_p * 128.f);
-    p.drop_keep = (128.f - (float)p.drop_thresh) / 128.f;
+    p.drop_thresh = dropout_threshold(dropout_p);
+    p.drop_keep = ((float)kDropOne - (float)p.drop_thresh) / (float)kDropOne;
     p.drop_log2_scale = -log2f(p.drop_keep);
     p.seed = seed; p.seed_ptr = seed_ptr;
     p.dbg = g_bwd_dbg;

@@ -76,8 +76,8 @@ struct AttnFwdParams {
     const uint8_t* amask;                  // attention mask (L, S) bytes, may be null
     int B, nh, L, S;
     float scale_log2;                      // log2(e) / sqrt(32)
-    uint32_t drop_thresh;                  // 0 = no dropout; a key is dropped if its 7 random bits < thresh
-    float drop_scale;                      // 128 / (128 - thresh)
+    uint32_t drop_thresh;                  // 0 = no dropout; a key is dropped if its 15 random bits < thresh
+    float drop_scale;                      // 32768 / (32768 - thresh)
     float drop_log2_scale;                 // log2(drop_scale): folded into the exponent
     uint64_t seed; const uint64_t* seed_ptr; // effective seed = seed + *seed_ptr (device side: CUDA-graph replays get fresh masks)
     long long* dbg;                        // optional clock64 timeline of CTA 0 (DETR_FWD_TIMELINE builds), NULL in production
@@ -245,7 +245,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
         const bool drop = p.drop_thresh != 0;
         const uint64_t seed = drop ? p.seed + (p.seed_ptr ? *p.seed_ptr : 0ull) : 0ull;
-        const uint32_t thr4 = p.drop_thresh * 0x01010101u;
+        const uint32_t thr2 = p.drop_thresh * 0x00010001u;
         const float sc_l2 = p.scale_log2;
         // this thread's row inside a [query][64-key block] SWIZZLE_128B tile; its 4 chunks are (kq&1)*4 + g
         const uint32_t row_off = (uint32_t)((kq >> 1) * 16384 + (row >> 3) * 1024 + (row & 7) * 128);
@@ -411,9 +411,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     w[jj] = pack_bf16x2(x.x, x.y);
                 }
                 if (drop) {   // the row sum is of the un-dropped probabilities; dropped entries are cleared in the packed bf16 words
-                    const uint32_t t0 = dropout_quad(rng, thr4), t1 = dropout_quad(rng, thr4);
-                    w[0] &= dropout_mask_bf16x2<0>(t0); w[1] &= dropout_mask_bf16x2<1>(t0);
-                    w[2] &= dropout_mask_bf16x2<0>(t1); w[3] &= dropout_mask_bf16x2<1>(t1);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) w[jj] &= dropout_mask_bf16x2(dropout_pair(rng, thr2));
                 }
                 *reinterpret_cast<uint4*>(p_row + (((chunk0 + g) ^ (uint32_t)(row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
@@ -604,8 +603,8 @@ extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.kpm = key_padding_mask; p.kpm_sb = kpm_sb; p.amask = attention_mask;
     p.B = B; p.nh = nh; p.L = L; p.S = S;
     p.scale_log2 = 1.4426950408889634f / sqrtf((float)kD);
-    p.drop_thresh = (uint32_t)lrintf(dropout_p * 128.f);
-    p.drop_scale = 128.f / (128.f - (float)p.drop_thresh);
+    p.drop_thresh = dropout_threshold(dropout_p);
+    p.drop_scale = (float)kDropOne / ((float)kDropOne - (float)p.drop_thresh);
     p.drop_log2_scale = log2f(p.drop_scale);
     p.seed = seed; p.seed_ptr = seed_ptr;
     p.dbg = g_fwd_dbg;

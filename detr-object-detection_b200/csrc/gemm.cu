@@ -55,7 +55,7 @@ enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_RES = 2, EPI_GELU_BWD = 3 };
 struct EpiParams {
     const float* bias;                       // fp32 [N] or null
     int M, N;
-    uint32_t thr4; float scale;              // dropout: thresh * 0x01010101 (0 = off), 1 / keep
+    uint32_t thr4; float scale;              // dropout: thresh * 0x00010001 (0 = off; thresh in 1/32768), 1 / keep
     uint64_t seed; const uint64_t* seed_ptr;
 };
 
@@ -84,16 +84,16 @@ __device__ __forceinline__ float2 gelu_grad2(float2 y, float hs) {
     const float2 q = __ffma2_rn(make_float2(-rt.x, -rt.y), t, r);                            // r (1 - t^2)
     return __ffma2_rn(__fadd2_rn(t, q), f2(hs), f2(hs));
 }
-// keep masks of the 8 elements of chunk idx8 (same generator and indexing as ew_keep8 / epilogue_bwd_kernel): byte e of t0 / t1
-// has bit 7 set iff element e / 4 + e is kept
-__device__ __forceinline__ void drop_quads(uint32_t key, uint32_t idx8, uint32_t thr4, uint32_t& t0, uint32_t& t1) {
+// keep masks of the 8 elements of chunk idx8 (same generator and indexing as ew_keep8 / epilogue_bwd_kernel): half e of t[i] has
+// bit 15 set iff element 2 i + e is kept
+__device__ __forceinline__ void drop_pairs(uint32_t key, uint32_t idx8, uint32_t thr2, uint32_t (&t)[4]) {
     uint32_t st = dropout_group_state(key, idx8);
-    t0 = dropout_quad(st, thr4);
-    t1 = dropout_quad(st, thr4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = dropout_pair(st, thr2);
 }
-__device__ __forceinline__ void mask_packed8(uint32_t (&w)[4], uint32_t t0, uint32_t t1) {
-    w[0] &= dropout_mask_bf16x2<0>(t0); w[1] &= dropout_mask_bf16x2<1>(t0);
-    w[2] &= dropout_mask_bf16x2<0>(t1); w[3] &= dropout_mask_bf16x2<1>(t1);
+__device__ __forceinline__ void mask_packed8(uint32_t (&w)[4], const uint32_t (&t)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] &= dropout_mask_bf16x2(t[i]);
 }
 
 // 16-byte chunk c (0..7) of row r (0..31) of a SWIZZLE_128B staging box
@@ -141,7 +141,7 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& e, uint32_t key, in
             uint32_t wo[4];
 #pragma unroll
             for (int p = 0; p < 4; ++p) { const float2 o = gelu2(bf16x2_to_f2(wy4[p]), hs); wo[p] = pack_bf16x2(o.x, o.y); }
-            if (drop) { uint32_t t0, t1; drop_quads(key, idx8 + j, e.thr4, t0, t1); mask_packed8(wo, t0, t1); }
+            if (drop) { uint32_t t[4]; drop_pairs(key, idx8 + j, e.thr4, t); mask_packed8(wo, t); }
             *box_chunk(stg + kBoxBytes, r, half * 4 + j) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
         }
         return;
@@ -159,7 +159,7 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& e, uint32_t key, in
                 const float2 d = __fmul2_rn(make_float2(x[8 * j + 2 * p], x[8 * j + 2 * p + 1]), g);
                 wo[p] = pack_bf16x2(d.x, d.y);
             }
-            if (drop) { uint32_t t0, t1; drop_quads(key, idx8 + j, e.thr4, t0, t1); mask_packed8(wo, t0, t1); }
+            if (drop) { uint32_t t[4]; drop_pairs(key, idx8 + j, e.thr4, t); mask_packed8(wo, t); }
             *box_chunk(stg, r, half * 4 + j) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
         }
         return;
@@ -167,17 +167,14 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& e, uint32_t key, in
     if (EPI == EPI_RES && drop) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            uint32_t t0, t1;
-            drop_quads(key, idx8 + j, e.thr4, t0, t1);
+            uint32_t t[4];
+            drop_pairs(key, idx8 + j, e.thr4, t);
             float* y = x + 8 * j;
-            y[0] = __uint_as_float(__float_as_uint(y[0] * e.scale) & dropout_mask_f32<0>(t0));
-            y[1] = __uint_as_float(__float_as_uint(y[1] * e.scale) & dropout_mask_f32<1>(t0));
-            y[2] = __uint_as_float(__float_as_uint(y[2] * e.scale) & dropout_mask_f32<2>(t0));
-            y[3] = __uint_as_float(__float_as_uint(y[3] * e.scale) & dropout_mask_f32<3>(t0));
-            y[4] = __uint_as_float(__float_as_uint(y[4] * e.scale) & dropout_mask_f32<0>(t1));
-            y[5] = __uint_as_float(__float_as_uint(y[5] * e.scale) & dropout_mask_f32<1>(t1));
-            y[6] = __uint_as_float(__float_as_uint(y[6] * e.scale) & dropout_mask_f32<2>(t1));
-            y[7] = __uint_as_float(__float_as_uint(y[7] * e.scale) & dropout_mask_f32<3>(t1));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                y[2 * i] = __uint_as_float(__float_as_uint(y[2 * i] * e.scale) & dropout_mask_f32<0>(t[i]));
+                y[2 * i + 1] = __uint_as_float(__float_as_uint(y[2 * i + 1] * e.scale) & dropout_mask_f32<1>(t[i]));
+            }
         }
     }
     if (kOutF32) {
@@ -882,8 +879,8 @@ template <typename K> static int opt_in_smem(K kern, uint32_t bytes, const char*
 static int fill_epi(EpiParams& e, int M, int N, const float* bias, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, const char* who) {
     if (!(dropout_p >= 0.f && dropout_p < 1.f)) { set_error("%s: dropout_p must be in [0,1)", who); return 1; }
     if (!((int64_t)M * (N / 8) < (1ll << 32))) { set_error("%s: tensor too large for the 32-bit dropout chunk counter", who); return 1; }
-    const uint32_t th = (uint32_t)lrintf(dropout_p * 128.f);
-    e.bias = bias; e.M = M; e.N = N; e.thr4 = th * 0x01010101u; e.scale = 128.f / (128.f - (float)th); e.seed = seed; e.seed_ptr = seed_ptr;
+    const uint32_t th = dropout_threshold(dropout_p);
+    e.bias = bias; e.M = M; e.N = N; e.thr4 = th * 0x00010001u; e.scale = (float)kDropOne / ((float)kDropOne - (float)th); e.seed = seed; e.seed_ptr = seed_ptr;
     return 0;
 }
 

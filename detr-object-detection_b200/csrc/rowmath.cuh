@@ -20,12 +20,14 @@ __device__ __forceinline__ float gelu_tanh_grad(float a) {
     return 0.5f * (1.f + t) + 0.5f * a * (1.f - t * t) * du;
 }
 
-// keep[e] for the 8 elements of chunk `idx8`
-__device__ __forceinline__ void ew_keep8(uint32_t key, uint32_t idx8, uint32_t thr4, bool* keep) {
+// keep[e] for the 8 elements of chunk `idx8` (thr2 = threshold * 0x00010001, threshold in 1/32768: tc::dropout_threshold)
+__device__ __forceinline__ void ew_keep8(uint32_t key, uint32_t idx8, uint32_t thr2, bool* keep) {
     uint32_t st = tc::dropout_group_state(key, idx8);
-    const uint32_t t0 = tc::dropout_quad(st, thr4), t1 = tc::dropout_quad(st, thr4);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { keep[e] = (t0 >> (8 * e + 7)) & 1u; keep[4 + e] = (t1 >> (8 * e + 7)) & 1u; }
+    for (int e = 0; e < 4; ++e) {
+        const uint32_t t = tc::dropout_pair(st, thr2);
+        keep[2 * e] = (t >> 15) & 1u; keep[2 * e + 1] = (t >> 31) & 1u;
+    }
 }
 __device__ __forceinline__ uint32_t ew_key(uint64_t seed, const uint64_t* seed_ptr) {
     const uint64_t s = seed + (seed_ptr ? *seed_ptr : 0ull);

@@ -403,8 +403,8 @@ static int layernorm_bwd_impl(const void* dy, const void* dy2, int g_dtype, cons
     p.dy = dy; p.dy2 = dy2; p.dres = dres; p.dx = dx; p.partial = partial; p.dgamma = dgamma; p.dbeta = dbeta; p.counters = counters;
     p.dz = dz; p.dbias = dbias; p.has_dz = dz != nullptr; p.seed = seed; p.seed_ptr = seed_ptr;
     {
-        const uint32_t th = (uint32_t)lrintf(dropout_p * 128.f);
-        p.thr4 = th * 0x01010101u; p.scale = 128.f / (128.f - (float)th);
+        const uint32_t th = tc::dropout_threshold(dropout_p);
+        p.thr4 = th * 0x00010001u; p.scale = (float)tc::kDropOne / ((float)tc::kDropOne - (float)th);
     }
     const int grid = ln_grid(rows);
     const size_t smem = (size_t)(kLnThreads / 32) * 3 * C * sizeof(float);
@@ -437,7 +437,7 @@ static int layernorm_bwd_impl(const void* dy, const void* dy2, int g_dtype, cons
 //   MODE 0   dy = dropout_mask(g) / (1-p)              (the residual branch's gradient is g itself)
 //   MODE 1   dy = dropout_mask(g) / (1-p) * gelu'(y)
 // The dropout mask is the 7-bit counter-based generator of the attention kernels (tc.cuh), indexed by the 8-element
-// chunk (row * N/8 + column/8): nothing is stored for backward, p is quantised to k/128.
+// chunk (row * N/8 + column/8): nothing is stored for backward, p is quantised to k/32768.
 // =========================================================================================================
 #include "tc.cuh"
 #include "rowmath.cuh"
@@ -452,7 +452,7 @@ struct EwParams {
     float* partial;                // backward: [row chunks][N] column sums of dy
     float* db; unsigned* counters; // backward: bias gradient, per-column-tile counters (zero on entry and exit)
     int M, N, rows_per_cta;
-    uint32_t thr4; float scale;    // dropout: thresh * 0x01010101 (0 = off), 1 / keep
+    uint32_t thr4; float scale;    // dropout: thresh * 0x00010001 (0 = off; thresh in 1/32768), 1 / keep
     uint64_t seed; const uint64_t* seed_ptr;
 };
 
@@ -566,8 +566,8 @@ static int ew_fill(EwParams& p, int M, int N, float dropout_p, uint64_t seed, co
     if (!(M >= 1 && N >= 8 && N % 8 == 0)) { set_error("%s: need M >= 1 and N %% 8 == 0 (M=%d N=%d)", who, M, N); return 1; }
     if (!((int64_t)M * (N / 8) < (1ll << 32))) { set_error("%s: tensor too large for the 32-bit chunk counter", who); return 1; }
     if (!(dropout_p >= 0.f && dropout_p < 1.f)) { set_error("%s: dropout_p must be in [0,1)", who); return 1; }
-    const uint32_t th = (uint32_t)lrintf(dropout_p * 128.f);
-    p.M = M; p.N = N; p.thr4 = th * 0x01010101u; p.scale = 128.f / (128.f - (float)th); p.seed = seed; p.seed_ptr = seed_ptr;
+    const uint32_t th = tc::dropout_threshold(dropout_p);
+    p.M = M; p.N = N; p.thr4 = th * 0x00010001u; p.scale = (float)tc::kDropOne / ((float)tc::kDropOne - (float)th); p.seed = seed; p.seed_ptr = seed_ptr;
     return 0;
 }
 

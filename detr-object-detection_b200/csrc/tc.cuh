@@ -195,9 +195,12 @@ __device__ __forceinline__ float ex2(float x) {
 
 // ---- counter-based dropout -------------------------------------------------------------------------------
 // Keep/drop decisions come in groups of 32 consecutive keys of one (batch*head, query) row: one seed hash per group,
-// then one multiply-with-carry step (IMAD.WIDE + LOP3) per 4 keys.  Each key owns 7 random bits, so the dropout
-// probability is quantised to k/128.  The mask depends only on (seed, batch*head, query, key): forward and backward
-// regenerate it identically whatever their tiling, as long as they walk a 32-key group in order.
+// then one multiply-with-carry step (IMAD.WIDE + LOP3) per 2 keys.  Each key owns 15 random bits, so the dropout
+// probability is quantised to k/32768 (p = 0.1 -> 3277/32768 = 0.100006; detr/model.py:345,355,408,410 use 0.1).
+// The mask depends only on (seed, batch*head, query, key): forward and backward regenerate it identically whatever
+// their tiling, as long as they walk a 32-key group in order.
+constexpr uint32_t kDropOne = 32768u;   // thresholds are in units of 1/32768
+__host__ __device__ inline uint32_t dropout_threshold(float p) { return (uint32_t)(p * (float)kDropOne + 0.5f); }
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
@@ -211,12 +214,12 @@ __device__ __forceinline__ uint32_t dropout_group_state(uint32_t row_key, uint32
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15;
     return x;
 }
-// Advance the group state by 4 keys.  Byte e of the result has bit 7 set iff key e of the quad is KEPT
-// (7 random bits r: (128 + r) - thresh keeps bit 7 iff r >= thresh; no borrow crosses a byte).
-__device__ __forceinline__ uint32_t dropout_quad(uint32_t& x, uint32_t thr4 /* thresh * 0x01010101 */) {
+// Advance the group state by 2 keys.  Half e of the result has bit 15 set iff key e of the pair is KEPT
+// (15 random bits r: (32768 + r) - thresh keeps bit 15 iff r >= thresh; no borrow crosses a half).
+__device__ __forceinline__ uint32_t dropout_pair(uint32_t& x, uint32_t thr2 /* thresh * 0x00010001 */) {
     const uint64_t p = (uint64_t)x * 0x9E3779B1u + 0x7F4A7C15u;
     x = (uint32_t)p;
-    return (((uint32_t)(p >> 32) ^ x) | 0x80808080u) - thr4;
+    return (((uint32_t)(p >> 32) ^ x) | 0x80008000u) - thr2;
 }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {
     uint32_t d;
@@ -224,9 +227,9 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {
     return d;
 }
 // selector nibbles with bit 3 set replicate the SIGN of the chosen byte over the whole output byte:
-// all-ones / all-zeros masks for a packed bf16 pair (keys 2*PAIR, 2*PAIR+1) and for one fp32 value (key E)
-template <int PAIR> __device__ __forceinline__ uint32_t dropout_mask_bf16x2(uint32_t t) { return prmt(t, PAIR == 0 ? 0x9988u : 0xBBAAu); }
-template <int E> __device__ __forceinline__ uint32_t dropout_mask_f32(uint32_t t) { return prmt(t, 0x8888u + 0x1111u * E); }
+// all-ones / all-zeros masks for the packed bf16 pair of the two keys, and for the fp32 value of key E
+__device__ __forceinline__ uint32_t dropout_mask_bf16x2(uint32_t t) { return prmt(t, 0xBB99u); }
+template <int E> __device__ __forceinline__ uint32_t dropout_mask_f32(uint32_t t) { return prmt(t, E == 0 ? 0x9999u : 0xBBBBu); }
 
 }  // namespace tc
 }  // namespace detr

@@ -117,7 +117,7 @@ int detr_criterion_bwd_f32(const float* grad_losses,
  * detr/model.py:317-319,352 disappear.  lse float[B*nh*L] (natural log, saved for backward).
  * key_padding_mask: (B,S) bytes, non-zero = ignore (detr/model.py:326-330), row stride kpm_sb, may be NULL;
  * attention_mask: (L,S) bytes contiguous, non-zero = ignore (detr/model.py:332-334), may be NULL.
- * dropout_p is quantised to k/128 (in-kernel counter-based mask; 0 disables, as in eval()).  The mask seed is
+ * dropout_p is quantised to k/32768 (0.1 -> 0.100006; in-kernel counter-based mask; 0 disables, as in eval()).  The mask seed is
  * `seed + *seed_ptr` (seed_ptr: optional DEVICE uint64, so that CUDA-graph replays draw fresh masks).
  * workspace float[detr_attention_fwd_workspace_floats(B,nh,L,S)]: partial results of the (batch, head, query tile) items
  * that the persistent kernel splits between two CTAs (merged by a second small launch). */
@@ -184,7 +184,7 @@ int detr_layernorm_bwd_tail(const void* dy, const void* dy2, int g_dtype, const 
  * mode 0: out(x's dtype) = x + dropout(y)  -- residual add after the attention output / second FFN projection;
  * mode 1: out(bf16) = dropout(gelu_tanh(y)) -- between the FFN projections (x unused).
  * y bf16 (M,N) contiguous = the producing Linear's output; x_dtype / g_dtype: 0 float32, 1 bfloat16.  The dropout mask
- * is counter-based (7 bits per element, p quantised to k/128, seed + *seed_ptr as in the attention kernels) and is
+ * is counter-based (15 bits per element, p quantised to k/32768, seed + *seed_ptr as in the attention kernels) and is
  * regenerated by the backward call, which also returns the producing Linear's bias gradient:
  *   dy(bf16) = mask(g)/(1-p) [* gelu'(y) in mode 1],  db[n] = sum_m dy[m][n]
  * partial float[detr_epilogue_chunks(M,N) * N] is scratch; counters as for detr_colsum_bf16.  N % 8 == 0. */

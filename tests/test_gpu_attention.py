@@ -197,3 +197,19 @@ def test_fused_qk_node_matches_separate_projections(cuda, B, L, nh, masked):
     yb.backward(do)
     assert torch.equal(ya, yb)
     assert torch.equal(a_qk.grad, b_qk.grad) and torch.equal(a_v.grad, b_v.grad)
+
+
+def test_attention_dropout_rate_is_the_references(cuda):
+    """detr/model.py:345 drops attention probabilities with p = 0.1: the in-kernel generator has 15 random bits per element
+    (p = 3277/32768 = 0.100006).  With V = 1 and one key tile the output of a row is sum_j keep_j * softmax_j / (1 - p): for
+    uniform attention over S keys it is (#kept / S) / (1 - p) -- its mean over many rows estimates (1 - p_actual) / (1 - p)."""
+    from detr_b200.attention import attention_forward
+    B, nh, L, S = 4, 8, 1024, 128
+    q = torch.zeros(B, L, nh * 32, device=cuda, dtype=torch.bfloat16)          # zero scores: uniform attention
+    k = torch.zeros(B, S, nh * 32, device=cuda, dtype=torch.bfloat16)
+    v = torch.ones(B, S, nh * 32, device=cuda, dtype=torch.bfloat16)
+    out, _ = attention_forward(q, k, v, dropout_p=0.1, seed=77)
+    kept_frac = out.float().mean().item() * (1 - 3277 / 32768)                  # mean of (#kept / S)
+    n = B * nh * L * S
+    sigma = (0.1 * 0.9 / n) ** 0.5
+    assert abs(kept_frac - 0.9) < 6 * sigma + 2e-3, (kept_frac, sigma)         # (+ bf16 rounding of the output)
