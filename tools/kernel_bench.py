@@ -59,8 +59,11 @@ class Flush:
             self.sink = self.buf.sum()
 
 
+WARMUP = 3
+
+
 def timeit(fn, iters, flush):
-    for _ in range(3):
+    for _ in range(WARMUP):
         fn()
     torch.cuda.synchronize()
     ts = []
@@ -78,9 +81,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3, help="untimed calls before each measurement (0 under ncu: one launch per shape)")
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--flush", choices=("read", "write"), default="read")
     args = ap.parse_args()
+    global WARMUP
+    WARMUP = args.warmup
     dev = torch.device("cuda:0")
     tf, hbm, src = peaks()
     flush = Flush(dev, args.flush)
@@ -129,7 +135,7 @@ def main():
                 loss = sum(v for k, v in crit({"pred_logits": lg, "pred_boxes": bx}, tg).items() if k.startswith("loss"))
                 flush()
                 loss.backward()
-            for _ in range(3):
+            for _ in range(WARMUP):
                 crit_step()
             with _lib.profile() as prof:
                 for _ in range(args.iters):
