@@ -353,7 +353,7 @@ def run_dc5(args, dev, world, rank, C):
     """BASELINE config 4: the 6 + 6 layer transformer on stride-16 tokens (50 x 67 = 3 350 per image), forward + backward captured
     in one CUDA graph.  No backbone (the reference's is stride 32 only), no optimizer: this is the attention-dominated workload."""
     import torch.distributed as dist
-    from detr_b200 import _lib, attention
+    from detr_b200 import _lib, attention, gemm as gemm_mod
     from detr_b200.harness import positional_encoding_tokens
     from detr_b200.model import DETRConfig, Decoder, Encoder
     eh, ew = (int(v) for v in args.grid.split("x"))       # default 50 x 67 (stride 16); 25x34 = the stride-32 map of config 2
@@ -384,7 +384,12 @@ def run_dc5(args, dev, world, rank, C):
             mem = enc(xin, position_embedding=pos, key_padding_mask=mask)
             out = dec(mem, position_embedding=pos, object_query_embedding=qe[None].expand(B, -1, -1), key_padding_mask=mask)
         loss = (out.float() * w).mean()
-        loss.backward()
+        # weight-gradient GEMMs on a parallel branch of the graph (detr_b200/gemm.py), as in GraphedTrainStep
+        prev = gemm_mod.wgrad_side_stream(os.environ.get("DETR_B200_WGRAD_STREAM", "1") != "0")
+        try:
+            loss.backward()
+        finally:
+            gemm_mod.wgrad_side_stream(prev)
         loss_buf.copy_(loss.detach())
 
     side = torch.cuda.Stream()

@@ -4,6 +4,8 @@
 Everything here is 2-D: activations are (M, features) views of the (B, L, C) tensors."""
 from __future__ import annotations
 
+import contextlib
+import os
 from typing import Optional
 
 import torch
@@ -85,6 +87,59 @@ def gemm_ln(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float
     return out, a_plain, a_pos, stats
 
 
+class _SideStream:
+    """Weight gradients leave the critical path: inside a backward pass `gemm_wgrad` may launch on a second stream, forked from
+    the caller's stream at the call and joined back ONCE, by an autograd engine callback at the end of the pass (under stream
+    capture: a parallel branch of the graph).  The small decoder GEMMs occupy 4-32 of 148 SMs, so the branch runs beside the
+    input-gradient chain instead of between its links.  Operands and outputs are allocated on the caller's stream and kept
+    alive until the join.  Anything that reads a weight gradient BEFORE the backward pass ends (DistributedDataParallel's or
+    the harness' bucketed all-reduce hooks) must leave this off -- hence opt-in: `wgrad_side_stream(True)`, which
+    `harness.GraphedTrainStep` does when its own all-reduce follows the backward pass."""
+
+    def __init__(self):
+        self.enabled = os.environ.get("DETR_B200_WGRAD_STREAM", "0") == "1"
+        self.streams = {}
+        self.pending = {}          # graph task id -> [device, tensors kept alive until the join]
+
+    def stream(self, dev: torch.device) -> "torch.cuda.Stream":
+        st = self.streams.get(dev.index)
+        if st is None:
+            st = self.streams[dev.index] = torch.cuda.Stream(dev)
+        return st
+
+    def fork(self, dev: torch.device, keep):
+        """Returns the side stream to launch on (already waiting for the caller's stream), or None outside a backward pass."""
+        task = torch._C._current_graph_task_id()
+        if not self.enabled or task < 0:
+            return None
+        side = self.stream(dev)
+        entry = self.pending.get(task)
+        if entry is None:
+            entry = self.pending[task] = [dev, []]
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: self.join(task))
+        entry[1].append(keep)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        side.wait_event(ev)
+        return side
+
+    def join(self, task: int) -> None:
+        dev, keep = self.pending.pop(task)
+        ev = torch.cuda.Event()
+        ev.record(self.stream(dev))
+        torch.cuda.current_stream(dev).wait_event(ev)
+        keep.clear()
+
+
+_SIDE = _SideStream()
+
+
+def wgrad_side_stream(enabled: bool) -> bool:
+    """Switch the side-stream launch of weight-gradient GEMMs (see _SideStream); returns the previous setting."""
+    prev, _SIDE.enabled = _SIDE.enabled, bool(enabled)
+    return prev
+
+
 def gemm_wgrad(dy: torch.Tensor, x0: torch.Tensor, x1: Optional[torch.Tensor] = None, n_switch: int = 0, want_db: bool = True):
     """(dw (N, K) fp32, db (N,) fp32 | None) = (dy^T @ x, column sums of dy); rows >= n_switch of dw use x1.  See detr_gemm_wgrad_bf16."""
     _lib.require_cuda(dy, "gemm_wgrad")
@@ -98,7 +153,9 @@ def gemm_wgrad(dy: torch.Tensor, x0: torch.Tensor, x1: Optional[torch.Tensor] = 
     db = torch.empty(N, dtype=torch.float32, device=dev) if want_db else None
     nws = _lib.load().detr_gemm_wgrad_workspace_floats(M, N, K)
     ws = torch.empty(nws, dtype=torch.float32, device=dev) if nws else None
-    _lib.call("detr_gemm_wgrad_bf16", dy.data_ptr(), dy.stride(0), x0.data_ptr(), x0.stride(0), _lib.ptr(x1), x1.stride(0) if x1 is not None else 0,
-              n_switch if x1 is not None else N, M, N, K, dw.data_ptr(), _lib.ptr(db), _lib.ptr(ws), _lib.stream_ptr(),
-              tag=("wgrad", M, N, K), launches=2 if nws else 1)
+    side = _SIDE.fork(dev, (dy, x0, x1, dw, db, ws))
+    with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+        _lib.call("detr_gemm_wgrad_bf16", dy.data_ptr(), dy.stride(0), x0.data_ptr(), x0.stride(0), _lib.ptr(x1), x1.stride(0) if x1 is not None else 0,
+                  n_switch if x1 is not None else N, M, N, K, dw.data_ptr(), _lib.ptr(db), _lib.ptr(ws), _lib.stream_ptr(),
+                  tag=("wgrad", M, N, K), launches=2 if nws else 1)
     return dw, db

@@ -9,12 +9,14 @@ host loops of detr/position_encoding.py:57-67 and detr/model.py:96-114 replaced 
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, Dict, Optional
 
 import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import gemm
 from .model import DETRConfig, Decoder, Encoder
 
 
@@ -790,7 +792,13 @@ class GraphedTrainStep:
         out = {k: v.float() for k, v in out.items()}
         losses = self.criterion(out, {"packed": self.targets.packed, "num_boxes": self.targets.num_boxes})
         loss = sum(v for k, v in losses.items() if k.startswith("loss"))
-        loss.backward()
+        # weight-gradient GEMMs on a parallel branch (gemm._SideStream): safe here because nothing reads a weight gradient
+        # before backward() returns -- unless the bucketed all-reduce hooks are live
+        prev = gemm.wgrad_side_stream(self._buckets is None and os.environ.get("DETR_B200_WGRAD_STREAM", "1") != "0")
+        try:
+            loss.backward()
+        finally:
+            gemm.wgrad_side_stream(prev)
         self.loss.copy_(loss.detach())
         if self._buckets is not None:
             self._hooks_live = False

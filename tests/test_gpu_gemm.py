@@ -200,3 +200,40 @@ def test_gemm_wgrad_two_operands(cuda):
     ref = torch.cat([dy[:, :512].float().t() @ x0.float(), dy[:, 512:].float().t() @ x1.float()], 0)
     _close(dw, ref, rel=1e-4)
     _close(db, dy.float().sum(0), rel=1e-4)
+
+
+def test_wgrad_side_stream(cuda):
+    """Weight gradients launched on the second stream inside a backward pass (gemm._SideStream) are joined before backward() returns
+    and are bit-identical to the in-line launch; outside a backward pass the switch changes nothing."""
+    from detr_b200 import blocks, gemm as G
+    torch.manual_seed(3)
+    norm = torch.nn.LayerNorm(256).cuda()
+    fc1, fc2 = torch.nn.Linear(256, 2048).cuda(), torch.nn.Linear(2048, 256).cuda()
+    x0 = torch.randn(2, 400, 256, device="cuda")
+    grads = []
+    for side in (False, True, True):
+        for m in (norm, fc1, fc2):
+            m.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True)
+        prev = G.wgrad_side_stream(side)
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = blocks.ln_ffn(x * 1.0, norm, fc1, fc2, 0.0, 0.0)
+            y.float().square().sum().backward()
+            # consumer on the caller's stream right after backward(): must already see the side stream's results
+            got = [p.grad.clone() for m in (norm, fc1, fc2) for p in m.parameters()] + [x.grad.clone()]
+        finally:
+            G.wgrad_side_stream(prev)
+        assert not G._SIDE.pending
+        grads.append(got)
+    for a, b in zip(grads[0], grads[1]):
+        assert torch.equal(a, b)
+    for a, b in zip(grads[1], grads[2]):
+        assert torch.equal(a, b)
+    G.wgrad_side_stream(True)
+    try:
+        dy, xx = _rand((800, 256), 50, 0.1), _rand((800, 256), 51)
+        dw, _ = G.gemm_wgrad(dy, xx)           # not inside backward: launched in line
+        _close(dw, dy.float().t() @ xx.float(), rel=1e-4)
+    finally:
+        G.wgrad_side_stream(False)
