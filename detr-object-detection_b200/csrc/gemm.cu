@@ -17,6 +17,7 @@
 //   EPI_GELU      aux = bf16(acc + bias);  out = dropout(gelu_tanh(aux))             (first FFN layer, :405-408)
 //   EPI_RES       out = res + dropout(acc + bias)                                    (output projection / second FFN layer + residual)
 //   EPI_GELU_BWD  out = acc * dropout_mask/(1-p) * gelu'(aux)                         (backward through :406-408)
+//   EPI_SIGMOID   out = sigmoid(acc + bias), fp32                                    (box head, detr/model.py:93)
 //
 // All kernels: 128 x 128 output tiles, one elected thread issues tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators
 // in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1), operands staged by TMA into a
@@ -50,7 +51,7 @@ constexpr uint32_t kBoxBytes = 32 * 128;       // one staging box: 32 rows x 128
 constexpr uint32_t kStgBytes = 2 * kBoxBytes;  // per epilogue warp
 constexpr uint32_t kStgTotal = kEpiWarps * kStgBytes;
 
-enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_RES = 2, EPI_GELU_BWD = 3 };
+enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_RES = 2, EPI_GELU_BWD = 3, EPI_SIGMOID = 4 };
 
 struct EpiParams {
     const float* bias;                       // fp32 [N] or null
@@ -164,6 +165,10 @@ __device__ __forceinline__ void epi_chunk32(const EpiParams& e, uint32_t key, in
         }
         return;
     }
+    if (EPI == EPI_SIGMOID) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = 1.f / (1.f + expf(-x[i]));
+    }
     if (EPI == EPI_RES && drop) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -256,7 +261,7 @@ __device__ __forceinline__ void epi_tile(const EpiParams& e, const CUtensorMap* 
             tma_store_2d(tm_out, stg + kBoxBytes, nc, mr);
         } else if (kOutF32) {
             tma_store_2d(tm_out, stg, nc, mr);
-            tma_store_2d(tm_out, stg + kBoxBytes, nc + 32, mr);
+            if (nc + 32 < e.N) tma_store_2d(tm_out, stg + kBoxBytes, nc + 32, mr);
         } else {
             tma_store_2d(tm_out, stg, nc, mr);
         }
@@ -905,12 +910,18 @@ extern "C" void detr_gemm_set_debug(long long* buf) { g_gemm_dbg = buf; }
 
 /* dtype codes: 0 = float32, 1 = bfloat16.  epilogue: 0 bias, 1 bias + GELU(tanh) + dropout (aux receives the bf16
  * pre-activation), 2 bias + dropout + residual (out and res share out_dtype), 3 GELU backward (aux = pre-activation,
- * no bias, bf16 out).  b_kn = 0: b is [N][K] (nn.Linear weight, C = A B^T); 1: b is [K][N] (C = A B). */
+ * no bias, bf16 out), 4 sigmoid(acc + bias) (fp32 out).  b_kn = 0: b is [N][K] (nn.Linear weight, C = A B^T); 1: b is [K][N] (C = A B). */
 extern "C" int detr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int b_kn, int M, int N, int K, int epilogue,
                               const float* bias, void* out, int out_dtype, int64_t ldo, void* aux, int64_t ld_aux, const void* res,
                               int64_t ld_res, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream) {
-    DETR_CHECK_ARG(M >= 1 && N >= 32 && N % 32 == 0 && K >= 64 && K % 64 == 0, "gemm: need M >= 1, N %% 32 == 0, K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
-    DETR_CHECK_ARG(epilogue >= 0 && epilogue <= 3 && (out_dtype == 0 || out_dtype == 1), "gemm: bad epilogue / dtype code");
+    // N: whole 32-column boxes, except for the plain fp32 outputs of the prediction heads (N = 92 / 4): there the TMA store clips
+    // the last box, the weight rows beyond N are zero-filled by the TMA load and the bias is read up to the next multiple of 64
+    const bool ragged_n = N % 32 != 0;
+    DETR_CHECK_ARG(M >= 1 && N >= 4 && K >= 64 && K % 64 == 0 &&
+                   (!ragged_n || (N % 4 == 0 && out_dtype == 0 && !b_kn && (epilogue == EPI_BIAS || epilogue == EPI_SIGMOID))),
+                   "gemm: need M >= 1, K %% 64 == 0, N %% 32 == 0 (fp32 bias / sigmoid outputs: N %% 4 == 0) (M=%d N=%d K=%d)", M, N, K);
+    DETR_CHECK_ARG(epilogue >= 0 && epilogue <= 4 && (out_dtype == 0 || out_dtype == 1), "gemm: bad epilogue / dtype code");
+    DETR_CHECK_ARG(epilogue != EPI_SIGMOID || (out_dtype == 0 && !b_kn), "gemm: the sigmoid epilogue writes fp32 and takes b as [N][K]");
     DETR_CHECK_ARG(out != nullptr, "gemm: out is null");
     DETR_CHECK_ARG(!bias || ((uintptr_t)bias % 16) == 0, "gemm: bias must be 16-byte aligned");
     DETR_CHECK_ARG((epilogue != EPI_GELU && epilogue != EPI_GELU_BWD) || aux != nullptr, "gemm: aux required");
@@ -934,6 +945,7 @@ extern "C" int detr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t
         case EPI_BIAS: if (f32) GEMM_GO(EPI_BIAS, float); else GEMM_GO(EPI_BIAS, __nv_bfloat16);
         case EPI_GELU: GEMM_GO(EPI_GELU, __nv_bfloat16);
         case EPI_RES: if (f32) GEMM_GO(EPI_RES, float); else GEMM_GO(EPI_RES, __nv_bfloat16);
+        case EPI_SIGMOID: return launch_stream<EPI_SIGMOID, float, false>(ta, tb, to, tx, tr, p, st);
         default: GEMM_GO(EPI_GELU_BWD, __nv_bfloat16);
     }
 #undef GEMM_GO

@@ -421,8 +421,20 @@ static int layernorm_bwd_impl(const void* dy, const void* dy2, int g_dtype, cons
 #undef LN_BWD
     DETR_CHECK_LAUNCH("layernorm_bwd");
     (void)counters;
+    if (dgamma == nullptr) return 0;          // the caller folds the partials itself (detr_layernorm_bwd_fold, e.g. on another stream)
     const int NP = p.has_dz ? 3 : 2;
     fold_partials_kernel<<<(NP * C + 31) / 32, kFoldThreads, 0, st>>>(partial, grid, NP * C, dgamma, dbeta, C, dbias);
+    DETR_CHECK_LAUNCH("layernorm_bwd_fold");
+    return 0;
+}
+
+// Second half of detr_layernorm_bwd[_tail] when it was called with dgamma == NULL: fold the per-CTA partials of `rows` rows into
+// dgamma, dbeta (and dbias when the call had a tail).  Parameter gradients are not on the critical path of the backward pass,
+// so the host launches this on a second stream.
+extern "C" int detr_layernorm_bwd_fold(const float* partial, int rows, int C, float* dgamma, float* dbeta, float* dbias, void* stream) {
+    DETR_CHECK_ARG(partial != nullptr && dgamma != nullptr && dbeta != nullptr && rows >= 1 && C >= 32, "layernorm_bwd_fold: bad arguments");
+    const int NP = dbias != nullptr ? 3 : 2;
+    fold_partials_kernel<<<(NP * C + 31) / 32, kFoldThreads, 0, (cudaStream_t)stream>>>(partial, ln_grid(rows), NP * C, dgamma, dbeta, C, dbias);
     DETR_CHECK_LAUNCH("layernorm_bwd_fold");
     return 0;
 }
@@ -613,5 +625,52 @@ extern "C" int detr_epilogue_bwd(int mode, const void* g, int g_dtype, const voi
     else if (g_dtype == 0) epilogue_bwd_kernel<1, float><<<grid, kCsThreads, 0, st>>>(p);
     else epilogue_bwd_kernel<1, __nv_bfloat16><<<grid, kCsThreads, 0, st>>>(p);
     DETR_CHECK_LAUNCH("epilogue_bwd");
+    return 0;
+}
+
+// =========================================================================================================
+// Backward entry of the prediction heads (detr/model.py:92-93: class_embedding, bbox_embedding(.).sigmoid()).
+// The criterion hands back fp32 d_logits [rows][K] and d_boxes [rows][4]; the heads' input- and weight-gradient GEMMs
+// (csrc/gemm.cu) want bf16 operands whose widths are whole MMA tiles.  One pass writes both:
+//   dl16[rows][ld_l]  = bf16(d_logits), zero beyond column K
+//   dz16[rows][ld_z]  = bf16(d_boxes * b * (1 - b)), b = the sigmoid output, zero beyond column 4
+// One warp per row.
+// =========================================================================================================
+namespace detr {
+
+__global__ void __launch_bounds__(256) heads_grad_prep_kernel(const float* __restrict__ d_logits, int K, const float* __restrict__ d_boxes,
+                                                              const float* __restrict__ boxes, __nv_bfloat16* __restrict__ dl16, int ld_l,
+                                                              __nv_bfloat16* __restrict__ dz16, int ld_z, int rows) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* g = d_logits + (int64_t)row * K;
+    for (int c = lane * 2; c < ld_l; c += 64) {
+        const float a = c < K ? __ldg(g + c) : 0.f, b = c + 1 < K ? __ldg(g + c + 1) : 0.f;
+        *reinterpret_cast<__nv_bfloat162*>(dl16 + (int64_t)row * ld_l + c) = __floats2bfloat162_rn(a, b);
+    }
+    for (int c = lane * 2; c < ld_z; c += 64) {
+        float v[2] = {0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if (c + i < 4) {
+                const float s = __ldg(boxes + (int64_t)row * 4 + c + i);
+                v[i] = __ldg(d_boxes + (int64_t)row * 4 + c + i) * s * (1.f - s);
+            }
+        *reinterpret_cast<__nv_bfloat162*>(dz16 + (int64_t)row * ld_z + c) = __floats2bfloat162_rn(v[0], v[1]);
+    }
+}
+
+}  // namespace detr
+
+extern "C" int detr_heads_grad_prep(const float* d_logits, int K, const float* d_boxes, const float* boxes, void* dl16, int ld_l,
+                                    void* dz16, int ld_z, int rows, void* stream) {
+    DETR_CHECK_ARG(d_logits && d_boxes && boxes && dl16 && dz16 && rows >= 1 && K >= 1, "heads_grad_prep: null argument");
+    DETR_CHECK_ARG(ld_l >= K && ld_l % 2 == 0 && ld_z >= 4 && ld_z % 2 == 0 && ((uintptr_t)dl16 % 4) == 0 && ((uintptr_t)dz16 % 4) == 0,
+                   "heads_grad_prep: ld_l >= K, ld_z >= 4, both even");
+    detr::heads_grad_prep_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d_logits, K, d_boxes, boxes,
+                                                                                   reinterpret_cast<__nv_bfloat16*>(dl16), ld_l,
+                                                                                   reinterpret_cast<__nv_bfloat16*>(dz16), ld_z, rows);
+    DETR_CHECK_LAUNCH("heads_grad_prep");
     return 0;
 }

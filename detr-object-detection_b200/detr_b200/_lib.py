@@ -47,6 +47,8 @@ SIGNATURES = {
     "detr_layernorm_fwd": [P, c_int, c_int64, P, P, P, c_int, c_int64, c_int64, c_int, P, P, c_int, P, P, c_int, c_int, c_float, P],
     "detr_layernorm_bwd": [P, P, c_int, P, P, c_int, c_int64, P, P, P, P, P, P, P, P, c_int, c_int, P],
     "detr_layernorm_bwd_tail": [P, P, c_int, P, P, c_int, c_int64, P, P, P, P, P, P, P, P, c_int, c_int, P, P, c_float, ctypes.c_uint64, P, P],
+    "detr_layernorm_bwd_fold": [P, c_int, c_int, P, P, P, P],
+    "detr_heads_grad_prep": [P, c_int, P, P, P, c_int, P, c_int, c_int, P],
     "detr_epilogue_fwd": [c_int, P, c_int, P, P, c_int, c_int, c_float, ctypes.c_uint64, P, P],
     "detr_epilogue_chunks": [c_int, c_int],
     "detr_scale_cast_multi": [P, c_int, c_int, P],
@@ -102,7 +104,7 @@ class FoldTable(ctypes.Structure):
 # the shape pass the exact number through call(..., launches=))
 KERNELS_PER_CALL = {"detr_cost_matrix_f32": 1, "detr_hungarian_match_f32": 1, "detr_lsap_f32": 1, "detr_lsap_f64": 1,
                     "detr_criterion_fwd_f32": 3, "detr_criterion_bwd_f32": 1, "detr_attention_fwd_bf16": 2,
-                    "detr_attention_bwd_bf16": 4, "detr_colsum_bf16": 1, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2, "detr_layernorm_bwd_tail": 2,
+                    "detr_attention_bwd_bf16": 4, "detr_colsum_bf16": 1, "detr_layernorm_fwd": 1, "detr_layernorm_bwd": 2, "detr_layernorm_bwd_tail": 2, "detr_layernorm_bwd_fold": 1, "detr_heads_grad_prep": 1,
                     "detr_epilogue_fwd": 1, "detr_epilogue_bwd": 1, "detr_scale_cast_multi": 1,
                     "detr_maxpool3x3s2_fwd_bf16": 1, "detr_maxpool3x3s2_bwd_bf16": 1,
                     "detr_gemm_bf16": 1, "detr_gemm_ln_bf16": 1, "detr_gemm_wgrad_bf16": 2,

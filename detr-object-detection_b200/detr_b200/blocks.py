@@ -77,24 +77,35 @@ def _ln_backward(dy, dy2, dres, x2, gamma32, stats, tail=None):
             dres = dres.to(x2.dtype).contiguous()
     dx = torch.empty(rows, C, dtype=x2.dtype, device=x2.device)
     grid = _lib.load().detr_layernorm_grid(rows)
-    if tail is not None and C == C_MODEL:
+    with_tail = tail is not None and C == C_MODEL
+    NP = 3 if with_tail else 2
+    partial = torch.empty(grid * NP * C, dtype=torch.float32, device=x2.device)
+    dgb = torch.empty(NP, C, dtype=torch.float32, device=x2.device)
+    # the fold of the per-CTA partials into dgamma / dbeta (/ dbias) feeds parameter gradients only: inside a backward pass with the
+    # second stream enabled (gemm._SideStream) it leaves the critical path, otherwise the same C call launches it
+    side = G._SIDE.fork(x2.device, (partial,))      # outputs are never kept: see gemm._SideStream
+    dg_ptr = dgb[0].data_ptr() if side is None else None
+    if with_tail:
         p, seed, seed_t = tail
-        partial = torch.empty(grid * 3 * C, dtype=torch.float32, device=x2.device)
-        dgb = torch.empty(3, C, dtype=torch.float32, device=x2.device)
         dz = torch.empty(rows, C, dtype=torch.bfloat16, device=x2.device)
         _lib.call("detr_layernorm_bwd_tail", _lib.ptr(dy), _lib.ptr(dy2), _DT[gdt], _lib.ptr(dres), x2.data_ptr(), _DT[x2.dtype], x2.stride(0),
                   gamma32.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), dx.data_ptr(), partial.data_ptr(),
-                  dgb[0].data_ptr(), dgb[1].data_ptr(), _lib.zero_counters(x2.device).data_ptr(), rows, C, dz.data_ptr(), dgb[2].data_ptr(),
-                  float(p), seed & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_t), _lib.stream_ptr())
+                  dg_ptr, dgb[1].data_ptr(), _lib.zero_counters(x2.device).data_ptr(), rows, C, dz.data_ptr(), dgb[2].data_ptr(),
+                  float(p), seed & 0xFFFFFFFFFFFFFFFF, _lib.ptr(seed_t), _lib.stream_ptr(), launches=2 if side is None else 1)
         if len(_DZ_FOR) > 64:          # entries whose consumer never came (a branch of the graph that was not a block tail)
             _DZ_FOR.clear()
         _DZ_FOR[dx.data_ptr()] = (dx, dz, dgb[2])
-        return dx, dgb[0], dgb[1]
-    partial = torch.empty(grid * 2 * C, dtype=torch.float32, device=x2.device)
-    dgb = torch.empty(2, C, dtype=torch.float32, device=x2.device)
-    _lib.call("detr_layernorm_bwd", _lib.ptr(dy), _lib.ptr(dy2), _DT[gdt], _lib.ptr(dres), x2.data_ptr(), _DT[x2.dtype], x2.stride(0),
-              gamma32.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), dx.data_ptr(), partial.data_ptr(),
-              dgb[0].data_ptr(), dgb[1].data_ptr(), _lib.zero_counters(x2.device).data_ptr(), rows, C, _lib.stream_ptr())
+    else:
+        _lib.call("detr_layernorm_bwd", _lib.ptr(dy), _lib.ptr(dy2), _DT[gdt], _lib.ptr(dres), x2.data_ptr(), _DT[x2.dtype], x2.stride(0),
+                  gamma32.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), dx.data_ptr(), partial.data_ptr(),
+                  dg_ptr, dgb[1].data_ptr(), _lib.zero_counters(x2.device).data_ptr(), rows, C, _lib.stream_ptr(),
+                  launches=2 if side is None else 1)
+    if side is not None:
+        G._SIDE.refork(x2.device)      # the fold waits for the row pass just launched
+        with torch.cuda.stream(side):
+            _lib.call("detr_layernorm_bwd_fold", partial.data_ptr(), rows, C, dgb[0].data_ptr(), dgb[1].data_ptr(),
+                      dgb[2].data_ptr() if with_tail else None, _lib.stream_ptr())
+        G._SIDE.debug_after_launch(x2.device)
     return dx, dgb[0], dgb[1]
 
 

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-EPI_BIAS, EPI_GELU, EPI_RES, EPI_GELU_BWD = 0, 1, 2, 3
+EPI_BIAS, EPI_GELU, EPI_RES, EPI_GELU_BWD, EPI_SIGMOID = 0, 1, 2, 3, 4
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
 
@@ -91,10 +91,17 @@ class _SideStream:
     """Weight gradients leave the critical path: inside a backward pass `gemm_wgrad` may launch on a second stream, forked from
     the caller's stream at the call and joined back ONCE, by an autograd engine callback at the end of the pass (under stream
     capture: a parallel branch of the graph).  The small decoder GEMMs occupy 4-32 of 148 SMs, so the branch runs beside the
-    input-gradient chain instead of between its links.  Operands and outputs are allocated on the caller's stream and kept
-    alive until the join.  Anything that reads a weight gradient BEFORE the backward pass ends (DistributedDataParallel's or
-    the harness' bucketed all-reduce hooks) must leave this off -- hence opt-in: `wgrad_side_stream(True)`, which
-    `harness.GraphedTrainStep` does when its own all-reduce follows the backward pass."""
+    input-gradient chain instead of between its links.  Operands and scratch are allocated on the caller's stream and kept
+    alive until the join.
+
+    Contract (why this is opt-in, `wgrad_side_stream(True)`): nothing may READ a weight gradient before the backward pass ends.
+    That excludes DistributedDataParallel's and the harness' bucketed all-reduce hooks, and it excludes every case in which
+    autograd's AccumulateGrad launches a kernel of its own: `p.grad` must be None when backward starts (otherwise it adds in place),
+    and the gradient tensor must be stealable -- sole owner, parameter's layout -- (otherwise it clones).  For that reason the
+    OUTPUTS are not in the keep-alive list: a second reference turns the steal into a clone on the caller's stream, which under
+    graph replay reads the buffer before the side stream has written it (found the hard way: tests/test_gpu_graph.py).
+    `harness.GraphedTrainStep` meets the contract: it resets every `.grad` to None before each forward/backward and reads the
+    gradients only after backward() has returned."""
 
     def __init__(self):
         self.enabled = os.environ.get("DETR_B200_WGRAD_STREAM", "0") == "1"
@@ -118,10 +125,18 @@ class _SideStream:
             entry = self.pending[task] = [dev, []]
             torch.autograd.Variable._execution_engine.queue_callback(lambda: self.join(task))
         entry[1].append(keep)
+        self.refork(dev)
+        return side
+
+    def refork(self, dev: torch.device) -> None:
+        """Make the side stream wait for everything launched on the caller's stream so far."""
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
-        side.wait_event(ev)
-        return side
+        self.stream(dev).wait_event(ev)
+
+    def debug_after_launch(self, dev) -> None:
+        if os.environ.get("DETR_B200_WGRAD_STREAM_DEBUG", "") == "sync" and not torch.cuda.is_current_stream_capturing():
+            self.stream(dev).synchronize()
 
     def join(self, task: int) -> None:
         dev, keep = self.pending.pop(task)
@@ -153,9 +168,11 @@ def gemm_wgrad(dy: torch.Tensor, x0: torch.Tensor, x1: Optional[torch.Tensor] = 
     db = torch.empty(N, dtype=torch.float32, device=dev) if want_db else None
     nws = _lib.load().detr_gemm_wgrad_workspace_floats(M, N, K)
     ws = torch.empty(nws, dtype=torch.float32, device=dev) if nws else None
-    side = _SIDE.fork(dev, (dy, x0, x1, dw, db, ws))
+    side = _SIDE.fork(dev, (dy, x0, x1, ws))       # operands and scratch only -- NOT the outputs, see _SideStream
     with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
         _lib.call("detr_gemm_wgrad_bf16", dy.data_ptr(), dy.stride(0), x0.data_ptr(), x0.stride(0), _lib.ptr(x1), x1.stride(0) if x1 is not None else 0,
                   n_switch if x1 is not None else N, M, N, K, dw.data_ptr(), _lib.ptr(db), _lib.ptr(ws), _lib.stream_ptr(),
                   tag=("wgrad", M, N, K), launches=2 if nws else 1)
+    if side is not None:
+        _SIDE.debug_after_launch(dev)
     return dw, db

@@ -16,7 +16,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import gemm
+from . import gemm, heads
 from .model import DETRConfig, Decoder, Encoder
 
 
@@ -492,7 +492,13 @@ class DetrHarness(nn.Module):
         else:
             memory = self._encoder_fn(self.encoder, x, pos, mask)
             decoded = self._decoder_fn(self.decoder, memory, pos, query_embed, mask)
-        return {"pred_logits": self.class_embedding(decoded), "pred_boxes": self.bbox_embedding(decoded).sigmoid()}
+        # detr/model.py:92-93 on the GEMM kernels: fp32 logits and sigmoid boxes in the dense layout matcher and criterion read
+        # (heads.predict runs the plain modules for anything outside the kernels' contract; DETR_B200_FUSED_HEADS=0 forces that)
+        if os.environ.get("DETR_B200_FUSED_HEADS", "1") != "0":
+            logits, boxes = heads.predict(decoded, self.class_embedding, self.bbox_embedding)
+        else:
+            logits, boxes = self.class_embedding(decoded), self.bbox_embedding(decoded).sigmoid()
+        return {"pred_logits": logits, "pred_boxes": boxes}
 
 
 def make_optimizer(model: nn.Module, lr: float = 3e-4, lr_backbone_scale: float = 0.1, weight_decay: float = 1e-4, fused: bool = True,

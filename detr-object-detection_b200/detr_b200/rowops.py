@@ -203,23 +203,27 @@ class ShadowedLinears:
         self._src, self._dst = [], []
         self._device = None
 
-    def register(self, key, weights, biases):
-        self.groups.append((key, list(weights), list(biases)))
+    def register(self, key, weights, biases, pad_rows=None):
+        """`pad_rows[i]` >= weights[i].shape[0]: rows the i-th weight occupies in the stacked shadow (the rest stays zero) -- the
+        prediction heads' 92- and 4-row weights padded to whole MMA tiles."""
+        self.groups.append((key, list(weights), list(biases), list(pad_rows) if pad_rows else None))
 
     def _build(self, device):
         self.shadow.clear(); self._src, self._dst = [], []
-        for key, ws, bs in self.groups:
-            out = sum(w.shape[0] for w in ws)
-            w16 = torch.empty(out, ws[0].shape[1], dtype=torch.bfloat16, device=device)
-            b16 = torch.empty(out, dtype=torch.bfloat16, device=device) if bs else None
-            b32 = torch.empty(out, dtype=torch.float32, device=device) if bs else None   # stacked fp32 bias for the GEMM epilogues
+        for key, ws, bs, pads in self.groups:
+            rows = pads if pads else [w.shape[0] for w in ws]
+            out = sum(rows)
+            make = torch.zeros if pads else torch.empty
+            w16 = make(out, ws[0].shape[1], dtype=torch.bfloat16, device=device)
+            b16 = make(out, dtype=torch.bfloat16, device=device) if bs else None
+            b32 = make(out, dtype=torch.float32, device=device) if bs else None   # stacked fp32 bias for the GEMM epilogues
             o = 0
             for i, w in enumerate(ws):
                 self._src.append(w); self._dst.append(w16[o:o + w.shape[0]])
                 if bs:
                     self._src.append(bs[i]); self._dst.append(b16[o:o + w.shape[0]])
                     self._src.append(bs[i]); self._dst.append(b32[o:o + w.shape[0]])
-                o += w.shape[0]
+                o += rows[i]
             self.shadow[key] = (w16, b16)
             self.shadow32[key] = b32
         self._device = device

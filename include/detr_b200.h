@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DETR_B200_ABI_VERSION 5
+#define DETR_B200_ABI_VERSION 6
 
 /* status bits (device-side, sticky) -- mirror the reference's failure modes */
 #define DETR_ST_DEGENERATE_BOX 1 /* AssertionError at detr/utils.py:87-88 */
@@ -180,6 +180,12 @@ int detr_layernorm_bwd_tail(const void* dy, const void* dy2, int g_dtype, const 
                             float* dgamma, float* dbeta, uint32_t* counters, int rows, int C, void* dz, float* dbias,
                             float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
 
+/* Both calls above launch two kernels: the row pass (dx, dz, per-CTA partial sums) and the fold of the partials into the
+ * PARAMETER gradients dgamma / dbeta (/ dbias).  Called with dgamma == NULL they launch only the row pass; the caller then
+ * folds with this entry point -- on another stream if it likes: nothing on the critical path of the backward pass reads
+ * parameter gradients.  dbias: NULL unless the row pass was detr_layernorm_bwd_tail. */
+int detr_layernorm_bwd_fold(const float* partial, int rows, int C, float* dgamma, float* dbeta, float* dbias, void* stream);
+
 /* Block epilogues of the pre-LN layers, one pass each (detr/model.py:223-224, 176-182, FFN 405-411).
  * mode 0: out(x's dtype) = x + dropout(y)  -- residual add after the attention output / second FFN projection;
  * mode 1: out(bf16) = dropout(gelu_tanh(y)) -- between the FFN projections (x unused).
@@ -194,14 +200,24 @@ int detr_epilogue_chunks(int M, int N);
 int detr_epilogue_bwd(int mode, const void* g, int g_dtype, const void* y, void* dy, float* partial, float* db,
                       uint32_t* counters, int M, int N, float dropout_p, uint64_t seed, const uint64_t* seed_ptr, void* stream);
 
+/* Backward entry of the prediction heads (detr/model.py:92-93 `class_embedding(.)`, `bbox_embedding(.).sigmoid()`): the criterion's
+ * fp32 gradients d_logits [rows][K], d_boxes [rows][4] become the bf16 operands of the heads' gradient GEMMs, in one pass:
+ * dl16 [rows][ld_l] = bf16(d_logits) zero-padded to ld_l columns; dz16 [rows][ld_z] = bf16(d_boxes * b * (1 - b)) (b = `boxes`, the
+ * sigmoid output) zero-padded to ld_z columns. */
+int detr_heads_grad_prep(const float* d_logits, int K, const float* d_boxes, const float* boxes, void* dl16, int ld_l,
+                         void* dz16, int ld_z, int rows, void* stream);
+
 /* ---- tcgen05 GEMMs of the transformer's nn.Linear layers (detr/model.py:312-314,354 attention projections;
  *      :405-411 FFN) with the surrounding row work fused in (csrc/gemm.cu) -------------------------------------- */
 /* C[M][N] = epilogue(A[M][K] . B^T): a, b bf16 row-major with row strides lda / ldb (elements); b_kn = 0: b is [N][K]
- * (an nn.Linear weight), b_kn = 1: b is [K][N] (C = A . B, the input-gradient form dX = dY . W).  N % 32 == 0, K % 64 == 0.
+ * (an nn.Linear weight), b_kn = 1: b is [K][N] (C = A . B, the input-gradient form dX = dY . W).  N % 32 == 0, K % 64 == 0;
+ * the fp32 outputs of epilogues 0 and 4 with b_kn = 0 also take N % 4 == 0 (the prediction heads' 92 / 4 columns): bias must
+ * then be readable up to the next multiple of 64 entries.
  * epilogue 0: out = acc + bias                                   (bias fp32 [N] or NULL; out_dtype 0 fp32 / 1 bf16)
  *          1: aux = bf16(acc + bias); out = dropout(gelu_tanh(aux))          (detr/model.py:405-408; out bf16)
  *          2: out = res + dropout(acc + bias)                    (detr/model.py:223-224,354-355,410; res has out's dtype)
  *          3: out = acc * dropout_mask/(1-p) * gelu_tanh'(aux)   (backward of 1; no bias)
+ *          4: out = sigmoid(acc + bias)                          (box head, detr/model.py:93; out fp32, b_kn = 0)
  * dropout as detr_epilogue_*: counter-based, regenerated by the backward launches from (seed + *seed_ptr). */
 int detr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int b_kn, int M, int N, int K, int epilogue,
                    const float* bias, void* out, int out_dtype, int64_t ldo, void* aux, int64_t ld_aux, const void* res,

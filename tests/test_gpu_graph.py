@@ -184,3 +184,25 @@ def test_gradient_accumulation_matches_single_step(cuda):
     torch.cuda.synchronize()
     d = (g1.fopt.flat_p - g2.fopt.flat_p).abs()
     assert d.max().item() <= 2.5e-4 and (d > 1e-5).float().mean().item() <= 0.01, (d.max().item(), (d > 1e-5).float().mean().item())
+
+
+def test_side_stream_weight_gradients_are_identical(cuda, monkeypatch):
+    """The captured step launches weight-gradient GEMMs and LayerNorm folds on a second stream (gemm._SideStream).  Every parameter
+    gradient must be bit-identical to the single-stream capture: a replay has no launch gaps to hide a missing dependency
+    (an AccumulateGrad clone on the main stream once read out_proj's gradient before the side stream had written it)."""
+    from detr_b200.harness import GraphedTrainStep, make_optimizer, synthetic_batch
+    m0, c0 = _make(cuda, train=False)
+    b = synthetic_batch(2, 160, 200, 11, 6, seed=1)
+    grads = {}
+    for side in ("0", "1"):
+        monkeypatch.setenv("DETR_B200_WGRAD_STREAM", side)
+        m, c = copy.deepcopy(m0), copy.deepcopy(c0)
+        g = GraphedTrainStep(m, c, make_optimizer(m, lr=1e-4, capturable=True), b, gt_cap=8, warmup=2)
+        g.load(b)
+        for _ in range(2):
+            g.step()
+        torch.cuda.synchronize()
+        names = {id(p): n for n, p in m.named_parameters()}
+        grads[side] = {names[id(p)]: v.detach().clone() for p, v in zip(g.fopt.params, g.fopt.grad_views)}
+    bad = [n for n, v in grads["1"].items() if not torch.equal(v, grads["0"][n])]
+    assert not bad, bad

@@ -20,7 +20,11 @@ OUT = os.path.join(ROOT, "profiles", "r02_ncu_numbers.json")
 
 
 def raw_rows(rep):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """`rep`: an .ncu-rep, or the text of `ncu -i <rep> --page raw --csv` made on the GPU box (the report itself can exceed what
+    travels back)."""
+    txt = open(rep, errors="replace").read() if rep.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    txt = txt[txt.index('"ID"'):]
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     ik = hdr.index("Kernel Name")
