@@ -134,6 +134,15 @@ class _SideStream:
         ev.record(torch.cuda.current_stream(dev))
         self.stream(dev).wait_event(ev)
 
+    def join_now(self) -> None:
+        """Inside a backward pass: make the caller's stream wait for everything launched on the side stream so far (for a node that
+        consumes side-stream results before the pass ends, e.g. the unfold of the backbone's weight gradients)."""
+        entry = self.pending.get(torch._C._current_graph_task_id())
+        if entry is not None:
+            ev = torch.cuda.Event()
+            ev.record(self.stream(entry[0]))
+            torch.cuda.current_stream(entry[0]).wait_event(ev)
+
     def debug_after_launch(self, dev) -> None:
         if os.environ.get("DETR_B200_WGRAD_STREAM_DEBUG", "") == "sync" and not torch.cuda.is_current_stream_capturing():
             self.stream(dev).synchronize()

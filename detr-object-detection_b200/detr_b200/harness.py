@@ -200,6 +200,7 @@ class _FoldFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
+        gemm._SIDE.join_now()        # the bottlenecks' weight gradients may come from the second stream (_conv_backward)
         return (None, *ctx.pack.unfold(grads))
 
 
@@ -299,6 +300,21 @@ def _conv_conf(conv: nn.Conv2d):
     return (tuple(conv.stride), tuple(conv.padding), tuple(conv.dilation), conv.groups)
 
 
+def _conv_backward(g, inp, w, conf, need_dx: bool):
+    """(dx, dw) of a convolution.  With the second stream enabled (gemm._SideStream, inside a backward pass) the weight gradient is
+    launched there: the input-gradient chain of the backbone does not wait for it, and `_FoldFn.backward` -- the only consumer,
+    at the very end of the pass -- joins the stream before it reads.  Library kernels either way."""
+    cb = torch.ops.aten.convolution_backward
+    side = gemm._SIDE.fork(g.device, (g, inp, w))
+    if side is None:
+        dx, dw, _ = cb(g, inp, w, None, conf[0], conf[1], conf[2], False, [0, 0], conf[3], [need_dx, True, False])
+        return dx, dw
+    dx = cb(g, inp, w, None, conf[0], conf[1], conf[2], False, [0, 0], conf[3], [True, False, False])[0] if need_dx else None
+    with torch.cuda.stream(side):
+        dw = cb(g, inp, w, None, conf[0], conf[1], conf[2], False, [0, 0], conf[3], [False, True, False])[1]
+    return dx, dw
+
+
 class _BottleneckFn(torch.autograd.Function):
     """One torchvision Bottleneck (frozen BN folded) as a single autograd node: three / four cuDNN fused convolutions forward,
     a hand-ordered backward in which the residual-gradient add of the block input is fused with the PREVIOUS block's ReLU
@@ -323,19 +339,19 @@ class _BottleneckFn(torch.autograd.Function):
         from . import _lib
         x, w1, w2, w3, wd, o1, o2, y = ctx.saved_tensors
         c1, c2, c3, cd = ctx.confs
-        tb, cb = torch.ops.aten.threshold_backward, torch.ops.aten.convolution_backward
+        tb = torch.ops.aten.threshold_backward
         cl = torch.channels_last
         g = g.contiguous(memory_format=cl)
         g3 = g if ctx.premasked_in else tb(g, y, 0)
-        d2, dw3, _ = cb(g3, o2, w3, None, c3[0], c3[1], c3[2], False, [0, 0], c3[3], [True, True, False])
+        d2, dw3 = _conv_backward(g3, o2, w3, c3, True)
         g2 = tb(d2, o2, 0)
-        d1, dw2, _ = cb(g2, o1, w2, None, c2[0], c2[1], c2[2], False, [0, 0], c2[3], [True, True, False])
+        d1, dw2 = _conv_backward(g2, o1, w2, c2, True)
         g1 = tb(d1, o1, 0)
         need_dx = ctx.needs_input_grad[0]
-        dx1, dw1, _ = cb(g1, x, w1, None, c1[0], c1[1], c1[2], False, [0, 0], c1[3], [need_dx, True, False])
+        dx1, dw1 = _conv_backward(g1, x, w1, c1, need_dx)
         dwd, b = None, g3
         if wd is not None:
-            b, dwd, _ = cb(g3, x, wd, None, cd[0], cd[1], cd[2], False, [0, 0], cd[3], [need_dx, True, False])
+            b, dwd = _conv_backward(g3, x, wd, cd, need_dx)
         dx = None
         if need_dx:
             same = (dx1.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dx1.stride() == x.stride()
