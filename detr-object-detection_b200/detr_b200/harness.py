@@ -712,7 +712,10 @@ class GraphedTrainStep:
         # from exactly the state the caller handed in (loss-curve parity with detr/train.py from init or from a checkpoint).
         snap = self._snapshot_state() if restore_state else None
         # warm-up on a side stream, then capture
-        side = torch.cuda.Stream()
+        # warm-up and capture run on ONE high-priority stream: the captured kernels of the critical path (forward, input gradients)
+        # then win SMs over the weight-gradient branch on the second stream (default priority) whenever both have blocks ready,
+        # and autograd's AccumulateGrad nodes (created during warm-up) live on the stream the capture uses
+        side = torch.cuda.Stream(priority=int(os.environ.get("DETR_B200_MAIN_PRIORITY", "-1")))
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -725,10 +728,10 @@ class GraphedTrainStep:
         from . import _lib
         l0 = _lib.launch_count
         self.graph_a = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_a):
+        with torch.cuda.graph(self.graph_a, stream=side):
             self._forward_backward()
         self.graph_b = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool(), stream=side):
             self._update()
         self.own_launches_per_step = _lib.launch_count - l0   # kernels of libdetr_b200.so inside one replay of both graphs
         if snap is not None:
