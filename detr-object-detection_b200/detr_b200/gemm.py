@@ -122,8 +122,14 @@ class _SideStream:
         side = self.stream(dev)
         entry = self.pending.get(task)
         if entry is None:
+            # entries of passes that never reached their callback (backward raised): join them now so that the side stream never
+            # stays forked and their tensors are released
+            for stale in [t for t in self.pending if t != task]:
+                self.join(stale)
             entry = self.pending[task] = [dev, []]
             torch.autograd.Variable._execution_engine.queue_callback(lambda: self.join(task))
+        elif entry[0] != dev:
+            raise RuntimeError("weight-gradient side stream: one process drives one GPU (backward pass spans several devices)")
         entry[1].append(keep)
         self.refork(dev)
         return side
@@ -148,6 +154,8 @@ class _SideStream:
             self.stream(dev).synchronize()
 
     def join(self, task: int) -> None:
+        if task not in self.pending:
+            return
         dev, keep = self.pending.pop(task)
         ev = torch.cuda.Event()
         ev.record(self.stream(dev))
