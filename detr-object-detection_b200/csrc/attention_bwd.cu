@@ -507,6 +507,7 @@ __global__ void attention_delta_kernel(const __nv_bfloat16* __restrict__ dO, int
                                        const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ O_lo, int64_t o_sb, int64_t o_sl,
                                        float* __restrict__ delta, int B, int nh, int L) {
     pdl_trigger();   // the main kernel's prologue may start while this grid drains; it waits before reading delta
+    pdl_wait();      // (decoder-sized calls are themselves launched programmatically behind the GEMM that wrote dO)
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)B * L * nh) return;
     const int h = (int)(idx % nh);
@@ -637,7 +638,7 @@ extern "C" int detr_attention_bwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     if (int rc = make_head_tile_map(&tdo, d_o, C, L, B, do_sl, do_sb, kT, "attention_bwd(dO)")) return rc;
 
     const int64_t n = (int64_t)B * L * nh;
-    attention_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+    launch_pdl_if(L <= 256, attention_delta_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st,
         reinterpret_cast<const __nv_bfloat16*>(d_o), do_sb, do_sl, reinterpret_cast<const __nv_bfloat16*>(o),
         reinterpret_cast<const __nv_bfloat16*>(o_lo), o_sb, o_sl, delta, B, nh, L);
     DETR_CHECK_LAUNCH("attention_delta");

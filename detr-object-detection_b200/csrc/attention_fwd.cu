@@ -162,6 +162,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 256;
+    pdl_wait();      // small calls are launched programmatically behind the projection GEMM: the prologue above overlaps its tail
     pdl_trigger();   // the combine launch may be scheduled as SMs free up (it waits for this grid before reading the partial slots)
 
     if (warp >= kSoftmaxWarps) {
@@ -623,7 +624,8 @@ extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     const int64_t items = (int64_t)((L + kBM - 1) / kBM) * nh * B;
     const int G = (int)(items < num_sms ? items : num_sms);   // G <= items: a CTA's pair range is never shorter than one item
     cudaStream_t st = (cudaStream_t)stream;
-    attention_fwd_kernel<<<G, kFwdThreads, FwdSmem::total, st>>>(tq, tk, tv, p);
+    // decoder-sized calls (latency bound, at most 96 CTAs) may be scheduled while the projection GEMM in front of them drains
+    launch_pdl_if(L <= 256, attention_fwd_kernel, dim3(G), dim3(kFwdThreads), FwdSmem::total, st, tq, tk, tv, p);
     DETR_CHECK_LAUNCH("attention_fwd");
     if (items > G) {   // only then can a boundary between two CTAs fall inside an item
         launch_pdl(attention_fwd_combine_kernel, dim3(G - 1), dim3(512), 0, st, p, G);

@@ -58,6 +58,7 @@ struct EpiParams {
     int M, N;
     uint32_t thr4; float scale;              // dropout: thresh * 0x00010001 (0 = off; thresh in 1/32768), 1 / keep
     uint64_t seed; const uint64_t* seed_ptr;
+    int early_trigger;                       // small grid: let the next (programmatically launched) kernel be scheduled at once
 };
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
@@ -309,6 +310,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const uint32_t tmem = *tmem_slot;
     const int tiles = p.m_tiles * p.n_tiles;
     pdl_wait();      // everything below reads what the previous kernel of the stream wrote
+    if (p.e.early_trigger) pdl_trigger();
 
     if (warp == kEpiWarps) {
         if (lane == 0) {
@@ -577,6 +579,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     const int mt = blockIdx.x / p.groups, gi = blockIdx.x - mt * p.groups;
     const int nt0 = p.n_tiles * gi / p.groups, nt1 = p.n_tiles * (gi + 1) / p.groups;
     pdl_wait();
+    if (p.e.early_trigger) pdl_trigger();
     LN_STAMP(1);
 
     if (warp == kEpiWarps) {
@@ -848,14 +851,6 @@ static int make_map_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t
     return 0;
 }
 
-// Programmatic dependent launch of the GEMM kernels: OFF by default.  Measured on the captured training step (B200): with the
-// attribute the step is 0.14-0.18 ms SLOWER (12.76 vs 12.58 ms) whether the kernels trigger early or late -- every CTA of these
-// kernels needs the whole SM (225 KB of shared memory, TMEM), so a dependent grid can only sit and wait.  DETR_B200_GEMM_PDL=1 turns it on.
-static bool gemm_pdl() {
-    static const bool on = []() { const char* e = getenv("DETR_B200_GEMM_PDL"); return e && e[0] && e[0] != '0'; }();
-    return on;
-}
-
 static int device_sms() {
     static int sms[64] = {0};
     int dev = 0;
@@ -864,6 +859,17 @@ static int device_sms() {
     if (sms[dev] == 0 && (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0)) sms[dev] = 148;
     return sms[dev];
 }
+
+// Programmatic dependent launch of the GEMM kernels: OFF by default.  Measured on the captured training step (B200): with the
+// attribute the step is 0.14-0.18 ms SLOWER (12.76 vs 12.58 ms) whether the kernels trigger early or late -- every CTA of these
+// kernels needs the whole SM (225 KB of shared memory, TMEM), so a dependent grid can only sit and wait.  DETR_B200_GEMM_PDL=1 turns it on.
+static int gemm_pdl_mode() {   // 0 off, 1 every GEMM launch, 2 only grids that leave at least half of the SMs free (early trigger)
+    static const int mode = []() { const char* e = getenv("DETR_B200_GEMM_PDL"); return e && e[0] ? atoi(e) : 2; }();
+    return mode;
+}
+static bool gemm_pdl() { return gemm_pdl_mode() == 1; }
+static bool gemm_pdl_small(int grid) { return gemm_pdl_mode() == 2 && grid * 2 <= device_sms(); }
+
 
 // cudaFuncSetAttribute is per (kernel, device): remember which pairs are done (keyed by the kernel's address -- kernels
 // that share a signature share the template instantiation below)
@@ -895,7 +901,9 @@ static int launch_stream(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
     auto kern = gemm_stream_kernel<EPI, TO, kBMn>;
     if (int rc = opt_in_smem(kern, kStSmem, "gemm")) return rc;
     const int tiles = p.m_tiles * p.n_tiles, sms = device_sms();
-    launch_pdl_if(gemm_pdl(), kern, dim3(tiles < sms ? tiles : sms), dim3(kStThreads), kStSmem, st, ta, tb, to, tx, tr, p);
+    GemmParams q = p;
+    q.e.early_trigger = gemm_pdl_small(tiles) ? 1 : 0;
+    launch_pdl_if(gemm_pdl() || q.e.early_trigger, kern, dim3(tiles < sms ? tiles : sms), dim3(kStThreads), kStSmem, st, ta, tb, to, tx, tr, q);
     DETR_CHECK_LAUNCH("gemm");
     return 0;
 }
@@ -1003,7 +1011,8 @@ extern "C" int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const 
     do {                                                                         \
         auto kern = gemm_ln_kernel<E, TX>;                                       \
         if (int rc = opt_in_smem(kern, kLnSmem, "gemm_ln")) return rc;           \
-        launch_pdl_if(gemm_pdl(), kern, grid, dim3(kLnThreads), kLnSmem, st, tw, to, tx, tap, tao, p); \
+        p.e.early_trigger = gemm_pdl_small((int)grid.x) ? 1 : 0;                 \
+        launch_pdl_if(gemm_pdl() || p.e.early_trigger, kern, grid, dim3(kLnThreads), kLnSmem, st, tw, to, tx, tap, tao, p); \
     } while (0)
     if (epilogue == EPI_BIAS) { if (x_dtype == 0) LN_GO(EPI_BIAS, float); else LN_GO(EPI_BIAS, __nv_bfloat16); }
     else                      { if (x_dtype == 0) LN_GO(EPI_GELU, float); else LN_GO(EPI_GELU, __nv_bfloat16); }

@@ -222,6 +222,7 @@ struct LnParams {
     // (x = res + dropout(z), detr/model.py:223-224); its masked bf16 form dz = mask(dx) / (1 - p) and the bias gradient
     // column sums of dz are produced here, so that the tail's backward needs no pass of its own
     void* dz; float* dbias; uint32_t thr4; float scale; uint64_t seed; const uint64_t* seed_ptr; int has_dz;
+    int early_trigger;   // small launch (decoder rows): programmatic dependents may be scheduled at once
 };
 
 // KT > 0: compile-time columns per lane (rows stay in registers); KT == 0: run-time (local-memory arrays)
@@ -263,7 +264,9 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const LnParams p) {
     const int K = KT ? KT : p.C / 32, C = p.C;
     constexpr int KA = KT ? KT : kLnMaxPerLane;
     float g[KA], dg[KA], db[KA], dzs[KA];
-    load_row<float>(p.gamma, lane, K, g);
+    load_row<float>(p.gamma, lane, K, g);           // a parameter: not written by the kernel in front of this one
+    pdl_wait();
+    if (p.early_trigger) pdl_trigger();
     _Pragma("unroll") for (int i = 0; i < K; ++i) { dg[i] = 0.f; db[i] = 0.f; dzs[i] = 0.f; }
     const bool has_dz = KT == 8 && p.has_dz;   // (the 8-columns-per-lane layout is exactly one dropout chunk per lane)
     const uint32_t zkey = (has_dz && p.thr4) ? ew_key(p.seed, p.seed_ptr) : 0u;
@@ -409,10 +412,13 @@ static int layernorm_bwd_impl(const void* dy, const void* dy2, int g_dtype, cons
     const int grid = ln_grid(rows);
     const size_t smem = (size_t)(kLnThreads / 32) * 3 * C * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    // decoder-sized calls sit in a chain of launch-latency-bound kernels: let them be scheduled behind the GEMM in front (and
+    // the GEMM behind them be scheduled at once)
+    p.early_trigger = rows <= 2400 ? 1 : 0;
 #define LN_BWD(TX, TG)                                                               \
     do {                                                                             \
-        if (C == 256) ln_bwd_kernel<TX, TG, 8><<<grid, kLnThreads, smem, st>>>(p);   \
-        else ln_bwd_kernel<TX, TG, 0><<<grid, kLnThreads, smem, st>>>(p);            \
+        if (C == 256) launch_pdl_if(p.early_trigger != 0, ln_bwd_kernel<TX, TG, 8>, dim3(grid), dim3(kLnThreads), smem, st, p);   \
+        else launch_pdl_if(p.early_trigger != 0, ln_bwd_kernel<TX, TG, 0>, dim3(grid), dim3(kLnThreads), smem, st, p);            \
     } while (0)
     if (x_dtype == 0 && g_dtype == 0) LN_BWD(float, float);
     else if (x_dtype == 0) LN_BWD(float, __nv_bfloat16);
