@@ -860,9 +860,12 @@ static int device_sms() {
     return sms[dev];
 }
 
-// Programmatic dependent launch of the GEMM kernels: OFF by default.  Measured on the captured training step (B200): with the
-// attribute the step is 0.14-0.18 ms SLOWER (12.76 vs 12.58 ms) whether the kernels trigger early or late -- every CTA of these
-// kernels needs the whole SM (225 KB of shared memory, TMEM), so a dependent grid can only sit and wait.  DETR_B200_GEMM_PDL=1 turns it on.
+// Programmatic dependent launch of the GEMM kernels (DETR_B200_GEMM_PDL = 0 never, 1 always, 2 default).  Measured on the captured
+// training step (B200): with the attribute on EVERY launch the step is 0.14-0.18 ms slower (12.76 vs 12.58 ms) whether the kernels
+// trigger early or late -- every CTA needs the whole SM (225 KB of shared memory, TMEM), so behind a machine-filling grid a
+// dependent grid can only sit and wait.  Mode 2 uses it where the chain is launch-latency bound: grids that leave at least half
+// of the SMs free (the decoder's) are launched programmatically and trigger their dependents right after their own wait
+// (transformer forward + backward at S = 850: 3.35 -> 3.30 ms).
 static int gemm_pdl_mode() {   // 0 off, 1 every GEMM launch, 2 only grids that leave at least half of the SMs free (early trigger)
     static const int mode = []() { const char* e = getenv("DETR_B200_GEMM_PDL"); return e && e[0] ? atoi(e) : 2; }();
     return mode;
