@@ -609,18 +609,20 @@ extern "C" int detr_attention_fwd_bf16(const void* q, int64_t q_sb, int64_t q_sl
     p.drop_log2_scale = log2f(p.drop_scale);
     p.seed = seed; p.seed_ptr = seed_ptr;
     p.dbg = g_fwd_dbg;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // cudaFuncSetAttribute and the SM count are per DEVICE: remember them per device id
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    if (dev_id < 0 || dev_id >= 64) dev_id = 0;
+    static bool attr_set[64] = {false};
+    if (!attr_set[dev_id]) {
         cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem::total);
         if (e != cudaSuccess) { set_error("attention_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 2; }
-        attr_set = true;
+        attr_set[dev_id] = true;
     }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-    }
+    static int sms_of[64] = {0};
+    if (sms_of[dev_id] == 0 && (cudaDeviceGetAttribute(&sms_of[dev_id], cudaDevAttrMultiProcessorCount, dev_id) != cudaSuccess || sms_of[dev_id] <= 0))
+        sms_of[dev_id] = 148;
+    const int num_sms = sms_of[dev_id];
     const int64_t items = (int64_t)((L + kBM - 1) / kBM) * nh * B;
     const int G = (int)(items < num_sms ? items : num_sms);   // G <= items: a CTA's pair range is never shorter than one item
     cudaStream_t st = (cudaStream_t)stream;
