@@ -962,6 +962,35 @@ extern "C" int detr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t
 #undef GEMM_GO
 }
 
+// How a LayerNorm-prologue GEMM is cut into CTAs.  A CTA normalises `rpc` real rows (32 / 64 / 96 / 128; the MMA tile always has 128
+// rows, the accumulator rows beyond rpc are never stored) and computes n_tiles / groups column tiles of them.  Cost model in
+// cycles per CTA, from the clock64 timeline (tools/gemm_ln_timeline.py): prologue 1 000 + 2 000 per round of 32 rows (its warps
+// work through the rounds one after the other); a column tile costs its epilogue whatever rpc is (every warp owns 32 rows of
+// it): ~2 200 cycles with bias, ~4 000 with GELU + dropout.  The launch takes waves x (prologue + tiles per CTA x tile).  For
+// M = 6 800 this picks 96-row blocks (71 x 2 = 142 CTAs on 148 SMs instead of 54 x 2 = 108): measured 21.5 -> 19.5 us (q|k|v),
+// 33.7 -> 32.7 us (FFN1 + GELU), DC5 102 -> 97 us -- the epilogue, not the partition, is what bounds these kernels.
+// DETR_B200_LN_PARTITION=0: the old rule (128 rows, or 32 below a quarter wave).
+static void ln_partition(int M, int n_tiles, bool gelu, int sms, int* rpc_out, int* groups_out) {
+    static const bool model = []() { const char* e = getenv("DETR_B200_LN_PARTITION"); return !(e && e[0] == '0'); }();
+    if (!model) {
+        const int rpc = (M + 127) / 128 >= sms / 4 ? 128 : 32;
+        int g = sms / ((M + rpc - 1) / rpc);
+        g = g > n_tiles ? n_tiles : (g < 1 ? 1 : g);
+        *rpc_out = rpc; *groups_out = g;
+        return;
+    }
+    double best = 1e30;
+    for (int rpc = 128; rpc >= 32; rpc -= 32) {
+        const int m_tiles = (M + rpc - 1) / rpc;
+        const double prologue = 1000.0 + 2000.0 * rpc / 32, tile = gelu ? 4000.0 : 2200.0;
+        for (int g = 1; g <= n_tiles; ++g) {
+            const int waves = (m_tiles * g + sms - 1) / sms, per = (n_tiles + g - 1) / g;
+            const double cost = waves * (prologue + per * tile);
+            if (cost < best - 1e-6) { best = cost; *rpc_out = rpc; *groups_out = g; }   // ties: larger blocks, fewer CTAs
+        }
+    }
+}
+
 /* out[M][N] (bf16) = epilogue((LayerNorm(x) [+ addend]) . w[N][256]^T): detr/model.py:221-224,173-182 fused with the projections
  * that consume the normalised rows.  Output columns < n_pos_end are computed from LN(x) + addend, the others from LN(x).
  * addend: fp32, row of flattened row m at (m / rows_per_batch) * add_sb + (m % rows_per_batch) * add_sr.
@@ -989,9 +1018,9 @@ extern "C" int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const 
     if (int rc = make_map_2d(&tw, w, N, kLnC, ldw, kGN, false, "gemm_ln(W)")) return rc;
     if (int rc = make_map_2d(&to, out, M, N, ldo, 32, false, "gemm_ln(out)")) return rc;
     tx = to; tap = to; tao = to;
-    // real rows per row block: 128 unless that leaves most of the machine idle (fewer than a quarter wave of row blocks: the
-    // decoder's 800 / 2 400 rows) -- then 32, so that the prologue's latency chain (one round per 32 rows) is one round long
-    const int rpc = (M + 127) / 128 >= device_sms() / 4 ? 128 : 32;
+    // (rows per row block, column groups per row block): see ln_partition
+    int rpc = 128, groups = 1;
+    ln_partition(M, (N + kGN - 1) / kGN, epilogue == EPI_GELU, device_sms(), &rpc, &groups);
     if (a_plain) { if (int rc = make_map_2d(&tap, a_plain, M, kLnC, kLnC, rpc, false, "gemm_ln(a_plain)")) return rc; }
     if (a_pos) { if (int rc = make_map_2d(&tao, a_pos, M, kLnC, kLnC, rpc, false, "gemm_ln(a_pos)")) return rc; }
     if (epilogue == EPI_GELU) { if (int rc = make_map_2d(&tx, aux, M, N, ld_aux, 32, false, "gemm_ln(aux)")) return rc; }
@@ -1003,10 +1032,6 @@ extern "C" int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const 
     p.rows_per_cta = rpc;
     p.m_tiles = (M + rpc - 1) / rpc; p.n_tiles = (N + kGN - 1) / kGN;
     p.dbg = g_gemm_dbg;
-    // column groups per row block: as many as fit in one wave (each group repeats the prologue of its row block)
-    int groups = device_sms() / p.m_tiles;
-    if (groups > p.n_tiles) groups = p.n_tiles;
-    if (groups < 1) groups = 1;
     p.groups = groups;
     const dim3 grid(p.m_tiles * groups);
     cudaStream_t st = (cudaStream_t)stream;
