@@ -138,12 +138,16 @@ class ScaledDotProductAttention(nn.Module):
     def _shadow(self, name):
         return self._shadows.get_w_b32((self._skey, name)) if self._shadows is not None else (None, None)
 
-    def self_block(self, x, norm: nn.LayerNorm, addend, key_padding_mask=None, attention_mask=None):
+    def self_block(self, x, norm: nn.LayerNorm, addend, key_padding_mask=None, attention_mask=None, tap: Optional[list] = None):
         """x + dropout(output_proj(attention(q = k = LN(x) + addend, v = LN(x))))  (detr/model.py:221-223, 173-175):
         LayerNorm, the "+ embedding" and the q|k|v projections are ONE launch, the output projection with bias, dropout and
-        the residual add another."""
+        the residual add another.  `tap`: receives the block's input as handed back by the LayerNorm node (same values as x; a
+        second consumer of x should read THIS tensor: its gradient then enters the LayerNorm backward kernel as part of the
+        residual gradient instead of making autograd sum two gradients of x, which would break the hand-over in blocks.py)."""
         C = self.hidden_size
         qkv, x = blocks.ln_proj(x, norm, (self.query_proj, self.key_proj, self.value_proj), addend, 2 * C, *self._shadow("qkv"))
+        if tap is not None:
+            tap.append(x)
         y = flash_attention_qkv(qkv, key_padding_mask, attention_mask, self.dropout_attn.p if self.training else 0.0)
         return blocks.proj_res(y, x, self.output_proj, self.dropout.p if self.training else 0.0, self._shadow("output")[0])
 
@@ -267,9 +271,9 @@ class DecoderLayer(nn.Module):
 
     def forward(self, x: torch.Tensor, encoded_image_tokens: torch.Tensor, object_query_embedding: torch.Tensor,
                 position_embedding: torch.Tensor, key_padding_mask: torch.BoolTensor,
-                cross_key: Optional[torch.Tensor] = None, cross_kv: Optional[tuple] = None):
+                cross_key: Optional[torch.Tensor] = None, cross_kv: Optional[tuple] = None, tap: Optional[list] = None):
         if cross_kv is not None and _fused_blocks_enabled(encoded_image_tokens, self.self_attention.hidden_size):
-            x = self.self_attention.self_block(x, self.norm1, object_query_embedding)
+            x = self.self_attention.self_block(x, self.norm1, object_query_embedding, tap=tap)
             x = self.cross_attention.cross_block(x, self.norm2, object_query_embedding, cross_kv, key_padding_mask)
             return self.ffn.block(x, self.norm3)
         x_attn, query, x = layer_norm_add(x, self.norm1, object_query_embedding, pass_x=True)
@@ -314,11 +318,15 @@ class Decoder(nn.Module):
             ks = stacked_linear(cross_key, [l.cross_attention.key_proj for l in self.layers], *sh.get(("", "cross_keys")))
             vs = stacked_linear(encoded_image_tokens, [l.cross_attention.value_proj for l in self.layers], *sh.get(("", "cross_values")))
             kvs = list(zip(ks, vs))
-        outputs = []
+        outputs, taps = [], []
         for layer, kv in zip(self.layers, kvs):
             x = layer(x, encoded_image_tokens, object_query_embedding, position_embedding, key_padding_mask,
-                      cross_key=cross_key, cross_kv=kv)
+                      cross_key=cross_key, cross_kv=kv, tap=taps)
             outputs.append(x)
+        if len(taps) == len(outputs):
+            # fused path: the final LayerNorm reads layer i's output through the tensor layer i + 1's first block handed back
+            # (taps[i + 1] aliases outputs[i]), so that each layer output keeps ONE consumer in the autograd graph
+            outputs = taps[1:] + outputs[-1:]
         # one LayerNorm launch over all layers' outputs instead of one per layer
         stacked = torch.stack(outputs, dim=1)
         B, L, Q, C = stacked.shape
