@@ -198,8 +198,11 @@ class _LnProj(torch.autograd.Function):
         # gradient of the normalised operand(s): one GEMM on the whole stacked weight unless the addend needs its own gradient
         d_add = None
         if ctx.addend_grad:
-            g_pos = G.gemm(d2[:, :npe], w16[:npe], b_kn=True)
-            g_plain = G.gemm(d2[:, npe:], w16[npe:], b_kn=True) if npe < N else None
+            # the addend's gradient IS g_pos: written by the GEMM in the addend's dtype (fp32 for the query embedding), so that
+            # no cast kernel sits between this node and autograd's accumulation of the 12 uses of the embedding
+            gdt = ctx.addend_dtype if ctx.addend_dtype in (torch.float32, torch.bfloat16) else torch.bfloat16
+            g_pos = G.gemm(d2[:, :npe], w16[:npe], b_kn=True, out_dtype=gdt)
+            g_plain = G.gemm(d2[:, npe:], w16[npe:], b_kn=True, out_dtype=gdt) if npe < N else None
             dx, dgam, dbet = _ln_backward(g_plain, g_pos, dres, x2, g32, stats, ctx.tail)
             d_add = g_pos.view(B, L, C).to(ctx.addend_dtype)
         else:
@@ -329,7 +332,9 @@ class _Proj(torch.autograd.Function):
         g2 = gs[0] if len(gs) == 1 else torch.cat(gs, dim=1)
         if g2.dtype != torch.bfloat16:
             g2 = g2.to(torch.bfloat16)
-        da = G.gemm(g2, w16, b_kn=True).view(ctx.a_shape).to(ctx.a_dtype) if ctx.needs_input_grad[0] else None
+        # the input gradient leaves the GEMM in the input's dtype (fp32 for the encoder memory): no cast kernel behind it
+        odt = ctx.a_dtype if ctx.a_dtype in (torch.float32, torch.bfloat16) else torch.bfloat16
+        da = G.gemm(g2, w16, b_kn=True, out_dtype=odt).view(ctx.a_shape).to(ctx.a_dtype) if ctx.needs_input_grad[0] else None
         dw, db = G.gemm_wgrad(g2, a16)
         return (da, None, None, None, *_split_rows(dw, ctx.splits), *_split_rows(db, ctx.splits))
 
