@@ -495,7 +495,28 @@ class DetrHarness(nn.Module):
         self._decoder_fn = decoder_fn
         self._posenc_fn = posenc_fn   # (H', W', heights, widths, scale, F, T) -> (pos (B,S,C), mask (B,S)); default: the CUDA kernel
 
+    _prefetch_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+    def _prefetch_shadows(self, dev: torch.device) -> None:
+        """bf16 weight shadows of encoder, decoder and heads on a second stream while the ResNet runs: they depend on the parameters
+        only (their consumers' `refresh` calls wait for the event instead of copying again)."""
+        if not (dev.type == "cuda" and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16
+                and os.environ.get("DETR_B200_PREFETCH_SHADOWS", "1") != "0"):
+            return
+        packs = [getattr(self.encoder, "_shadows", None), getattr(self.decoder, "_shadows", None), heads._SHADOWS.get(self.class_embedding)]
+        packs = [p for p in packs if p is not None]
+        if self._encoder_fn is not None or not packs:
+            return
+        side = self._prefetch_streams.get(dev.index)
+        if side is None:
+            side = self._prefetch_streams[dev.index] = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for p in packs:
+                p.prefetch(dev)
+
     def forward(self, images: torch.Tensor, heights: torch.Tensor, widths: torch.Tensor) -> Dict[str, torch.Tensor]:
+        self._prefetch_shadows(images.device)
         x = self.input_proj(self.backbone(images))
         B, C, H, W = x.shape
         posenc = self._posenc_fn or positional_encoding_tokens

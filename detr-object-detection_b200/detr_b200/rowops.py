@@ -202,6 +202,7 @@ class ShadowedLinears:
         self.shadow32 = {}    # key -> stacked fp32 bias
         self._src, self._dst = [], []
         self._device = None
+        self._fresh = None    # event of a prefetch that the next refresh() only has to wait for
 
     def register(self, key, weights, biases, pad_rows=None):
         """`pad_rows[i]` >= weights[i].shape[0]: rows the i-th weight occupies in the stacked shadow (the rest stays zero) -- the
@@ -230,6 +231,26 @@ class ShadowedLinears:
 
     @torch.no_grad()
     def refresh(self, device):
+        """Bring the shadows up to date on the current stream -- or, if `prefetch` already did it on another stream, just make
+        the current stream wait for that."""
+        ev = self._fresh
+        if ev is not None:
+            self._fresh = None
+            if self._device == device:
+                torch.cuda.current_stream(device).wait_event(ev)
+                return
+        self._copy(device)
+
+    @torch.no_grad()
+    def prefetch(self, device):
+        """Refresh on the CURRENT stream (the caller switched to a side stream) and leave an event for the `refresh` call of the
+        consumer: the copies depend on the parameters only, so they can run beside whatever precedes the consumer (the ResNet
+        forward in the full model)."""
+        self._copy(device)
+        self._fresh = torch.cuda.Event()
+        self._fresh.record(torch.cuda.current_stream(device))
+
+    def _copy(self, device):
         if self._device != device:
             self._build(device)
         # one multi-tensor launch per destination dtype (a list that mixes dtypes makes _foreach_copy_ fall back to one copy
