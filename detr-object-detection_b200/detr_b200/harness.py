@@ -213,6 +213,8 @@ class FoldedConvWeights:
             raise ValueError(f"at most {_lib.FOLD_MAX_TENSORS} convolutions per fold pack")
         self.pairs = list(pairs)
         self.views, self.flat, self._device = [], None, None
+        self.async_stream = None          # set by the owner: fold() then launches there and leaves an event for wait_ready()
+        self._ready, self._keep = None, None
 
     def _build(self, device):
         total = sum(c.weight.numel() for c, _ in self.pairs)
@@ -245,7 +247,23 @@ class FoldedConvWeights:
         if self._device != dev:
             self._build(dev)
         srcs = [w.detach() if _hw_flat(w) is not None else w.detach().contiguous() for w in weights]
-        self._launch(srcs, self.views, 0, 1)
+        if self.async_stream is None:
+            self._launch(srcs, self.views, 0, 1)
+            return
+        # the fold depends on the parameters only: launched on a second stream it runs beside whatever the caller does next (the
+        # ResNet stem, whose own weight sits in a pack of its own); the first consumer calls wait_ready()
+        side, main = self.async_stream, torch.cuda.current_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._launch(srcs, self.views, 0, 1)
+            self._ready = torch.cuda.Event()
+            self._ready.record(side)
+        self._keep = srcs
+
+    def wait_ready(self) -> None:
+        if self._ready is not None:
+            torch.cuda.current_stream(self._device).wait_event(self._ready)
+            self._ready, self._keep = None, None
 
     def unfold(self, grads):
         outs, srcs = [], []
@@ -445,8 +463,14 @@ class _Backbone(nn.Module):
                         pairs += [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2), (blk.conv3, blk.bn3)]
                         if blk.downsample is not None:
                             pairs.append((blk.downsample[0], blk.downsample[1]))
-                # R101 has 104 convolutions: several packs of <= 64
-                object.__setattr__(self, "_fold", [FoldedConvWeights(pairs[i:i + 64]) for i in range(0, len(pairs), 64)])
+                # the stem's weight in a pack of its own (needed at once), the rest in packs of <= 64 (R101 has 104 convolutions)
+                # that fold on a second stream while the stem runs
+                packs = [FoldedConvWeights(pairs[:1])] + [FoldedConvWeights(pairs[i:i + 64]) for i in range(1, len(pairs), 64)]
+                if os.environ.get("DETR_B200_PREFETCH_SHADOWS", "1") != "0":
+                    side = torch.cuda.Stream(x.device)
+                    for pk in packs[1:]:
+                        pk.async_stream = side
+                object.__setattr__(self, "_fold", packs)
             w16 = {}
             for pack in self._fold:
                 w16.update(pack())
@@ -459,6 +483,9 @@ class _Backbone(nn.Module):
         else:
             x = F.relu(_conv_bn(x, m.conv1, m.bn1), inplace=True)
         x = _stem_maxpool(m.maxpool, x) if fused else m.maxpool(x)
+        if self._fold is not None and w16 is not None:
+            for pack in self._fold:
+                pack.wait_ready()           # the folded weights of layer1..4 (launched on the second stream before the stem)
         blocks = [blk for layer in (m.layer1, m.layer2, m.layer3, m.layer4) for blk in layer]
         if w16 is not None and self.fuse_block_backward and all(type(b).__name__ == "Bottleneck" for b in blocks):
             for i, blk in enumerate(blocks):
