@@ -188,6 +188,19 @@ def _stem_maxpool(pool: nn.MaxPool2d, x: torch.Tensor) -> torch.Tensor:
     return _MaxPool3x3s2.apply(x) if ok else pool(x)
 
 
+_PREFETCH_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _prefetch_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """The per-device second stream of the FORWARD pass: work that depends on the parameters only (weight shadows, frozen-BN fold).
+    Kept here, not on the modules: they stay deep-copyable / picklable."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _PREFETCH_STREAMS.get(idx)
+    if st is None:
+        st = _PREFETCH_STREAMS[idx] = torch.cuda.Stream(dev)
+    return st
+
+
 class _FoldFn(torch.autograd.Function):
     """All frozen-BN folds of the network in one launch each way: w16_k = bf16(W_k * s_k) forward (OHWI storage, i.e.
     channels_last weights for cuDNN), dW_k = fp32(dW16_k * s_k) backward."""
@@ -213,8 +226,16 @@ class FoldedConvWeights:
             raise ValueError(f"at most {_lib.FOLD_MAX_TENSORS} convolutions per fold pack")
         self.pairs = list(pairs)
         self.views, self.flat, self._device = [], None, None
-        self.async_stream = None          # set by the owner: fold() then launches there and leaves an event for wait_ready()
-        self._ready, self._keep = None, None
+        self.run_async = False            # set by the owner: fold() then launches on the prefetch stream and leaves an event for wait_ready()
+        self._ready, self._keep = None, None   # transient (None between forwards): the objects stay deep-copyable
+
+    def __deepcopy__(self, memo):
+        """A copy starts unbuilt: the folded views become outputs of an autograd node during forward (not deep-copyable), and the
+        flat buffer is rebuilt on first use anyway."""
+        import copy as _copy
+        new = FoldedConvWeights(_copy.deepcopy(self.pairs, memo))
+        new.run_async = self.run_async
+        return new
 
     def _build(self, device):
         total = sum(c.weight.numel() for c, _ in self.pairs)
@@ -247,12 +268,12 @@ class FoldedConvWeights:
         if self._device != dev:
             self._build(dev)
         srcs = [w.detach() if _hw_flat(w) is not None else w.detach().contiguous() for w in weights]
-        if self.async_stream is None:
+        if not self.run_async or dev.type != "cuda":
             self._launch(srcs, self.views, 0, 1)
             return
         # the fold depends on the parameters only: launched on a second stream it runs beside whatever the caller does next (the
         # ResNet stem, whose own weight sits in a pack of its own); the first consumer calls wait_ready()
-        side, main = self.async_stream, torch.cuda.current_stream(dev)
+        side, main = _prefetch_stream(dev), torch.cuda.current_stream(dev)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             self._launch(srcs, self.views, 0, 1)
@@ -467,9 +488,8 @@ class _Backbone(nn.Module):
                 # that fold on a second stream while the stem runs
                 packs = [FoldedConvWeights(pairs[:1])] + [FoldedConvWeights(pairs[i:i + 64]) for i in range(1, len(pairs), 64)]
                 if os.environ.get("DETR_B200_PREFETCH_SHADOWS", "1") != "0":
-                    side = torch.cuda.Stream(x.device)
                     for pk in packs[1:]:
-                        pk.async_stream = side
+                        pk.run_async = True
                 object.__setattr__(self, "_fold", packs)
             w16 = {}
             for pack in self._fold:
@@ -522,8 +542,6 @@ class DetrHarness(nn.Module):
         self._decoder_fn = decoder_fn
         self._posenc_fn = posenc_fn   # (H', W', heights, widths, scale, F, T) -> (pos (B,S,C), mask (B,S)); default: the CUDA kernel
 
-    _prefetch_streams: Dict[int, "torch.cuda.Stream"] = {}
-
     def _prefetch_shadows(self, dev: torch.device) -> None:
         """bf16 weight shadows of encoder, decoder and heads on a second stream while the ResNet runs: they depend on the parameters
         only (their consumers' `refresh` calls wait for the event instead of copying again)."""
@@ -534,9 +552,7 @@ class DetrHarness(nn.Module):
         packs = [p for p in packs if p is not None]
         if self._encoder_fn is not None or not packs:
             return
-        side = self._prefetch_streams.get(dev.index)
-        if side is None:
-            side = self._prefetch_streams[dev.index] = torch.cuda.Stream(dev)
+        side = _prefetch_stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for p in packs:

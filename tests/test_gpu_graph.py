@@ -206,3 +206,19 @@ def test_side_stream_weight_gradients_are_identical(cuda, monkeypatch):
         grads[side] = {names[id(p)]: v.detach().clone() for p, v in zip(g.fopt.params, g.fopt.grad_views)}
     bad = [n for n, v in grads["1"].items() if not torch.equal(v, grads["0"][n])]
     assert not bad, bad
+
+
+def test_model_stays_deepcopyable_after_forward(cuda):
+    """The second-stream plumbing (streams, events) lives outside the modules: a model that has run forward / backward can still be
+    deep-copied (EMA copies, checkpoint tooling), and the copy computes the same thing."""
+    from detr_b200.harness import batch_to, synthetic_batch
+    m, _ = _make(cuda, train=False)
+    b = batch_to(synthetic_batch(2, 160, 200, 11, 6, seed=5), cuda)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m(b["image"], b["height"], b["width"])
+    out["pred_logits"].float().sum().backward()
+    m2 = copy.deepcopy(m)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        o1 = m(b["image"], b["height"], b["width"])
+        o2 = m2(b["image"], b["height"], b["width"])
+    assert torch.equal(o1["pred_logits"], o2["pred_logits"]) and torch.equal(o1["pred_boxes"], o2["pred_boxes"])
