@@ -991,6 +991,14 @@ static void ln_partition(int M, int n_tiles, bool gelu, int sms, int* rpc_out, i
     }
 }
 
+/* Host-only query (no launch): how detr_gemm_ln_bf16 would cut an (M, N) problem into CTAs on a device with `sms` SMs -- real rows per
+ * row block (32 / 64 / 96 / 128) and column groups per row block.  Lets callers and tests inspect the partition model. */
+extern "C" int detr_gemm_ln_partition(int M, int N, int gelu, int sms, int* rows_per_cta, int* groups) {
+    DETR_CHECK_ARG(M >= 1 && N >= 1 && sms >= 1 && rows_per_cta != nullptr && groups != nullptr, "gemm_ln_partition: bad arguments");
+    ln_partition(M, (N + kGN - 1) / kGN, gelu != 0, sms, rows_per_cta, groups);
+    return 0;
+}
+
 /* out[M][N] (bf16) = epilogue((LayerNorm(x) [+ addend]) . w[N][256]^T): detr/model.py:221-224,173-182 fused with the projections
  * that consume the normalised rows.  Output columns < n_pos_end are computed from LN(x) + addend, the others from LN(x).
  * addend: fp32, row of flattened row m at (m / rows_per_batch) * add_sb + (m % rows_per_batch) * add_sr.

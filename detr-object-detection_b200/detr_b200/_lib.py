@@ -48,6 +48,7 @@ SIGNATURES = {
     "detr_layernorm_bwd": [P, P, c_int, P, P, c_int, c_int64, P, P, P, P, P, P, P, P, c_int, c_int, P],
     "detr_layernorm_bwd_tail": [P, P, c_int, P, P, c_int, c_int64, P, P, P, P, P, P, P, P, c_int, c_int, P, P, c_float, ctypes.c_uint64, P, P],
     "detr_layernorm_bwd_fold": [P, c_int, c_int, P, P, P, P],
+    "detr_gemm_ln_partition": [c_int, c_int, c_int, c_int, P, P],
     "detr_heads_grad_prep": [P, c_int, P, P, P, c_int, P, c_int, c_int, P],
     "detr_epilogue_fwd": [c_int, P, c_int, P, P, c_int, c_int, c_float, ctypes.c_uint64, P, P],
     "detr_epilogue_chunks": [c_int, c_int],

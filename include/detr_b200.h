@@ -234,6 +234,9 @@ int detr_gemm_ln_bf16(const void* x, int x_dtype, int64_t ldx, const float* gamm
                       const void* w, int64_t ldw, int M, int N, int epilogue, const float* bias, void* out, int64_t ldo,
                       void* aux, int64_t ld_aux, void* a_plain, void* a_pos, float* mean, float* rstd, float dropout_p,
                       uint64_t seed, const uint64_t* seed_ptr, void* stream);
+/* Host-only: the (rows per row block, column groups per row block) detr_gemm_ln_bf16 uses for an (M, N) problem on `sms` SMs. */
+int detr_gemm_ln_partition(int M, int N, int gelu, int sms, int* rows_per_cta, int* groups);
+
 /* Weight and bias gradients of nn.Linear: dw[N][K] (fp32, contiguous) = dy[M][N]^T . x[M][K], db[N] (optional) = column
  * sums of dy; dy, x bf16 row-major.  Rows n >= n_switch (a multiple of 128) of dw are computed from x1 instead of x0
  * (fused q|k|v projection: q/k rows from LN(x)+pos, v rows from LN(x)); x1 may be NULL.  Split over M with fp32

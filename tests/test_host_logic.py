@@ -68,3 +68,29 @@ def test_product_path_refuses_cpu_tensors():
         G.gemm(a, w)
     with pytest.raises(RuntimeError):
         G.gemm_wgrad(a, a)
+
+
+def test_ln_gemm_partition_model():
+    """detr_gemm_ln_partition (host only): row blocks of 32..128 rows, groups within the column tiles, one wave whenever one wave
+    is possible, and the documented choices at the BASELINE shapes."""
+    import ctypes
+    from detr_b200 import _lib
+    lib = _lib.load()
+    fn = lib.detr_gemm_ln_partition
+
+    def part(M, N, gelu, sms=148):
+        r, g = ctypes.c_int(0), ctypes.c_int(0)
+        assert fn(M, N, gelu, sms, ctypes.byref(r), ctypes.byref(g)) == 0
+        return r.value, g.value
+
+    for M in (1, 70, 800, 1200, 2400, 3400, 6800, 26800, 100000):
+        for N in (256, 768, 1536, 2048):
+            for gelu in (0, 1):
+                rpc, groups = part(M, N, gelu)
+                n_tiles = (N + 127) // 128
+                assert rpc in (32, 64, 96, 128) and 1 <= groups <= n_tiles
+                if -(-M // 128) <= 148:                      # one wave is possible: the model must not pick more
+                    assert -(-M // rpc) * groups <= 148, (M, N, rpc, groups)
+    assert part(6800, 768, 0) == (96, 2) and part(6800, 2048, 1) == (96, 2)     # 71 x 2 = 142 CTAs on 148 SMs
+    assert part(800, 2048, 1) == (96, 16)                                       # decoder FFN: one column tile per CTA
+    assert part(800, 256, 0)[0] == 32
